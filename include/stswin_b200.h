@@ -1,0 +1,118 @@
+/* stswin_b200 -- C ABI of the B200-native (sm_100a) STswinCL hot paths.
+ *
+ * The reference (YuemingJin/STswinCL) is pure Python/PyTorch and has no FFI of its own; its
+ * boundary for these paths is the nn.Module / function API.  This header
+ * is the C boundary underneath the drop-in Python modules of `stswincl_b200/`: each entry point
+ * names the reference op sequence it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch) unless stated otherwise;
+ *   - `stream` is a cudaStream_t passed as void*; functions only enqueue work and never synchronise;
+ *   - return value 0 = success, negative = error (STSWIN_ERR_*); the message of the last error of
+ *     the calling thread is available from stswin_last_error();
+ *   - activations are bf16 (uint16 storage), statistics / gradients of parameters are fp32;
+ *   - no global mutable state besides per-device read-only attribute caches.
+ */
+#ifndef STSWIN_B200_H_
+#define STSWIN_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STSWIN_OK 0
+#define STSWIN_ERR_INVALID_ARG (-1)
+#define STSWIN_ERR_UNSUPPORTED (-2)
+#define STSWIN_ERR_CUDA (-3)
+#define STSWIN_ERR_DRIVER (-4)
+
+/* ABI version of this header; bumped on any signature change. */
+int stswin_abi_version(void);
+/* Text of the last error raised on the calling thread ("" if none). */
+const char* stswin_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Dense layers: D[M,N] = sum_k A[m,k] * B[n,k]   (bf16 x bf16 -> fp32 accumulate, tcgen05)
+ *
+ * Replaces nn.Linear forward/backward inside the block:
+ *   qkv   seg18/net/Ours/swin_512.py:116     proj  :139     fc1/fc2  :18,22 (Mlp.forward)
+ *   PatchMerging.reduction :275
+ *
+ *   a_major / b_major : 0 = K-major  (A is [M,K] row-major with leading dim lda; B is [N,K], ldb)
+ *                       1 = MN-major (A is [K,M] row-major;                      B is [K,N])
+ *                       (1,0) is not provided.
+ *   mode : STSWIN_EPI_*.  `bias` ([N] fp32) may be NULL.  `colsum` ([N] fp32, may be NULL)
+ *          receives += the column sums of the bf16-rounded D (bias gradient of the producer).
+ *   STSWIN_EPI_F32_REDUCE: D is fp32 [M,N] with leading dim ldd and receives += the product;
+ *          the K range is split `k_splits` ways across CTAs (weight gradients reduce over tokens).
+ */
+#define STSWIN_EPI_BIAS 0          /* D = acc + bias                                  */
+#define STSWIN_EPI_BIAS_RES 1      /* D = acc + bias + aux            (residual add)  */
+#define STSWIN_EPI_BIAS_GELU 2     /* D2 = acc + bias ; D = gelu_erf(D2)              */
+#define STSWIN_EPI_MUL_DGELU 3     /* D = acc * gelu_erf'(aux)                        */
+#define STSWIN_EPI_F32_REDUCE 4    /* D(fp32) += acc, split-K                          */
+
+int stswin_gemm_bf16(const void* A, int a_major, int64_t lda,
+                     const void* B, int b_major, int64_t ldb,
+                     void* D, int64_t ldd, void* D2,
+                     const void* aux, int64_t ld_aux,
+                     const float* bias, float* colsum,
+                     int M, int N, int K, int mode, int k_splits, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Spatio-temporal shifted-window attention core (K1+K3+K5 of SURVEY.md section 2c).
+ *
+ * Replaces, for one SwinTransformerBlock call (seg18/net/Ours/swin_512.py):
+ *   torch.roll + window_partition + permute   :210-218      (gather = TMA box coordinates)
+ *   q*scale, q@k^T, bias gather, mask, softmax, attn@v      :119-138 (WindowAttention.forward)
+ *   window_reverse + torch.roll               :224-231      (scatter = TMA store coordinates)
+ *
+ *   qkv        [B, T, H, W, 3C] bf16, tokens in natural (un-rolled) order, channel =
+ *              which*C + head*(C/nH) + d  (the layout nn.Linear(dim, 3*dim) produces, :116)
+ *   bias_table [(2*ws-1)^2, nH] fp32   (relative_position_bias_table, :81-82; the relative
+ *              position index :88-99 and the shift mask :171-192 are closed forms in-kernel)
+ *   out        [B, T, H, W, C] bf16, same token order
+ *   lse2       [stswin_winattn_lse_elems(...)] fp32 workspace written by fwd, read by bwd
+ *   shift      0 or ws/2.  T*ws*ws must be 16, 32, 64 or 128; C/nH a multiple of 64, <= 256.
+ */
+int64_t stswin_winattn_lse_elems(int B, int T, int H, int W, int C, int nH, int ws);
+int stswin_winattn_fwd(const void* qkv, const float* bias_table, void* out, float* lse2,
+                       int B, int T, int H, int W, int C, int nH, int ws, int shift, void* stream);
+/* Backward of the same op sequence (what autograd derives for swin_512.py:119-138 + :210-231).
+ *   d_out        [B, T, H, W, C]  bf16  gradient w.r.t. `out`
+ *   d_qkv        [B, T, H, W, 3C] bf16  written (every element)
+ *   d_bias_table [(2*ws-1)^2, nH] fp32  += (zero it for a fresh gradient)
+ *   d_qkv_colsum [3C] fp32 or NULL      += column sums of d_qkv (= gradient of qkv.bias)
+ */
+int stswin_winattn_bwd(const void* qkv, const float* bias_table, const float* lse2, const void* d_out,
+                       void* d_qkv, float* d_bias_table, float* d_qkv_colsum,
+                       int B, int T, int H, int W, int C, int nH, int ws, int shift, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * LayerNorm (eps inside the rsqrt, fp32 statistics) over rows of `row_len` bf16 channels.
+ * Replaces nn.LayerNorm at swin_512.py:235 (norm2, norm1) and, with pm = 1, the PatchMerging
+ * prologue  x[:,0::2,0::2] | x[:,1::2,0::2] | x[:,0::2,1::2] | x[:,1::2,1::2] -> cat -> norm
+ * (swin_512.py:266-274): logical row r of the normalised matrix is then the 2x2 neighbourhood
+ * of output token r, gathered from x [BT, H, W, C] with row_len = 4*C (H, W, C describe x).
+ *   fwd: y [M,row_len] bf16 (dense), mean/rstd [M] fp32
+ *   bwd: dx has the layout of x (scattered through the same 2x2 map when pm = 1);
+ *        dres (optional, same layout as dy) is added to dx (residual branch);
+ *        dgamma/dbeta [row_len] fp32 +=; dx_colsum [row_len] fp32 += column sums of dx or NULL
+ */
+int stswin_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                         int64_t M, int row_len, float eps, int pm, int H, int W, int C, void* stream);
+int stswin_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
+                         const void* dres, void* dx, float* dgamma, float* dbeta, float* dx_colsum,
+                         int64_t M, int row_len, int pm, int H, int W, int C, void* stream);
+
+/* [batch, R, Cc] -> [batch, Cc, R] with dtype conversion (1 = fp32, 0 = bf16 on either side).
+ * Replaces permute(0,1,3,4,2).contiguous() / permute(0,1,3,2) of SwinTransformerLayerv5.forward
+ * (swin_512.py:314,319,326). */
+int stswin_transpose(const void* in, int in_is_f32, void* out, int out_is_f32, int64_t batch, int R, int Cc, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STSWIN_B200_H_ */

@@ -41,34 +41,65 @@ def expanded_bias(table: torch.Tensor, ws: int, T: int) -> torch.Tensor:
     return b.repeat(1, T, T)
 
 
-def window_attention(x_win: torch.Tensor, p: Params, ws: int, num_heads: int,
-                     mask: Optional[torch.Tensor] = None,
-                     qk_scale: Optional[float] = None) -> torch.Tensor:
-    """x_win [B_, T, N, C] -> [B_, T, N, C]   (swin_512.py:109-141).
+def attention_core(qkv: torch.Tensor, table: torch.Tensor, ws: int, num_heads: int,
+                   mask: Optional[torch.Tensor] = None, T: int = 2,
+                   qk_scale: Optional[float] = None) -> torch.Tensor:
+    """Per-window multi-head attention on projected tokens (swin_512.py:117-138).
 
-    ``mask`` is the [nW, N, N] {0,-100} buffer or None.  Token order inside a
-    window is t-major then row-major spatial; qkv output channels are ordered
-    [which][head][hd] (swin_512.py:116).
+    qkv [B_, L, 3C] with L = T*N, channels ordered [which][head][hd] (:116) -> [B_, L, C].
+    ``mask`` is the [nW, N, N] {0,-100} buffer or None; bias and mask are tiled T x T (:124,128).
     """
-    B_, T, N, C = x_win.shape
+    B_, L, C3 = qkv.shape
+    C = C3 // 3
     hd = C // num_heads
     scale = qk_scale if qk_scale is not None else hd ** -0.5
-    L = T * N
-    qkv = F.linear(x_win.reshape(B_, L, C), p["qkv.weight"], p.get("qkv.bias"))
     qkv = qkv.reshape(B_, L, 3, num_heads, hd)
     q = qkv[:, :, 0] * scale          # scale after the bias add (:119)
     k = qkv[:, :, 1]
     v = qkv[:, :, 2]
     s = torch.einsum("blhd,bmhd->bhlm", q, k)
-    s = s + expanded_bias(p["relative_position_bias_table"], ws, T).unsqueeze(0)
+    s = s + expanded_bias(table, ws, T).unsqueeze(0)
     if mask is not None:
         nW = mask.shape[0]
         m = mask.to(s.dtype).repeat(1, T, T)                       # (:128)
         s = (s.reshape(B_ // nW, nW, num_heads, L, L) + m[None, :, None]).reshape(B_, num_heads, L, L)
     pattn = torch.softmax(s, dim=-1)
-    o = torch.einsum("bhlm,bmhd->blhd", pattn, v).reshape(B_, L, C)
+    return torch.einsum("bhlm,bmhd->blhd", pattn, v).reshape(B_, L, C)
+
+
+def window_attention(x_win: torch.Tensor, p: Params, ws: int, num_heads: int,
+                     mask: Optional[torch.Tensor] = None,
+                     qk_scale: Optional[float] = None) -> torch.Tensor:
+    """x_win [B_, T, N, C] -> [B_, T, N, C]   (WindowAttention.forward, swin_512.py:109-141).
+
+    Token order inside a window is t-major then row-major spatial."""
+    B_, T, N, C = x_win.shape
+    qkv = F.linear(x_win.reshape(B_, T * N, C), p["qkv.weight"], p.get("qkv.bias"))
+    o = attention_core(qkv, p["relative_position_bias_table"], ws, num_heads, mask, T, qk_scale)
     o = F.linear(o, p["proj.weight"], p["proj.bias"])
     return o.reshape(B_, T, N, C)
+
+
+def attention_core_unrolled(qkv: torch.Tensor, table: torch.Tensor, input_resolution, ws: int, shift: int,
+                            num_heads: int) -> torch.Tensor:
+    """The same core on tokens in their natural (un-rolled, un-partitioned) order:
+    qkv [B, T, H*W, 3C] -> [B, T, H*W, C].  Gather by the window index of SURVEY Appx A.3
+    (= roll + window_partition, swin_512.py:210-218), attend, scatter back to the same
+    coordinates (= window_reverse + inverse roll, :224-231).  This is the exact contract of the
+    CUDA kernel ``stswin_winattn_fwd``."""
+    H, W = input_resolution
+    B, T, L, C3 = qkv.shape
+    N = ws * ws
+    nW = (H // ws) * (W // ws)
+    gidx = torch.from_numpy(ix.window_gather_index(H, W, ws, shift)).reshape(-1)   # [nW*N]
+    mask_np = ix.shift_attn_mask(H, W, ws, shift)
+    mask = torch.from_numpy(mask_np) if mask_np is not None else None
+    qw = qkv[:, :, gidx, :].reshape(B, T, nW, N, C3).permute(0, 2, 1, 3, 4).reshape(B * nW, T * N, C3)
+    ow = attention_core(qw, table, ws, num_heads, mask, T)
+    ow = ow.reshape(B, nW, T, N, C3 // 3).permute(0, 2, 1, 3, 4).reshape(B, T, nW * N, C3 // 3)
+    out = torch.empty_like(ow)
+    out[:, :, gidx, :] = ow
+    return out
 
 
 def mlp(x: torch.Tensor, p: Params) -> torch.Tensor:
@@ -96,19 +127,11 @@ def swin_block(x: torch.Tensor, p: Params, input_resolution, num_heads: int,
     ws, shift = ix.effective_window(input_resolution, window_size, shift_size)
     B, T, L, C = x.shape
     assert L == H * W, "input feature has wrong size"
-    N = ws * ws
-    nW = (H // ws) * (W // ws)
-    gidx = torch.from_numpy(ix.window_gather_index(H, W, ws, shift)).reshape(-1)   # [nW*N]
-    mask_np = ix.shift_attn_mask(H, W, ws, shift)
-    mask = torch.from_numpy(mask_np) if mask_np is not None else None
-
-    # gather: [B, T, nW*N, C] -> [B, nW, T, N, C] -> [B*nW, T, N, C]   (:210-218)
-    xw = x[:, :, gidx, :].reshape(B, T, nW, N, C).permute(0, 2, 1, 3, 4).reshape(B * nW, T, N, C)
-    aw = window_attention(xw, _sub(p, "attn."), ws, num_heads, mask)
-    # scatter back to the same coordinates (:224-231)
-    aw = aw.reshape(B, nW, T, N, C).permute(0, 2, 1, 3, 4).reshape(B, T, nW * N, C)
-    attn_out = torch.empty_like(aw)
-    attn_out[:, :, gidx, :] = aw
+    # the qkv / proj Linears act per token, so they commute with the window gather / scatter
+    a = _sub(p, "attn.")
+    qkv = F.linear(x, a["qkv.weight"], a.get("qkv.bias"))
+    core = attention_core_unrolled(qkv, a["relative_position_bias_table"], (H, W), ws, shift, num_heads)
+    attn_out = F.linear(core, a["proj.weight"], a["proj.bias"])
 
     y = x + attn_out                                                           # (:234)
     z = y + mlp(layer_norm(y, p["norm2.weight"], p["norm2.bias"]), _sub(p, "mlp."))

@@ -1,0 +1,50 @@
+// extern "C" surface of libstswin_b200.so -- see include/stswin_b200.h
+#include "../../include/stswin_b200.h"
+#include "host_util.h"
+#include "kernels.h"
+
+extern "C" {
+
+int stswin_abi_version(void) { return 1; }
+const char* stswin_last_error(void) { return stswin::last_error(); }
+
+int stswin_gemm_bf16(const void* A, int a_major, int64_t lda, const void* B, int b_major, int64_t ldb, void* D,
+                     int64_t ldd, void* D2, const void* aux, int64_t ld_aux, const float* bias, float* colsum, int M,
+                     int N, int K, int mode, int k_splits, void* stream) {
+  return stswin::gemm_bf16(A, a_major, lda, B, b_major, ldb, D, ldd, D2, aux, ld_aux, bias, colsum, M, N, K, mode,
+                           k_splits, static_cast<cudaStream_t>(stream));
+}
+
+int64_t stswin_winattn_lse_elems(int B, int T, int H, int W, int C, int nH, int ws) {
+  return stswin::winattn_lse_elems(B, T, H, W, C, nH, ws);
+}
+int stswin_winattn_fwd(const void* qkv, const float* bias_table, void* out, float* lse2, int B, int T, int H, int W,
+                       int C, int nH, int ws, int shift, void* stream) {
+  return stswin::winattn_fwd(qkv, bias_table, out, lse2, B, T, H, W, C, nH, ws, shift,
+                             static_cast<cudaStream_t>(stream));
+}
+
+int stswin_winattn_bwd(const void* qkv, const float* bias_table, const float* lse2, const void* d_out, void* d_qkv,
+                       float* d_bias_table, float* d_qkv_colsum, int B, int T, int H, int W, int C, int nH, int ws,
+                       int shift, void* stream) {
+  return stswin::winattn_bwd(qkv, bias_table, lse2, d_out, d_qkv, d_bias_table, d_qkv_colsum, B, T, H, W, C, nH, ws,
+                             shift, static_cast<cudaStream_t>(stream));
+}
+
+int stswin_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                         int64_t M, int row_len, float eps, int pm, int H, int W, int C, void* stream) {
+  return stswin::layernorm_fwd(x, gamma, beta, y, mean, rstd, M, row_len, eps, pm, H, W, C,
+                               static_cast<cudaStream_t>(stream));
+}
+int stswin_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
+                         const void* dres, void* dx, float* dgamma, float* dbeta, float* dx_colsum, int64_t M,
+                         int row_len, int pm, int H, int W, int C, void* stream) {
+  return stswin::layernorm_bwd(dy, x, mean, rstd, gamma, dres, dx, dgamma, dbeta, dx_colsum, M, row_len, pm, H, W, C,
+                               static_cast<cudaStream_t>(stream));
+}
+int stswin_transpose(const void* in, int in_is_f32, void* out, int out_is_f32, int64_t batch, int R, int Cc,
+                     void* stream) {
+  return stswin::transpose_cvt(in, in_is_f32, out, out_is_f32, batch, R, Cc, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

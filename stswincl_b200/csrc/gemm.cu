@@ -1,0 +1,414 @@
+// Persistent, warp-specialised tcgen05 GEMM for the dense layers of the Swin block
+// (K2 qkv, K4 proj, K6 fc1/fc2 of SURVEY.md section 2c; their dgrad and wgrad twins;
+// the PatchMerging reduction).
+//
+//   D[M,N] = sum_k A[m,k] * B[n,k]          bf16 operands, fp32 accumulation in TMEM
+//
+// Operand storage ("major"): 0 = K-major  (A stored [M,K] row-major / B stored [N,K] row-major)
+//                            1 = MN-major (A stored [K,M] row-major / B stored [K,N] row-major)
+// so forward (x W^T) and dgrad (dy Wt^T, with a pre-transposed weight) are (0,0) and the
+// weight gradient dW = dy^T x, which reduces over tokens, is (1,1) without any transposed
+// copy of an activation.
+//
+// CTA = 6 warps: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM allocation), warps 2-5 epilogue.
+// Tile 128 x 256 x 64, 4-stage TMA->smem ring (128B swizzle), two 256-column TMEM accumulators so
+// the epilogue of tile i overlaps the main loop of tile i+1.  The epilogue goes TMEM -> registers
+// -> swizzled smem (transpose) -> coalesced 128-bit global stores, with an optional auxiliary tile
+// (residual or pre-activation, prefetched one chunk ahead with coalesced loads), bias, exact GELU,
+// GELU', column sums (bias gradients), and an fp32 TMA add-reduction for split-K weight gradients.
+// (A first version stored through TMA from a single staging buffer and serialised on the store's
+// read latency: 315 TFLOP/s at K=512; see profiles/.)
+#include "common.cuh"
+#include "host_util.h"
+
+namespace stswin {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BN = 256;
+constexpr int BK = 64;
+constexpr int STAGES = 4;
+constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KB
+constexpr int B_STAGE_BYTES = BN * BK * 2;   // 32 KB
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int EPI_WARPS = 4;
+constexpr int EPI_BUF_BYTES = 32 * 128;      // 32 rows x 128 B per epilogue warp
+constexpr int NUM_THREADS = 32 * (2 + EPI_WARPS);
+constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + 2 * EPI_WARPS * EPI_BUF_BYTES + 256;
+
+enum Mode : int {
+  kBias = 0,        // D = acc + bias
+  kBiasRes = 1,     // D = acc + bias + aux
+  kBiasGelu = 2,    // D2 = u = acc + bias ; D = gelu(u)
+  kMulDGelu = 3,    // D = acc * gelu'(aux)
+  kF32Reduce = 4,   // D(fp32) += acc          (split-K, TMA add-reduction)
+};
+
+struct GemmArgs {
+  int M, N, K;
+  int mode;
+  int k_splits;
+  const float* bias;   // [N] or null
+  float* colsum;       // [N] fp32, += column sums of the (bf16-rounded) D, or null
+  __nv_bfloat16* D;    // bf16 outputs / aux are accessed with plain coalesced loads and stores
+  __nv_bfloat16* D2;
+  const __nv_bfloat16* aux;
+  long ldd, ld_aux;
+};
+
+template <int A_MN, int B_MN, int MODE>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmD /* fp32 reduce target only */, const GemmArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_stage = smem;
+  uint8_t* s_out = smem + STAGES * STAGE_BYTES;
+  uint8_t* s_aux = s_out + EPI_WARPS * EPI_BUF_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_aux + EPI_WARPS * EPI_BUF_BYTES);
+  uint64_t* full_bar = bars;                 // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;       // [STAGES]
+  uint64_t* acc_full = bars + 2 * STAGES;    // [2]
+  uint64_t* acc_empty = acc_full + 2;        // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int num_m = (p.M + BM - 1) / BM;
+  const int num_n = (p.N + BN - 1) / BN;
+  const int kb_total = (p.K + BK - 1) / BK;
+  const int kb_per_split = (kb_total + p.k_splits - 1) / p.k_splits;
+  const int num_items = num_m * num_n * p.k_splits;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmD);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], EPI_WARPS);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const int n_blk = item % num_n;
+        const int m_blk = (item / num_n) % num_m;
+        const int split = item / (num_n * num_m);
+        const int kb0 = split * kb_per_split;
+        const int kb1 = min(kb_total, kb0 + kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sA = s_stage + stage * STAGE_BYTES;
+          uint8_t* sB = sA + A_STAGE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+          if (A_MN) {
+#pragma unroll
+            for (int c = 0; c < BM / 64; ++c) tma_load_2d(sA + c * (BK * 128), &tmA, &full_bar[stage], m_blk * BM + c * 64, kb * BK);
+          } else {
+            tma_load_2d(sA, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c) tma_load_2d(sB + c * (BK * 128), &tmB, &full_bar[stage], n_blk * BN + c * 64, kb * BK);
+          } else {
+            tma_load_2d(sB, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const int split = item / (num_n * num_m);
+        const int kb0 = split * kb_per_split;
+        const int kb1 = min(kb_total, kb0 + kb_per_split);
+        mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sA = smem_u32(s_stage + stage * STAGE_BYTES);
+          const uint32_t sB = sA + A_STAGE_BYTES;
+#pragma unroll
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            const uint64_t adesc = A_MN ? umma_smem_desc(sA + kk * 2048, BK * 128, 1024)
+                                        : umma_smem_desc(sA + kk * 32, 16, 1024);
+            const uint64_t bdesc = B_MN ? umma_smem_desc(sB + kk * 2048, BK * 128, 1024)
+                                        : umma_smem_desc(sB + kk * 32, 16, 1024);
+            umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);     // smem slot reusable once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&acc_full[acc]);          // accumulator complete
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (4 warps)
+    const int wq = warp & 3;                         // TMEM lane quarter this warp may access
+    uint8_t* my_out = s_out + wq * EPI_BUF_BYTES;
+    uint8_t* my_aux = s_aux + wq * EPI_BUF_BYTES;
+    constexpr bool has_aux = (MODE == kBiasRes || MODE == kMulDGelu);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    // coalesced access pattern of a 32-row x 64-col bf16 chunk: instruction i of lane l touches
+    // row 4*i + l/8, 16-byte column group l%8  (8 lanes = one 128-byte line)
+    const int crow = lane >> 3, cchunk = lane & 7;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      const int n_blk = item % num_n;
+      const int m_blk = (item / num_n) % num_m;
+      const int row0 = m_blk * BM + wq * 32;
+      const int col0 = n_blk * BN;
+      const bool row_ok = (row0 + lane) < p.M;
+      const uint32_t t_row = tmem_base + (uint32_t(wq * 32) << 16) + acc * BN;
+
+      if constexpr (MODE == kF32Reduce) {
+        mbar_wait(&acc_full[acc], acc_phase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld32(t_row + c * 32, v);
+          tmem_ld_wait();
+          if (lane == 0) tma_wait_group_read<0>();
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            uint4 q = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            *reinterpret_cast<uint4*>(my_out + sw128_offset(lane, j)) = q;
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && col0 + c * 32 < p.N && row0 < p.M) {
+            tma_reduce_add_2d(&tmD, my_out, col0 + c * 32, row0);
+            tma_commit_group();
+          }
+        }
+      } else {
+        uint4 auxr[8];
+        auto aux_fetch = [&](int cb) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = row0 + 4 * i + crow, n = cb + cchunk * 8;
+            auxr[i] = (r < p.M && n < p.N)
+                          ? __ldg(reinterpret_cast<const uint4*>(p.aux + (size_t)r * p.ld_aux + n))
+                          : make_uint4(0, 0, 0, 0);
+          }
+        };
+        // staged 32 x 64 chunk -> global, 128-byte lines
+        auto store_staged = [&](const uint8_t* stg, __nv_bfloat16* dst, int cb) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rl = 4 * i + crow;
+            const uint4 q = *reinterpret_cast<const uint4*>(stg + sw128_offset(rl, cchunk));
+            const int r = row0 + rl, n = cb + cchunk * 8;
+            if (r < p.M && n < p.N) *reinterpret_cast<uint4*>(dst + (size_t)r * p.ldd + n) = q;
+          }
+        };
+        if (has_aux) aux_fetch(col0);                 // in flight while the main loop finishes
+        mbar_wait(&acc_full[acc], acc_phase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < BN / 64; ++c) {
+          const int cbase = col0 + c * 64;
+          if (has_aux) {
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              *reinterpret_cast<uint4*>(my_aux + sw128_offset(4 * i + crow, cchunk)) = auxr[i];
+            if (c + 1 < BN / 64) aux_fetch(cbase + 64);   // in flight while this chunk is processed
+          }
+          __syncwarp();                                   // aux staged; earlier readers of my_out are done
+          // the 64 columns are processed as two rolled halves of 32 to keep the code I-cache resident
+#pragma unroll 1
+          for (int half = 0; half < 2; ++half) {
+            uint32_t v[32];
+            tmem_ld32(t_row + c * 64 + half * 32, v);
+            float bias_l = 0.f;                          // lane l holds the bias of column l of this half
+            if (p.bias != nullptr) {
+              const int n = cbase + half * 32 + lane;
+              if (n < p.N) bias_l = __ldg(p.bias + n);
+            }
+            uint32_t auxw[16];
+            if (has_aux) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint4 q = *reinterpret_cast<const uint4*>(my_aux + sw128_offset(lane, half * 4 + j));
+                auxw[4 * j] = q.x; auxw[4 * j + 1] = q.y; auxw[4 * j + 2] = q.z; auxw[4 * j + 3] = q.w;
+              }
+            }
+            tmem_ld_wait();
+            uint32_t outw[16];    // bf16 pairs
+            uint32_t out2w[16];   // pre-activation for kBiasGelu
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float a0 = __uint_as_float(v[2 * j]);
+              float a1 = __uint_as_float(v[2 * j + 1]);
+              a0 += __shfl_sync(0xffffffffu, bias_l, 2 * j);
+              a1 += __shfl_sync(0xffffffffu, bias_l, 2 * j + 1);
+              if constexpr (MODE == kBiasRes) {
+                const float2 r = unpack_bf16(auxw[j]);
+                a0 += r.x; a1 += r.y;
+              } else if constexpr (MODE == kBiasGelu) {
+                out2w[j] = pack_bf16(a0, a1);
+                a0 = gelu_erf(a0); a1 = gelu_erf(a1);
+              } else if constexpr (MODE == kMulDGelu) {
+                const float2 u = unpack_bf16(auxw[j]);
+                a0 *= gelu_erf_grad(u.x); a1 *= gelu_erf_grad(u.y);
+              }
+              if (!row_ok) { a0 = 0.f; a1 = 0.f; }
+              outw[j] = pack_bf16(a0, a1);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              *reinterpret_cast<uint4*>(my_out + sw128_offset(lane, half * 4 + j)) =
+                  make_uint4(outw[4 * j], outw[4 * j + 1], outw[4 * j + 2], outw[4 * j + 3]);
+              if constexpr (MODE == kBiasGelu)     // my_aux is free in this mode: stage the second output there
+                *reinterpret_cast<uint4*>(my_aux + sw128_offset(lane, half * 4 + j)) =
+                    make_uint4(out2w[4 * j], out2w[4 * j + 1], out2w[4 * j + 2], out2w[4 * j + 3]);
+            }
+          }
+          __syncwarp();
+          store_staged(my_out, p.D, cbase);
+          if constexpr (MODE == kBiasGelu) store_staged(my_aux, p.D2, cbase);
+          if (p.colsum != nullptr) {
+            // lane owns columns (2*lane, 2*lane+1) of this 64-wide chunk: sum the 32 staged rows
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) {
+              const uint32_t w = *reinterpret_cast<const uint32_t*>(my_out + sw128_offset(r, lane >> 2) + (lane & 3) * 4);
+              const float2 f = unpack_bf16(w);
+              s0 += f.x; s1 += f.y;
+            }
+            const int n = cbase + 2 * lane;
+            if (n < p.N) atomicAdd(p.colsum + n, s0);
+            if (n + 1 < p.N) atomicAdd(p.colsum + n + 1, s1);
+          }
+        }
+      }
+      // all TMEM reads of this accumulator are done -> hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (lane == 0) tma_wait_group<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+template <int A_MN, int B_MN, int MODE>
+int launch_mode(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const GemmArgs& args,
+           cudaStream_t stream) {
+  auto kern = gemm_kernel<A_MN, B_MN, MODE>;
+  STSWIN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  const int num_m = (args.M + BM - 1) / BM, num_n = (args.N + BN - 1) / BN;
+  const int items = num_m * num_n * args.k_splits;
+  const int grid = items < num_sms() ? items : num_sms();
+  kern<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, tmD, args);
+  STSWIN_CUDA(cudaGetLastError());
+  return kOk;
+}
+
+template <int A_MN, int B_MN>
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const GemmArgs& args,
+           cudaStream_t stream) {
+  switch (args.mode) {
+    case kBias: return launch_mode<A_MN, B_MN, kBias>(tmA, tmB, tmD, args, stream);
+    case kBiasRes: return launch_mode<A_MN, B_MN, kBiasRes>(tmA, tmB, tmD, args, stream);
+    case kBiasGelu: return launch_mode<A_MN, B_MN, kBiasGelu>(tmA, tmB, tmD, args, stream);
+    case kMulDGelu: return launch_mode<A_MN, B_MN, kMulDGelu>(tmA, tmB, tmD, args, stream);
+    default: return launch_mode<A_MN, B_MN, kF32Reduce>(tmA, tmB, tmD, args, stream);
+  }
+}
+
+}  // namespace
+
+// see include/stswin_b200.h : stswin_gemm_bf16
+int gemm_bf16(const void* A, int a_major, long lda, const void* B, int b_major, long ldb, void* D, long ldd, void* D2,
+              const void* aux, long ld_aux, const float* bias, float* colsum, int M, int N, int K, int mode,
+              int k_splits, cudaStream_t stream) {
+  STSWIN_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
+  STSWIN_CHECK_ARG(mode >= kBias && mode <= kF32Reduce, "gemm: unknown epilogue mode %d", mode);
+  STSWIN_CHECK_ARG(a_major == 0 || a_major == 1, "gemm: a_major must be 0 or 1");
+  STSWIN_CHECK_ARG(b_major == 0 || b_major == 1, "gemm: b_major must be 0 or 1");
+  STSWIN_CHECK_ARG(!(a_major == 1 && b_major == 0), "gemm: (A MN-major, B K-major) is not instantiated");
+  STSWIN_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0, "gemm: lda/ldb must be multiples of 8 elements");
+  STSWIN_CHECK_ARG(A && B && D, "gemm: null operand");
+  if (k_splits < 1) k_splits = 1;
+  STSWIN_CHECK_ARG(k_splits == 1 || mode == kF32Reduce, "gemm: split-K requires the fp32 reduce epilogue");
+  STSWIN_CHECK_ARG(mode != kBiasGelu || D2 != nullptr, "gemm: gelu epilogue needs the pre-activation output D2");
+  STSWIN_CHECK_ARG((mode != kBiasRes && mode != kMulDGelu) || aux != nullptr, "gemm: epilogue mode %d needs aux", mode);
+  const int kb_total = (K + BK - 1) / BK;
+  if (k_splits > kb_total) k_splits = kb_total;
+  // every split must own at least one k-block (an empty split would publish an unwritten accumulator)
+  while (k_splits > 1 && (k_splits - 1) * ((kb_total + k_splits - 1) / k_splits) >= kb_total) --k_splits;
+
+  CUtensorMap tmA, tmB, tmD;
+  int rc;
+  {
+    uint64_t dims[2], str[1];
+    uint32_t box[2];
+    if (a_major == 0) { dims[0] = K; dims[1] = M; box[0] = BK; box[1] = BM; }
+    else              { dims[0] = M; dims[1] = K; box[0] = 64; box[1] = BK; }
+    str[0] = (uint64_t)lda * 2;
+    if ((rc = make_tmap(&tmA, TmapDtype::BF16, 2, A, dims, str, box, true)) != kOk) return rc;
+    if (b_major == 0) { dims[0] = K; dims[1] = N; box[0] = BK; box[1] = BN; }
+    else              { dims[0] = N; dims[1] = K; box[0] = 64; box[1] = BK; }
+    str[0] = (uint64_t)ldb * 2;
+    if ((rc = make_tmap(&tmB, TmapDtype::BF16, 2, B, dims, str, box, true)) != kOk) return rc;
+    tmD = tmA;
+    if (mode == kF32Reduce) {
+      STSWIN_CHECK_ARG(ldd % 4 == 0, "gemm: fp32 ldd must be a multiple of 4");
+      dims[0] = N; dims[1] = M;
+      str[0] = (uint64_t)ldd * 4; box[0] = 32; box[1] = 32;
+      if ((rc = make_tmap(&tmD, TmapDtype::F32, 2, D, dims, str, box, true)) != kOk) return rc;
+    } else {
+      STSWIN_CHECK_ARG(ldd % 8 == 0 && N % 8 == 0, "gemm: N and ldd must be multiples of 8 elements");
+      STSWIN_CHECK_ARG((reinterpret_cast<uintptr_t>(D) & 15) == 0, "gemm: D must be 16-byte aligned");
+      STSWIN_CHECK_ARG(D2 == nullptr || (reinterpret_cast<uintptr_t>(D2) & 15) == 0, "gemm: D2 must be 16-byte aligned");
+      if (mode == kBiasRes || mode == kMulDGelu)
+        STSWIN_CHECK_ARG(ld_aux % 8 == 0 && (reinterpret_cast<uintptr_t>(aux) & 15) == 0,
+                         "gemm: aux must be 16-byte aligned with ld_aux a multiple of 8");
+    }
+  }
+  GemmArgs args{M, N, K, mode, k_splits, bias, colsum, static_cast<__nv_bfloat16*>(D), static_cast<__nv_bfloat16*>(D2),
+                static_cast<const __nv_bfloat16*>(aux), ldd, ld_aux};
+  if (a_major == 0 && b_major == 0) return launch<0, 0>(tmA, tmB, tmD, args, stream);
+  if (a_major == 0 && b_major == 1) return launch<0, 1>(tmA, tmB, tmD, args, stream);
+  return launch<1, 1>(tmA, tmB, tmD, args, stream);
+}
+
+}  // namespace stswin

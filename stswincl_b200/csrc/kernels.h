@@ -1,0 +1,26 @@
+// Internal C++ declarations of the launchers behind the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace stswin {
+
+int gemm_bf16(const void* A, int a_major, long lda, const void* B, int b_major, long ldb, void* D, long ldd, void* D2,
+              const void* aux, long ld_aux, const float* bias, float* colsum, int M, int N, int K, int mode,
+              int k_splits, cudaStream_t stream);
+
+int winattn_fwd(const void* qkv, const float* bias_table, void* out, float* lse2, int B, int T, int H, int W, int C,
+                int nH, int ws, int shift, cudaStream_t stream);
+int winattn_bwd(const void* qkv, const float* bias_table, const float* lse2, const void* d_out, void* d_qkv,
+                float* d_table, float* d_qkv_colsum, int B, int T, int H, int W, int C, int nH, int ws, int shift,
+                cudaStream_t stream);
+long winattn_lse_elems(int B, int T, int H, int W, int C, int nH, int ws);
+
+int layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, long M,
+                  int Ctot, float eps, int pm, int H, int W, int C, cudaStream_t stream);
+int layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
+                  const void* dres, void* dx, float* dgamma, float* dbeta, float* dx_colsum, long M, int Ctot, int pm,
+                  int H, int W, int C, cudaStream_t stream);
+int transpose_cvt(const void* in, int in_f32, void* out, int out_f32, long batch, int R, int Cc, cudaStream_t stream);
+
+}  // namespace stswin

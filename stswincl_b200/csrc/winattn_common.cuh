@@ -1,0 +1,157 @@
+// Geometry shared by the window-attention forward and backward kernels.
+//
+// A "tile" is 128 token rows = G consecutive windows of L = T*ws*ws tokens each (G = 128/L).
+// Work item = (tile, head).  Each operand chunk is [128 rows x 64 channels] bf16 in the
+// 128B-swizzled K-major layout, filled by TMA boxes taken straight from the un-rolled,
+// un-partitioned [B, T, H, W, channels] tensor: the cyclic shift and the window partition
+// (swin_512.py:210-218) are the box coordinates; window_reverse + the inverse roll (:224-231)
+// are the same coordinates on the store side.  A window that wraps around the image border
+// (last window row / column of a shifted block) is moved as four quadrant boxes, which changes
+// the order of its tokens inside the tile; the per-row geometry below (`row_geom`) is the single
+// place that knows the order, and bias / mask lookups go through it.
+#pragma once
+
+#include "common.cuh"
+
+namespace stswin {
+
+struct WinGeom {
+  int B, T, H, W, C, nH, ws, shift;
+  int hd, N, L, G, nWh, nWw, nW, total_windows, num_tiles, nc;   // nc = hd / 64
+  float scale_log2e;                                              // hd^-0.5 * log2(e)
+  float scale;                                                    // hd^-0.5
+  int uniform_quad;   // 1: every window of a shifted block is moved as four quadrant boxes (one token
+                      //    order per launch; the backward kernel needs that to sum dS across tiles)
+};
+
+struct RowGeom {
+  int g;       // window slot inside the tile
+  int rr, cc;  // token coordinates inside its window (shifted frame)
+  int id;      // shift-mask region id 0..8 (swin_512.py:173-184), 0 when unshifted
+  int canon;   // g*L + t*N + rr*ws + cc : position in the reference's own window-token order
+  bool wraps;  // window crosses the image border (the only windows with a non-zero mask)
+  bool valid;  // false for rows of a padding window in the last tile
+};
+
+__device__ __forceinline__ bool quad_order(const WinGeom& gm, bool wraps) {
+  return gm.uniform_quad ? (gm.shift > 0) : wraps;
+}
+
+__device__ __forceinline__ void window_coords(const WinGeom& gm, int gw, int& b, int& wh, int& ww, bool& wraps) {
+  b = gw / gm.nW;
+  const int win = gw - b * gm.nW;
+  wh = win / gm.nWw;
+  ww = win - wh * gm.nWw;
+  wraps = gm.shift > 0 && (wh == gm.nWh - 1 || ww == gm.nWw - 1);
+}
+
+__device__ __forceinline__ int region_band(int p, int extent, int ws, int shift) {
+  return (p >= extent - ws ? 1 : 0) + (p >= extent - shift ? 1 : 0);
+}
+
+// geometry of tile row r of tile `tile`
+__device__ __forceinline__ RowGeom row_geom(const WinGeom& gm, int tile, int r) {
+  RowGeom o;
+  o.g = r / gm.L;
+  const int rem = r - o.g * gm.L;
+  int gw = tile * gm.G + o.g;
+  o.valid = gw < gm.total_windows;
+  if (!o.valid) gw = gm.total_windows - 1;
+  int b, wh, ww, t;
+  window_coords(gm, gw, b, wh, ww, o.wraps);
+  if (!quad_order(gm, o.wraps)) {
+    t = rem / gm.N;
+    const int pos = rem - t * gm.N;
+    o.rr = pos / gm.ws;
+    o.cc = pos - o.rr * gm.ws;
+  } else {
+    const int hw = gm.ws >> 1, qn = gm.L >> 2, qs = gm.N >> 2;
+    const int q = rem / qn;
+    const int r2 = rem - q * qn;
+    t = r2 / qs;
+    const int p = r2 - t * qs;
+    o.rr = (q >> 1) * hw + p / hw;
+    o.cc = (q & 1) * hw + p % hw;
+  }
+  o.canon = o.g * gm.L + t * gm.N + o.rr * gm.ws + o.cc;
+  o.id = 0;
+  if (gm.shift > 0)
+    o.id = 3 * region_band(wh * gm.ws + o.rr, gm.H, gm.ws, gm.shift) +
+           region_band(ww * gm.ws + o.cc, gm.W, gm.ws, gm.shift);
+  return o;
+}
+
+// Issue the TMA boxes that fill (LOAD) or drain (STORE) one [128 x 64ch] chunk buffer for `tile`.
+//   ch0 : first channel of the chunk in the global tensor
+// Called by all 32 lanes of one warp; box k of the chunk is issued by lane k % 32.
+template <bool LOAD>
+__device__ __forceinline__ void tile_boxes(const WinGeom& gm, int tile, int ch0, uint8_t* buf,
+                                           const CUtensorMap* tm_full, const CUtensorMap* tm_quad, uint64_t* bar,
+                                           int lane) {
+  const int hw = gm.ws >> 1;
+  for (int k = lane; k < gm.G * 4; k += 32) {
+    const int g = k >> 2, q = k & 3;
+    int gw = tile * gm.G + g;
+    if (gw >= gm.total_windows) {
+      if (!LOAD) continue;            // nothing to store for a padding window
+      gw = gm.total_windows - 1;      // loads: finite filler data, never stored
+    }
+    int b, wh, ww;
+    bool wraps;
+    window_coords(gm, gw, b, wh, ww, wraps);
+    uint8_t* dst = buf + (g * gm.L) * 128;
+    if (!quad_order(gm, wraps)) {
+      if (q != 0) continue;
+      const int w0 = ww * gm.ws + gm.shift, h0 = wh * gm.ws + gm.shift;
+      if (LOAD) tma_load_4d(dst, tm_full, bar, ch0, w0, h0, b * gm.T);
+      else      tma_store_4d(tm_full, dst, ch0, w0, h0, b * gm.T);
+    } else {
+      const int h0 = (wh * gm.ws + gm.shift + (q >> 1) * hw) % gm.H;
+      const int w0 = (ww * gm.ws + gm.shift + (q & 1) * hw) % gm.W;
+      uint8_t* d = dst + q * (gm.L >> 2) * 128;
+      if (LOAD) tma_load_4d(d, tm_quad, bar, ch0, w0, h0, b * gm.T);
+      else      tma_store_4d(tm_quad, d, ch0, w0, h0, b * gm.T);
+    }
+  }
+}
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+      "[%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+// Load this thread's CH = min(L, 32) columns [col0 + cb*CH, +CH) of TMEM row `t_lane` into v[0..CH).
+// tcgen05.ld is warp-collective and needs a warp-uniform address: for L == 16 two windows share a
+// warp, so the warp loads its 32-column band and each half-warp keeps its own 16 columns.
+template <int L>
+__device__ __forceinline__ void tmem_ld_row_chunk(uint32_t tmem_mat, uint32_t t_lane, int col0, int cb, int wq, int lane,
+                                                  uint32_t (&v)[32]) {
+  if (L >= 32) {
+    tmem_ld32(tmem_mat + t_lane + col0 + cb * 32, v);
+    tmem_ld_wait();
+  } else {
+    tmem_ld32(tmem_mat + t_lane + wq * 32, v);
+    tmem_ld_wait();
+    if (lane >= 16) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = v[j + 16];
+    }
+  }
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+}  // namespace stswin

@@ -1,0 +1,356 @@
+// K3 forward: spatio-temporal shifted-window attention core.
+//
+// Replaces, in one kernel (reference: seg18/net/Ours/swin_512.py)
+//   torch.roll(-s) + window_partition + view/permute           :210-218   -> TMA box coordinates
+//   q*scale, q @ k^T                                            :119-120   -> tcgen05 (S in TMEM)
+//   relative_position_bias gather + repeat(1,T,T), + mask       :122-131   -> registers
+//   softmax                                                     :132-134   -> registers (exp2)
+//   attn @ v, transpose/reshape                                 :138       -> tcgen05 (O in TMEM)
+//   window_reverse + torch.roll(+s)                             :224-231   -> TMA store coordinates
+//
+// Input  qkv [B, T, H, W, 3C] bf16 (un-rolled token order; channel = which*C + head*hd + d, :116)
+// Output out [B, T, H, W, C]  bf16 (same token order), lse2 [num_tiles, nH, 128] fp32
+//        (base-2 log-sum-exp of every tile row, consumed by the backward kernel).
+//
+// CTA = 6 warps: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 softmax + epilogue
+// (thread <-> tile row <-> TMEM lane).  Operand chunks stream through a ring of 16 KB slots.
+#include "winattn_common.cuh"
+#include "host_util.h"
+
+namespace stswin {
+
+namespace {
+
+constexpr int NSLOT = 9;
+constexpr int SLOT_BYTES = 128 * 128;          // 128 rows x 64 bf16
+constexpr int P_BYTES = 2 * SLOT_BYTES;        // P [128 x 128] bf16 as two K-major halves
+constexpr int STG_BYTES = 2 * SLOT_BYTES;      // two output staging chunks
+constexpr int TAB_MAX = 15 * 15;               // (2*ws-1)^2 for ws <= 8
+constexpr int NUM_THREADS = 192;
+constexpr int SMEM_BYTES = 1024 + NSLOT * SLOT_BYTES + P_BYTES + STG_BYTES + 128 * 4 + TAB_MAX * 4 + 256;
+constexpr float kMaskLog2e = -100.0f * 1.4426950408889634f;
+
+template <int L>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+winattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid_constant__ CUtensorMap tm_qkv_quad,
+                   const __grid_constant__ CUtensorMap tm_out_full, const __grid_constant__ CUtensorMap tm_out_quad,
+                   const float* __restrict__ bias_table, float* __restrict__ lse2, const WinGeom gm) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_ring = smem;
+  uint8_t* s_p = s_ring + NSLOT * SLOT_BYTES;
+  uint8_t* s_stg = s_p + P_BYTES;
+  uint32_t* s_lut = reinterpret_cast<uint32_t*>(s_stg + STG_BYTES);     // [128] key | id<<8
+  float* s_tab = reinterpret_cast<float*>(s_lut + 128);                 // [TAB_MAX] bias * log2e for this head
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_tab + TAB_MAX + 1);
+  bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(bars) + 7) & ~uintptr_t(7));
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + NSLOT;
+  uint64_t* s_full = bars + 2 * NSLOT;
+  uint64_t* s_free = s_full + 1;
+  uint64_t* p_full = s_full + 2;
+  uint64_t* o_full = s_full + 3;
+  uint64_t* o_free = s_full + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 5);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_items = gm.num_tiles * gm.nH;
+  const int nc = gm.nc;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_qkv_full);
+    tma_prefetch_desc(&tm_qkv_quad);
+    tma_prefetch_desc(&tm_out_full);
+    tma_prefetch_desc(&tm_out_quad);
+    for (int i = 0; i < NSLOT; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(s_free, 128);
+    mbar_init(p_full, 128);
+    mbar_init(o_full, 1);
+    mbar_init(o_free, 128);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  // P buffer: entries outside a row's own window stay zero for the whole kernel
+  for (int i = threadIdx.x; i < P_BYTES / 16; i += NUM_THREADS) reinterpret_cast<uint4*>(s_p)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base;          // 128 columns
+  const uint32_t tmem_O = tmem_base + 128;    // hd columns (<= 256)
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- TMA producer
+    int slot = 0;
+    uint32_t phase = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      const int tile = item / gm.nH, head = item - tile * gm.nH;
+      for (int step = 0; step < 3 * nc; ++step) {
+        // order: Q0 K0 Q1 K1 ... then V0 V1 ...
+        int which, c;
+        if (step < 2 * nc) { which = step & 1; c = step >> 1; }
+        else               { which = 2; c = step - 2 * nc; }
+        mbar_wait(&empty_bar[slot], phase ^ 1);
+        if (lane == 0) mbar_arrive_expect_tx(&full_bar[slot], SLOT_BYTES);
+        __syncwarp();
+        tile_boxes<true>(gm, tile, which * gm.C + head * gm.hd + c * 64, s_ring + slot * SLOT_BYTES, &tm_qkv_full,
+                         &tm_qkv_quad, &full_bar[slot], lane);
+        if (++slot == NSLOT) { slot = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);
+      int slot = 0;
+      uint32_t phase = 0;
+      uint32_t it_phase = 0;
+      const uint32_t p_addr = smem_u32(s_p);
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, it_phase ^= 1) {
+        // S = Q K^T
+        mbar_wait(s_free, it_phase ^ 1);
+        tc_fence_after();
+        for (int c = 0; c < nc; ++c) {
+          const int slot_q = slot;
+          mbar_wait(&full_bar[slot], phase);
+          if (++slot == NSLOT) { slot = 0; phase ^= 1; }
+          const int slot_k = slot;
+          mbar_wait(&full_bar[slot], phase);
+          if (++slot == NSLOT) { slot = 0; phase ^= 1; }
+          tc_fence_after();
+          const uint32_t qa = smem_u32(s_ring + slot_q * SLOT_BYTES), ka = smem_u32(s_ring + slot_k * SLOT_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_bf16(tmem_S, umma_smem_desc(qa + kk * 32, 16, 1024), umma_smem_desc(ka + kk * 32, 16, 1024), idesc_s,
+                      (c > 0 || kk > 0) ? 1u : 0u);
+          umma_commit(&empty_bar[slot_q]);
+          umma_commit(&empty_bar[slot_k]);
+        }
+        umma_commit(s_full);
+        // O = P V
+        mbar_wait(p_full, it_phase);
+        mbar_wait(o_free, it_phase ^ 1);
+        tc_fence_after();
+        for (int c = 0; c < nc; ++c) {
+          mbar_wait(&full_bar[slot], phase);
+          tc_fence_after();
+          const uint32_t va = smem_u32(s_ring + slot * SLOT_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {
+            const uint64_t adesc = umma_smem_desc(p_addr + (kk >> 2) * SLOT_BYTES + (kk & 3) * 32, 16, 1024);
+            const uint64_t bdesc = umma_smem_desc(va + kk * 2048, SLOT_BYTES, 1024);
+            umma_bf16(tmem_O + c * 64, adesc, bdesc, idesc_o, kk > 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[slot]);
+          if (++slot == NSLOT) { slot = 0; phase ^= 1; }
+        }
+        umma_commit(o_full);
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- softmax + epilogue
+    const int wq = warp & 3;
+    const int row = wq * 32 + lane;           // tile row == TMEM lane
+    const int sm_tid = threadIdx.x - 64;      // 0..127
+    const uint32_t t_lane = uint32_t(wq * 32) << 16;
+    const int nbias = (2 * gm.ws - 1) * (2 * gm.ws - 1);
+    uint32_t it_phase = 0;
+    int stg_sel = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, it_phase ^= 1) {
+      const int tile = item / gm.nH, head = item - tile * gm.nH;
+      const RowGeom rg = row_geom(gm, tile, row);
+      s_lut[row] = uint32_t(rg.rr * (2 * gm.ws - 1) + rg.cc) | (uint32_t(rg.id) << 8);
+      for (int i = sm_tid; i < nbias; i += 128) s_tab[i] = __ldg(bias_table + i * gm.nH + head) * 1.4426950408889634f;
+      named_bar_sync(1, 128);
+      const int key_i = (rg.rr + gm.ws - 1) * (2 * gm.ws - 1) + rg.cc + gm.ws - 1;
+      const int col0 = rg.g * L;
+      const bool use_mask = rg.wraps;
+
+      mbar_wait(s_full, it_phase);
+      tc_fence_after();
+      float s[L];
+      float mx = -INFINITY;
+      constexpr int CH = (L >= 32) ? 32 : 16;
+#pragma unroll
+      for (int cb = 0; cb < L / CH; ++cb) {
+        uint32_t v[32];
+        tmem_ld_row_chunk<L>(tmem_S, t_lane, col0, cb, wq, lane, v);
+#pragma unroll
+        for (int jj = 0; jj < CH; ++jj) {
+          const uint32_t lj = s_lut[col0 + cb * CH + jj];
+          float x = fmaf(__uint_as_float(v[jj]), gm.scale_log2e, s_tab[key_i - int(lj & 0xff)]);
+          if (use_mask && (lj >> 8) != uint32_t(rg.id)) x += kMaskLog2e;
+          s[cb * CH + jj] = x;
+          mx = fmaxf(mx, x);
+        }
+      }
+      // S is in registers: the next item's QK^T may overwrite TMEM now
+      tc_fence_before();
+      mbar_arrive(s_free);
+
+      float sum = 0.f;
+#pragma unroll
+      for (int j8 = 0; j8 < L / 8; ++j8) {
+        uint32_t w[4];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          const float p0 = fast_exp2(s[j8 * 8 + 2 * h] - mx);
+          const float p1 = fast_exp2(s[j8 * 8 + 2 * h + 1] - mx);
+          // accumulate what the tensor core will actually see (bf16-rounded probabilities)
+          const uint32_t pk = pack_bf16(p0, p1);
+          const float2 pr = unpack_bf16(pk);
+          sum += pr.x + pr.y;
+          w[h] = pk;
+        }
+        const int col = col0 + j8 * 8;
+        *reinterpret_cast<uint4*>(s_p + (col >> 6) * SLOT_BYTES + sw128_offset(row, (col & 63) >> 3)) =
+            make_uint4(w[0], w[1], w[2], w[3]);
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(p_full);
+      const float inv = 1.0f / sum;
+      lse2[(size_t)item * 128 + rg.canon] = mx + log2f(sum);
+
+      // ---- epilogue: O * (1/sum) -> bf16 -> staging -> TMA store at the un-rolled coordinates
+      mbar_wait(o_full, it_phase);
+      tc_fence_after();
+      for (int c = 0; c < nc; ++c) {
+        uint32_t v0[32], v1[32];
+        tmem_ld32(tmem_O + t_lane + c * 64, v0);
+        tmem_ld32(tmem_O + t_lane + c * 64 + 32, v1);
+        tmem_ld_wait();
+        if (c == nc - 1) {
+          tc_fence_before();
+          mbar_arrive(o_free);
+        }
+        uint8_t* stg = s_stg + stg_sel * SLOT_BYTES;
+        if (sm_tid < 32) tma_wait_group_read<1>();     // the stores that last used this buffer have drained
+        named_bar_sync(1, 128);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 q;
+          q.x = pack_bf16(__uint_as_float(v0[8 * j + 0]) * inv, __uint_as_float(v0[8 * j + 1]) * inv);
+          q.y = pack_bf16(__uint_as_float(v0[8 * j + 2]) * inv, __uint_as_float(v0[8 * j + 3]) * inv);
+          q.z = pack_bf16(__uint_as_float(v0[8 * j + 4]) * inv, __uint_as_float(v0[8 * j + 5]) * inv);
+          q.w = pack_bf16(__uint_as_float(v0[8 * j + 6]) * inv, __uint_as_float(v0[8 * j + 7]) * inv);
+          *reinterpret_cast<uint4*>(stg + sw128_offset(row, j)) = q;
+          q.x = pack_bf16(__uint_as_float(v1[8 * j + 0]) * inv, __uint_as_float(v1[8 * j + 1]) * inv);
+          q.y = pack_bf16(__uint_as_float(v1[8 * j + 2]) * inv, __uint_as_float(v1[8 * j + 3]) * inv);
+          q.z = pack_bf16(__uint_as_float(v1[8 * j + 4]) * inv, __uint_as_float(v1[8 * j + 5]) * inv);
+          q.w = pack_bf16(__uint_as_float(v1[8 * j + 6]) * inv, __uint_as_float(v1[8 * j + 7]) * inv);
+          *reinterpret_cast<uint4*>(stg + sw128_offset(row, 4 + j)) = q;
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, 128);
+        if (sm_tid < 32) {                             // warp 2 issues the scatter, one box per lane
+          tile_boxes<false>(gm, tile, head * gm.hd + c * 64, stg, &tm_out_full, &tm_out_quad, nullptr, lane);
+          tma_commit_group();
+        }
+        stg_sel ^= 1;
+      }
+    }
+    if (sm_tid < 32) tma_wait_group<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace
+
+int fill_geom(WinGeom* gm, int B, int T, int H, int W, int C, int nH, int ws, int shift) {
+  STSWIN_CHECK_ARG(B > 0 && T > 0 && H > 0 && W > 0 && C > 0 && nH > 0 && ws > 0, "winattn: non-positive dimension");
+  STSWIN_CHECK_ARG(H % ws == 0 && W % ws == 0, "winattn: H=%d, W=%d must be multiples of the window size %d", H, W, ws);
+  STSWIN_CHECK_ARG(C % nH == 0, "winattn: C=%d not divisible by num_heads=%d", C, nH);
+  gm->B = B; gm->T = T; gm->H = H; gm->W = W; gm->C = C; gm->nH = nH; gm->ws = ws; gm->shift = shift;
+  gm->hd = C / nH;
+  gm->N = ws * ws;
+  gm->L = T * ws * ws;
+  if (gm->hd % 64 != 0 || gm->hd > 256)
+    return set_error(kErrUnsupported, "winattn: head_dim %d unsupported (need a multiple of 64, <= 256)", gm->hd);
+  if (gm->L > 128 || 128 % gm->L != 0 || gm->L < 16)
+    return set_error(kErrUnsupported, "winattn: T*ws*ws = %d tokens per window unsupported (need 16, 32, 64 or 128)", gm->L);
+  if (!(shift == 0 || (ws % 2 == 0 && shift == ws / 2)))
+    return set_error(kErrUnsupported, "winattn: shift %d unsupported (need 0 or window_size/2 = %d)", shift, ws / 2);
+  if (ws > 8) return set_error(kErrUnsupported, "winattn: window size %d > 8 unsupported", ws);
+  gm->G = 128 / gm->L;
+  gm->nWh = H / ws; gm->nWw = W / ws; gm->nW = gm->nWh * gm->nWw;
+  gm->total_windows = B * gm->nW;
+  gm->num_tiles = (gm->total_windows + gm->G - 1) / gm->G;
+  gm->nc = gm->hd / 64;
+  gm->scale_log2e = 1.4426950408889634f / sqrtf((float)gm->hd);
+  gm->scale = 1.0f / sqrtf((float)gm->hd);
+  gm->uniform_quad = 0;
+  return kOk;
+}
+
+// tensor maps over a [B*T, H, W, channels] bf16 tensor: full-window box and quadrant box
+int make_window_tmaps(CUtensorMap* full, CUtensorMap* quad, const void* base, const WinGeom& gm, int channels) {
+  uint64_t dims[4] = {(uint64_t)channels, (uint64_t)gm.W, (uint64_t)gm.H, (uint64_t)gm.B * gm.T};
+  uint64_t str[3] = {(uint64_t)channels * 2, (uint64_t)gm.W * channels * 2, (uint64_t)gm.H * gm.W * channels * 2};
+  uint32_t box_full[4] = {64, (uint32_t)gm.ws, (uint32_t)gm.ws, (uint32_t)gm.T};
+  int rc = make_tmap(full, TmapDtype::BF16, 4, base, dims, str, box_full, true);
+  if (rc != kOk) return rc;
+  *quad = *full;
+  if (gm.shift > 0) {
+    uint32_t box_quad[4] = {64, (uint32_t)gm.ws / 2, (uint32_t)gm.ws / 2, (uint32_t)gm.T};
+    rc = make_tmap(quad, TmapDtype::BF16, 4, base, dims, str, box_quad, true);
+  }
+  return rc;
+}
+
+template <typename K>
+static int set_smem(K kern, int bytes) {
+  STSWIN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  return kOk;
+}
+
+long winattn_lse_elems(int B, int T, int H, int W, int C, int nH, int ws) {
+  WinGeom gm;
+  if (fill_geom(&gm, B, T, H, W, C, nH, ws, 0) != kOk) return -1;
+  return (long)gm.num_tiles * gm.nH * 128;
+}
+
+// see include/stswin_b200.h : stswin_winattn_fwd
+int winattn_fwd(const void* qkv, const float* bias_table, void* out, float* lse2, int B, int T, int H, int W, int C,
+                int nH, int ws, int shift, cudaStream_t stream) {
+  STSWIN_CHECK_ARG(qkv && bias_table && out && lse2, "winattn_fwd: null pointer");
+  WinGeom gm;
+  int rc = fill_geom(&gm, B, T, H, W, C, nH, ws, shift);
+  if (rc != kOk) return rc;
+  CUtensorMap tq_full, tq_quad, to_full, to_quad;
+  if ((rc = make_window_tmaps(&tq_full, &tq_quad, qkv, gm, 3 * C)) != kOk) return rc;
+  if ((rc = make_window_tmaps(&to_full, &to_quad, out, gm, C)) != kOk) return rc;
+  const int items = gm.num_tiles * gm.nH;
+  const int grid = items < num_sms() ? items : num_sms();
+#define STSWIN_LAUNCH_FWD(LL)                                                                                       \
+  case LL: {                                                                                                        \
+    if ((rc = set_smem(winattn_fwd_kernel<LL>, SMEM_BYTES)) != kOk) return rc;                                      \
+    winattn_fwd_kernel<LL><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tq_full, tq_quad, to_full, to_quad, bias_table, \
+                                                                      lse2, gm);                                    \
+    break;                                                                                                          \
+  }
+  switch (gm.L) {
+    STSWIN_LAUNCH_FWD(16)
+    STSWIN_LAUNCH_FWD(32)
+    STSWIN_LAUNCH_FWD(64)
+    STSWIN_LAUNCH_FWD(128)
+    default: return set_error(kErrUnsupported, "winattn_fwd: L=%d", gm.L);
+  }
+#undef STSWIN_LAUNCH_FWD
+  STSWIN_CUDA(cudaGetLastError());
+  return kOk;
+}
+
+}  // namespace stswin

@@ -1,0 +1,173 @@
+"""Thin torch-tensor wrappers over the C ABI (include/stswin_b200.h).
+
+Each function checks shapes/dtypes, passes raw device pointers and the *current*
+CUDA stream, and raises ``StswinError`` on a non-zero status.  No fallbacks.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import StswinError
+
+EPI_BIAS, EPI_BIAS_RES, EPI_BIAS_GELU, EPI_MUL_DGELU, EPI_F32_REDUCE = 0, 1, 2, 3, 4
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream(t: torch.Tensor):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _req(t: torch.Tensor, dtype, name: str) -> None:
+    if not t.is_cuda:
+        raise StswinError(f"{name} must be a CUDA tensor (stswincl_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise StswinError(f"{name} must be {dtype}, got {t.dtype}")
+
+
+def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn_major: bool = False, b_mn_major: bool = False,
+         mode: int = EPI_BIAS, bias: Optional[torch.Tensor] = None, aux: Optional[torch.Tensor] = None,
+         out: Optional[torch.Tensor] = None, out2: Optional[torch.Tensor] = None,
+         colsum: Optional[torch.Tensor] = None, k_splits: int = 1) -> torch.Tensor:
+    """D[M,N] = sum_k A[m,k] B[n,k] with a fused epilogue (stswin_gemm_bf16).
+
+    a: [M,K] (K-major) or [K,M] (``a_mn_major``); b: [N,K] or [K,N] (``b_mn_major``).
+    Rows may be strided (last dim contiguous)."""
+    _req(a, torch.bfloat16, "a"); _req(b, torch.bfloat16, "b")
+    assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
+    (K, M) = a.shape if a_mn_major else a.shape[::-1]
+    (Kb, N) = b.shape if b_mn_major else b.shape[::-1]
+    assert K == Kb, f"reduction dims differ: {K} vs {Kb}"
+    if mode == EPI_F32_REDUCE:
+        assert out is not None and out.dtype == torch.float32, "fp32 reduce epilogue accumulates into `out`"
+    elif out is None:
+        out = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+    assert out.shape == (M, N) and out.stride(1) == 1
+    if mode == EPI_BIAS_GELU and out2 is None:
+        out2 = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+    if out2 is not None:
+        assert out2.shape == (M, N) and out2.stride() == out.stride()
+    if aux is not None:
+        _req(aux, torch.bfloat16, "aux"); assert aux.shape == (M, N) and aux.stride(1) == 1
+    if bias is not None:
+        _req(bias, torch.float32, "bias"); assert bias.numel() == N and bias.is_contiguous()
+    if colsum is not None:
+        _req(colsum, torch.float32, "colsum"); assert colsum.numel() == N and colsum.is_contiguous()
+    lib = _lib.load()
+    st = lib.stswin_gemm_bf16(a.data_ptr(), int(a_mn_major), a.stride(0), b.data_ptr(), int(b_mn_major), b.stride(0),
+                              out.data_ptr(), out.stride(0), _ptr(out2), _ptr(aux), aux.stride(0) if aux is not None else 0,
+                              _ptr(bias), _ptr(colsum), M, N, K, mode, k_splits, _stream(a))
+    _lib.check(st, "stswin_gemm_bf16")
+    return out
+
+
+def winattn_lse_elems(B, T, H, W, C, nH, ws) -> int:
+    n = _lib.load().stswin_winattn_lse_elems(B, T, H, W, C, nH, ws)
+    if n < 0:
+        _lib.check(-2, "stswin_winattn_lse_elems")
+    return n
+
+
+def winattn_fwd(qkv: torch.Tensor, bias_table: torch.Tensor, H: int, W: int, num_heads: int, ws: int, shift: int,
+                out: Optional[torch.Tensor] = None):
+    """qkv [B, T, H*W, 3C] bf16 (natural token order) -> (out [B, T, H*W, C] bf16, lse2 fp32).
+    stswin_winattn_fwd: gather (roll+partition) / QK^T / bias+mask / softmax / PV / scatter."""
+    _req(qkv, torch.bfloat16, "qkv"); _req(bias_table, torch.float32, "bias_table")
+    B, T, L, C3 = qkv.shape
+    assert L == H * W and C3 % 3 == 0 and qkv.is_contiguous() and bias_table.is_contiguous()
+    C = C3 // 3
+    assert bias_table.shape == ((2 * ws - 1) ** 2, num_heads)
+    if out is None:
+        out = torch.empty((B, T, L, C), dtype=torch.bfloat16, device=qkv.device)
+    lse2 = torch.empty(winattn_lse_elems(B, T, H, W, C, num_heads, ws), dtype=torch.float32, device=qkv.device)
+    st = _lib.load().stswin_winattn_fwd(qkv.data_ptr(), bias_table.data_ptr(), out.data_ptr(), lse2.data_ptr(),
+                                        B, T, H, W, C, num_heads, ws, shift, _stream(qkv))
+    _lib.check(st, "stswin_winattn_fwd")
+    return out, lse2
+
+
+def winattn_bwd(qkv: torch.Tensor, bias_table: torch.Tensor, lse2: torch.Tensor, d_out: torch.Tensor,
+                H: int, W: int, num_heads: int, ws: int, shift: int, d_table: torch.Tensor,
+                d_qkv_colsum: Optional[torch.Tensor] = None, d_qkv: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Gradient of winattn_fwd: returns d_qkv [B,T,H*W,3C] bf16; accumulates into d_table (fp32
+    [(2ws-1)^2, nH]) and, if given, into d_qkv_colsum (fp32 [3C])."""
+    _req(qkv, torch.bfloat16, "qkv"); _req(d_out, torch.bfloat16, "d_out")
+    _req(d_table, torch.float32, "d_table"); _req(lse2, torch.float32, "lse2")
+    B, T, L, C3 = qkv.shape
+    C = C3 // 3
+    assert d_out.shape == (B, T, L, C) and d_out.is_contiguous() and qkv.is_contiguous()
+    assert d_table.shape == bias_table.shape and d_table.is_contiguous()
+    if d_qkv is None:
+        d_qkv = torch.empty_like(qkv)
+    if d_qkv_colsum is not None:
+        _req(d_qkv_colsum, torch.float32, "d_qkv_colsum"); assert d_qkv_colsum.numel() == C3
+    st = _lib.load().stswin_winattn_bwd(qkv.data_ptr(), bias_table.data_ptr(), lse2.data_ptr(), d_out.data_ptr(),
+                                        d_qkv.data_ptr(), d_table.data_ptr(), _ptr(d_qkv_colsum),
+                                        B, T, H, W, C, num_heads, ws, shift, _stream(qkv))
+    _lib.check(st, "stswin_winattn_bwd")
+    return d_qkv
+
+
+def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5, *,
+                  patch_merge_hw=None):
+    """LayerNorm over the last dim of x [M, C] (bf16) -> (y bf16, mean fp32 [M], rstd fp32 [M]).
+    With ``patch_merge_hw=(H, W)``: x is [BT, H*W, C]; rows are the 2x2-gathered 4C vectors of
+    PatchMerging (swin_512.py:266-274) and y is [BT*H*W/4, 4C]."""
+    _req(x, torch.bfloat16, "x"); _req(gamma, torch.float32, "gamma"); _req(beta, torch.float32, "beta")
+    assert x.is_contiguous()
+    if patch_merge_hw is None:
+        M, row_len = x.numel() // x.shape[-1], x.shape[-1]
+        pm, H, W, C = 0, 0, 0, 0
+    else:
+        H, W = patch_merge_hw
+        C = x.shape[-1]
+        M, row_len, pm = x.numel() // C // 4, 4 * C, 1
+    assert gamma.numel() == row_len and beta.numel() == row_len
+    y = torch.empty((M, row_len), dtype=torch.bfloat16, device=x.device)
+    mean = torch.empty(M, dtype=torch.float32, device=x.device)
+    rstd = torch.empty(M, dtype=torch.float32, device=x.device)
+    st = _lib.load().stswin_layernorm_fwd(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), mean.data_ptr(),
+                                          rstd.data_ptr(), M, row_len, eps, pm, H, W, C, _stream(x))
+    _lib.check(st, "stswin_layernorm_fwd")
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, mean: torch.Tensor, rstd: torch.Tensor, gamma: torch.Tensor,
+                  dgamma: torch.Tensor, dbeta: torch.Tensor, *, dres: Optional[torch.Tensor] = None,
+                  dx_colsum: Optional[torch.Tensor] = None, patch_merge_hw=None) -> torch.Tensor:
+    """Returns dx (layout of x); accumulates dgamma / dbeta (fp32) and optionally the column sums of dx."""
+    _req(dy, torch.bfloat16, "dy"); _req(x, torch.bfloat16, "x")
+    assert dy.is_contiguous() and x.is_contiguous()
+    if patch_merge_hw is None:
+        M, row_len = x.numel() // x.shape[-1], x.shape[-1]
+        pm, H, W, C = 0, 0, 0, 0
+    else:
+        H, W = patch_merge_hw
+        C = x.shape[-1]
+        M, row_len, pm = x.numel() // C // 4, 4 * C, 1
+    assert dy.numel() == M * row_len
+    dx = torch.empty_like(x)
+    if dres is not None:
+        _req(dres, torch.bfloat16, "dres"); assert dres.is_contiguous() and dres.numel() == dy.numel()
+    st = _lib.load().stswin_layernorm_bwd(dy.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
+                                          _ptr(dres), dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), _ptr(dx_colsum),
+                                          M, row_len, pm, H, W, C, _stream(x))
+    _lib.check(st, "stswin_layernorm_bwd")
+    return dx
+
+
+def transpose(x: torch.Tensor, out_dtype: torch.dtype) -> torch.Tensor:
+    """[batch, R, Cc] -> [batch, Cc, R] with fp32/bf16 conversion (stswin_transpose)."""
+    assert x.dim() == 3 and x.is_contiguous() and x.is_cuda
+    assert x.dtype in (torch.float32, torch.bfloat16) and out_dtype in (torch.float32, torch.bfloat16)
+    b, R, Cc = x.shape
+    out = torch.empty((b, Cc, R), dtype=out_dtype, device=x.device)
+    st = _lib.load().stswin_transpose(x.data_ptr(), int(x.dtype == torch.float32), out.data_ptr(),
+                                      int(out_dtype == torch.float32), b, R, Cc, _stream(x))
+    _lib.check(st, "stswin_transpose")
+    return out

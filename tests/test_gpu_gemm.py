@@ -1,0 +1,74 @@
+"""GPU: tcgen05 GEMM (stswin_gemm_bf16) against torch fp32 matmul on the same bf16 inputs."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(torch.bfloat16).cuda()
+
+
+def _rel(a, b):
+    return float((a.double() - b.double()).abs().max() / b.double().abs().max())
+
+
+SHAPES = [(128, 256, 64), (256, 512, 512), (384, 1536, 512), (1000, 520, 200), (128, 256, 2048), (4096, 2048, 512)]
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+@pytest.mark.parametrize("majors", [(False, False), (False, True), (True, True)])
+def test_gemm_plain(M, N, K, majors):
+    from stswincl_b200 import ops
+    a_mn, b_mn = majors
+    A = _mk((M, K), 1, K ** -0.5)
+    B = _mk((N, K), 2)
+    bias = torch.randn(N, generator=torch.Generator().manual_seed(3)).cuda()
+    ref = A.float() @ B.float().t() + bias
+    a_in = A.t().contiguous() if a_mn else A
+    b_in = B.t().contiguous() if b_mn else B
+    out = ops.gemm(a_in, b_in, a_mn_major=a_mn, b_mn_major=b_mn, bias=bias)
+    torch.cuda.synchronize()
+    assert _rel(out.float(), ref) < 1e-2
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 512, 512), (1000, 520, 200)])
+def test_gemm_epilogues(M, N, K):
+    from stswincl_b200 import ops
+    A = _mk((M, K), 1, K ** -0.5)
+    B = _mk((N, K), 2)
+    R = _mk((M, N), 4)
+    bias = torch.randn(N, generator=torch.Generator().manual_seed(3)).cuda()
+    acc = A.float() @ B.float().t()
+    # residual
+    out = ops.gemm(A, B, mode=ops.EPI_BIAS_RES, bias=bias, aux=R)
+    assert _rel(out.float(), acc + bias + R.float()) < 1e-2
+    # gelu with pre-activation output + column sums
+    cs = torch.zeros(N, device="cuda")
+    u = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    h = ops.gemm(A, B, mode=ops.EPI_BIAS_GELU, bias=bias, out2=u, colsum=cs)
+    uref = acc + bias
+    assert _rel(u.float(), uref) < 1e-2
+    assert _rel(h.float(), torch.nn.functional.gelu(uref)) < 1e-2
+    assert _rel(cs, h.float().sum(0)) < 1e-3
+    # gelu'(aux) multiply
+    d = ops.gemm(A, B, mode=ops.EPI_MUL_DGELU, aux=R)
+    x = R.float().double().requires_grad_(True)
+    torch.nn.functional.gelu(x).sum().backward()
+    assert _rel(d.float(), acc * x.grad.float()) < 1e-2
+
+
+@pytest.mark.parametrize("M,N,K,splits", [(512, 512, 8192, 16), (1536, 512, 4096, 6), (200, 300, 1000, 3)])
+def test_gemm_wgrad_splitk(M, N, K, splits):
+    """dW[M,N] += dy^T x : both operands stored [K, .] (MN-major), fp32 TMA add-reduction."""
+    from stswincl_b200 import ops
+    if N % 4:
+        pytest.skip("fp32 ldd must be a multiple of 4")
+    dy = _mk((K, M), 5)
+    x = _mk((K, N + (8 - N % 8) % 8), 6)[:, :N]
+    base = torch.randn(M, N, generator=torch.Generator().manual_seed(7)).cuda()
+    out = base.clone()
+    ops.gemm(dy, x, a_mn_major=True, b_mn_major=True, mode=ops.EPI_F32_REDUCE, out=out, k_splits=splits)
+    ref = base + dy.float().t() @ x.float()
+    assert _rel(out, ref) < 2e-3

@@ -1,0 +1,69 @@
+"""GPU: window-attention core kernels against the CPU oracle (oracle.swin_oracle.attention_core_unrolled)
+on the same seeded, bf16-rounded inputs.  Tolerance: 2e-2 relative (bf16 path, BASELINE north_star)."""
+import pytest
+import torch
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL_BF16 = 2e-2
+
+# (B, T, H, W, C, nH, ws, shift)
+CASES = [
+    (2, 2, 16, 24, 256, 2, 8, 0),     # L=128, hd=128, unshifted
+    (2, 2, 16, 24, 256, 2, 8, 4),     # shifted: wrap windows + mask
+    (1, 2, 8, 12, 512, 2, 4, 2),      # stage-2 like: L=32, hd=256, 4 windows per tile
+    (3, 2, 8, 12, 256, 4, 4, 0),      # hd=64
+    (2, 1, 16, 24, 256, 2, 8, 4),     # T=1: L=64, 2 windows per tile
+    (4, 1, 8, 12, 128, 2, 4, 0),      # T=1, ws=4: L=16, 8 windows per tile
+    (4, 1, 8, 12, 128, 2, 4, 2),      # ... shifted: 4-row quadrant boxes (512-byte smem offsets)
+    (3, 1, 8, 12, 128, 2, 4, 0),      # ... partial last tile
+    (3, 1, 8, 12, 128, 2, 4, 2),
+    (1, 2, 64, 80, 512, 4, 8, 4),     # the real stage-1 geometry
+    (1, 2, 32, 40, 1024, 4, 4, 2),    # the real stage-2 geometry
+]
+
+
+def make_case(B, T, H, W, C, nH, ws, shift, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    qkv = (torch.randn(B, T, H * W, 3 * C, generator=g) * 1.2).to(torch.bfloat16)
+    table = torch.randn((2 * ws - 1) ** 2, nH, generator=g) * 0.5
+    return qkv, table
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "B%d_T%d_%dx%d_C%d_h%d_ws%d_s%d" % c)
+def test_winattn_fwd_matches_oracle(case):
+    from oracle import swin_oracle as so
+    from stswincl_b200 import ops
+    B, T, H, W, C, nH, ws, shift = case
+    qkv, table = make_case(*case)
+    ref = so.attention_core_unrolled(qkv.float(), table, (H, W), ws, shift, nH)
+    out, lse2 = ops.winattn_fwd(qkv.cuda(), table.cuda(), H, W, nH, ws, shift)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all()
+    assert rel_err(out.float().cpu(), ref) < TOL_BF16
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "B%d_T%d_%dx%d_C%d_h%d_ws%d_s%d" % c)
+def test_winattn_bwd_matches_oracle(case):
+    from oracle import swin_oracle as so
+    from stswincl_b200 import ops
+    B, T, H, W, C, nH, ws, shift = case
+    qkv, table = make_case(*case)
+    g = torch.Generator().manual_seed(5)
+    d_out = torch.randn(B, T, H * W, C, generator=g).to(torch.bfloat16)
+    q32 = qkv.float().requires_grad_(True)
+    t32 = table.clone().requires_grad_(True)
+    ref = so.attention_core_unrolled(q32, t32, (H, W), ws, shift, nH)
+    (ref * d_out.float()).sum().backward()
+    qkv_d, table_d = qkv.cuda(), table.cuda()
+    out, lse2 = ops.winattn_fwd(qkv_d, table_d, H, W, nH, ws, shift)
+    d_table = torch.zeros_like(table_d)
+    colsum = torch.zeros(3 * C, device="cuda")
+    d_qkv = ops.winattn_bwd(qkv_d, table_d, lse2, d_out.cuda(), H, W, nH, ws, shift, d_table, colsum)
+    torch.cuda.synchronize()
+    assert torch.isfinite(d_qkv.float()).all()
+    assert rel_err(d_qkv.float().cpu(), q32.grad) < TOL_BF16
+    assert rel_err(d_table.cpu(), t32.grad) < TOL_BF16
+    assert rel_err(colsum.cpu(), q32.grad.sum((0, 1, 2))) < TOL_BF16
