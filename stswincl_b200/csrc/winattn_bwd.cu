@@ -400,12 +400,13 @@ int set_smem_bwd(K kern, int bytes) {
 // see include/stswin_b200.h : stswin_winattn_bwd
 int winattn_bwd(const void* qkv, const float* bias_table, const float* lse2, const void* d_out, void* d_qkv,
                 float* d_table, float* d_qkv_colsum, int B, int T, int H, int W, int C, int nH, int ws, int shift,
-                cudaStream_t stream) {
+                float qk_scale, cudaStream_t stream) {
   STSWIN_CHECK_ARG(qkv && bias_table && lse2 && d_out && d_qkv && d_table, "winattn_bwd: null pointer");
   WinGeom gm;
   int rc = fill_geom(&gm, B, T, H, W, C, nH, ws, shift);
   if (rc != kOk) return rc;
   gm.uniform_quad = 1;
+  if (qk_scale > 0.f) { gm.scale = qk_scale; gm.scale_log2e = qk_scale * 1.4426950408889634f; }
   CUtensorMap tq_full, tq_quad, td_full, td_quad, tg_full, tg_quad;
   if ((rc = make_window_tmaps(&tq_full, &tq_quad, qkv, gm, 3 * C)) != kOk) return rc;
   if ((rc = make_window_tmaps(&td_full, &td_quad, d_out, gm, C)) != kOk) return rc;

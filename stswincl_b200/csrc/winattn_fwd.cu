@@ -324,11 +324,12 @@ long winattn_lse_elems(int B, int T, int H, int W, int C, int nH, int ws) {
 
 // see include/stswin_b200.h : stswin_winattn_fwd
 int winattn_fwd(const void* qkv, const float* bias_table, void* out, float* lse2, int B, int T, int H, int W, int C,
-                int nH, int ws, int shift, cudaStream_t stream) {
+                int nH, int ws, int shift, float qk_scale, cudaStream_t stream) {
   STSWIN_CHECK_ARG(qkv && bias_table && out && lse2, "winattn_fwd: null pointer");
   WinGeom gm;
   int rc = fill_geom(&gm, B, T, H, W, C, nH, ws, shift);
   if (rc != kOk) return rc;
+  if (qk_scale > 0.f) { gm.scale = qk_scale; gm.scale_log2e = qk_scale * 1.4426950408889634f; }
   CUtensorMap tq_full, tq_quad, to_full, to_quad;
   if ((rc = make_window_tmaps(&tq_full, &tq_quad, qkv, gm, 3 * C)) != kOk) return rc;
   if ((rc = make_window_tmaps(&to_full, &to_quad, out, gm, C)) != kOk) return rc;

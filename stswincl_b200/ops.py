@@ -74,7 +74,7 @@ def winattn_lse_elems(B, T, H, W, C, nH, ws) -> int:
 
 
 def winattn_fwd(qkv: torch.Tensor, bias_table: torch.Tensor, H: int, W: int, num_heads: int, ws: int, shift: int,
-                out: Optional[torch.Tensor] = None):
+                out: Optional[torch.Tensor] = None, qk_scale: float = 0.0):
     """qkv [B, T, H*W, 3C] bf16 (natural token order) -> (out [B, T, H*W, C] bf16, lse2 fp32).
     stswin_winattn_fwd: gather (roll+partition) / QK^T / bias+mask / softmax / PV / scatter."""
     _req(qkv, torch.bfloat16, "qkv"); _req(bias_table, torch.float32, "bias_table")
@@ -86,14 +86,15 @@ def winattn_fwd(qkv: torch.Tensor, bias_table: torch.Tensor, H: int, W: int, num
         out = torch.empty((B, T, L, C), dtype=torch.bfloat16, device=qkv.device)
     lse2 = torch.empty(winattn_lse_elems(B, T, H, W, C, num_heads, ws), dtype=torch.float32, device=qkv.device)
     st = _lib.load().stswin_winattn_fwd(qkv.data_ptr(), bias_table.data_ptr(), out.data_ptr(), lse2.data_ptr(),
-                                        B, T, H, W, C, num_heads, ws, shift, _stream(qkv))
+                                        B, T, H, W, C, num_heads, ws, shift, float(qk_scale), _stream(qkv))
     _lib.check(st, "stswin_winattn_fwd")
     return out, lse2
 
 
 def winattn_bwd(qkv: torch.Tensor, bias_table: torch.Tensor, lse2: torch.Tensor, d_out: torch.Tensor,
                 H: int, W: int, num_heads: int, ws: int, shift: int, d_table: torch.Tensor,
-                d_qkv_colsum: Optional[torch.Tensor] = None, d_qkv: Optional[torch.Tensor] = None) -> torch.Tensor:
+                d_qkv_colsum: Optional[torch.Tensor] = None, d_qkv: Optional[torch.Tensor] = None,
+                qk_scale: float = 0.0) -> torch.Tensor:
     """Gradient of winattn_fwd: returns d_qkv [B,T,H*W,3C] bf16; accumulates into d_table (fp32
     [(2ws-1)^2, nH]) and, if given, into d_qkv_colsum (fp32 [3C])."""
     _req(qkv, torch.bfloat16, "qkv"); _req(d_out, torch.bfloat16, "d_out")
@@ -108,7 +109,7 @@ def winattn_bwd(qkv: torch.Tensor, bias_table: torch.Tensor, lse2: torch.Tensor,
         _req(d_qkv_colsum, torch.float32, "d_qkv_colsum"); assert d_qkv_colsum.numel() == C3
     st = _lib.load().stswin_winattn_bwd(qkv.data_ptr(), bias_table.data_ptr(), lse2.data_ptr(), d_out.data_ptr(),
                                         d_qkv.data_ptr(), d_table.data_ptr(), _ptr(d_qkv_colsum),
-                                        B, T, H, W, C, num_heads, ws, shift, _stream(qkv))
+                                        B, T, H, W, C, num_heads, ws, shift, float(qk_scale), _stream(qkv))
     _lib.check(st, "stswin_winattn_bwd")
     return d_qkv
 

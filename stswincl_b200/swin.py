@@ -1,0 +1,422 @@
+"""Drop-in replacements for the reference's spatio-temporal Swin head.
+
+Same constructor signatures, same ``state_dict`` keys and shapes, same forward
+contracts as ``seg18/net/Ours/swin_512.py`` (== ``segcata/net/Ours/swin_tem_cata.py``
+== ``pixcontrast_*/contrast/models/Ours/swin_tem.py``):
+
+  * ``WindowAttention``          swin_512.py:73-141
+  * ``Mlp``                      swin_512.py:7-23
+  * ``SwinTransformerBlock``     swin_512.py:143-237  (post-norm, mask fill -100)
+  * ``PatchMerging``             swin_512.py:239-277
+  * ``SwinTransformerLayerv5``   swin_512.py:280-327
+
+so ``model.swin = stswincl_b200.swin.SwinTransformerLayerv5(...)`` followed by
+``load_state_dict(reference_state, strict=True)`` is the whole integration.
+
+All arithmetic runs in the sm_100a kernels behind ``include/stswin_b200.h`` through
+``torch.autograd.Function`` wrappers: bf16 storage, fp32 accumulation / statistics.
+Parameters stay fp32 (the reference's master copy under AMP) and are rounded to bf16
+per call.  There is no CPU path and no PyTorch fallback: CPU tensors raise.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from ._lib import StswinError
+
+_BF16 = torch.bfloat16
+
+
+def to_2tuple(x):
+    return tuple(x) if isinstance(x, (tuple, list)) else (x, x)
+
+
+def _relative_position_index(ws_h: int, ws_w: int) -> torch.Tensor:
+    """Closed form of swin_512.py:88-99."""
+    n = torch.arange(ws_h * ws_w)
+    h, w = n // ws_w, n % ws_w
+    dh = h[:, None] - h[None, :] + ws_h - 1
+    dw = w[:, None] - w[None, :] + ws_w - 1
+    return dh * (2 * ws_w - 1) + dw
+
+
+def _shift_attn_mask(H: int, W: int, ws: int, shift: int) -> torch.Tensor:
+    """Closed form of swin_512.py:171-192 -- kept as a buffer for state_dict parity only; the
+    kernels rebuild the mask from (H, W, ws, shift)."""
+    def band(p, extent):
+        return (p >= extent - ws).long() + (p >= extent - shift).long()
+    ids = 3 * band(torch.arange(H), H)[:, None] + band(torch.arange(W), W)[None, :]
+    per_win = ids.view(H // ws, ws, W // ws, ws).permute(0, 2, 1, 3).reshape(-1, ws * ws)
+    differ = per_win[:, None, :] != per_win[:, :, None]
+    return torch.where(differ, torch.tensor(-100.0), torch.tensor(0.0))
+
+
+def _wgrad_splits(n_out: int, k_in: int, tokens: int) -> int:
+    tiles = ((n_out + 127) // 128) * ((k_in + 255) // 256)
+    return max(1, min((tokens + 63) // 64, round(2 * 148 / tiles)))
+
+
+def _linear_wgrad(dy2d: torch.Tensor, x2d: torch.Tensor, shape) -> torch.Tensor:
+    """dW[N_out, K_in] = dy^T x, reduced over tokens on the tensor cores (fp32, split-K)."""
+    dw = torch.zeros(shape, dtype=torch.float32, device=dy2d.device)
+    ops.gemm(dy2d, x2d, a_mn_major=True, b_mn_major=True, mode=ops.EPI_F32_REDUCE, out=dw,
+             k_splits=_wgrad_splits(shape[0], shape[1], dy2d.shape[0]))
+    return dw
+
+
+class _AttentionFn(torch.autograd.Function):
+    """qkv Linear -> window attention core -> proj Linear on tokens in natural order.
+
+    x [Bp, T, H*W, C] bf16.  Gradients for x, table, qkv.{weight,bias}, proj.{weight,bias}."""
+
+    @staticmethod
+    def forward(ctx, x, table, w_qkv, b_qkv, w_proj, b_proj, geom):
+        H, W, nH, ws, shift, qk_scale = geom
+        Bp, T, L, C = x.shape
+        x2 = x.reshape(-1, C)
+        wq, wp = w_qkv.to(_BF16), w_proj.to(_BF16)
+        qkv = ops.gemm(x2, wq, bias=b_qkv)
+        attn, lse2 = ops.winattn_fwd(qkv.view(Bp, T, L, 3 * C), table, H, W, nH, ws, shift, qk_scale=qk_scale)
+        out = ops.gemm(attn.view(-1, C), wp, bias=b_proj)
+        ctx.save_for_backward(x2, qkv, attn, lse2, table, wq, wp)
+        ctx.geom = geom
+        ctx.has_qkv_bias = b_qkv is not None
+        return out.view(Bp, T, L, C)
+
+    @staticmethod
+    def backward(ctx, d_out):
+        x2, qkv, attn, lse2, table, wq, wp = ctx.saved_tensors
+        H, W, nH, ws, shift, qk_scale = ctx.geom
+        C = x2.shape[1]
+        Bp_T_L = d_out.shape[:3]
+        d2 = d_out.contiguous().view(-1, C)
+        d_bproj = d2.float().sum(0)
+        d_attn = ops.gemm(d2, wp, b_mn_major=True)
+        d_wproj = _linear_wgrad(d2, attn.view(-1, C), wp.shape)
+        d_table = torch.zeros_like(table)
+        d_bqkv = torch.zeros(3 * C, dtype=torch.float32, device=d2.device) if ctx.has_qkv_bias else None
+        d_qkv = ops.winattn_bwd(qkv.view(*Bp_T_L, 3 * C), table, lse2, d_attn.view(*Bp_T_L, C), H, W, nH, ws, shift,
+                                d_table, d_bqkv, qk_scale=qk_scale)
+        dq2 = d_qkv.view(-1, 3 * C)
+        d_x = ops.gemm(dq2, wq, b_mn_major=True)
+        d_wqkv = _linear_wgrad(dq2, x2, wq.shape)
+        return d_x.view(*Bp_T_L, C), d_table, d_wqkv, d_bqkv, d_wproj, d_bproj, None
+
+
+class _BlockFn(torch.autograd.Function):
+    """One post-norm SwinTransformerBlock (swin_512.py:196-237) on bf16 tokens [Bp, T, H*W, C]:
+
+        y   = x + proj(attn_core(qkv(x)))           residual fused into the proj GEMM epilogue
+        z   = y + fc2(gelu(fc1(norm2(y))))          GELU / residual fused into the GEMM epilogues
+        out = norm1(z)
+    """
+
+    @staticmethod
+    def forward(ctx, x, table, w_qkv, b_qkv, w_proj, b_proj, g1, be1, g2, be2, w_fc1, b_fc1, w_fc2, b_fc2, geom):
+        H, W, nH, ws, shift, qk_scale, eps = geom
+        Bp, T, L, C = x.shape
+        x2 = x.reshape(-1, C)
+        wq, wp, w1, w2 = w_qkv.to(_BF16), w_proj.to(_BF16), w_fc1.to(_BF16), w_fc2.to(_BF16)
+        qkv = ops.gemm(x2, wq, bias=b_qkv)
+        attn, lse2 = ops.winattn_fwd(qkv.view(Bp, T, L, 3 * C), table, H, W, nH, ws, shift, qk_scale=qk_scale)
+        y = ops.gemm(attn.view(-1, C), wp, bias=b_proj, aux=x2, mode=ops.EPI_BIAS_RES)
+        yn, mean2, rstd2 = ops.layernorm_fwd(y, g2, be2, eps)
+        u = torch.empty((x2.shape[0], w1.shape[0]), dtype=_BF16, device=x.device)
+        h = ops.gemm(yn, w1, bias=b_fc1, mode=ops.EPI_BIAS_GELU, out2=u)
+        z = ops.gemm(h, w2, bias=b_fc2, aux=y, mode=ops.EPI_BIAS_RES)
+        out, mean1, rstd1 = ops.layernorm_fwd(z, g1, be1, eps)
+        ctx.save_for_backward(x2, qkv, attn, lse2, y, yn, mean2, rstd2, u, h, z, mean1, rstd1,
+                              table, wq, wp, w1, w2, g1, g2)
+        ctx.geom = geom
+        ctx.has_qkv_bias = b_qkv is not None
+        return out.view(Bp, T, L, C)
+
+    @staticmethod
+    def backward(ctx, d_out):
+        (x2, qkv, attn, lse2, y, yn, mean2, rstd2, u, h, z, mean1, rstd1,
+         table, wq, wp, w1, w2, g1, g2) = ctx.saved_tensors
+        H, W, nH, ws, shift, qk_scale, eps = ctx.geom
+        C = x2.shape[1]
+        shp = d_out.shape[:3]
+        dev = x2.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        d2 = d_out.contiguous().view(-1, C)
+        # out = norm1(z)
+        d_g1, d_be1, d_bfc2 = torch.zeros(C, **f32), torch.zeros(C, **f32), torch.zeros(C, **f32)
+        dz = ops.layernorm_bwd(d2, z, mean1, rstd1, g1, d_g1, d_be1, dx_colsum=d_bfc2)
+        # z = y + h W2^T + b2 ; h = gelu(u)
+        d_bfc1 = torch.zeros(w1.shape[0], **f32)
+        du = ops.gemm(dz, w2, b_mn_major=True, mode=ops.EPI_MUL_DGELU, aux=u, colsum=d_bfc1)
+        d_wfc2 = _linear_wgrad(dz, h, w2.shape)
+        # u = yn W1^T + b1 ; yn = norm2(y)
+        dyn = ops.gemm(du, w1, b_mn_major=True)
+        d_wfc1 = _linear_wgrad(du, yn, w1.shape)
+        d_g2, d_be2, d_bproj = torch.zeros(C, **f32), torch.zeros(C, **f32), torch.zeros(C, **f32)
+        dy = ops.layernorm_bwd(dyn, y, mean2, rstd2, g2, d_g2, d_be2, dres=dz, dx_colsum=d_bproj)
+        # y = x + attn Wp^T + bp
+        d_attn = ops.gemm(dy, wp, b_mn_major=True)
+        d_wproj = _linear_wgrad(dy, attn.view(-1, C), wp.shape)
+        d_table = torch.zeros_like(table)
+        d_bqkv = torch.zeros(3 * C, **f32) if ctx.has_qkv_bias else None
+        d_qkv = ops.winattn_bwd(qkv.view(*shp, 3 * C), table, lse2, d_attn.view(*shp, C), H, W, nH, ws, shift,
+                                d_table, d_bqkv, qk_scale=qk_scale)
+        dq2 = d_qkv.view(-1, 3 * C)
+        d_x = ops.gemm(dq2, wq, b_mn_major=True, mode=ops.EPI_BIAS_RES, aux=dy)      # + residual path
+        d_wqkv = _linear_wgrad(dq2, x2, wq.shape)
+        return (d_x.view(*shp, C), d_table, d_wqkv, d_bqkv, d_wproj, d_bproj, d_g1, d_be1, d_g2, d_be2,
+                d_wfc1, d_bfc1, d_wfc2, d_bfc2, None)
+
+
+class _PatchMergeFn(torch.autograd.Function):
+    """2x2 gather + LayerNorm(4C) in one pass, then the bias-free reduction GEMM (swin_512.py:255-277)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, w_red, geom):
+        H, W, eps = geom
+        B, T, L, C = x.shape
+        xn, mean, rstd = ops.layernorm_fwd(x.reshape(B * T, L, C), gamma, beta, eps, patch_merge_hw=(H, W))
+        wr = w_red.to(_BF16)
+        out = ops.gemm(xn, wr)
+        ctx.save_for_backward(x, xn, mean, rstd, gamma, wr)
+        ctx.geom = geom
+        return out.view(B, T, L // 4, wr.shape[0])
+
+    @staticmethod
+    def backward(ctx, d_out):
+        x, xn, mean, rstd, gamma, wr = ctx.saved_tensors
+        H, W, eps = ctx.geom
+        B, T, L, C = x.shape
+        d2 = d_out.contiguous().view(-1, wr.shape[0])
+        dxn = ops.gemm(d2, wr, b_mn_major=True)
+        d_w = _linear_wgrad(d2, xn, wr.shape)
+        d_gamma = torch.zeros(4 * C, dtype=torch.float32, device=x.device)
+        d_beta = torch.zeros_like(d_gamma)
+        dx = ops.layernorm_bwd(dxn, x.reshape(B * T, L, C), mean, rstd, gamma, d_gamma, d_beta, patch_merge_hw=(H, W))
+        return dx.view(B, T, L, C), d_gamma, d_beta, d_w, None
+
+
+class _TransposeFn(torch.autograd.Function):
+    """[batch, R, Cc] -> [batch, Cc, R] with dtype change; the backward is the inverse move."""
+
+    @staticmethod
+    def forward(ctx, x, out_dtype):
+        ctx.in_dtype = x.dtype
+        return ops.transpose(x.contiguous(), out_dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ops.transpose(g.contiguous(), ctx.in_dtype), None
+
+
+def _as_tokens_bf16(x: torch.Tensor) -> torch.Tensor:
+    if not x.is_cuda:
+        raise StswinError("stswincl_b200 modules need CUDA tensors (no CPU path)")
+    return x if x.dtype == _BF16 else x.to(_BF16)
+
+
+class Mlp(nn.Module):
+    """Parameter container with the reference's names (swin_512.py:7-23); the math runs fused
+    inside the block (fc1 + GELU epilogue, fc2 + residual epilogue)."""
+
+    def __init__(self, in_features, hidden_features=None, out_features=None, act_layer=nn.GELU, drop=0.):
+        super().__init__()
+        out_features = out_features or in_features
+        hidden_features = hidden_features or in_features
+        if act_layer is not nn.GELU:
+            raise NotImplementedError("only nn.GELU (erf) is implemented, as used by every reference config")
+        if drop != 0.:
+            raise NotImplementedError("dropout > 0 is not used by any reference config and is not implemented")
+        self.fc1 = nn.Linear(in_features, hidden_features)
+        self.act = act_layer()
+        self.fc2 = nn.Linear(hidden_features, out_features)
+        self.drop = nn.Dropout(drop)
+
+
+class WindowAttention(nn.Module):
+    """swin_512.py:73-141.  ``forward(x_v [B_, T, N, C], mask=None) -> [B_, T, N, C]``.
+
+    Called stand-alone, every window is attended independently (it is treated as a ws x ws image
+    with one un-shifted window).  An explicit ``mask`` tensor is accepted only through
+    ``SwinTransformerBlock`` (which passes geometry instead of the dense mask)."""
+
+    def __init__(self, dim, window_size, num_heads, qkv_bias=True, qk_scale=None, attn_drop=0., proj_drop=0.):
+        super().__init__()
+        self.dim = dim
+        self.window_size = to_2tuple(window_size)
+        self.num_heads = num_heads
+        head_dim = dim // num_heads
+        self.scale = qk_scale or head_dim ** -0.5
+        if attn_drop != 0. or proj_drop != 0.:
+            raise NotImplementedError("dropout > 0 is not used by any reference config and is not implemented")
+        if self.window_size[0] != self.window_size[1]:
+            raise NotImplementedError("square windows only (the reference always passes to_2tuple(ws))")
+        ws = self.window_size[0]
+        self.relative_position_bias_table = nn.Parameter(torch.zeros((2 * ws - 1) * (2 * ws - 1), num_heads))
+        self.register_buffer("relative_position_index", _relative_position_index(ws, ws))
+        self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+        self.attn_drop = nn.Dropout(attn_drop)
+        self.proj = nn.Linear(dim, dim)
+        self.proj_drop = nn.Dropout(proj_drop)
+        nn.init.trunc_normal_(self.relative_position_bias_table, std=.02)
+        self.softmax = nn.Softmax(dim=-1)
+
+    def _qk_scale_arg(self) -> float:
+        default = (self.dim // self.num_heads) ** -0.5
+        return 0.0 if abs(self.scale - default) < 1e-12 else float(self.scale)
+
+    def forward(self, x_v, mask=None):
+        if mask is not None:
+            raise NotImplementedError(
+                "stand-alone WindowAttention with a dense mask tensor is not implemented; use "
+                "SwinTransformerBlock, whose kernels rebuild the shift mask from the geometry")
+        B_, T, N, C = x_v.shape
+        ws = self.window_size[0]
+        assert N == ws * ws and C == self.dim, "input feature has wrong size"
+        in_dtype = x_v.dtype
+        geom = (ws, ws, self.num_heads, ws, 0, self._qk_scale_arg())
+        out = _AttentionFn.apply(_as_tokens_bf16(x_v).contiguous(), self.relative_position_bias_table,
+                                 self.qkv.weight, self.qkv.bias, self.proj.weight, self.proj.bias, geom)
+        return out if in_dtype == _BF16 else out.to(in_dtype)
+
+
+class SwinTransformerBlock(nn.Module):
+    """swin_512.py:143-237.  ``forward(x_v [B, T, L, C]) -> [B, T, L, C]`` (same dtype as the input).
+
+    The reference asserts T == 2; T == 1 is also accepted here as long as
+    T * window_size**2 is 16, 32, 64 or 128."""
+
+    def __init__(self, dim, input_resolution, num_heads, window_size=8, shift_size=0, mlp_ratio=4., qkv_bias=True,
+                 qk_scale=None, drop=0., attn_drop=0., drop_path=0., act_layer=nn.GELU, norm_layer=nn.LayerNorm):
+        super().__init__()
+        self.dim = dim
+        self.input_resolution = tuple(input_resolution)
+        self.num_heads = num_heads
+        self.window_size = window_size
+        self.shift_size = shift_size
+        self.mlp_ratio = mlp_ratio
+        if min(self.input_resolution) <= self.window_size:
+            self.shift_size = 0
+            self.window_size = min(self.input_resolution)
+        assert 0 <= self.shift_size < self.window_size, "shift_size must in 0-window_size"
+        if norm_layer is not nn.LayerNorm:
+            raise NotImplementedError("only nn.LayerNorm is implemented")
+        if drop_path != 0.:
+            raise NotImplementedError("drop_path > 0 is not used by any reference config and is not implemented")
+        self.norm1 = norm_layer(dim)
+        self.attn = WindowAttention(dim, window_size=to_2tuple(self.window_size), num_heads=num_heads,
+                                    qkv_bias=qkv_bias, qk_scale=qk_scale, attn_drop=attn_drop, proj_drop=drop)
+        self.drop_path = nn.Identity()
+        self.norm2 = norm_layer(dim)
+        self.mlp = Mlp(in_features=dim, hidden_features=int(dim * mlp_ratio), act_layer=act_layer, drop=drop)
+        if self.shift_size > 0:
+            H, W = self.input_resolution
+            attn_mask = _shift_attn_mask(H, W, self.window_size, self.shift_size)
+        else:
+            attn_mask = None
+        self.register_buffer("attn_mask", attn_mask)
+
+    def _geom(self):
+        H, W = self.input_resolution
+        return (H, W, self.num_heads, self.window_size, self.shift_size, self.attn._qk_scale_arg(), self.norm1.eps)
+
+    def forward_tokens(self, x: torch.Tensor) -> torch.Tensor:
+        """bf16 in, bf16 out; no dtype round trip (used by the layer container)."""
+        a, m = self.attn, self.mlp
+        return _BlockFn.apply(x, a.relative_position_bias_table, a.qkv.weight, a.qkv.bias, a.proj.weight, a.proj.bias,
+                              self.norm1.weight, self.norm1.bias, self.norm2.weight, self.norm2.bias,
+                              m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias, self._geom())
+
+    def forward(self, x_v):
+        H, W = self.input_resolution
+        B, T, L, C = x_v.shape
+        assert L == H * W, "input feature has wrong size"
+        in_dtype = x_v.dtype
+        out = self.forward_tokens(_as_tokens_bf16(x_v).contiguous())
+        return out if in_dtype == _BF16 else out.to(in_dtype)
+
+
+class PatchMerging(nn.Module):
+    """swin_512.py:239-277.  ``forward(x [B, T, L, C]) -> [B, T, L/4, 2C]``."""
+
+    def __init__(self, input_resolution, dim, norm_layer=nn.LayerNorm):
+        super().__init__()
+        self.input_resolution = tuple(input_resolution)
+        self.dim = dim
+        self.reduction = nn.Linear(4 * dim, 2 * dim, bias=False)
+        self.norm = norm_layer(4 * dim)
+
+    def forward_tokens(self, x: torch.Tensor) -> torch.Tensor:
+        H, W = self.input_resolution
+        return _PatchMergeFn.apply(x, self.norm.weight, self.norm.bias, self.reduction.weight, (H, W, self.norm.eps))
+
+    def forward(self, x):
+        H, W = self.input_resolution
+        B, T, L, C = x.shape
+        assert L == H * W, "input feature has wrong size"
+        assert H % 2 == 0 and W % 2 == 0, f"x size ({H}*{W}) are not even."
+        in_dtype = x.dtype
+        out = self.forward_tokens(_as_tokens_bf16(x).contiguous())
+        return out if in_dtype == _BF16 else out.to(in_dtype)
+
+
+class SwinTransformerLayerv5(nn.Module):
+    """swin_512.py:280-327.  ``forward(x [B, 4, C, H, W]) -> (x3 [B,4,C,H,W], x6 [B,4,2C,H/2,W/2])``.
+
+    Differences in mechanism, not in result: tokens stay bf16 and token-major between blocks;
+    the two frame pairs of layers 0 / 2 (which are independent, :302-307) run as one batch of 2B;
+    the NCHW <-> token-major moves are single transposing kernels."""
+
+    def __init__(self, dim=512, input_resolution=(64, 80), num_heads=4):
+        super().__init__()
+        self.dim = dim
+        self.input_resolution = tuple(input_resolution)
+        self.num_heads = num_heads
+        self.num_layers = 3
+        self.pairs = [[slice(0, 2), slice(2, 4)], [slice(1, 3)], [slice(0, 2), slice(2, 4)]]  # t=4
+        H, W = self.input_resolution
+        self.layers = nn.ModuleList()
+        for _ in range(self.num_layers):
+            self.layers.append(nn.Sequential(
+                SwinTransformerBlock(dim, (H, W), num_heads),
+                SwinTransformerBlock(dim, (H, W), num_heads, shift_size=4)))
+        for _ in range(self.num_layers):
+            self.layers.append(nn.Sequential(
+                SwinTransformerBlock(dim * 2, (H // 2, W // 2), num_heads, window_size=4),
+                SwinTransformerBlock(dim * 2, (H // 2, W // 2), num_heads, window_size=4, shift_size=2)))
+        self.downsample = PatchMerging((H, W), dim)
+
+    def _run_layer(self, x: torch.Tensor, layer_idx: int, both_pairs: bool) -> torch.Tensor:
+        """x [B, 4, L, C] bf16 -> same.  ``both_pairs``: frames (0,1) and (2,3); else frames (1,2),
+        with frames 0 and 3 passing through (swin_512.py:302-307)."""
+        B, T, L, C = x.shape
+        blk0, blk1 = self.layers[layer_idx][0], self.layers[layer_idx][1]
+        if both_pairs:
+            y = blk1.forward_tokens(blk0.forward_tokens(x.view(B * 2, 2, L, C)))
+            return y.view(B, 4, L, C)
+        y = blk1.forward_tokens(blk0.forward_tokens(x[:, 1:3].contiguous()))
+        return torch.cat([x[:, 0:1], y, x[:, 3:4]], dim=1)
+
+    def forward(self, x_v):
+        B, T, C, H, W = x_v.shape
+        assert T == 4, "input feature has wrong size"
+        assert (H, W) == self.input_resolution and C == self.dim, "input feature has wrong size"
+        if not x_v.is_cuda:
+            raise StswinError("stswincl_b200 modules need CUDA tensors (no CPU path)")
+        out_dtype = x_v.dtype if x_v.dtype in (torch.float32, _BF16) else torch.float32
+        x_in = x_v if x_v.dtype in (torch.float32, _BF16) else x_v.float()
+        t = _TransposeFn.apply(x_in.reshape(B * T, C, H * W), _BF16).view(B, T, H * W, C)
+        t = self._run_layer(t, 0, True)
+        t = self._run_layer(t, 1, False)
+        t = self._run_layer(t, 2, True)
+        out1 = _TransposeFn.apply(t.reshape(B * T, H * W, C), out_dtype).view(B, T, C, H, W)
+        t = self.downsample.forward_tokens(t.contiguous())
+        t = self._run_layer(t, 3, True)
+        t = self._run_layer(t, 4, False)
+        t = self._run_layer(t, 5, True)
+        out2 = _TransposeFn.apply(t.reshape(B * T, (H // 2) * (W // 2), 2 * C), out_dtype).view(B, T, 2 * C, H // 2, W // 2)
+        return out1, out2

@@ -1,0 +1,156 @@
+"""GPU: the drop-in Swin modules against (a) the reference's own outputs stored in tests/golden
+(produced by oracle/make_goldens.py from the unmodified reference) and (b) the CPU oracle.
+Tolerance: 2e-2 relative error for the bf16 path (BASELINE north_star)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-2
+
+
+def _g(name):
+    return np.load(os.path.join(GOLDEN, name))
+
+
+def _load(module, params):
+    missing, unexpected = module.load_state_dict(params, strict=True)
+    assert not missing and not unexpected
+    return module.cuda()
+
+
+@pytest.mark.parametrize("case", [("a0", 128, 4, 2, 2, (8, 12), 2, 2), ("a1", 128, 4, 2, 1, (8, 12), 0, 2),
+                                  ("a2", 256, 8, 2, 2, (16, 24), 4, 1)], ids=lambda c: c[0])
+def test_attention_module_vs_reference_golden(case):
+    """WindowAttention.forward semantics (windows in, windows out) reproduced by moving the
+    golden's window-ordered tokens to natural order, running the fused path with the block's
+    geometry, and moving the result back."""
+    from oracle import index_oracle as ix, swin_oracle as so
+    from stswincl_b200 import swin
+    tag, dim, ws, heads, T, (H, W), shift, B = case
+    g = _g("swin_attention.npz")
+    nW, N = (H // ws) * (W // ws), ws * ws
+    params = so.make_attention_params(dim, ws, heads, seed=11)
+    m = _load(swin.WindowAttention(dim, (ws, ws), heads), params)
+    x_win = so.make_features(21, B * nW, T, N, dim) - 0.4
+    w_win = so.make_features(22, B * nW, T, N, dim) - 0.4
+    gidx = torch.from_numpy(ix.window_gather_index(H, W, ws, shift)).reshape(-1)
+
+    def to_natural(t):     # [B*nW, T, N, C] -> [B, T, H*W, C]
+        t = t.reshape(B, nW, T, N, dim).permute(0, 2, 1, 3, 4).reshape(B, T, nW * N, dim)
+        out = torch.empty_like(t)
+        out[:, :, gidx] = t
+        return out
+
+    def to_windows(t):     # inverse
+        return t[:, :, gidx].reshape(B, T, nW, N, dim).permute(0, 2, 1, 3, 4).reshape(B * nW, T, N, dim)
+
+    x = to_natural(x_win).to(torch.bfloat16).cuda().requires_grad_(True)
+    geom = (H, W, heads, ws, shift, 0.0)
+    y = swin._AttentionFn.apply(x, m.relative_position_bias_table, m.qkv.weight, m.qkv.bias, m.proj.weight, m.proj.bias, geom)
+    (y.float() * to_natural(w_win).cuda()).sum().backward()
+    torch.cuda.synchronize()
+    assert rel_err(to_windows(y.float().cpu()), g[f"{tag}_y"]) < TOL
+    assert rel_err(to_windows(x.grad.float().cpu()), g[f"{tag}_dx"]) < TOL
+    assert rel_err(m.relative_position_bias_table.grad.cpu(), g[f"{tag}_d_relative_position_bias_table"]) < TOL
+    assert rel_err(m.qkv.bias.grad.cpu(), g[f"{tag}_d_qkv.bias"]) < TOL
+    assert rel_err(m.proj.bias.grad.cpu(), g[f"{tag}_d_proj.bias"]) < TOL
+    assert rel_err(m.qkv.weight.grad.cpu()[::17], g[f"{tag}_d_qkv.weight_rows"]) < TOL
+    assert rel_err(m.proj.weight.grad.cpu()[::17], g[f"{tag}_d_proj.weight_rows"]) < TOL
+
+
+def test_attention_module_standalone_unmasked():
+    """Stand-alone WindowAttention(x_windows, mask=None) == oracle.window_attention."""
+    from oracle import swin_oracle as so
+    from stswincl_b200 import swin
+    dim, ws, heads, T, Bw = 128, 4, 2, 2, 12
+    params = so.make_attention_params(dim, ws, heads, seed=11)
+    m = _load(swin.WindowAttention(dim, (ws, ws), heads), params)
+    x = so.make_features(21, Bw, T, ws * ws, dim) - 0.4
+    ref = so.window_attention(x.to(torch.bfloat16).float(), params, ws, heads, None)
+    y = m(x.cuda())
+    assert y.dtype == torch.float32
+    assert rel_err(y.cpu(), ref) < TOL
+    with pytest.raises(NotImplementedError):
+        m(x.cuda(), mask=torch.zeros(6, 16, 16).cuda())
+
+
+BLOCK_CASES = [("b0", 128, (16, 24), 2, 8, 0, 2, 1), ("b1", 128, (16, 24), 2, 8, 4, 2, 1),
+               ("b2", 256, (8, 12), 4, 4, 2, 2, 2), ("b3", 128, (16, 24), 2, 8, 4, 1, 1)]
+
+
+@pytest.mark.parametrize("case", BLOCK_CASES, ids=lambda c: c[0])
+def test_block_vs_reference_golden(case):
+    from oracle import swin_oracle as so
+    from stswincl_b200 import swin
+    tag, dim, (H, W), heads, ws, shift, T, B = case
+    g = _g("swin_block.npz")
+    params = so.make_block_params(dim, (H, W), heads, ws, shift, seed=31)
+    m = _load(swin.SwinTransformerBlock(dim, (H, W), heads, window_size=ws, shift_size=shift), params)
+    x = so.make_features(41, B, T, H * W, dim).cuda().requires_grad_(True)
+    w = (so.make_features(42, B, T, H * W, dim) - 0.4).cuda()
+    y = m(x)
+    assert y.dtype == torch.float32 and y.shape == x.shape
+    (y * w).sum().backward()
+    torch.cuda.synchronize()
+    assert rel_err(y.cpu(), g[f"{tag}_y"]) < TOL
+    assert rel_err(x.grad.cpu(), g[f"{tag}_dx"]) < TOL
+    sd = dict(m.named_parameters())
+    for n in ["attn.relative_position_bias_table", "attn.qkv.bias", "attn.proj.bias", "norm1.weight", "norm1.bias",
+              "norm2.weight", "norm2.bias", "mlp.fc1.bias", "mlp.fc2.bias"]:
+        assert rel_err(sd[n].grad.cpu(), g[f"{tag}_d_{n}"]) < TOL, n
+    for n in ["attn.qkv.weight", "attn.proj.weight", "mlp.fc1.weight", "mlp.fc2.weight"]:
+        assert rel_err(sd[n].grad.cpu()[::23], g[f"{tag}_d_{n}_rows"]) < TOL, n
+
+
+def test_layer_vs_reference_golden():
+    from oracle import make_goldens as mg, swin_oracle as so
+    from stswincl_b200 import swin
+    c = mg.LAYER_CASE
+    g = _g("swin_layer.npz")
+    H, W = c["res"]
+    params = so.make_layer_params(c["dim"], c["res"], c["heads"], c["seed"])
+    m = _load(swin.SwinTransformerLayerv5(dim=c["dim"], input_resolution=c["res"], num_heads=c["heads"]), params)
+    x = so.make_features(61, c["B"], 4, c["dim"], H, W).cuda().requires_grad_(True)
+    w1 = (so.make_features(62, c["B"], 4, c["dim"], H, W) - 0.4).cuda()
+    w2 = (so.make_features(63, c["B"], 4, 2 * c["dim"], H // 2, W // 2) - 0.4).cuda()
+    y1, y2 = m(x)
+    assert y1.shape == (c["B"], 4, c["dim"], H, W) and y2.shape == (c["B"], 4, 2 * c["dim"], H // 2, W // 2)
+    ((y1 * w1).sum() + (y2 * w2).sum()).backward()
+    torch.cuda.synchronize()
+    assert rel_err(y1.cpu(), g["y1"]) < TOL
+    assert rel_err(y2.cpu(), g["y2"]) < TOL
+    assert rel_err(x.grad.cpu(), g["dx"]) < 2 * TOL          # 12 blocks deep in bf16
+    sd = dict(m.named_parameters())
+    for n in ["layers.0.0.attn.relative_position_bias_table", "layers.1.1.attn.relative_position_bias_table",
+              "layers.4.1.attn.relative_position_bias_table", "layers.2.1.norm1.weight", "layers.5.0.mlp.fc2.bias",
+              "downsample.norm.weight", "downsample.norm.bias"]:
+        assert rel_err(sd[n].grad.cpu(), g[f"d_{n}"]) < 2 * TOL, n
+    assert rel_err(sd["downsample.reduction.weight"].grad.cpu()[::29], g["d_downsample.reduction.weight_rows"]) < 2 * TOL
+    assert rel_err(sd["layers.1.0.attn.qkv.weight"].grad.cpu()[::29], g["d_layers.1.0.attn.qkv.weight_rows"]) < 2 * TOL
+
+
+def test_full_size_block_vs_oracle():
+    """The real stage-1 geometry (C=512, 64x80, ws 8, shift 4, 4 heads), one clip pair."""
+    from oracle import swin_oracle as so
+    from stswincl_b200 import swin
+    dim, res, heads, ws, shift = 512, (64, 80), 4, 8, 4
+    params = so.make_block_params(dim, res, heads, ws, shift, seed=77)
+    m = _load(swin.SwinTransformerBlock(dim, res, heads, window_size=ws, shift_size=shift), params)
+    x = so.make_features(78, 1, 2, res[0] * res[1], dim)
+    ref = so.swin_block(x.to(torch.bfloat16).float(), params, res, heads, ws, shift)
+    y = m(x.cuda())
+    torch.cuda.synchronize()
+    assert rel_err(y.cpu(), ref) < TOL
+
+
+def test_cpu_tensor_raises():
+    from stswincl_b200 import swin
+    from stswincl_b200._lib import StswinError
+    m = swin.SwinTransformerBlock(128, (16, 24), 2)
+    with pytest.raises(StswinError):
+        m(torch.zeros(1, 2, 384, 128))
