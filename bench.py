@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""Headline benchmark: one training step of the STswinCL Swin head (the window-attention hot
+path, BASELINE.json north_star) on synthetic EndoVis18-shaped clips.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A step = forward + backward + optimizer step of ``SwinTransformerLayerv5`` (dim 512, 64x80
+tokens, 4 heads, 12 blocks + PatchMerging -- seg18/net/Ours/swin_512.py:280-327) over one batch
+of ``--clips`` clips x 4 frames of OS-8 features [clips, 4, 512, 64, 80] (configs[1] of
+BASELINE.json: batch 8, bf16, 1 B200).  frames/s counts input frames (clips x 4 per step).
+
+Prints ONE JSON line (rank 0).  ``value`` has the inputs resident in HBM; ``e2e`` feeds the same
+module from pinned HOST buffers (H2D copy every step, loss read back every step).  ``roofline``
+is measured with CUDA events around every launch of the dominant kernel family during extra,
+separately timed steps; ``cpu_baseline`` is the CPU oracle (a port of the reference path, see
+oracle/) timed on this box's host cores on a bounded sample (N=1, rank 0 only).
+
+``--impl reference`` times the reference's CPU path (the oracle port: the reference is pure
+Python/PyTorch with no compiled artefact to build; /root/reference does not exist on the GPU
+box) with all host threads and prints the same line with "impl": "reference".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "STswin-T train frames/s at 1/2/4/8 B200; window-attn TFLOP/s vs tensor peak"
+DIM, RES, HEADS, T = 512, (64, 80), 4, 4
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--clips", type=int, default=8, help="clips per GPU per step (reference recipe: batch 8)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "tflops_burst": d["bf16_tflops"], "tflops_sustained": d["bf16_tflops_sustained"],
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "tflops_burst": 1590.0, "tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.path = index, None, None
+
+    def __enter__(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        return False
+
+    def summary(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.path or not os.path.exists(self.path):
+            return out
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU path (oracle port of the reference) -- cpu_baseline leg and --impl reference
+# ----------------------------------------------------------------------------------------------
+def cpu_step_factory():
+    import torch
+    from oracle import swin_oracle as so          # checker / CPU baseline only (never on the product path)
+    torch.set_num_threads(os.cpu_count() or 1)
+    params = so.make_layer_params(DIM, RES, HEADS, seed=0)
+    leaf = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and not k.endswith("attn_mask") else v)
+            for k, v in params.items()}
+    x = so.make_features(1, 1, T, DIM, RES[0], RES[1])
+    g1 = so.make_features(2, 1, T, DIM, RES[0], RES[1]) - 0.4
+    g2 = so.make_features(3, 1, T, 2 * DIM, RES[0] // 2, RES[1] // 2) - 0.4
+
+    def step():
+        for v in leaf.values():
+            if v.is_floating_point() and v.requires_grad:
+                v.grad = None
+        y1, y2 = so.swin_layer_v5(x, leaf, DIM, RES, HEADS)
+        loss = (y1 * g1).sum() + (y2 * g2).sum()
+        loss.backward()
+        return float(loss)
+
+    return step, torch.get_num_threads()
+
+
+SAMPLE = "1 clip (4 frames) of the same workload [1,4,512,64,80], fp32, forward+backward, oracle port of the reference"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    step, threads = cpu_step_factory()
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / max(1, args.steps)
+    fps = T / dt
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.clips),
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port", "sample": SAMPLE},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(clips):
+    return {"workload": "configs[1]: Swin head train step (SwinTransformerLayerv5 dim 512, 64x80 tokens, 4 heads; "
+                        "fwd+bwd+Adam) on EndoVis18-shaped OS-8 features, bf16",
+            "clips_per_gpu": clips, "frames_per_clip": T, "feature_shape": [clips, T, DIM, RES[0], RES[1]],
+            "optimizer": "torch.optim.Adam(fused=True) on the 96.6M Swin-head parameters",
+            "l2": "inputs larger than L2 (168 MB of features per step, >10 GB of activations touched)"}
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU path
+# ----------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU path); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from stswincl_b200 import ops, swin
+
+    torch.manual_seed(0)
+    model = swin.SwinTransformerLayerv5(dim=DIM, input_resolution=RES, num_heads=HEADS).to(dev)
+    for blk in model.modules():
+        if isinstance(blk, swin.WindowAttention):       # sigma 0.02 init is nearly a no-op bias; use a visible one
+            torch.nn.init.normal_(blk.relative_position_bias_table, std=0.5)
+    net = model
+    if world > 1:
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True,
+                                                        bucket_cap_mb=64, broadcast_buffers=False)
+    opt = torch.optim.Adam(model.parameters(), lr=3e-5, fused=True)
+    B = args.clips
+    g = torch.Generator(device=dev).manual_seed(1 + rank)
+    x_dev = torch.relu(torch.randn(B, T, DIM, RES[0], RES[1], generator=g, device=dev)).to(torch.bfloat16)
+    g1 = (torch.randn(B, T, DIM, RES[0], RES[1], generator=g, device=dev) * 0.1).to(torch.bfloat16)
+    g2 = (torch.randn(B, T, 2 * DIM, RES[0] // 2, RES[1] // 2, generator=g, device=dev) * 0.1).to(torch.bfloat16)
+
+    def step(x):
+        opt.zero_grad(set_to_none=True)
+        y1, y2 = net(x)
+        loss = (y1.float() * g1).sum() + (y2.float() * g2).sum()
+        loss.backward()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / n
+
+    # ---- device-resident throughput
+    for _ in range(args.warmup):
+        step(x_dev)
+    launches0 = ops.LAUNCHES
+    with ClockSampler(local) as clk:
+        ms_step = timed(lambda i: step(x_dev), args.steps)
+    launches = ops.LAUNCHES - launches0
+    clocks = clk.summary()
+
+    # ---- end to end: pinned host features -> H2D (copy stream, double buffered) -> step -> loss.item()
+    x_host = x_dev.cpu().pin_memory()
+    bufs = [torch.empty_like(x_dev), torch.empty_like(x_dev)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+    d2h_bytes = 4
+
+    def prefetch(i):
+        b = i & 1
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[b])
+            bufs[b].copy_(x_host, non_blocking=True)
+            ready[b].record(copy_stream)
+
+    def e2e_step(i):
+        b = i & 1
+        if i == 0:
+            prefetch(0)
+        prefetch(i + 1)                      # next step's features travel while this step computes
+        torch.cuda.current_stream().wait_event(ready[b])
+        loss = step(bufs[b])
+        consumed[b].record(torch.cuda.current_stream())
+        return loss.item()                   # D2H read of the step's result
+
+    for b in range(2):
+        consumed[b].record(torch.cuda.current_stream())
+    for i in range(max(2, args.warmup)):
+        e2e_step(i)
+    ms_e2e = timed(e2e_step, args.steps)
+
+    # ---- roofline of the dominant kernel family: CUDA events around every launch (separate steps)
+    pk = peaks()
+    prof = ops.EventProfiler()
+    ops.set_profiler(prof)
+    step(x_dev); step(x_dev)
+    ops.set_profiler(None)
+    fam = prof.summary()
+    total_ms = sum(v["ms"] for v in fam.values()) or 1.0
+    shares = {k: round(v["ms"] / total_ms, 4) for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}
+    dom = max(("gemm", "gemm_wgrad"), key=lambda k: fam.get(k, {"ms": 0})["ms"])
+    gsum = {"ms": fam["gemm"]["ms"] + fam["gemm_wgrad"]["ms"], "work": fam["gemm"]["work"] + fam["gemm_wgrad"]["work"],
+            "launches": fam["gemm"]["launches"] + fam["gemm_wgrad"]["launches"]}
+    achieved = gsum["work"] / (gsum["ms"] * 1e-3) / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("gemm_dram_bytes_per_launch")
+    roofline = {"kernel": "stswin::gemm_kernel (tcgen05 dense layers, fwd + dgrad + wgrad)", "bound": "tensor",
+                "achieved": achieved, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
+                "frac": achieved / pk["tflops_sustained"], "traffic": traffic, "peak_source": pk["source"] + ", sustained",
+                "launches_timed": gsum["launches"], "avg_launch_ms": gsum["ms"] / gsum["launches"],
+                "share_of_step": round(gsum["ms"] / total_ms, 4), "family_time_shares": shares}
+    # secondary, HBM-bound: the window-attention core kernels
+    for k in ("winattn_fwd", "winattn_bwd"):
+        if k in fam:
+            gbs = fam[k]["work"] / (fam[k]["ms"] * 1e-3) / 1e9
+            roofline[k] = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
+                           "avg_launch_ms": fam[k]["ms"] / fam[k]["launches"]}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cstep, threads = cpu_step_factory()
+        cstep()                                           # warm-up (page-in, thread pool)
+        t0 = time.perf_counter(); cstep(); dt = time.perf_counter() - t0
+        cpu = {"value": T / dt, "unit": "frames/s", "cores": threads, "kind": "port", "sample": SAMPLE, "seconds": dt}
+
+    if rank == 0:
+        frames = B * T * world
+        line = {"metric": METRIC, "value": frames / (ms_step * 1e-3), "unit": "frames/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": workload_config(B), "clocks": clocks,
+                "e2e": {"value": frames / (ms_e2e * 1e-3), "unit": "frames/s", "ms_per_step": ms_e2e,
+                        "h2d_bytes_per_step": x_host.numel() * x_host.element_size(), "d2h_bytes_per_step": d2h_bytes},
+                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+                "clips_per_s": B * world / (ms_step * 1e-3)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        # convenience: self-launch one rank per GPU (the driver launches torchrun itself)
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29531", os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -32,6 +32,11 @@ extern "C" {
 int stswin_abi_version(void);
 /* Text of the last error raised on the calling thread ("" if none). */
 const char* stswin_last_error(void);
+/* Bind the calling thread to `device` (cudaSetDevice in this library's runtime).  Call before the
+ * other entry points from any thread that has not used the device yet -- e.g. an autograd worker
+ * or an nn.DataParallel replica thread (seg18/train_swin.py:131-135): tensor-map encoding is a
+ * driver call and needs the device's context current on the thread. */
+int stswin_set_device(int device);
 
 /* ---------------------------------------------------------------------------------------------
  * Dense layers: D[M,N] = sum_k A[m,k] * B[n,k]   (bf16 x bf16 -> fp32 accumulate, tcgen05)
@@ -50,8 +55,8 @@ const char* stswin_last_error(void);
  */
 #define STSWIN_EPI_BIAS 0          /* D = acc + bias                                  */
 #define STSWIN_EPI_BIAS_RES 1      /* D = acc + bias + aux            (residual add)  */
-#define STSWIN_EPI_BIAS_GELU 2     /* D2 = acc + bias ; D = gelu_erf(D2)              */
-#define STSWIN_EPI_MUL_DGELU 3     /* D = acc * gelu_erf'(aux)                        */
+#define STSWIN_EPI_BIAS_GELU 2     /* u = acc + bias ; D = gelu_erf(u) ; D2 = gelu_erf'(u) */
+#define STSWIN_EPI_MUL_AUX 3       /* D = acc * aux     (dgrad through GELU: aux = D2)  */
 #define STSWIN_EPI_F32_REDUCE 4    /* D(fp32) += acc, split-K                          */
 
 int stswin_gemm_bf16(const void* A, int a_major, int64_t lda,
@@ -112,6 +117,34 @@ int stswin_layernorm_bwd(const void* dy, const void* x, const float* mean, const
  * Replaces permute(0,1,3,4,2).contiguous() / permute(0,1,3,2) of SwinTransformerLayerv5.forward
  * (swin_512.py:314,319,326). */
 int stswin_transpose(const void* in, int in_is_f32, void* out, int out_is_f32, int64_t batch, int R, int Cc, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Pixel-level contrastive loss (K7).  Replaces regression_loss / posMask / negMask of
+ * pixcontrast_18/contrast/models/PixPro_swin_v5.py:48-129 and the F.normalize(dim=1) calls
+ * feeding it (:330,362,400,432,463,494,526,557).
+ *
+ * stswin_pix_normalize : x [N,C,HW] (fp32 if x_is_f32 else bf16) -> xn [N,C,HW] bf16 =
+ *     x / max(||x||_2 over C, 1e-12) when do_normalize, else a plain cast; inv_norm [N,HW] fp32
+ *     (may be NULL); ksum [N,C] fp32 = per-channel sums of xn over pixels (may be NULL).
+ * stswin_pixloss_fwd   : q, keys[s] [N,C,HW] bf16 (unit-norm pixel embeddings, channel-major as
+ *     in the reference); lq, lk[s] [N,HW] u8 labels.  `keys` / `lk` are HOST arrays of n_sets
+ *     device pointers, ordered (k, adj1, adj2, adj3, neg3) like the reference's arguments; any
+ *     1 <= n_sets <= 8 is accepted (extra sets extend the positive pool and the negative sum).
+ *     row_stats [N,HW,n_sets,4] fp32 workspace; loss: device scalar, overwritten with
+ *     -mean log(e^P/(e^P+e^N)+1e-6); coef [N,HW,1+n_sets] fp32 (may be NULL when no gradient
+ *     is needed): per-row dloss/dz coefficients for the backward.
+ * stswin_pixloss_bwd   : dq32 [N,HW,C] fp32 (overwritten) = d_loss * dloss/dq, pixel-major;
+ *     ksum [n_sets,N,C] fp32 are the per-channel key sums from stswin_pix_normalize;
+ *     d_loss is a device scalar (the upstream gradient).  Keys receive no gradient (they are
+ *     built under no_grad in the reference, :366).
+ */
+int stswin_pix_normalize(const void* x, int x_is_f32, void* xn, float* inv_norm, float* ksum,
+                         int N, int C, int HW, int do_normalize, void* stream);
+int stswin_pixloss_fwd(const void* q, const void* const* keys, const uint8_t* lq, const uint8_t* const* lk,
+                       int n_sets, int N, int C, int HW, float* row_stats, float* loss, float* coef, void* stream);
+int stswin_pixloss_bwd(const void* const* keys, const uint8_t* lq, const uint8_t* const* lk, const float* coef,
+                       const float* ksum, const float* d_loss, int n_sets, int N, int C, int HW, float* dq32,
+                       void* stream);
 
 #ifdef __cplusplus
 }

@@ -7,6 +7,10 @@ extern "C" {
 
 int stswin_abi_version(void) { return 1; }
 const char* stswin_last_error(void) { return stswin::last_error(); }
+int stswin_set_device(int device) {
+  STSWIN_CUDA(cudaSetDevice(device));
+  return stswin::kOk;
+}
 
 int stswin_gemm_bf16(const void* A, int a_major, int64_t lda, const void* B, int b_major, int64_t ldb, void* D,
                      int64_t ldd, void* D2, const void* aux, int64_t ld_aux, const float* bias, float* colsum, int M,
@@ -45,6 +49,20 @@ int stswin_layernorm_bwd(const void* dy, const void* x, const float* mean, const
 int stswin_transpose(const void* in, int in_is_f32, void* out, int out_is_f32, int64_t batch, int R, int Cc,
                      void* stream) {
   return stswin::transpose_cvt(in, in_is_f32, out, out_is_f32, batch, R, Cc, static_cast<cudaStream_t>(stream));
+}
+
+int stswin_pix_normalize(const void* x, int x_is_f32, void* xn, float* inv_norm, float* ksum, int N, int C, int HW,
+                         int do_normalize, void* stream) {
+  return stswin::pix_normalize(x, x_is_f32, xn, inv_norm, ksum, N, C, HW, do_normalize, static_cast<cudaStream_t>(stream));
+}
+int stswin_pixloss_fwd(const void* q, const void* const* keys, const uint8_t* lq, const uint8_t* const* lk, int n_sets,
+                       int N, int C, int HW, float* row_stats, float* loss, float* coef, void* stream) {
+  return stswin::pixloss_fwd(q, keys, lq, lk, n_sets, N, C, HW, row_stats, loss, coef, static_cast<cudaStream_t>(stream));
+}
+int stswin_pixloss_bwd(const void* const* keys, const uint8_t* lq, const uint8_t* const* lk, const float* coef,
+                       const float* ksum, const float* d_loss, int n_sets, int N, int C, int HW, float* dq32,
+                       void* stream) {
+  return stswin::pixloss_bwd(keys, lq, lk, coef, ksum, d_loss, n_sets, N, C, HW, dq32, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -124,6 +124,12 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const vo
                "r"(smem_u32(smem)), "r"(c0), "r"(c1)
                : "memory");
 }
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* m, const void* smem, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 __device__ __forceinline__ void tma_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void tma_wait_group_read() {
@@ -217,6 +223,21 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
   const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
   return cdf + x * pdf;
+}
+// erf-GELU and its derivative in one go (nn.GELU default, swin_512.py:13).  erf through
+// Abramowitz-Stegun 7.1.26 (|abs err| < 1.5e-7), sharing exp(-u^2/2) with the Gaussian pdf:
+//   gelu(u) = u * Phi(u)        gelu'(u) = Phi(u) + u * phi(u)
+__device__ __forceinline__ void gelu_and_grad(float u, float& h, float& g) {
+  const float e = exp2f(-0.72134752044448170f * u * u);            // exp(-u^2 / 2)
+  const float t = __fdividef(1.0f, fmaf(0.23164189463f, fabsf(u), 1.0f));   // p / sqrt(2) = 0.3275911 / 1.41421356
+  float q = fmaf(1.061405429f, t, -1.453152027f);
+  q = fmaf(q, t, 1.421413741f);
+  q = fmaf(q, t, -0.284496736f);
+  q = fmaf(q, t, 0.254829592f);
+  q = 0.5f * q * t * e;                                             // 0.5 * (1 - erf(|u| / sqrt 2))
+  const float cdf = u >= 0.f ? 1.0f - q : q;
+  h = u * cdf;
+  g = fmaf(u * 0.3989422804014327f, e, cdf);
 }
 // byte offset of 16-byte chunk `chunk` (0..7) of row `row` inside a 128B-swizzled tile whose
 // rows are 128 bytes and whose base is 1024-byte aligned (the pattern TMA and UMMA both use)

@@ -10,12 +10,13 @@
 // weight gradient dW = dy^T x, which reduces over tokens, is (1,1) without any transposed
 // copy of an activation.
 //
-// CTA = 6 warps: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM allocation), warps 2-5 epilogue.
+// CTA = 10 warps: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM allocation), warps 2-9 epilogue.
 // Tile 128 x 256 x 64, 4-stage TMA->smem ring (128B swizzle), two 256-column TMEM accumulators so
 // the epilogue of tile i overlaps the main loop of tile i+1.  The epilogue goes TMEM -> registers
 // -> swizzled smem (transpose) -> coalesced 128-bit global stores, with an optional auxiliary tile
-// (residual or pre-activation, prefetched one chunk ahead with coalesced loads), bias, exact GELU,
-// GELU', column sums (bias gradients), and an fp32 TMA add-reduction for split-K weight gradients.
+// (residual or multiplier, prefetched one chunk ahead with coalesced loads), bias, erf-GELU together
+// with its derivative (stored for the backward, which then only multiplies), column sums (bias
+// gradients), and an fp32 TMA add-reduction for split-K weight gradients.
 // (A first version stored through TMA from a single staging buffer and serialised on the store's
 // read latency: 315 TFLOP/s at K=512; see profiles/.)
 #include "common.cuh"
@@ -32,16 +33,16 @@ constexpr int STAGES = 4;
 constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KB
 constexpr int B_STAGE_BYTES = BN * BK * 2;   // 32 KB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-constexpr int EPI_WARPS = 4;
+constexpr int EPI_WARPS = 8;
 constexpr int EPI_BUF_BYTES = 32 * 128;      // 32 rows x 128 B per epilogue warp
 constexpr int NUM_THREADS = 32 * (2 + EPI_WARPS);
-constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + 2 * EPI_WARPS * EPI_BUF_BYTES + 256;
+constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + EPI_WARPS * EPI_BUF_BYTES + 256;
 
 enum Mode : int {
   kBias = 0,        // D = acc + bias
   kBiasRes = 1,     // D = acc + bias + aux
-  kBiasGelu = 2,    // D2 = u = acc + bias ; D = gelu(u)
-  kMulDGelu = 3,    // D = acc * gelu'(aux)
+  kBiasGelu = 2,    // u = acc + bias ; D = gelu(u) ; D2 = gelu'(u)
+  kMulAux = 3,      // D = acc * aux
   kF32Reduce = 4,   // D(fp32) += acc          (split-K, TMA add-reduction)
 };
 
@@ -65,8 +66,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* s_stage = smem;
   uint8_t* s_out = smem + STAGES * STAGE_BYTES;
-  uint8_t* s_aux = s_out + EPI_WARPS * EPI_BUF_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_aux + EPI_WARPS * EPI_BUF_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_out + EPI_WARPS * EPI_BUF_BYTES);
   uint64_t* full_bar = bars;                 // [STAGES]
   uint64_t* empty_bar = bars + STAGES;       // [STAGES]
   uint64_t* acc_full = bars + 2 * STAGES;    // [2]
@@ -170,11 +170,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (4 warps)
-    const int wq = warp & 3;                         // TMEM lane quarter this warp may access
-    uint8_t* my_out = s_out + wq * EPI_BUF_BYTES;
-    uint8_t* my_aux = s_aux + wq * EPI_BUF_BYTES;
-    constexpr bool has_aux = (MODE == kBiasRes || MODE == kMulDGelu);
+    // ------------------------------------------------------------------ epilogue (8 warps)
+    // warp w may touch TMEM lanes 32*(w%4)..+31; the two warps of a lane quarter split the 256
+    // accumulator columns in halves (two 64-column chunks each).
+    const int ew = warp - 2;                         // 0..7
+    const int wq = warp & 3;                         // TMEM lane quarter
+    const int chalf = ew >> 2;                       // column half of the tile
+    uint8_t* my_buf = s_out + ew * EPI_BUF_BYTES;    // one 32-row x 128-byte staging tile, reused
+    constexpr bool has_aux = (MODE == kBiasRes || MODE == kMulAux);
     int acc = 0;
     uint32_t acc_phase = 0;
     // coalesced access pattern of a 32-row x 64-col bf16 chunk: instruction i of lane l touches
@@ -184,15 +187,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int n_blk = item % num_n;
       const int m_blk = (item / num_n) % num_m;
       const int row0 = m_blk * BM + wq * 32;
-      const int col0 = n_blk * BN;
+      const int col0 = n_blk * BN + chalf * (BN / 2);
       const bool row_ok = (row0 + lane) < p.M;
-      const uint32_t t_row = tmem_base + (uint32_t(wq * 32) << 16) + acc * BN;
+      const uint32_t t_row = tmem_base + (uint32_t(wq * 32) << 16) + acc * BN + chalf * (BN / 2);
 
       if constexpr (MODE == kF32Reduce) {
         mbar_wait(&acc_full[acc], acc_phase);
         tc_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = 0; c < BN / 64; ++c) {
           uint32_t v[32];
           tmem_ld32(t_row + c * 32, v);
           tmem_ld_wait();
@@ -201,12 +204,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             uint4 q = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            *reinterpret_cast<uint4*>(my_out + sw128_offset(lane, j)) = q;
+            *reinterpret_cast<uint4*>(my_buf + sw128_offset(lane, j)) = q;
           }
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0 && col0 + c * 32 < p.N && row0 < p.M) {
-            tma_reduce_add_2d(&tmD, my_out, col0 + c * 32, row0);
+            tma_reduce_add_2d(&tmD, my_buf, col0 + c * 32, row0);
             tma_commit_group();
           }
         }
@@ -222,11 +225,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         };
         // staged 32 x 64 chunk -> global, 128-byte lines
-        auto store_staged = [&](const uint8_t* stg, __nv_bfloat16* dst, int cb) {
+        auto store_staged = [&](__nv_bfloat16* dst, int cb) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int rl = 4 * i + crow;
-            const uint4 q = *reinterpret_cast<const uint4*>(stg + sw128_offset(rl, cchunk));
+            const uint4 q = *reinterpret_cast<const uint4*>(my_buf + sw128_offset(rl, cchunk));
             const int r = row0 + rl, n = cb + cchunk * 8;
             if (r < p.M && n < p.N) *reinterpret_cast<uint4*>(dst + (size_t)r * p.ldd + n) = q;
           }
@@ -235,19 +238,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         mbar_wait(&acc_full[acc], acc_phase);
         tc_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < BN / 64; ++c) {
+        for (int c = 0; c < BN / 128; ++c) {
           const int cbase = col0 + c * 64;
+          uint32_t auxw[32];
           if (has_aux) {
-            __syncwarp();
+            __syncwarp();                                 // earlier readers of my_buf are done
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-              *reinterpret_cast<uint4*>(my_aux + sw128_offset(4 * i + crow, cchunk)) = auxr[i];
-            if (c + 1 < BN / 64) aux_fetch(cbase + 64);   // in flight while this chunk is processed
+              *reinterpret_cast<uint4*>(my_buf + sw128_offset(4 * i + crow, cchunk)) = auxr[i];
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint4 q = *reinterpret_cast<const uint4*>(my_buf + sw128_offset(lane, j));
+              auxw[4 * j] = q.x; auxw[4 * j + 1] = q.y; auxw[4 * j + 2] = q.z; auxw[4 * j + 3] = q.w;
+            }
+            if (c + 1 < BN / 128) aux_fetch(cbase + 64);  // in flight while this chunk is processed
           }
-          __syncwarp();                                   // aux staged; earlier readers of my_out are done
-          // the 64 columns are processed as two rolled halves of 32 to keep the code I-cache resident
-#pragma unroll 1
-          for (int half = 0; half < 2; ++half) {
+          __syncwarp();                                   // my_buf may be overwritten with the output now
+          uint32_t out2w[MODE == kBiasGelu ? 32 : 1];     // second output of the GELU mode (gelu'(u))
+          // the 64 columns are processed as two halves of 32 (rolled, except in the two-output mode
+          // whose second output has to stay in registers) to keep the code I-cache resident
+          auto do_half = [&](int half) {
             uint32_t v[32];
             tmem_ld32(t_row + c * 64 + half * 32, v);
             float bias_l = 0.f;                          // lane l holds the bias of column l of this half
@@ -255,60 +266,63 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               const int n = cbase + half * 32 + lane;
               if (n < p.N) bias_l = __ldg(p.bias + n);
             }
-            uint32_t auxw[16];
-            if (has_aux) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const uint4 q = *reinterpret_cast<const uint4*>(my_aux + sw128_offset(lane, half * 4 + j));
-                auxw[4 * j] = q.x; auxw[4 * j + 1] = q.y; auxw[4 * j + 2] = q.z; auxw[4 * j + 3] = q.w;
-              }
-            }
             tmem_ld_wait();
-            uint32_t outw[16];    // bf16 pairs
-            uint32_t out2w[16];   // pre-activation for kBiasGelu
+            uint32_t outw[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              float a0 = __uint_as_float(v[2 * j]);
-              float a1 = __uint_as_float(v[2 * j + 1]);
-              a0 += __shfl_sync(0xffffffffu, bias_l, 2 * j);
-              a1 += __shfl_sync(0xffffffffu, bias_l, 2 * j + 1);
+              float a0 = __uint_as_float(v[2 * j]) + __shfl_sync(0xffffffffu, bias_l, 2 * j);
+              float a1 = __uint_as_float(v[2 * j + 1]) + __shfl_sync(0xffffffffu, bias_l, 2 * j + 1);
               if constexpr (MODE == kBiasRes) {
-                const float2 r = unpack_bf16(auxw[j]);
+                const float2 r = unpack_bf16(auxw[half * 16 + j]);
                 a0 += r.x; a1 += r.y;
               } else if constexpr (MODE == kBiasGelu) {
-                out2w[j] = pack_bf16(a0, a1);
-                a0 = gelu_erf(a0); a1 = gelu_erf(a1);
-              } else if constexpr (MODE == kMulDGelu) {
-                const float2 u = unpack_bf16(auxw[j]);
-                a0 *= gelu_erf_grad(u.x); a1 *= gelu_erf_grad(u.y);
+                float g0, g1;
+                gelu_and_grad(a0, a0, g0);
+                gelu_and_grad(a1, a1, g1);
+                if (!row_ok) { g0 = 0.f; g1 = 0.f; }
+                out2w[half * 16 + j] = pack_bf16(g0, g1);
+              } else if constexpr (MODE == kMulAux) {
+                const float2 u = unpack_bf16(auxw[half * 16 + j]);
+                a0 *= u.x; a1 *= u.y;
               }
               if (!row_ok) { a0 = 0.f; a1 = 0.f; }
               outw[j] = pack_bf16(a0, a1);
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              *reinterpret_cast<uint4*>(my_out + sw128_offset(lane, half * 4 + j)) =
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(my_buf + sw128_offset(lane, half * 4 + j)) =
                   make_uint4(outw[4 * j], outw[4 * j + 1], outw[4 * j + 2], outw[4 * j + 3]);
-              if constexpr (MODE == kBiasGelu)     // my_aux is free in this mode: stage the second output there
-                *reinterpret_cast<uint4*>(my_aux + sw128_offset(lane, half * 4 + j)) =
-                    make_uint4(out2w[4 * j], out2w[4 * j + 1], out2w[4 * j + 2], out2w[4 * j + 3]);
-            }
+          };
+          if constexpr (MODE == kBiasGelu) {
+            do_half(0);
+            do_half(1);
+          } else {
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) do_half(half);
           }
           __syncwarp();
-          store_staged(my_out, p.D, cbase);
-          if constexpr (MODE == kBiasGelu) store_staged(my_aux, p.D2, cbase);
+          store_staged(p.D, cbase);
           if (p.colsum != nullptr) {
             // lane owns columns (2*lane, 2*lane+1) of this 64-wide chunk: sum the 32 staged rows
             float s0 = 0.f, s1 = 0.f;
 #pragma unroll 8
             for (int r = 0; r < 32; ++r) {
-              const uint32_t w = *reinterpret_cast<const uint32_t*>(my_out + sw128_offset(r, lane >> 2) + (lane & 3) * 4);
+              const uint32_t w = *reinterpret_cast<const uint32_t*>(my_buf + sw128_offset(r, lane >> 2) + (lane & 3) * 4);
               const float2 f = unpack_bf16(w);
               s0 += f.x; s1 += f.y;
             }
             const int n = cbase + 2 * lane;
             if (n < p.N) atomicAdd(p.colsum + n, s0);
             if (n + 1 < p.N) atomicAdd(p.colsum + n + 1, s1);
+          }
+          if constexpr (MODE == kBiasGelu) {
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<uint4*>(my_buf + sw128_offset(lane, j)) =
+                  make_uint4(out2w[4 * j], out2w[4 * j + 1], out2w[4 * j + 2], out2w[4 * j + 3]);
+            __syncwarp();
+            store_staged(p.D2, cbase);
           }
         }
       }
@@ -349,7 +363,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tm
     case kBias: return launch_mode<A_MN, B_MN, kBias>(tmA, tmB, tmD, args, stream);
     case kBiasRes: return launch_mode<A_MN, B_MN, kBiasRes>(tmA, tmB, tmD, args, stream);
     case kBiasGelu: return launch_mode<A_MN, B_MN, kBiasGelu>(tmA, tmB, tmD, args, stream);
-    case kMulDGelu: return launch_mode<A_MN, B_MN, kMulDGelu>(tmA, tmB, tmD, args, stream);
+    case kMulAux: return launch_mode<A_MN, B_MN, kMulAux>(tmA, tmB, tmD, args, stream);
     default: return launch_mode<A_MN, B_MN, kF32Reduce>(tmA, tmB, tmD, args, stream);
   }
 }
@@ -370,7 +384,7 @@ int gemm_bf16(const void* A, int a_major, long lda, const void* B, int b_major, 
   if (k_splits < 1) k_splits = 1;
   STSWIN_CHECK_ARG(k_splits == 1 || mode == kF32Reduce, "gemm: split-K requires the fp32 reduce epilogue");
   STSWIN_CHECK_ARG(mode != kBiasGelu || D2 != nullptr, "gemm: gelu epilogue needs the pre-activation output D2");
-  STSWIN_CHECK_ARG((mode != kBiasRes && mode != kMulDGelu) || aux != nullptr, "gemm: epilogue mode %d needs aux", mode);
+  STSWIN_CHECK_ARG((mode != kBiasRes && mode != kMulAux) || aux != nullptr, "gemm: epilogue mode %d needs aux", mode);
   const int kb_total = (K + BK - 1) / BK;
   if (k_splits > kb_total) k_splits = kb_total;
   // every split must own at least one k-block (an empty split would publish an unwritten accumulator)
@@ -399,7 +413,7 @@ int gemm_bf16(const void* A, int a_major, long lda, const void* B, int b_major, 
       STSWIN_CHECK_ARG(ldd % 8 == 0 && N % 8 == 0, "gemm: N and ldd must be multiples of 8 elements");
       STSWIN_CHECK_ARG((reinterpret_cast<uintptr_t>(D) & 15) == 0, "gemm: D must be 16-byte aligned");
       STSWIN_CHECK_ARG(D2 == nullptr || (reinterpret_cast<uintptr_t>(D2) & 15) == 0, "gemm: D2 must be 16-byte aligned");
-      if (mode == kBiasRes || mode == kMulDGelu)
+      if (mode == kBiasRes || mode == kMulAux)
         STSWIN_CHECK_ARG(ld_aux % 8 == 0 && (reinterpret_cast<uintptr_t>(aux) & 15) == 0,
                          "gemm: aux must be 16-byte aligned with ld_aux a multiple of 8");
     }

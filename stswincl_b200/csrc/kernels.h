@@ -23,4 +23,12 @@ int layernorm_bwd(const void* dy, const void* x, const float* mean, const float*
                   int H, int W, int C, cudaStream_t stream);
 int transpose_cvt(const void* in, int in_f32, void* out, int out_f32, long batch, int R, int Cc, cudaStream_t stream);
 
+int pix_normalize(const void* x, int x_is_f32, void* xn, float* inv_norm, float* ksum, int N, int C, int HW,
+                  int do_normalize, cudaStream_t stream);
+int pixloss_fwd(const void* q, const void* const* keys, const uint8_t* lq, const uint8_t* const* lk, int n_sets, int N,
+                int C, int HW, float* row_stats, float* loss, float* coef, cudaStream_t stream);
+int pixloss_bwd(const void* const* keys, const uint8_t* lq, const uint8_t* const* lk, const float* coef,
+                const float* ksum, const float* d_loss, int n_sets, int N, int C, int HW, float* dq32,
+                cudaStream_t stream);
+
 }  // namespace stswin

@@ -106,7 +106,7 @@ ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gam
 }
 
 template <int NV, bool COLSUM>
-__global__ void __launch_bounds__(LN_THREADS)
+__global__ void __launch_bounds__(LN_THREADS, (NV <= 2 ? 2 : 1))
 ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
               const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
               const __nv_bfloat16* __restrict__ dres, __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma,
@@ -115,43 +115,58 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = Ctot >> 3;
   float a_dg[NV][8], a_db[NV][8], a_cs[COLSUM ? NV : 1][8];
-  float gmm[NV][8];
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int vi = lane + 32 * i;
+  for (int i = 0; i < NV; ++i)
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       a_dg[i][k] = 0.f; a_db[i][k] = 0.f;
       if (COLSUM) a_cs[i][k] = 0.f;
-      gmm[i][k] = (vi < nvec) ? __ldg(gamma + vi * 8 + k) : 0.f;
     }
-  }
-  for (long row = (long)blockIdx.x * LN_WARPS + warp; row < M; row += (long)gridDim.x * LN_WARPS) {
-    const float mu = mean[row], rs = rstd[row];
-    float g[NV][8], xh[NV][8];
+  const bool has_res = dres != nullptr;
+  const long stride = (long)gridDim.x * LN_WARPS;
+  // raw 16-byte groups of the row being processed, and of the next row (prefetched while this one
+  // is reduced: one row per warp is otherwise a single dependent load -> shuffle -> store chain)
+  uint4 cd[NV], cx[NV], cr[NV];
+  float c_mu = 0.f, c_rs = 0.f;
+  auto load_row = [&](long row, uint4 (&d)[NV], uint4 (&xx)[NV], uint4 (&r)[NV], float& mu, float& rs) {
+    mu = mean[row]; rs = rstd[row];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int vi = lane + 32 * i;
+      if (vi < nvec) {
+        d[i] = __ldg(reinterpret_cast<const uint4*>(dy + row * Ctot + vi * 8));
+        xx[i] = __ldg(reinterpret_cast<const uint4*>(row_ptr(x, row, vi, Ctot, pg)));
+        if (has_res) r[i] = __ldg(reinterpret_cast<const uint4*>(dres + row * Ctot + vi * 8));
+      }
+    }
+  };
+  long row = (long)blockIdx.x * LN_WARPS + warp;
+  if (row < M) load_row(row, cd, cx, cr, c_mu, c_rs);
+  while (row < M) {
+    const long nxt = row + stride;
+    uint4 nd[NV], nx[NV], nr[NV];
+    float n_mu = 0.f, n_rs = 0.f;
+    if (nxt < M) load_row(nxt, nd, nx, nr, n_mu, n_rs);
+    const float mu = c_mu, rs = c_rs;
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int vi = lane + 32 * i;
       if (vi < nvec) {
-        const uint4 qd = __ldg(reinterpret_cast<const uint4*>(dy + row * Ctot + vi * 8));
-        const uint4 qx = __ldg(reinterpret_cast<const uint4*>(row_ptr(x, row, vi, Ctot, pg)));
-        const uint32_t wd[4] = {qd.x, qd.y, qd.z, qd.w}, wx[4] = {qx.x, qx.y, qx.z, qx.w};
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8 + 4));
+        const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const uint32_t wd[4] = {cd[i].x, cd[i].y, cd[i].z, cd[i].w}, wx[4] = {cx[i].x, cx[i].y, cx[i].z, cx[i].w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const float2 fd = unpack_bf16(wd[k]), fx = unpack_bf16(wx[k]);
           const float h0 = (fx.x - mu) * rs, h1 = (fx.y - mu) * rs;
-          xh[i][2 * k] = h0; xh[i][2 * k + 1] = h1;
           a_dg[i][2 * k] += fd.x * h0; a_dg[i][2 * k + 1] += fd.y * h1;
           a_db[i][2 * k] += fd.x;      a_db[i][2 * k + 1] += fd.y;
-          const float g0 = fd.x * gmm[i][2 * k], g1 = fd.y * gmm[i][2 * k + 1];
-          g[i][2 * k] = g0; g[i][2 * k + 1] = g1;
-          s1 += g0 + g1;
-          s2 += g0 * h0 + g1 * h1;
+          const float q0 = fd.x * gm[2 * k], q1 = fd.y * gm[2 * k + 1];
+          s1 += q0 + q1;
+          s2 += q0 * h0 + q1 * h1;
         }
-      } else {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) { g[i][k] = 0.f; xh[i][k] = 0.f; }
       }
     }
     const float m1 = warp_sum(s1) / Ctot, m2 = warp_sum(s2) / Ctot;
@@ -159,32 +174,34 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
     for (int i = 0; i < NV; ++i) {
       const int vi = lane + 32 * i;
       if (vi < nvec) {
-        float o[8];
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8 + 4));
+        const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const uint32_t wd[4] = {cd[i].x, cd[i].y, cd[i].z, cd[i].w}, wx[4] = {cx[i].x, cx[i].y, cx[i].z, cx[i].w};
+        const uint32_t wr[4] = {cr[i].x, cr[i].y, cr[i].z, cr[i].w};
+        uint32_t wo[4];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) o[k] = rs * (g[i][k] - m1 - xh[i][k] * m2);
-        if (dres != nullptr) {
-          const uint4 qr = __ldg(reinterpret_cast<const uint4*>(dres + row * Ctot + vi * 8));
-          const uint32_t wr[4] = {qr.x, qr.y, qr.z, qr.w};
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < 4; ++k) {
+          const float2 fd = unpack_bf16(wd[k]), fx = unpack_bf16(wx[k]);
+          float o0 = rs * (fd.x * gm[2 * k] - m1 - (fx.x - mu) * rs * m2);
+          float o1 = rs * (fd.y * gm[2 * k + 1] - m1 - (fx.y - mu) * rs * m2);
+          if (has_res) {
             const float2 fr = unpack_bf16(wr[k]);
-            o[2 * k] += fr.x; o[2 * k + 1] += fr.y;
+            o0 += fr.x; o1 += fr.y;
           }
-        }
-        uint4 q;
-        q.x = pack_bf16(o[0], o[1]); q.y = pack_bf16(o[2], o[3]);
-        q.z = pack_bf16(o[4], o[5]); q.w = pack_bf16(o[6], o[7]);
-        *reinterpret_cast<uint4*>(row_ptr(dx, row, vi, Ctot, pg)) = q;
-        if (COLSUM) {
-          const uint32_t wo[4] = {q.x, q.y, q.z, q.w};      // sum what the consumer will read (bf16-rounded)
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
+          wo[k] = pack_bf16(o0, o1);
+          if (COLSUM) {                      // sum what the consumer will read (bf16-rounded)
             const float2 fo = unpack_bf16(wo[k]);
             a_cs[i][2 * k] += fo.x; a_cs[i][2 * k + 1] += fo.y;
           }
         }
+        *reinterpret_cast<uint4*>(row_ptr(dx, row, vi, Ctot, pg)) = make_uint4(wo[0], wo[1], wo[2], wo[3]);
       }
     }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) { cd[i] = nd[i]; cx[i] = nx[i]; cr[i] = nr[i]; }
+    c_mu = n_mu; c_rs = n_rs;
+    row = nxt;
   }
   // CTA-level column reduction, one quantity at a time through s_red[LN_WARPS][Ctot]
   auto flush = [&](float (&acc)[NV][8], float* out) {
@@ -280,7 +297,7 @@ int layernorm_bwd(const void* dy, const void* x, const float* mean, const float*
   PmGeom pg{pm, H, W, C};
   const int nv = (Ctot + 255) / 256;
   long want = (M + LN_WARPS - 1) / LN_WARPS;
-  const int grid = (int)(want < num_sms() * 2 ? want : num_sms() * 2);   // few CTAs: fewer column atomics
+  const int grid = (int)(want < num_sms() * 2 ? want : num_sms() * 2);   // 2 CTAs / SM when they fit; few column atomics
   const int smem = LN_WARPS * Ctot * 4;
   auto dyb = static_cast<const __nv_bfloat16*>(dy);
   auto xb = static_cast<const __nv_bfloat16*>(x);

@@ -12,7 +12,58 @@ import torch
 from . import _lib
 from ._lib import StswinError
 
-EPI_BIAS, EPI_BIAS_RES, EPI_BIAS_GELU, EPI_MUL_DGELU, EPI_F32_REDUCE = 0, 1, 2, 3, 4
+EPI_BIAS, EPI_BIAS_RES, EPI_BIAS_GELU, EPI_MUL_AUX, EPI_F32_REDUCE = 0, 1, 2, 3, 4
+
+# ---------------------------------------------------------------------------------------------
+# launch accounting (bench.py): every C-ABI kernel launch is counted; with an EventProfiler
+# installed each launch is also bracketed by CUDA events on the launching stream.
+LAUNCHES = 0
+
+
+class EventProfiler:
+    """Per-kernel-family device time from CUDA events recorded on the launching stream.
+    ``work`` is the algorithmic FLOPs (tensor-bound kernels) or bytes (HBM-bound) of the launch."""
+
+    def __init__(self):
+        self.records = []          # (family, work, start_event, end_event)
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for fam, work, e0, e1 in self.records:
+            d = out.setdefault(fam, {"launches": 0, "ms": 0.0, "work": 0.0})
+            d["launches"] += 1
+            d["ms"] += e0.elapsed_time(e1)
+            d["work"] += work
+        return out
+
+
+_PROFILER: Optional["EventProfiler"] = None
+
+
+def set_profiler(p: Optional["EventProfiler"]) -> None:
+    global _PROFILER
+    _PROFILER = p
+
+
+class _launch:
+    def __init__(self, family: str, work: float, ref: torch.Tensor):
+        self.family, self.work, self.ref = family, work, ref
+
+    def __enter__(self):
+        global LAUNCHES
+        LAUNCHES += 1
+        if _PROFILER is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record(torch.cuda.current_stream(self.ref.device))
+        return self
+
+    def __exit__(self, *exc):
+        if _PROFILER is not None and exc[0] is None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record(torch.cuda.current_stream(self.ref.device))
+            _PROFILER.records.append((self.family, self.work, self.e0, e1))
+        return False
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -20,6 +71,10 @@ def _ptr(t: Optional[torch.Tensor]):
 
 
 def _stream(t: torch.Tensor):
+    """Current stream of the tensor's device; also binds this thread to that device inside the
+    library (autograd worker / DataParallel replica threads start without a current context)."""
+    idx = t.device.index if t.device.index is not None else torch.cuda.current_device()
+    _lib.check(_lib.load().stswin_set_device(idx), "stswin_set_device")
     return torch.cuda.current_stream(t.device).cuda_stream
 
 
@@ -59,9 +114,11 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn_major: bool = False, b_mn_maj
     if colsum is not None:
         _req(colsum, torch.float32, "colsum"); assert colsum.numel() == N and colsum.is_contiguous()
     lib = _lib.load()
-    st = lib.stswin_gemm_bf16(a.data_ptr(), int(a_mn_major), a.stride(0), b.data_ptr(), int(b_mn_major), b.stride(0),
-                              out.data_ptr(), out.stride(0), _ptr(out2), _ptr(aux), aux.stride(0) if aux is not None else 0,
-                              _ptr(bias), _ptr(colsum), M, N, K, mode, k_splits, _stream(a))
+    fam = "gemm_wgrad" if mode == EPI_F32_REDUCE else "gemm"
+    with _launch(fam, 2.0 * M * N * K, a):
+        st = lib.stswin_gemm_bf16(a.data_ptr(), int(a_mn_major), a.stride(0), b.data_ptr(), int(b_mn_major), b.stride(0),
+                                  out.data_ptr(), out.stride(0), _ptr(out2), _ptr(aux), aux.stride(0) if aux is not None else 0,
+                                  _ptr(bias), _ptr(colsum), M, N, K, mode, k_splits, _stream(a))
     _lib.check(st, "stswin_gemm_bf16")
     return out
 
@@ -85,8 +142,9 @@ def winattn_fwd(qkv: torch.Tensor, bias_table: torch.Tensor, H: int, W: int, num
     if out is None:
         out = torch.empty((B, T, L, C), dtype=torch.bfloat16, device=qkv.device)
     lse2 = torch.empty(winattn_lse_elems(B, T, H, W, C, num_heads, ws), dtype=torch.float32, device=qkv.device)
-    st = _lib.load().stswin_winattn_fwd(qkv.data_ptr(), bias_table.data_ptr(), out.data_ptr(), lse2.data_ptr(),
-                                        B, T, H, W, C, num_heads, ws, shift, float(qk_scale), _stream(qkv))
+    with _launch("winattn_fwd", 8.0 * C * B * T * L * 2, qkv):     # q,k,v in + o out, bf16
+        st = _lib.load().stswin_winattn_fwd(qkv.data_ptr(), bias_table.data_ptr(), out.data_ptr(), lse2.data_ptr(),
+                                            B, T, H, W, C, num_heads, ws, shift, float(qk_scale), _stream(qkv))
     _lib.check(st, "stswin_winattn_fwd")
     return out, lse2
 
@@ -107,9 +165,10 @@ def winattn_bwd(qkv: torch.Tensor, bias_table: torch.Tensor, lse2: torch.Tensor,
         d_qkv = torch.empty_like(qkv)
     if d_qkv_colsum is not None:
         _req(d_qkv_colsum, torch.float32, "d_qkv_colsum"); assert d_qkv_colsum.numel() == C3
-    st = _lib.load().stswin_winattn_bwd(qkv.data_ptr(), bias_table.data_ptr(), lse2.data_ptr(), d_out.data_ptr(),
-                                        d_qkv.data_ptr(), d_table.data_ptr(), _ptr(d_qkv_colsum),
-                                        B, T, H, W, C, num_heads, ws, shift, float(qk_scale), _stream(qkv))
+    with _launch("winattn_bwd", 14.0 * C * B * T * L * 2, qkv):    # q,k,v,dO in + dq,dk,dv out, bf16
+        st = _lib.load().stswin_winattn_bwd(qkv.data_ptr(), bias_table.data_ptr(), lse2.data_ptr(), d_out.data_ptr(),
+                                            d_qkv.data_ptr(), d_table.data_ptr(), _ptr(d_qkv_colsum),
+                                            B, T, H, W, C, num_heads, ws, shift, float(qk_scale), _stream(qkv))
     _lib.check(st, "stswin_winattn_bwd")
     return d_qkv
 
@@ -132,8 +191,9 @@ def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps:
     y = torch.empty((M, row_len), dtype=torch.bfloat16, device=x.device)
     mean = torch.empty(M, dtype=torch.float32, device=x.device)
     rstd = torch.empty(M, dtype=torch.float32, device=x.device)
-    st = _lib.load().stswin_layernorm_fwd(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), mean.data_ptr(),
-                                          rstd.data_ptr(), M, row_len, eps, pm, H, W, C, _stream(x))
+    with _launch("layernorm_fwd", 4.0 * M * row_len, x):            # read x, write y (bf16)
+        st = _lib.load().stswin_layernorm_fwd(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), mean.data_ptr(),
+                                              rstd.data_ptr(), M, row_len, eps, pm, H, W, C, _stream(x))
     _lib.check(st, "stswin_layernorm_fwd")
     return y, mean, rstd
 
@@ -155,9 +215,10 @@ def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, mean: torch.Tensor, rstd: t
     dx = torch.empty_like(x)
     if dres is not None:
         _req(dres, torch.bfloat16, "dres"); assert dres.is_contiguous() and dres.numel() == dy.numel()
-    st = _lib.load().stswin_layernorm_bwd(dy.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
-                                          _ptr(dres), dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), _ptr(dx_colsum),
-                                          M, row_len, pm, H, W, C, _stream(x))
+    with _launch("layernorm_bwd", (6.0 + (2.0 if dres is not None else 0.0)) * M * row_len, x):
+        st = _lib.load().stswin_layernorm_bwd(dy.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
+                                              _ptr(dres), dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), _ptr(dx_colsum),
+                                              M, row_len, pm, H, W, C, _stream(x))
     _lib.check(st, "stswin_layernorm_bwd")
     return dx
 
@@ -168,7 +229,8 @@ def transpose(x: torch.Tensor, out_dtype: torch.dtype) -> torch.Tensor:
     assert x.dtype in (torch.float32, torch.bfloat16) and out_dtype in (torch.float32, torch.bfloat16)
     b, R, Cc = x.shape
     out = torch.empty((b, Cc, R), dtype=out_dtype, device=x.device)
-    st = _lib.load().stswin_transpose(x.data_ptr(), int(x.dtype == torch.float32), out.data_ptr(),
-                                      int(out_dtype == torch.float32), b, R, Cc, _stream(x))
+    with _launch("transpose", float(x.numel() * x.element_size() + out.numel() * out.element_size()), x):
+        st = _lib.load().stswin_transpose(x.data_ptr(), int(x.dtype == torch.float32), out.data_ptr(),
+                                          int(out_dtype == torch.float32), b, R, Cc, _stream(x))
     _lib.check(st, "stswin_transpose")
     return out

@@ -126,11 +126,11 @@ class _BlockFn(torch.autograd.Function):
         attn, lse2 = ops.winattn_fwd(qkv.view(Bp, T, L, 3 * C), table, H, W, nH, ws, shift, qk_scale=qk_scale)
         y = ops.gemm(attn.view(-1, C), wp, bias=b_proj, aux=x2, mode=ops.EPI_BIAS_RES)
         yn, mean2, rstd2 = ops.layernorm_fwd(y, g2, be2, eps)
-        u = torch.empty((x2.shape[0], w1.shape[0]), dtype=_BF16, device=x.device)
-        h = ops.gemm(yn, w1, bias=b_fc1, mode=ops.EPI_BIAS_GELU, out2=u)
+        dgelu = torch.empty((x2.shape[0], w1.shape[0]), dtype=_BF16, device=x.device)   # gelu'(fc1 out), for the backward
+        h = ops.gemm(yn, w1, bias=b_fc1, mode=ops.EPI_BIAS_GELU, out2=dgelu)
         z = ops.gemm(h, w2, bias=b_fc2, aux=y, mode=ops.EPI_BIAS_RES)
         out, mean1, rstd1 = ops.layernorm_fwd(z, g1, be1, eps)
-        ctx.save_for_backward(x2, qkv, attn, lse2, y, yn, mean2, rstd2, u, h, z, mean1, rstd1,
+        ctx.save_for_backward(x2, qkv, attn, lse2, y, yn, mean2, rstd2, dgelu, h, z, mean1, rstd1,
                               table, wq, wp, w1, w2, g1, g2)
         ctx.geom = geom
         ctx.has_qkv_bias = b_qkv is not None
@@ -138,7 +138,7 @@ class _BlockFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, d_out):
-        (x2, qkv, attn, lse2, y, yn, mean2, rstd2, u, h, z, mean1, rstd1,
+        (x2, qkv, attn, lse2, y, yn, mean2, rstd2, dgelu, h, z, mean1, rstd1,
          table, wq, wp, w1, w2, g1, g2) = ctx.saved_tensors
         H, W, nH, ws, shift, qk_scale, eps = ctx.geom
         C = x2.shape[1]
@@ -149,9 +149,9 @@ class _BlockFn(torch.autograd.Function):
         # out = norm1(z)
         d_g1, d_be1, d_bfc2 = torch.zeros(C, **f32), torch.zeros(C, **f32), torch.zeros(C, **f32)
         dz = ops.layernorm_bwd(d2, z, mean1, rstd1, g1, d_g1, d_be1, dx_colsum=d_bfc2)
-        # z = y + h W2^T + b2 ; h = gelu(u)
+        # z = y + h W2^T + b2 ; h = gelu(u), and the forward stored gelu'(u)
         d_bfc1 = torch.zeros(w1.shape[0], **f32)
-        du = ops.gemm(dz, w2, b_mn_major=True, mode=ops.EPI_MUL_DGELU, aux=u, colsum=d_bfc1)
+        du = ops.gemm(dz, w2, b_mn_major=True, mode=ops.EPI_MUL_AUX, aux=dgelu, colsum=d_bfc1)
         d_wfc2 = _linear_wgrad(dz, h, w2.shape)
         # u = yn W1^T + b1 ; yn = norm2(y)
         dyn = ops.gemm(du, w1, b_mn_major=True)

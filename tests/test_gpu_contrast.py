@@ -1,0 +1,113 @@
+"""GPU: fused pixel contrastive loss against the reference's goldens and the CPU oracle.
+Tolerance 2e-2 relative (bf16 embeddings on the tensor cores); masks / label resizing exact."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-2
+
+
+def _g():
+    return np.load(os.path.join(GOLDEN, "loss_cases.npz"))
+
+
+@pytest.mark.parametrize("idx", range(5))
+def test_regression_loss_vs_reference_golden(idx):
+    from oracle import make_goldens as mg
+    from stswincl_b200 import contrast
+    case = mg.LOSS_CASES[idx]
+    tag, N, C, H, W, K, special = case
+    g = _g()
+    labels, emb = mg.loss_case_inputs(*case)
+    q = emb[0].cuda().requires_grad_(True)
+    loss = contrast.regression_loss(q, *[e.cuda() for e in emb[1:]], *[l.cuda() for l in labels], K)
+    loss.backward()
+    torch.cuda.synchronize()
+    ref = float(g[f"{tag}_loss"])
+    assert abs(float(loss) - ref) < TOL * abs(ref)
+    assert rel_err(q.grad.cpu(), g[f"{tag}_dq"]) < TOL
+
+
+def test_masks_and_label_resize_exact():
+    from oracle import loss_oracle as lo
+    from stswincl_b200 import contrast
+    g = _g()
+    l1, l2 = lo.make_label_maps(73, 2, 2, 4, 6, 5, coarse=(2, 3))
+    assert np.array_equal(contrast.posMask(l1.cuda(), l2.cuda(), 5).cpu().numpy(), g["pos_small"].astype(np.float32))
+    assert np.array_equal(contrast.negMask(l1.cuda(), l2.cuda(), 5).cpu().numpy(), g["neg_small"].astype(np.float32))
+    big = lo.make_label_maps(74, 1, 1, 256, 448, 12, coarse=(16, 28))[0]
+    assert np.array_equal(contrast.downsample_labels(big.cuda(), 32, 56).cpu().numpy(), g["down_32x56"].astype(np.float32))
+    odd = lo.make_label_maps(75, 1, 1, 100, 150, 12, coarse=(10, 15))[0]
+    assert np.array_equal(contrast.downsample_labels(odd.cuda(), 24, 40).cpu().numpy(), g["down_odd_24x40"].astype(np.float32))
+
+
+def test_consistency_tail_vs_reference_golden():
+    from oracle import loss_oracle as lo
+    from stswincl_b200 import contrast
+    g = _g()
+    N, C, H, W, K = 2, 64, 8, 14, 12
+    full = lo.make_label_maps(76, 6, N, 64, 112, K, coarse=(4, 7))
+    ds = [torch.nn.functional.interpolate(m, size=[H, W], mode="nearest") for m in full]
+    emb = lo.make_embeddings(77, ds, C, K)
+    pred_1, pred_2 = emb[0], lo.make_embeddings(78, ds[1:2], C, K)[0]
+    proj_1, proj_2 = lo.make_embeddings(79, ds[0:1], C, K)[0], emb[1]
+    c = lambda t: t.cuda()
+    tail = contrast.consistency_loss_tail(c(pred_1), c(pred_2), c(proj_1), c(proj_2), c(emb[2]), c(emb[3]), c(emb[4]), c(emb[5]),
+                                          *[c(m) for m in full], K)
+    assert abs(float(tail) - float(g["tail_loss"])) < TOL * abs(float(g["tail_loss"]))
+
+
+@pytest.mark.parametrize("N,C,H,W,K", [(2, 256, 32, 56, 12), (1, 128, 16, 28, 9)])
+def test_full_size_loss_vs_oracle(N, C, H, W, K):
+    """The reference's pre-training geometry: 256 channels, 32x56 = 1792 pixels."""
+    from oracle import loss_oracle as lo
+    from stswincl_b200 import contrast
+    labels = lo.make_label_maps(81, 6, N, H, W, K, coarse=(4, 7))
+    emb = lo.make_embeddings(82, labels, C, K)
+    q_ref = emb[0].to(torch.bfloat16).float().requires_grad_(True)
+    ref = lo.regression_loss(q_ref, [e.to(torch.bfloat16).float() for e in emb[1:]], labels[0], labels[1:], K)
+    ref.backward()
+    q = emb[0].cuda().requires_grad_(True)
+    loss = contrast.regression_loss(q, *[e.cuda() for e in emb[1:]], *[l.cuda() for l in labels], K)
+    (3.0 * loss).backward()
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(ref)) < 2e-3 * abs(float(ref))
+    assert rel_err(q.grad.cpu(), 3.0 * q_ref.grad) < TOL
+
+
+def test_fused_normalize_and_extra_key_sets():
+    from oracle import loss_oracle as lo
+    from stswincl_b200 import contrast
+    N, C, H, W, K = 2, 64, 8, 14, 12
+    labels = lo.make_label_maps(91, 8, N, H, W, K)
+    emb = lo.make_embeddings(92, labels, C, K)
+    gen = torch.Generator().manual_seed(93)
+    raw = [e * (0.5 + 2.0 * torch.rand(N, 1, H, W, generator=gen)) for e in emb]      # un-normalised inputs
+    q_ref = raw[0].clone().requires_grad_(True)
+    ref = lo.regression_loss(lo.l2_normalize(q_ref), [lo.l2_normalize(r) for r in raw[1:]], labels[0], labels[1:], K)
+    ref.backward()
+    q = raw[0].cuda().requires_grad_(True)
+    loss = contrast.pixel_contrast_loss(q, [r.cuda() for r in raw[1:]], labels[0].cuda(), [l.cuda() for l in labels[1:]], K,
+                                        normalize=True)
+    loss.backward()
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(ref)) < TOL * abs(float(ref))
+    assert rel_err(q.grad.cpu(), q_ref.grad) < TOL
+
+
+def test_out_of_range_label_raises_and_cpu_raises():
+    from oracle import make_goldens as mg
+    from stswincl_b200 import contrast
+    from stswincl_b200._lib import StswinError
+    labels, emb = mg.loss_case_inputs("l0", 1, 64, 8, 14, 12, None)
+    bad = labels[2].clone(); bad[0, 0, 0, 0] = 12.0
+    with pytest.raises(RuntimeError):
+        contrast.regression_loss(*[e[:1].cuda() for e in emb], labels[0][:1].cuda(), labels[1][:1].cuda(), bad[:1].cuda(),
+                                 *[l[:1].cuda() for l in labels[3:]], 12)
+    with pytest.raises(StswinError):
+        contrast.regression_loss(*[e[:1] for e in emb], *[l[:1] for l in labels], 12)

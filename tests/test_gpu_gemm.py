@@ -44,19 +44,19 @@ def test_gemm_epilogues(M, N, K):
     # residual
     out = ops.gemm(A, B, mode=ops.EPI_BIAS_RES, bias=bias, aux=R)
     assert _rel(out.float(), acc + bias + R.float()) < 1e-2
-    # gelu with pre-activation output + column sums
+    # erf-GELU with its derivative as second output + column sums
     cs = torch.zeros(N, device="cuda")
-    u = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
-    h = ops.gemm(A, B, mode=ops.EPI_BIAS_GELU, bias=bias, out2=u, colsum=cs)
-    uref = acc + bias
-    assert _rel(u.float(), uref) < 1e-2
-    assert _rel(h.float(), torch.nn.functional.gelu(uref)) < 1e-2
+    dg = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    h = ops.gemm(A, B, mode=ops.EPI_BIAS_GELU, bias=bias, out2=dg, colsum=cs)
+    uref = (acc + bias).double().requires_grad_(True)
+    href = torch.nn.functional.gelu(uref)
+    href.sum().backward()
+    assert _rel(h.float(), href.detach().float()) < 1e-2
+    assert _rel(dg.float(), uref.grad.float()) < 1e-2
     assert _rel(cs, h.float().sum(0)) < 1e-3
-    # gelu'(aux) multiply
-    d = ops.gemm(A, B, mode=ops.EPI_MUL_DGELU, aux=R)
-    x = R.float().double().requires_grad_(True)
-    torch.nn.functional.gelu(x).sum().backward()
-    assert _rel(d.float(), acc * x.grad.float()) < 1e-2
+    # multiply by aux (dgrad through GELU)
+    d = ops.gemm(A, B, mode=ops.EPI_MUL_AUX, aux=R)
+    assert _rel(d.float(), acc * R.float()) < 1e-2
 
 
 @pytest.mark.parametrize("M,N,K,splits", [(512, 512, 8192, 16), (1536, 512, 4096, 6), (200, 300, 1000, 3)])
