@@ -202,7 +202,7 @@ def run_ours(args):
     def step(x):
         opt.zero_grad(set_to_none=True)
         y1, y2 = net(x)
-        loss = (y1.float() * g1).sum() + (y2.float() * g2).sum()
+        loss = torch.sum(y1 * g1, dtype=torch.float32) + torch.sum(y2 * g2, dtype=torch.float32)
         loss.backward()
         opt.step()
         return loss

@@ -129,7 +129,7 @@ int stswin_transpose(const void* in, int in_is_f32, void* out, int out_is_f32, i
  * stswin_pixloss_fwd   : q, keys[s] [N,C,HW] bf16 (unit-norm pixel embeddings, channel-major as
  *     in the reference); lq, lk[s] [N,HW] u8 labels.  `keys` / `lk` are HOST arrays of n_sets
  *     device pointers, ordered (k, adj1, adj2, adj3, neg3) like the reference's arguments; any
- *     1 <= n_sets <= 8 is accepted (extra sets extend the positive pool and the negative sum).
+ *     1 <= n_sets <= 64 is accepted (launched 8 sets at a time) (extra sets extend the positive pool and the negative sum).
  *     row_stats [N,HW,n_sets,4] fp32 workspace; loss: device scalar, overwritten with
  *     -mean log(e^P/(e^P+e^N)+1e-6); coef [N,HW,1+n_sets] fp32 (may be NULL when no gradient
  *     is needed): per-row dloss/dz coefficients for the backward.

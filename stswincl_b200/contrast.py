@@ -128,12 +128,12 @@ class _PixLossFn(torch.autograd.Function):
 def pixel_contrast_loss(q: torch.Tensor, keys: Sequence[torch.Tensor], label_q: torch.Tensor,
                         labels_k: Sequence[torch.Tensor], class_num: int, *, normalize: bool = False,
                         validate_labels: bool = True, _cache: Optional[dict] = None) -> torch.Tensor:
-    """General form: any 1..8 key sets.  ``normalize=True`` fuses ``F.normalize(dim=1)`` of q and of
+    """General form: any 1..64 key sets (e.g. key sets all-gathered from other ranks).  ``normalize=True`` fuses ``F.normalize(dim=1)`` of q and of
     every key into the loss (otherwise the inputs are taken as already unit-norm, like the
     reference's ``regression_loss``)."""
     if not q.is_cuda:
         raise StswinError("stswincl_b200.contrast needs CUDA tensors (no CPU path)")
-    assert len(keys) == len(labels_k) and 1 <= len(keys) <= 8
+    assert len(keys) == len(labels_k) and 1 <= len(keys) <= 64
     if validate_labels:       # F.one_hot raises for labels outside [0, class_num) (:54-55)
         hi = torch.stack([l.max() for l in (label_q, *labels_k)]).max()
         lo = torch.stack([l.min() for l in (label_q, *labels_k)]).min()

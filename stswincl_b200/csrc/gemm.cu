@@ -19,6 +19,8 @@
 // gradients), and an fp32 TMA add-reduction for split-K weight gradients.
 // (A first version stored through TMA from a single staging buffer and serialised on the store's
 // read latency: 315 TFLOP/s at K=512; see profiles/.)
+#include <type_traits>
+
 #include "common.cuh"
 #include "host_util.h"
 
@@ -214,16 +216,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         }
       } else {
-        uint4 auxr[8];
-        auto aux_fetch = [&](int cb) {
+        // aux (residual / multiplier) for BOTH 64-column chunks of this warp is requested up front:
+        // 8 KB per warp, 64 KB per SM in flight -- one chunk ahead left the loads latency-bound
+        uint4 auxr[has_aux ? 2 : 1][8];
+        if constexpr (has_aux) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = row0 + 4 * i + crow, n = cb + cchunk * 8;
-            auxr[i] = (r < p.M && n < p.N)
-                          ? __ldg(reinterpret_cast<const uint4*>(p.aux + (size_t)r * p.ld_aux + n))
-                          : make_uint4(0, 0, 0, 0);
-          }
-        };
+          for (int cc = 0; cc < 2; ++cc)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int r = row0 + 4 * i + crow, n = col0 + cc * 64 + cchunk * 8;
+              auxr[cc][i] = (r < p.M && n < p.N)
+                                ? __ldg(reinterpret_cast<const uint4*>(p.aux + (size_t)r * p.ld_aux + n))
+                                : make_uint4(0, 0, 0, 0);
+            }
+        }
         // staged 32 x 64 chunk -> global, 128-byte lines
         auto store_staged = [&](__nv_bfloat16* dst, int cb) {
 #pragma unroll
@@ -234,25 +240,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (r < p.M && n < p.N) *reinterpret_cast<uint4*>(dst + (size_t)r * p.ldd + n) = q;
           }
         };
-        if (has_aux) aux_fetch(col0);                 // in flight while the main loop finishes
         mbar_wait(&acc_full[acc], acc_phase);
         tc_fence_after();
-#pragma unroll 1
-        for (int c = 0; c < BN / 128; ++c) {
+        auto do_chunk = [&](const int c, auto aux_sel) {
+          constexpr int kAuxSel = decltype(aux_sel)::value;   // which prefetched aux register set to consume
           const int cbase = col0 + c * 64;
-          uint32_t auxw[32];
-          if (has_aux) {
+          uint32_t auxw[has_aux ? 32 : 1];
+          if constexpr (has_aux) {
             __syncwarp();                                 // earlier readers of my_buf are done
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-              *reinterpret_cast<uint4*>(my_buf + sw128_offset(4 * i + crow, cchunk)) = auxr[i];
+              *reinterpret_cast<uint4*>(my_buf + sw128_offset(4 * i + crow, cchunk)) = auxr[kAuxSel][i];
             __syncwarp();
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const uint4 q = *reinterpret_cast<const uint4*>(my_buf + sw128_offset(lane, j));
               auxw[4 * j] = q.x; auxw[4 * j + 1] = q.y; auxw[4 * j + 2] = q.z; auxw[4 * j + 3] = q.w;
             }
-            if (c + 1 < BN / 128) aux_fetch(cbase + 64);  // in flight while this chunk is processed
           }
           __syncwarp();                                   // my_buf may be overwritten with the output now
           uint32_t out2w[MODE == kBiasGelu ? 32 : 1];     // second output of the GELU mode (gelu'(u))
@@ -261,17 +265,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           auto do_half = [&](int half) {
             uint32_t v[32];
             tmem_ld32(t_row + c * 64 + half * 32, v);
-            float bias_l = 0.f;                          // lane l holds the bias of column l of this half
+            float bv[32];                                // bias of the 32 columns (same for every row)
             if (p.bias != nullptr) {
-              const int n = cbase + half * 32 + lane;
-              if (n < p.N) bias_l = __ldg(p.bias + n);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const int n = cbase + half * 32 + 4 * j;
+                const float4 b4 = (n + 3 < p.N) ? __ldg(reinterpret_cast<const float4*>(p.bias + n))
+                                                : make_float4(n < p.N ? __ldg(p.bias + n) : 0.f,
+                                                              n + 1 < p.N ? __ldg(p.bias + n + 1) : 0.f,
+                                                              n + 2 < p.N ? __ldg(p.bias + n + 2) : 0.f, 0.f);
+                bv[4 * j] = b4.x; bv[4 * j + 1] = b4.y; bv[4 * j + 2] = b4.z; bv[4 * j + 3] = b4.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) bv[j] = 0.f;
             }
             tmem_ld_wait();
             uint32_t outw[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              float a0 = __uint_as_float(v[2 * j]) + __shfl_sync(0xffffffffu, bias_l, 2 * j);
-              float a1 = __uint_as_float(v[2 * j + 1]) + __shfl_sync(0xffffffffu, bias_l, 2 * j + 1);
+              float a0 = __uint_as_float(v[2 * j]) + bv[2 * j];
+              float a1 = __uint_as_float(v[2 * j + 1]) + bv[2 * j + 1];
               if constexpr (MODE == kBiasRes) {
                 const float2 r = unpack_bf16(auxw[half * 16 + j]);
                 a0 += r.x; a1 += r.y;
@@ -279,14 +293,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 float g0, g1;
                 gelu_and_grad(a0, a0, g0);
                 gelu_and_grad(a1, a1, g1);
-                if (!row_ok) { g0 = 0.f; g1 = 0.f; }
                 out2w[half * 16 + j] = pack_bf16(g0, g1);
               } else if constexpr (MODE == kMulAux) {
                 const float2 u = unpack_bf16(auxw[half * 16 + j]);
                 a0 *= u.x; a1 *= u.y;
               }
-              if (!row_ok) { a0 = 0.f; a1 = 0.f; }
               outw[j] = pack_bf16(a0, a1);
+            }
+            if (!row_ok) {                               // rows past M (last tile only): keep them out of colsum
+#pragma unroll
+              for (int j = 0; j < 16; ++j) outw[j] = 0u;
+              if constexpr (MODE == kBiasGelu) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) out2w[half * 16 + j] = 0u;
+              }
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j)
@@ -324,6 +344,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             __syncwarp();
             store_staged(p.D2, cbase);
           }
+        };
+        if constexpr (has_aux) {       // unrolled: each chunk consumes its own prefetched registers
+          do_chunk(0, std::integral_constant<int, 0>{});
+          do_chunk(1, std::integral_constant<int, has_aux ? 1 : 0>{});
+        } else {
+#pragma unroll 1
+          for (int c = 0; c < BN / 128; ++c) do_chunk(c, std::integral_constant<int, 0>{});
         }
       }
       // all TMEM reads of this accumulator are done -> hand it back to the MMA warp

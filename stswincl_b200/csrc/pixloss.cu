@@ -84,6 +84,7 @@ constexpr int PF_THREADS = 192;
 
 struct PixFwdArgs {
   int N, C, HW, n_sets, num_mb, num_tiles, nkb;
+  int set_total, set_off;   // this launch handles sets [set_off, set_off + n_sets) of set_total
   const uint8_t* lq;
   float* stats;      // [N, HW, n_sets, 4] : pos_sum, pos_cnt, neg_sum, neg_cnt
 };
@@ -217,7 +218,7 @@ pixloss_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
       if (i < p.HW) {
         float4 o;
         o.x = pos; o.y = float(cnt); o.z = tot - pos; o.w = float(p.HW - cnt);
-        *reinterpret_cast<float4*>(p.stats + (((size_t)n * p.HW + i) * p.n_sets + s) * 4) = o;
+        *reinterpret_cast<float4*>(p.stats + (((size_t)n * p.HW + i) * p.set_total + p.set_off + s) * 4) = o;
       }
     }
   }
@@ -278,6 +279,7 @@ constexpr int PB_THREADS = 192;
 
 struct PixBwdArgs {
   int N, C, HW, n_sets, num_mb, nkb;   // nkb = ceil(HW / 64)
+  int set_total, set_off;
   const uint8_t* lq;
   const float* coef;     // [N, HW, 1 + n_sets]
   const float* ksum;     // [n_sets, N, C]
@@ -382,9 +384,9 @@ pixloss_bwd_kernel(const __grid_constant__ SetMaps tm_k, const __grid_constant__
       const uint32_t li = row_ok ? p.lq[(size_t)n * p.HW + i] : 254u;
       float ca = 0.f, cb_ = 0.f;
       if (row_ok) {
-        const float* cf = p.coef + ((size_t)n * p.HW + i) * (p.n_sets + 1);
+        const float* cf = p.coef + ((size_t)n * p.HW + i) * (p.set_total + 1);
         ca = cf[0] * g_up;
-        cb_ = cf[1 + s] * g_up;
+        cb_ = cf[1 + p.set_off + s] * g_up;
       }
       // ---- generate the 0/1 same-label operand, 64 keys at a time
       for (int kb = 0; kb < p.nkb; ++kb) {
@@ -409,7 +411,7 @@ pixloss_bwd_kernel(const __grid_constant__ SetMaps tm_k, const __grid_constant__
       // ---- epilogue: dq[i, :] += (a - b_s) * D[i, :] + b_s * ksum_s[:]
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
-      const float* ks = p.ksum + ((size_t)s * p.N + n) * p.C;
+      const float* ks = p.ksum + ((size_t)(p.set_off + s) * p.N + n) * p.C;
       const float cm = ca - cb_;
 #pragma unroll 1
       for (int c32 = 0; c32 < p.C / 32; ++c32) {
@@ -448,8 +450,10 @@ pixloss_bwd_kernel(const __grid_constant__ SetMaps tm_k, const __grid_constant__
   }
 }
 
+constexpr int MAX_TOTAL_SETS = 64;   // launches of MAX_SETS sets each (cross-rank gathered key sets)
+
 int check_pix_shape(int n_sets, int N, int C, int HW) {
-  STSWIN_CHECK_ARG(n_sets >= 1 && n_sets <= MAX_SETS, "pixloss: n_sets=%d out of range [1,%d]", n_sets, MAX_SETS);
+  STSWIN_CHECK_ARG(n_sets >= 1 && n_sets <= MAX_TOTAL_SETS, "pixloss: n_sets=%d out of range [1,%d]", n_sets, MAX_TOTAL_SETS);
   STSWIN_CHECK_ARG(N > 0 && HW > 0, "pixloss: empty input");
   if (C % 64 != 0 || C > 256) return set_error(kErrUnsupported, "pixloss: C=%d unsupported (multiple of 64, <= 256)", C);
   if (HW % 8 != 0) return set_error(kErrUnsupported, "pixloss: H*W=%d must be a multiple of 8", HW);
@@ -491,25 +495,28 @@ int pixloss_fwd(const void* q, const void* const* keys, const uint8_t* lq, const
   int rc = check_pix_shape(n_sets, N, C, HW);
   if (rc != kOk) return rc;
   CUtensorMap tq;
-  SetMaps tk;
-  SetPtrs lp;
   if ((rc = key_tmap(&tq, q, N, C, HW, 64)) != kOk) return rc;
-  for (int s = 0; s < MAX_SETS; ++s) {
-    const int src = s < n_sets ? s : 0;
-    STSWIN_CHECK_ARG(keys[src] && lk[src], "pixloss_fwd: null key set %d", src);
-    if ((rc = key_tmap(&tk.m[s], keys[src], N, C, HW, 64)) != kOk) return rc;
-    lp.lk[s] = lk[src];
+  for (int off = 0; off < n_sets; off += MAX_SETS) {
+    const int ns = (n_sets - off < MAX_SETS) ? n_sets - off : MAX_SETS;
+    SetMaps tk;
+    SetPtrs lp;
+    for (int s = 0; s < MAX_SETS; ++s) {
+      const int src = off + (s < ns ? s : 0);
+      STSWIN_CHECK_ARG(keys[src] && lk[src], "pixloss_fwd: null key set %d", src);
+      if ((rc = key_tmap(&tk.m[s], keys[src], N, C, HW, 64)) != kOk) return rc;
+      lp.lk[s] = lk[src];
+    }
+    PixFwdArgs a;
+    a.N = N; a.C = C; a.HW = HW; a.n_sets = ns; a.set_total = n_sets; a.set_off = off;
+    a.num_mb = (HW + 127) / 128; a.num_tiles = (HW + 127) / 128; a.nkb = C / 64;
+    a.lq = lq; a.stats = row_stats;
+    const int smem = 1024 + 4 * KB_BYTES + PF_STAGES * KB_BYTES + ((a.num_tiles * 128 + 15) & ~15) + 256;
+    STSWIN_CUDA(cudaFuncSetAttribute(pixloss_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int items = N * a.num_mb * ns;
+    const int grid = items < num_sms() ? items : num_sms();
+    pixloss_fwd_kernel<<<grid, PF_THREADS, smem, stream>>>(tq, tk, lp, a);
+    STSWIN_CUDA(cudaGetLastError());
   }
-  PixFwdArgs a;
-  a.N = N; a.C = C; a.HW = HW; a.n_sets = n_sets;
-  a.num_mb = (HW + 127) / 128; a.num_tiles = (HW + 127) / 128; a.nkb = C / 64;
-  a.lq = lq; a.stats = row_stats;
-  const int smem = 1024 + 4 * KB_BYTES + PF_STAGES * KB_BYTES + ((a.num_tiles * 128 + 15) & ~15) + 256;
-  STSWIN_CUDA(cudaFuncSetAttribute(pixloss_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  const int items = N * a.num_mb * n_sets;
-  const int grid = items < num_sms() ? items : num_sms();
-  pixloss_fwd_kernel<<<grid, PF_THREADS, smem, stream>>>(tq, tk, lp, a);
-  STSWIN_CUDA(cudaGetLastError());
   STSWIN_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), stream));
   const long rows = (long)N * HW;
   pixloss_finalize_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, stream>>>(row_stats, n_sets, rows, 1.0f / rows, loss, coef);
@@ -524,14 +531,6 @@ int pixloss_bwd(const void* const* keys, const uint8_t* lq, const uint8_t* const
   STSWIN_CHECK_ARG(keys && lq && lk && coef && ksum && d_loss && dq32, "pixloss_bwd: null pointer");
   int rc = check_pix_shape(n_sets, N, C, HW);
   if (rc != kOk) return rc;
-  SetMaps tk;
-  SetPtrs lp;
-  for (int s = 0; s < MAX_SETS; ++s) {
-    const int src = s < n_sets ? s : 0;
-    STSWIN_CHECK_ARG(keys[src] && lk[src], "pixloss_bwd: null key set %d", src);
-    if ((rc = key_tmap(&tk.m[s], keys[src], N, C, HW, (uint32_t)C)) != kOk) return rc;
-    lp.lk[s] = lk[src];
-  }
   CUtensorMap tdq;
   {
     uint64_t dims[3] = {(uint64_t)C, (uint64_t)HW, (uint64_t)N};
@@ -540,16 +539,27 @@ int pixloss_bwd(const void* const* keys, const uint8_t* lq, const uint8_t* const
     if ((rc = make_tmap(&tdq, TmapDtype::F32, 3, dq32, dims, str, box, true)) != kOk) return rc;
   }
   STSWIN_CUDA(cudaMemsetAsync(dq32, 0, sizeof(float) * (size_t)N * HW * C, stream));
-  PixBwdArgs a;
-  a.N = N; a.C = C; a.HW = HW; a.n_sets = n_sets;
-  a.num_mb = (HW + 127) / 128; a.nkb = (HW + 63) / 64;
-  a.lq = lq; a.coef = coef; a.ksum = ksum; a.d_loss = d_loss;
-  const int smem = 1024 + PB_GEN * 16384 + PB_STAGES * C * 128 + 4 * 4096 + ((a.nkb * 64 + 15) & ~15) + 256;
-  STSWIN_CUDA(cudaFuncSetAttribute(pixloss_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  const int items = N * a.num_mb * n_sets;
-  const int grid = items < num_sms() ? items : num_sms();
-  pixloss_bwd_kernel<<<grid, PB_THREADS, smem, stream>>>(tk, tdq, lp, a);
-  STSWIN_CUDA(cudaGetLastError());
+  for (int off = 0; off < n_sets; off += MAX_SETS) {
+    const int ns = (n_sets - off < MAX_SETS) ? n_sets - off : MAX_SETS;
+    SetMaps tk;
+    SetPtrs lp;
+    for (int s = 0; s < MAX_SETS; ++s) {
+      const int src = off + (s < ns ? s : 0);
+      STSWIN_CHECK_ARG(keys[src] && lk[src], "pixloss_bwd: null key set %d", src);
+      if ((rc = key_tmap(&tk.m[s], keys[src], N, C, HW, (uint32_t)C)) != kOk) return rc;
+      lp.lk[s] = lk[src];
+    }
+    PixBwdArgs a;
+    a.N = N; a.C = C; a.HW = HW; a.n_sets = ns; a.set_total = n_sets; a.set_off = off;
+    a.num_mb = (HW + 127) / 128; a.nkb = (HW + 63) / 64;
+    a.lq = lq; a.coef = coef; a.ksum = ksum; a.d_loss = d_loss;
+    const int smem = 1024 + PB_GEN * 16384 + PB_STAGES * C * 128 + 4 * 4096 + ((a.nkb * 64 + 15) & ~15) + 256;
+    STSWIN_CUDA(cudaFuncSetAttribute(pixloss_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int items = N * a.num_mb * ns;
+    const int grid = items < num_sms() ? items : num_sms();
+    pixloss_bwd_kernel<<<grid, PB_THREADS, smem, stream>>>(tk, tdq, lp, a);
+    STSWIN_CUDA(cudaGetLastError());
+  }
   return kOk;
 }
 

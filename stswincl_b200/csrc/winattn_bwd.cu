@@ -12,13 +12,25 @@
 // Outputs d_qkv [B,T,H,W,3C] bf16 (scattered to the un-rolled coordinates by TMA),
 //         d_table [(2ws-1)^2, nH] fp32 (+=), optional d_qkv_colsum [3C] fp32 (+=, the qkv bias grad).
 //
-// Streaming: operand chunks [128 rows x 64 ch] flow through a ring of 16 KB slots twice -- once
-// for S and dP, once more (from L2) for the three output products.  S, dP, the running sum of dS
-// and two 64-column output accumulators live in TMEM.  The bias-table gradient needs the sum of
-// dS over every tile this CTA processes; it is accumulated on the tensor core as dS * I (identity
-// tile in smem) so no per-element atomics are issued in the main loop.  For that sum to be
-// meaningful every tile of a launch uses ONE token order (gm.uniform_quad) and every CTA sees
-// ONE head (grid is a multiple of nH).
+// Streaming: operand chunks [128 rows x 64 ch] flow through 16 KB ring slots twice -- once from
+// HBM for S and dP (ring H, producer warp 0), once more from L2 for the three output products
+// (ring L, producer warp 6).  Two independent rings let the HBM loads of tile i+1 run while tile i
+// is still in its softmax-backward / second pass (a single ring serialised them: 46-60% of HBM
+// peak, profiles/r1_attn_bwd_ncu_summary.txt).  S, dP and two 64-column output accumulators live in
+// TMEM; outputs go TMEM -> registers -> global directly (each thread owns one token row and writes
+// its 128-byte line), so no staging buffer competes with the rings for shared memory.
+// The register-level work (softmax backward, output conversion, bias-gradient sums) is done by TWO
+// groups of four warps, i.e. two warps per SM sub-partition: with a single warp per sub-partition
+// every dependent instruction exposed its full latency and a tile took ~28k cycles.  For L >= 64
+// the groups take alternate 32-column chunks of S / dP (row sums are exchanged through shared
+// memory); the groups always alternate the 64-column output chunks (group g drains TMEM buffer g).  The bias-table gradient needs the sum of
+// dS over every tile this CTA processes: each thread (= query row) keeps N = ws*ws fp32 running
+// sums, one per key position (the TxT tiling folds onto the same entry), and bins them by relative
+// position once at the end of the kernel -- no per-element atomics in the main loop, and no bf16
+// rounding inside a sum that cancels heavily.  For that sum to be meaningful every tile of a
+// launch uses ONE token order (gm.uniform_quad) and every CTA sees ONE head (grid % nH == 0).
+// (A first version accumulated bf16 dS on the tensor core through an identity tile; its rounding
+// noise reached 6% of the gradient for a 6-window batch.)
 #include "winattn_common.cuh"
 #include "host_util.h"
 #include "kernels.h"
@@ -30,38 +42,38 @@ int make_window_tmaps(CUtensorMap* full, CUtensorMap* quad, const void* base, co
 
 namespace {
 
-constexpr int NR = 6;
+constexpr int NRH = 6;                         // ring H: first-pass chunks, streamed from HBM
+constexpr int NRL = 3;                         // ring L: second-pass chunks, re-read from L2
 constexpr int SLOT_BYTES = 128 * 128;
 constexpr int PD_BYTES = 2 * SLOT_BYTES;       // [128 x 128] bf16 as two K-major halves
-constexpr int STG_BYTES = 2 * SLOT_BYTES;
-constexpr int EYE_BYTES = 64 * 128;            // I64, K-major, 128B swizzle
 constexpr int TAB_MAX = 15 * 15;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 384;               // warp 0 producer H, 1 MMA, 2 producer L, 3 idle, 4-7 / 8-11 compute groups A / B
 constexpr int SMEM_BYTES =
-    1024 + NR * SLOT_BYTES + 2 * PD_BYTES + STG_BYTES + EYE_BYTES + 128 * 4 + 2 * (TAB_MAX + 1) * 4 + 256;
+    1024 + (NRH + NRL) * SLOT_BYTES + 2 * PD_BYTES + 128 * 4 + 2 * (TAB_MAX + 1) * 4 + 2 * 128 * 4 + 256;
 constexpr float kMaskLog2e = -100.0f * 1.4426950408889634f;
 
 template <int L>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 winattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid_constant__ CUtensorMap tm_qkv_quad,
                    const __grid_constant__ CUtensorMap tm_do_full, const __grid_constant__ CUtensorMap tm_do_quad,
-                   const __grid_constant__ CUtensorMap tm_dqkv_full, const __grid_constant__ CUtensorMap tm_dqkv_quad,
-                   const float* __restrict__ bias_table, const float* __restrict__ lse2, float* __restrict__ d_table,
+                   __nv_bfloat16* __restrict__ d_qkv, const float* __restrict__ bias_table, const float* __restrict__ lse2, float* __restrict__ d_table,
                    float* __restrict__ d_colsum, const WinGeom gm) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* s_ring = smem;
-  uint8_t* s_p = s_ring + NR * SLOT_BYTES;
+  uint8_t* s_ringh = smem;
+  uint8_t* s_ringl = s_ringh + NRH * SLOT_BYTES;
+  uint8_t* s_p = s_ringl + NRL * SLOT_BYTES;
   uint8_t* s_ds = s_p + PD_BYTES;
-  uint8_t* s_stg = s_ds + PD_BYTES;
-  uint8_t* s_eye = s_stg + STG_BYTES;
-  uint32_t* s_lut = reinterpret_cast<uint32_t*>(s_eye + EYE_BYTES);
+  uint32_t* s_lut = reinterpret_cast<uint32_t*>(s_ds + PD_BYTES);
   float* s_tab = reinterpret_cast<float*>(s_lut + 128);
   float* s_bacc = s_tab + TAB_MAX + 1;
-  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(s_bacc + TAB_MAX + 1) + 7) & ~uintptr_t(7));
-  uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + NR;
-  uint64_t* sdp_full = bars + 2 * NR;
+  float* s_delta = s_bacc + TAB_MAX + 1;          // [2][128] partial row sums of the two compute groups
+  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(s_delta + 256) + 7) & ~uintptr_t(7));
+  uint64_t* fullh = bars;
+  uint64_t* emptyh = fullh + NRH;
+  uint64_t* fulll = emptyh + NRH;
+  uint64_t* emptyl = fulll + NRL;
+  uint64_t* sdp_full = emptyl + NRL;
   uint64_t* sdp_free = sdp_full + 1;
   uint64_t* pds_full = sdp_full + 2;
   uint64_t* pds_free = sdp_full + 3;
@@ -80,15 +92,17 @@ winattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid
     tma_prefetch_desc(&tm_qkv_quad);
     tma_prefetch_desc(&tm_do_full);
     tma_prefetch_desc(&tm_do_quad);
-    tma_prefetch_desc(&tm_dqkv_full);
-    tma_prefetch_desc(&tm_dqkv_quad);
-    for (int i = 0; i < NR; ++i) {
-      mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+    for (int i = 0; i < NRH; ++i) {
+      mbar_init(&fullh[i], 1);
+      mbar_init(&emptyh[i], 1);
+    }
+    for (int i = 0; i < NRL; ++i) {
+      mbar_init(&fulll[i], 1);
+      mbar_init(&emptyl[i], 1);
     }
     mbar_init(sdp_full, 1);
-    mbar_init(sdp_free, 128);
-    mbar_init(pds_full, 128);
+    mbar_init(sdp_free, (L >= 64) ? 256 : 128);     // every thread that reads S / dP
+    mbar_init(pds_full, (L >= 64) ? 256 : 128);     // every thread that writes P / dS
     mbar_init(pds_free, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&obuf_full[i], 1);
@@ -97,19 +111,8 @@ winattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
-  // P / dS: entries outside a row's own window stay zero.  Identity tile for the dS running sum.
+  // P / dS: entries outside a row's own window stay zero.
   for (int i = threadIdx.x; i < 2 * PD_BYTES / 16; i += NUM_THREADS) reinterpret_cast<uint4*>(s_p)[i] = make_uint4(0, 0, 0, 0);
-  for (int i = threadIdx.x; i < 64 * 8; i += NUM_THREADS) {
-    const int n = i >> 3, ch = i & 7;            // row n, 16-byte chunk ch (columns 8*ch .. 8*ch+7)
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if ((n >> 3) == ch) {
-      const uint32_t one = 0x3F80u;              // bf16 1.0
-      const int e = n & 7;
-      uint32_t w = (e & 1) ? (one << 16) : one;
-      if ((e >> 1) == 0) v.x = w; else if ((e >> 1) == 1) v.y = w; else if ((e >> 1) == 2) v.z = w; else v.w = w;
-    }
-    *reinterpret_cast<uint4*>(s_eye + sw128_offset(n, ch)) = v;
-  }
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -117,89 +120,86 @@ winattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_S = tmem_base;
   const uint32_t tmem_dP = tmem_base + 128;
-  const uint32_t tmem_acc = tmem_base + 256;    // running sum of dS over this CTA's tiles
-  const uint32_t tmem_out = tmem_base + 384;    // two 64-column output accumulators
+  const uint32_t tmem_out = tmem_base + 256;    // two 64-column output accumulators
 
-  if (warp == 0) {
-    // ---------------------------------------------------------------- TMA producer (all lanes issue boxes)
+  if (warp == 0 || warp == 2) {
+    // ---------------------------------------------------------------- TMA producers (all lanes issue boxes)
+    const bool ring_h = (warp == 0);
+    uint8_t* ring = ring_h ? s_ringh : s_ringl;
+    uint64_t* fullb = ring_h ? fullh : fulll;
+    uint64_t* emptyb = ring_h ? emptyh : emptyl;
+    const int nslot = ring_h ? NRH : NRL;
     int slot = 0;
     uint32_t phase = 0;
     auto load = [&](int tile, bool from_do, int ch0) {
-      mbar_wait(&empty_bar[slot], phase ^ 1);
-      if (lane == 0) mbar_arrive_expect_tx(&full_bar[slot], SLOT_BYTES);
+      mbar_wait(&emptyb[slot], phase ^ 1);
+      if (lane == 0) mbar_arrive_expect_tx(&fullb[slot], SLOT_BYTES);
       __syncwarp();
-      tile_boxes<true>(gm, tile, ch0, s_ring + slot * SLOT_BYTES, from_do ? &tm_do_full : &tm_qkv_full,
-                       from_do ? &tm_do_quad : &tm_qkv_quad, &full_bar[slot], lane);
-      if (++slot == NR) { slot = 0; phase ^= 1; }
+      tile_boxes<true>(gm, tile, ch0, ring + slot * SLOT_BYTES, from_do ? &tm_do_full : &tm_qkv_full,
+                       from_do ? &tm_do_quad : &tm_qkv_quad, &fullb[slot], lane);
+      if (++slot == nslot) { slot = 0; phase ^= 1; }
     };
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
       const int tile = item / gm.nH;
       const int hq = head * gm.hd;
-      for (int c = 0; c < nc; ++c) {
-        load(tile, false, 0 * gm.C + hq + c * 64);   // Q_c
-        load(tile, false, 1 * gm.C + hq + c * 64);   // K_c
-        load(tile, true, hq + c * 64);               // dO_c
-        load(tile, false, 2 * gm.C + hq + c * 64);   // V_c
-      }
-      for (int c = 0; c < nc; ++c) {
-        load(tile, true, hq + c * 64);               // dO_c -> dV_c
-        load(tile, false, 1 * gm.C + hq + c * 64);   // K_c  -> dQ_c
-        load(tile, false, 0 * gm.C + hq + c * 64);   // Q_c  -> dK_c
+      if (ring_h) {
+        for (int c = 0; c < nc; ++c) {
+          load(tile, false, 0 * gm.C + hq + c * 64);   // Q_c
+          load(tile, false, 1 * gm.C + hq + c * 64);   // K_c
+          load(tile, true, hq + c * 64);               // dO_c
+          load(tile, false, 2 * gm.C + hq + c * 64);   // V_c
+        }
+      } else {
+        for (int c = 0; c < nc; ++c) {
+          load(tile, true, hq + c * 64);               // dO_c -> dV_c
+          load(tile, false, 1 * gm.C + hq + c * 64);   // K_c  -> dQ_c
+          load(tile, false, 0 * gm.C + hq + c * 64);   // Q_c  -> dK_c
+        }
       }
     }
   } else if (warp == 1) {
     // ---------------------------------------------------------------- MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc_kk = umma_idesc_bf16(128, 128, 0, 0);   // S, dP
-      constexpr uint32_t idesc_acc = umma_idesc_bf16(128, 64, 0, 0);   // dS * I64
       constexpr uint32_t idesc_kn = umma_idesc_bf16(128, 64, 0, 1);    // dQ = dS K
       constexpr uint32_t idesc_nn = umma_idesc_bf16(128, 64, 1, 1);    // dV = P^T dO, dK = dS^T Q
-      int slot = 0;
-      uint32_t phase = 0, itp = 0;
-      int ob = 0;
-      uint32_t ob_phase = 0;
-      bool first = true;
-      const uint32_t p_addr = smem_u32(s_p), ds_addr = smem_u32(s_ds), eye_addr = smem_u32(s_eye);
-      auto next_slot = [&]() { if (++slot == NR) { slot = 0; phase ^= 1; } };
+      int slot = 0, slotl = 0;
+      uint32_t phase = 0, phasel = 0, itp = 0;
+      uint32_t obp[2] = {0, 0};           // per output buffer: parity of its next use
+      const uint32_t p_addr = smem_u32(s_p), ds_addr = smem_u32(s_ds);
+      auto next_slot = [&]() { if (++slot == NRH) { slot = 0; phase ^= 1; } };
       for (int item = blockIdx.x; item < num_items; item += gridDim.x, itp ^= 1) {
         mbar_wait(sdp_free, itp ^ 1);
         tc_fence_after();
         for (int c = 0; c < nc; ++c) {
           for (int pair = 0; pair < 2; ++pair) {     // (Q_c, K_c) -> S ; (dO_c, V_c) -> dP
             const int sa = slot;
-            mbar_wait(&full_bar[slot], phase);
+            mbar_wait(&fullh[slot], phase);
             next_slot();
             const int sb = slot;
-            mbar_wait(&full_bar[slot], phase);
+            mbar_wait(&fullh[slot], phase);
             next_slot();
             tc_fence_after();
-            const uint32_t aa = smem_u32(s_ring + sa * SLOT_BYTES), ba = smem_u32(s_ring + sb * SLOT_BYTES);
+            const uint32_t aa = smem_u32(s_ringh + sa * SLOT_BYTES), ba = smem_u32(s_ringh + sb * SLOT_BYTES);
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)
               umma_bf16(pair == 0 ? tmem_S : tmem_dP, umma_smem_desc(aa + kk * 32, 16, 1024),
                         umma_smem_desc(ba + kk * 32, 16, 1024), idesc_kk, (c > 0 || kk > 0) ? 1u : 0u);
-            umma_commit(&empty_bar[sa]);
-            umma_commit(&empty_bar[sb]);
+            umma_commit(&emptyh[sa]);
+            umma_commit(&emptyh[sb]);
           }
         }
         umma_commit(sdp_full);
 
         mbar_wait(pds_full, itp);
         tc_fence_after();
-        // running sum of dS:  acc[:, 64h + n] += sum_k dS[:, 64h + k] * I64[n, k]
-#pragma unroll
-        for (int h = 0; h < 2; ++h)
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            umma_bf16(tmem_acc + h * 64, umma_smem_desc(ds_addr + h * SLOT_BYTES + kk * 32, 16, 1024),
-                      umma_smem_desc(eye_addr + kk * 32, 16, 1024), idesc_acc, (!first || kk > 0) ? 1u : 0u);
-        first = false;
         for (int c = 0; c < nc; ++c) {
           for (int o = 0; o < 3; ++o) {              // dV_c, dQ_c, dK_c
-            mbar_wait(&full_bar[slot], phase);
-            mbar_wait(&obuf_free[ob], ob_phase ^ 1);
+            const int ob = (3 * c + o) & 1;      // output chunk k of a tile uses TMEM buffer k % 2
+            mbar_wait(&fulll[slotl], phasel);
+            mbar_wait(&obuf_free[ob], obp[ob] ^ 1);
             tc_fence_after();
-            const uint32_t xa = smem_u32(s_ring + slot * SLOT_BYTES);
+            const uint32_t xa = smem_u32(s_ringl + slotl * SLOT_BYTES);
             const uint32_t dst = tmem_out + ob * 64;
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk) {
@@ -212,173 +212,183 @@ winattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid
               else               // dK = dS^T Q : A = dS viewed MN-major
                 umma_bf16(dst, umma_smem_desc(ds_addr + kk * 2048, SLOT_BYTES, 1024), bdesc, idesc_nn, kk > 0);
             }
-            umma_commit(&empty_bar[slot]);
+            umma_commit(&emptyl[slotl]);
             umma_commit(&obuf_full[ob]);
-            next_slot();
-            if (++ob == 2) { ob = 0; ob_phase ^= 1; }
+            obp[ob] ^= 1;
+            if (++slotl == NRL) { slotl = 0; phasel ^= 1; }
           }
         }
         umma_commit(pds_free);
       }
     }
-  } else {
-    // ---------------------------------------------------------------- softmax-backward + epilogue
-    const int wq = warp & 3;
+  } else if (warp >= 4) {
+    // ---------------------------------------------------------------- softmax-backward + epilogue (2 groups)
+    const int grp = (warp - 4) >> 2;              // 0: warps 4-7, 1: warps 8-11
+    const int wq = warp & 3;                      // TMEM lane quarter
     const int row = wq * 32 + lane;
-    const int sm_tid = threadIdx.x - 64;
+    const int cm_tid = threadIdx.x - 128;         // 0..255 over both groups
     const uint32_t t_lane = uint32_t(wq * 32) << 16;
     const int nbias = (2 * gm.ws - 1) * (2 * gm.ws - 1);
-    for (int i = sm_tid; i < nbias; i += 128) {
+    for (int i = cm_tid; i < nbias; i += 256) {
       s_tab[i] = __ldg(bias_table + i * gm.nH + head) * 1.4426950408889634f;
       s_bacc[i] = 0.f;
     }
-    uint32_t itp = 0;
-    int ob = 0, stg_sel = 0;
-    uint32_t ob_phase = 0;
+    constexpr bool COLSPLIT = (L >= 64);          // both groups work on S / dP (alternate 32-column chunks)
     constexpr int CH = (L >= 32) ? 32 : 16;
+    constexpr int NCHUNK = L / CH;                // chunks of the row's own window columns
+    // running sums over tiles of dS[row, key position], one accumulator per key position this
+    // thread sees.  L = 128: chunks cb and cb+2 of a thread hold the same positions (row-major order:
+    // the other frame; quadrant order folds the two frames inside each 32-column quadrant block).
+    constexpr int NACC = COLSPLIT ? 32 : L;
+    const bool quad = gm.shift > 0;               // uniform_quad: one token order per launch
+    float bacc[NACC];
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) bacc[k] = 0.f;
+    const bool softmax_role = COLSPLIT || grp == 0;
+    uint32_t itp = 0, ob_phase = 0;
     int key_i = 0, col0 = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, itp ^= 1) {
       const int tile = item / gm.nH;
       const RowGeom rg = row_geom(gm, tile, row);
-      s_lut[row] = uint32_t(rg.rr * (2 * gm.ws - 1) + rg.cc) | (uint32_t(rg.id) << 8);
-      named_bar_sync(1, 128);
+      if (grp == 0) s_lut[row] = uint32_t(rg.rr * (2 * gm.ws - 1) + rg.cc) | (uint32_t(rg.id) << 8);
+      named_bar_sync(1, 256);
       key_i = (rg.rr + gm.ws - 1) * (2 * gm.ws - 1) + rg.cc + gm.ws - 1;
       col0 = rg.g * L;
       const bool use_mask = rg.wraps;
-      const float lse_i = lse2[(size_t)item * 128 + rg.canon];
 
-      mbar_wait(sdp_full, itp);
-      mbar_wait(pds_free, itp ^ 1);
-      tc_fence_after();
-      // pass 1: P = exp2(S2 - lse2) -> smem (bf16), delta = sum_j P dP
-      float delta = 0.f;
+      if (softmax_role) {
+        const float lse_i = lse2[(size_t)item * 128 + rg.canon];
+        mbar_wait(sdp_full, itp);
+        mbar_wait(pds_free, itp ^ 1);
+        tc_fence_after();
+        // pass 1: P = exp2(S2 - lse2) -> smem (bf16), delta = sum_j P dP
+        float delta = 0.f;
 #pragma unroll
-      for (int cb = 0; cb < L / CH; ++cb) {
-        uint32_t v[32], w[32];
-        tmem_ld_row_chunk<L>(tmem_S, t_lane, col0, cb, wq, lane, v);
-        tmem_ld_row_chunk<L>(tmem_dP, t_lane, col0, cb, wq, lane, w);
+        for (int ci = 0; ci < (COLSPLIT ? NCHUNK / 2 : NCHUNK); ++ci) {
+          const int cb = COLSPLIT ? 2 * ci + grp : ci;
+          uint32_t v[32], w[32];
+          tmem_ld_row_chunk<L>(tmem_S, t_lane, col0, cb, wq, lane, v);
+          tmem_ld_row_chunk<L>(tmem_dP, t_lane, col0, cb, wq, lane, w);
 #pragma unroll
-        for (int j8 = 0; j8 < CH / 8; ++j8) {
-          uint32_t pk[4];
+          for (int j8 = 0; j8 < CH / 8; ++j8) {
+            uint32_t pk[4];
 #pragma unroll
-          for (int h = 0; h < 4; ++h) {
-            float pv[2];
+            for (int h = 0; h < 4; ++h) {
+              float pv[2];
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int jj = j8 * 8 + 2 * h + e;
-              const uint32_t lj = s_lut[col0 + cb * CH + jj];
-              float x = fmaf(__uint_as_float(v[jj]), gm.scale_log2e, s_tab[key_i - int(lj & 0xff)]);
-              if (use_mask && (lj >> 8) != uint32_t(rg.id)) x += kMaskLog2e;
-              pv[e] = fast_exp2(x - lse_i);
-              delta = fmaf(pv[e], __uint_as_float(w[jj]), delta);
+              for (int e = 0; e < 2; ++e) {
+                const int jj = j8 * 8 + 2 * h + e;
+                const uint32_t lj = s_lut[col0 + cb * CH + jj];
+                float x = fmaf(__uint_as_float(v[jj]), gm.scale_log2e, s_tab[key_i - int(lj & 0xff)]);
+                if (use_mask && (lj >> 8) != uint32_t(rg.id)) x += kMaskLog2e;
+                pv[e] = fast_exp2(x - lse_i);
+                delta = fmaf(pv[e], __uint_as_float(w[jj]), delta);
+              }
+              pk[h] = pack_bf16(pv[0], pv[1]);
             }
-            pk[h] = pack_bf16(pv[0], pv[1]);
+            const int col = col0 + cb * CH + j8 * 8;
+            *reinterpret_cast<uint4*>(s_p + (col >> 6) * SLOT_BYTES + sw128_offset(row, (col & 63) >> 3)) =
+                make_uint4(pk[0], pk[1], pk[2], pk[3]);
           }
-          const int col = col0 + cb * CH + j8 * 8;
-          *reinterpret_cast<uint4*>(s_p + (col >> 6) * SLOT_BYTES + sw128_offset(row, (col & 63) >> 3)) =
-              make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
-      }
-      // pass 2: dS = P o (dP - delta) -> smem (bf16)
+        if (COLSPLIT) {                            // row sum = own half + the other group's half
+          s_delta[grp * 128 + row] = delta;
+          named_bar_sync(2, 256);
+          delta += s_delta[(grp ^ 1) * 128 + row];
+        }
+        // pass 2: dS = P o (dP - delta) -> smem (bf16)
 #pragma unroll
-      for (int cb = 0; cb < L / CH; ++cb) {
-        uint32_t w[32];
-        tmem_ld_row_chunk<L>(tmem_dP, t_lane, col0, cb, wq, lane, w);
+        for (int ci = 0; ci < (COLSPLIT ? NCHUNK / 2 : NCHUNK); ++ci) {
+          const int cb = COLSPLIT ? 2 * ci + grp : ci;
+          uint32_t w[32];
+          tmem_ld_row_chunk<L>(tmem_dP, t_lane, col0, cb, wq, lane, w);
 #pragma unroll
-        for (int j8 = 0; j8 < CH / 8; ++j8) {
-          const int col = col0 + cb * CH + j8 * 8;
-          const uint32_t off = (col >> 6) * SLOT_BYTES + sw128_offset(row, (col & 63) >> 3);
-          const uint4 pq = *reinterpret_cast<const uint4*>(s_p + off);
-          const uint32_t pw[4] = {pq.x, pq.y, pq.z, pq.w};
-          uint32_t dk[4];
+          for (int j8 = 0; j8 < CH / 8; ++j8) {
+            const int col = col0 + cb * CH + j8 * 8;
+            const uint32_t off = (col >> 6) * SLOT_BYTES + sw128_offset(row, (col & 63) >> 3);
+            const uint4 pq = *reinterpret_cast<const uint4*>(s_p + off);
+            const uint32_t pw[4] = {pq.x, pq.y, pq.z, pq.w};
+            uint32_t dk[4];
 #pragma unroll
-          for (int h = 0; h < 4; ++h) {
-            const float2 pf = unpack_bf16(pw[h]);
-            // rows of a padding window hold filler data: keep them out of the bias-table sum
-            const float d0 = rg.valid ? pf.x * (__uint_as_float(w[j8 * 8 + 2 * h]) - delta) : 0.f;
-            const float d1 = rg.valid ? pf.y * (__uint_as_float(w[j8 * 8 + 2 * h + 1]) - delta) : 0.f;
-            dk[h] = pack_bf16(d0, d1);
+            for (int h = 0; h < 4; ++h) {
+              const float2 pf = unpack_bf16(pw[h]);
+              // rows of a padding window hold filler data: keep them out of the bias-table sum
+              const float d0 = rg.valid ? pf.x * (__uint_as_float(w[j8 * 8 + 2 * h]) - delta) : 0.f;
+              const float d1 = rg.valid ? pf.y * (__uint_as_float(w[j8 * 8 + 2 * h + 1]) - delta) : 0.f;
+              dk[h] = pack_bf16(d0, d1);
+              const int j = j8 * 8 + 2 * h;          // column inside the chunk, compile-time after unrolling
+              if (COLSPLIT) {
+                // row-major order: chunk = (frame, half of the 64 positions) -> position j of that half
+                // quadrant order : chunk = quadrant, 16 positions x 2 frames  -> (which quadrant)*16 + j%16
+                if (quad && L == 128) { bacc[ci * 16 + (j & 15)] += d0; bacc[ci * 16 + ((j + 1) & 15)] += d1; }
+                else                  { bacc[j] += d0; bacc[j + 1] += d1; }
+              } else {
+                bacc[ci * CH + j] += d0; bacc[ci * CH + j + 1] += d1;
+              }
+            }
+            *reinterpret_cast<uint4*>(s_ds + off) = make_uint4(dk[0], dk[1], dk[2], dk[3]);
           }
-          *reinterpret_cast<uint4*>(s_ds + off) = make_uint4(dk[0], dk[1], dk[2], dk[3]);
         }
+        tc_fence_before();
+        mbar_arrive(sdp_free);          // S / dP may be overwritten by the next tile
+        fence_proxy_async_smem();
+        mbar_arrive(pds_full);          // P / dS visible to the tensor core
       }
-      tc_fence_before();
-      mbar_arrive(sdp_free);          // S / dP may be overwritten by the next tile
-      fence_proxy_async_smem();
-      mbar_arrive(pds_full);          // P / dS visible to the tensor core
 
-      // ---- drain dV_c, dQ_c, dK_c : TMEM -> bf16 -> staging -> TMA scatter into d_qkv
-      for (int c = 0; c < nc; ++c) {
-        for (int o = 0; o < 3; ++o) {
-          const int which = (o == 0) ? 2 : (o == 1 ? 0 : 1);
-          const float mul = (o == 0) ? 1.0f : gm.scale;
-          mbar_wait(&obuf_full[ob], ob_phase);
-          tc_fence_after();
+      // ---- drain dV_c, dQ_c, dK_c : TMEM -> bf16 -> this row's 128-byte line of d_qkv
+      //      (window_reverse + inverse roll = the token index of the row).  Output chunk k of the tile
+      //      lands in TMEM buffer k % 2, which is group (k % 2)'s to drain.
+      __nv_bfloat16* row_out = d_qkv + rg.tok * (3 * gm.C) + head * gm.hd;
+      for (int k = grp; k < 3 * nc; k += 2) {
+        const int c = k / 3, o = k - 3 * c;
+        const int which = (o == 0) ? 2 : (o == 1 ? 0 : 1);
+        const float m2 = !rg.valid ? 0.f : (o == 0 ? 1.0f : gm.scale);
+        mbar_wait(&obuf_full[grp], ob_phase);
+        ob_phase ^= 1;
+        tc_fence_after();
+        float a[64];
+        {
           uint32_t v0[32], v1[32];
-          tmem_ld32(tmem_out + ob * 64 + t_lane, v0);
-          tmem_ld32(tmem_out + ob * 64 + t_lane + 32, v1);
+          tmem_ld32(tmem_out + grp * 64 + t_lane, v0);
+          tmem_ld32(tmem_out + grp * 64 + t_lane + 32, v1);
           tmem_ld_wait();
-          tc_fence_before();
-          mbar_arrive(&obuf_free[ob]);
-          if (++ob == 2) { ob = 0; ob_phase ^= 1; }
-          uint8_t* stg = s_stg + stg_sel * SLOT_BYTES;
-          if (sm_tid < 32) tma_wait_group_read<1>();
-          named_bar_sync(1, 128);
-          const float m2 = rg.valid ? mul : 0.f;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 q;
-            q.x = pack_bf16(__uint_as_float(v0[8 * j + 0]) * m2, __uint_as_float(v0[8 * j + 1]) * m2);
-            q.y = pack_bf16(__uint_as_float(v0[8 * j + 2]) * m2, __uint_as_float(v0[8 * j + 3]) * m2);
-            q.z = pack_bf16(__uint_as_float(v0[8 * j + 4]) * m2, __uint_as_float(v0[8 * j + 5]) * m2);
-            q.w = pack_bf16(__uint_as_float(v0[8 * j + 6]) * m2, __uint_as_float(v0[8 * j + 7]) * m2);
-            *reinterpret_cast<uint4*>(stg + sw128_offset(row, j)) = q;
-            q.x = pack_bf16(__uint_as_float(v1[8 * j + 0]) * m2, __uint_as_float(v1[8 * j + 1]) * m2);
-            q.y = pack_bf16(__uint_as_float(v1[8 * j + 2]) * m2, __uint_as_float(v1[8 * j + 3]) * m2);
-            q.z = pack_bf16(__uint_as_float(v1[8 * j + 4]) * m2, __uint_as_float(v1[8 * j + 5]) * m2);
-            q.w = pack_bf16(__uint_as_float(v1[8 * j + 6]) * m2, __uint_as_float(v1[8 * j + 7]) * m2);
-            *reinterpret_cast<uint4*>(stg + sw128_offset(row, 4 + j)) = q;
-          }
-          fence_proxy_async_smem();
-          named_bar_sync(1, 128);
-          const int ch0 = which * gm.C + head * gm.hd + c * 64;
-          if (sm_tid < 32) {
-            tile_boxes<false>(gm, tile, ch0, stg, &tm_dqkv_full, &tm_dqkv_quad, nullptr, lane);
-            tma_commit_group();
-          }
-          if (d_colsum != nullptr) {
-            // thread: column pair (lane), rows 32*wq .. 32*wq+31 of the staged chunk
-            float s0 = 0.f, s1 = 0.f;
-#pragma unroll 8
-            for (int r = 0; r < 32; ++r) {
-              const uint32_t wv = *reinterpret_cast<const uint32_t*>(stg + sw128_offset(wq * 32 + r, lane >> 2) + (lane & 3) * 4);
-              const float2 f = unpack_bf16(wv);
-              s0 += f.x; s1 += f.y;
-            }
-            atomicAdd(d_colsum + ch0 + 2 * lane, s0);
-            atomicAdd(d_colsum + ch0 + 2 * lane + 1, s1);
-          }
-          stg_sel ^= 1;
+          for (int q = 0; q < 32; ++q) { a[q] = __uint_as_float(v0[q]) * m2; a[32 + q] = __uint_as_float(v1[q]) * m2; }
+        }
+        tc_fence_before();
+        mbar_arrive(&obuf_free[grp]);
+        const int ch0 = which * gm.C + c * 64;
+        if (rg.valid) {
+          uint4* dst = reinterpret_cast<uint4*>(row_out + ch0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            dst[j] = make_uint4(pack_bf16(a[8 * j], a[8 * j + 1]), pack_bf16(a[8 * j + 2], a[8 * j + 3]),
+                                pack_bf16(a[8 * j + 4], a[8 * j + 5]), pack_bf16(a[8 * j + 6], a[8 * j + 7]));
+        }
+        if (d_colsum != nullptr) {
+          warp_colsum64(a, lane);          // lane l: columns 2l, 2l+1 summed over this warp's 32 rows
+          atomicAdd(d_colsum + ch0 + head * gm.hd + 2 * lane, a[0]);
+          atomicAdd(d_colsum + ch0 + head * gm.hd + 2 * lane + 1, a[1]);
         }
       }
+      // a tile has 3*nc output chunks; when that is odd the groups' buffer parities drift apart by design
+      // (each group tracks its own phase), nothing to do here.
     }
-    // ---- bias-table gradient: bin the running dS sum by relative position (all MMAs have retired:
-    //      the last obuf_full commit covers every earlier tcgen05.mma of the issuing thread)
-    named_bar_sync(1, 128);
-    tc_fence_after();
+    // ---- bias-table gradient: bin the per-row running sums by relative position, once per CTA
+    named_bar_sync(1, 256);
+    if (softmax_role) {
 #pragma unroll
-    for (int cb = 0; cb < L / CH; ++cb) {
-      uint32_t v[32];
-      tmem_ld_row_chunk<L>(tmem_acc, t_lane, col0, cb, wq, lane, v);
-#pragma unroll
-      for (int jj = 0; jj < CH; ++jj) {
-        const uint32_t lj = s_lut[col0 + cb * CH + jj];
-        atomicAdd(&s_bacc[key_i - int(lj & 0xff)], __uint_as_float(v[jj]));
+      for (int k = 0; k < NACC; ++k) {
+        // a column of this row's window that accumulator k stands for
+        int ck;
+        if (COLSPLIT) ck = (quad && L == 128) ? ((2 * (k >> 4) + grp) * 32 + (k & 15)) : (grp * 32 + k);
+        else          ck = k;
+        const uint32_t lj = s_lut[col0 + ck];
+        atomicAdd(&s_bacc[key_i - int(lj & 0xff)], bacc[k]);
       }
     }
-    named_bar_sync(1, 128);
-    for (int i = sm_tid; i < nbias; i += 128) atomicAdd(d_table + i * gm.nH + head, s_bacc[i]);
-    if (sm_tid < 32) tma_wait_group<0>();
+    named_bar_sync(1, 256);
+    for (int i = cm_tid; i < nbias; i += 256) atomicAdd(d_table + i * gm.nH + head, s_bacc[i]);
   }
 
   tc_fence_before();
@@ -407,10 +417,10 @@ int winattn_bwd(const void* qkv, const float* bias_table, const float* lse2, con
   if (rc != kOk) return rc;
   gm.uniform_quad = 1;
   if (qk_scale > 0.f) { gm.scale = qk_scale; gm.scale_log2e = qk_scale * 1.4426950408889634f; }
-  CUtensorMap tq_full, tq_quad, td_full, td_quad, tg_full, tg_quad;
+  CUtensorMap tq_full, tq_quad, td_full, td_quad;
   if ((rc = make_window_tmaps(&tq_full, &tq_quad, qkv, gm, 3 * C)) != kOk) return rc;
   if ((rc = make_window_tmaps(&td_full, &td_quad, d_out, gm, C)) != kOk) return rc;
-  if ((rc = make_window_tmaps(&tg_full, &tg_quad, d_qkv, gm, 3 * C)) != kOk) return rc;
+  STSWIN_CHECK_ARG((reinterpret_cast<uintptr_t>(d_qkv) & 15) == 0, "winattn_bwd: d_qkv must be 16-byte aligned");
   const int items = gm.num_tiles * gm.nH;
   int grid = items < num_sms() ? items : num_sms();
   grid -= grid % nH;                      // one head per CTA (items is a multiple of nH, so grid >= nH)
@@ -418,9 +428,9 @@ int winattn_bwd(const void* qkv, const float* bias_table, const float* lse2, con
 #define STSWIN_LAUNCH_BWD(LL)                                                                                      \
   case LL: {                                                                                                       \
     if ((rc = set_smem_bwd(winattn_bwd_kernel<LL>, SMEM_BYTES)) != kOk) return rc;                                 \
-    winattn_bwd_kernel<LL><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tq_full, tq_quad, td_full, td_quad, tg_full, \
-                                                                      tg_quad, bias_table, lse2, d_table,         \
-                                                                      d_qkv_colsum, gm);                           \
+    winattn_bwd_kernel<LL><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(                                             \
+        tq_full, tq_quad, td_full, td_quad, static_cast<__nv_bfloat16*>(d_qkv), bias_table, lse2, d_table,         \
+        d_qkv_colsum, gm);                                                                                         \
     break;                                                                                                         \
   }
   switch (gm.L) {

@@ -29,6 +29,7 @@ struct RowGeom {
   int rr, cc;  // token coordinates inside its window (shifted frame)
   int id;      // shift-mask region id 0..8 (swin_512.py:173-184), 0 when unshifted
   int canon;   // g*L + t*N + rr*ws + cc : position in the reference's own window-token order
+  long tok;    // index of the source token in the natural [B*T, H, W] order (roll + partition undone)
   bool wraps;  // window crosses the image border (the only windows with a non-zero mask)
   bool valid;  // false for rows of a padding window in the last tile
 };
@@ -74,6 +75,10 @@ __device__ __forceinline__ RowGeom row_geom(const WinGeom& gm, int tile, int r) 
     o.cc = (q & 1) * hw + p % hw;
   }
   o.canon = o.g * gm.L + t * gm.N + o.rr * gm.ws + o.cc;
+  {
+    const int hs = (wh * gm.ws + o.rr + gm.shift) % gm.H, wsrc = (ww * gm.ws + o.cc + gm.shift) % gm.W;
+    o.tok = ((long)(b * gm.T + t) * gm.H + hs) * gm.W + wsrc;
+  }
   o.id = 0;
   if (gm.shift > 0)
     o.id = 3 * region_band(wh * gm.ws + o.rr, gm.H, gm.ws, gm.shift) +
@@ -146,6 +151,22 @@ __device__ __forceinline__ void tmem_ld_row_chunk(uint32_t tmem_mat, uint32_t t_
     if (lane >= 16) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] = v[j + 16];
+    }
+  }
+}
+
+// Column sums over the 32 lanes of a warp for 64 per-lane values (lane = row): a butterfly that
+// halves the live values at every step (62 shuffles).  On return lane l holds the sums of
+// columns 2*l and 2*l+1 in a[0], a[1].
+__device__ __forceinline__ void warp_colsum64(float (&a)[64], int lane) {
+#pragma unroll
+  for (int n = 32, off = 16; n >= 2; n >>= 1, off >>= 1) {
+    const bool hi = (lane & off) != 0;
+#pragma unroll
+    for (int k = 0; k < n; ++k) {
+      const float send = hi ? a[k] : a[k + n];
+      const float recv = __shfl_xor_sync(0xffffffffu, send, off);
+      a[k] = (hi ? a[k + n] : a[k]) + recv;
     }
   }
 }

@@ -61,12 +61,24 @@ def _wgrad_splits(n_out: int, k_in: int, tokens: int) -> int:
     return max(1, min((tokens + 63) // 64, round(2 * 148 / tiles)))
 
 
-def _linear_wgrad(dy2d: torch.Tensor, x2d: torch.Tensor, shape) -> torch.Tensor:
-    """dW[N_out, K_in] = dy^T x, reduced over tokens on the tensor cores (fp32, split-K)."""
-    dw = torch.zeros(shape, dtype=torch.float32, device=dy2d.device)
+def _linear_wgrad(dy2d: torch.Tensor, x2d: torch.Tensor, shape, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dW[N_out, K_in] = dy^T x, reduced over tokens on the tensor cores (fp32, split-K).
+    ``out`` must be zero-filled (the split-K epilogue accumulates)."""
+    dw = out if out is not None else torch.zeros(shape, dtype=torch.float32, device=dy2d.device)
     ops.gemm(dy2d, x2d, a_mn_major=True, b_mn_major=True, mode=ops.EPI_F32_REDUCE, out=dw,
              k_splits=_wgrad_splits(shape[0], shape[1], dy2d.shape[0]))
     return dw
+
+
+def _zeros_like_many(shapes, device):
+    """One zero-filled fp32 allocation carved into the given shapes (one memset instead of many)."""
+    sizes = [int(math.prod(s)) for s in shapes]
+    offs, total = [], 0
+    for n in sizes:
+        offs.append(total)
+        total += (n + 3) // 4 * 4            # keep every view 16-byte aligned (TMA reduce target)
+    flat = torch.zeros(total, dtype=torch.float32, device=device)
+    return [flat[o:o + n].view(s) for o, n, s in zip(offs, sizes, shapes)]
 
 
 class _AttentionFn(torch.autograd.Function):
@@ -144,30 +156,29 @@ class _BlockFn(torch.autograd.Function):
         C = x2.shape[1]
         shp = d_out.shape[:3]
         dev = x2.device
-        f32 = dict(dtype=torch.float32, device=dev)
         d2 = d_out.contiguous().view(-1, C)
+        (d_g1, d_be1, d_bfc2, d_bfc1, d_g2, d_be2, d_bproj, d_table, d_bqkv, d_wfc2_, d_wfc1_, d_wproj_, d_wqkv_) = \
+            _zeros_like_many([(C,), (C,), (C,), (w1.shape[0],), (C,), (C,), (C,), tuple(table.shape), (3 * C,),
+                              tuple(w2.shape), tuple(w1.shape), tuple(wp.shape), tuple(wq.shape)], dev)
+        if not ctx.has_qkv_bias:
+            d_bqkv = None
         # out = norm1(z)
-        d_g1, d_be1, d_bfc2 = torch.zeros(C, **f32), torch.zeros(C, **f32), torch.zeros(C, **f32)
         dz = ops.layernorm_bwd(d2, z, mean1, rstd1, g1, d_g1, d_be1, dx_colsum=d_bfc2)
         # z = y + h W2^T + b2 ; h = gelu(u), and the forward stored gelu'(u)
-        d_bfc1 = torch.zeros(w1.shape[0], **f32)
         du = ops.gemm(dz, w2, b_mn_major=True, mode=ops.EPI_MUL_AUX, aux=dgelu, colsum=d_bfc1)
-        d_wfc2 = _linear_wgrad(dz, h, w2.shape)
+        d_wfc2 = _linear_wgrad(dz, h, w2.shape, d_wfc2_)
         # u = yn W1^T + b1 ; yn = norm2(y)
         dyn = ops.gemm(du, w1, b_mn_major=True)
-        d_wfc1 = _linear_wgrad(du, yn, w1.shape)
-        d_g2, d_be2, d_bproj = torch.zeros(C, **f32), torch.zeros(C, **f32), torch.zeros(C, **f32)
+        d_wfc1 = _linear_wgrad(du, yn, w1.shape, d_wfc1_)
         dy = ops.layernorm_bwd(dyn, y, mean2, rstd2, g2, d_g2, d_be2, dres=dz, dx_colsum=d_bproj)
         # y = x + attn Wp^T + bp
         d_attn = ops.gemm(dy, wp, b_mn_major=True)
-        d_wproj = _linear_wgrad(dy, attn.view(-1, C), wp.shape)
-        d_table = torch.zeros_like(table)
-        d_bqkv = torch.zeros(3 * C, **f32) if ctx.has_qkv_bias else None
+        d_wproj = _linear_wgrad(dy, attn.view(-1, C), wp.shape, d_wproj_)
         d_qkv = ops.winattn_bwd(qkv.view(*shp, 3 * C), table, lse2, d_attn.view(*shp, C), H, W, nH, ws, shift,
                                 d_table, d_bqkv, qk_scale=qk_scale)
         dq2 = d_qkv.view(-1, 3 * C)
         d_x = ops.gemm(dq2, wq, b_mn_major=True, mode=ops.EPI_BIAS_RES, aux=dy)      # + residual path
-        d_wqkv = _linear_wgrad(dq2, x2, wq.shape)
+        d_wqkv = _linear_wgrad(dq2, x2, wq.shape, d_wqkv_)
         return (d_x.view(*shp, C), d_table, d_wqkv, d_bqkv, d_wproj, d_bproj, d_g1, d_be1, d_g2, d_be2,
                 d_wfc1, d_bfc1, d_wfc2, d_bfc2, None)
 

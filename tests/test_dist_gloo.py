@@ -1,0 +1,61 @@
+"""CPU, world_size 2, gloo: the host-side data-parallel logic (clip sharding, gradient averaging,
+key-set gathering) -- the N>1 path of bench.py minus the kernels."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from stswincl_b200 import dist as sdist
+
+
+def _worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        model = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.GELU(), torch.nn.Linear(5, 3))
+        data = torch.randn(8, 6, generator=torch.Generator().manual_seed(1))
+        target = torch.randn(8, 3, generator=torch.Generator().manual_seed(2))
+        # single-process reference on the full batch
+        ref = [p.clone() for p in model.parameters()]
+        loss = ((model(data) - target) ** 2).mean()
+        full = torch.autograd.grad(loss, list(model.parameters()))
+        # this rank's shard
+        idx = sdist.shard_indices(8, rank, world)
+        loss = ((model(data[idx]) - target[idx]) ** 2).mean()
+        loss.backward()
+        n = sdist.average_gradients(model.parameters(), bucket_bytes=64)      # tiny buckets: several collectives
+        ok = all(torch.allclose(p.grad, g, atol=1e-6) for p, g in zip(model.parameters(), full)) and n >= 2
+        # bf16 on the wire: same up to rounding
+        model.zero_grad()
+        ((model(data[idx]) - target[idx]) ** 2).mean().backward()
+        sdist.average_gradients(model.parameters(), comm_dtype=torch.bfloat16)
+        ok = ok and all(torch.allclose(p.grad, g, atol=2e-2, rtol=2e-2) for p, g in zip(model.parameters(), full))
+        # gather: own copy first, then the others
+        t = torch.full((2, 3), float(rank))
+        got = sdist.gather_key_sets([t, t + 10])
+        ok = ok and len(got) == 2 * world and float(got[0][0, 0]) == rank and float(got[1][0, 0]) == 1 - rank \
+            and float(got[2][0, 0]) == rank + 10
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gradient_average_matches_full_batch():
+    world = 2
+    port = 29600 + os.getpid() % 200
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert dict(ret) == {0: True, 1: True}
+
+
+def test_shard_indices_cover_and_pad():
+    for n, world in [(8, 2), (7, 2), (5, 4), (3, 8)]:
+        shards = [sdist.shard_indices(n, r, world) for r in range(world)]
+        assert len({len(s) for s in shards}) == 1                      # equal length (wrap-padded)
+        assert set(i for s in shards for i in s) == set(range(n))      # every sample owned
+    assert sdist.shard_indices(7, 1, 2) == [1, 3, 5, 0]
+    assert sdist.scaled_lr(1.0, 4, 8) == 4 * 8 / 256

