@@ -84,6 +84,16 @@ __device__ __forceinline__ void tma_load_2d(void* smem, const CUtensorMap* m, ui
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// multicast variant: the box lands at the same smem offset in every CTA of `cta_mask`, and each of
+// those CTAs' mbarrier (same offset) receives the complete_tx
+__device__ __forceinline__ void tma_load_2d_mcast(void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                                  uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, "
+      "%4}], [%2], %5;" ::"r"(smem_u32(smem)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::
@@ -209,6 +219,25 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                : "memory");
 }
 
+// same, arriving on the mbarrier at this offset in every CTA of `cta_mask` (cluster multicast)
+__device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(cta_mask)
+               : "memory");
+}
+
+// ----------------------------------------------------------------------------- clusters
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // ----------------------------------------------------------------------------- small math helpers
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
@@ -224,18 +253,19 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
   return cdf + x * pdf;
 }
-// erf-GELU and its derivative in one go (nn.GELU default, swin_512.py:13).  erf through
-// Abramowitz-Stegun 7.1.26 (|abs err| < 1.5e-7), sharing exp(-u^2/2) with the Gaussian pdf:
+// erf-GELU and its derivative in one go (nn.GELU default, swin_512.py:13):
 //   gelu(u) = u * Phi(u)        gelu'(u) = Phi(u) + u * phi(u)
+// Phi through the hardware tanh: Phi(u) = 0.5 + 0.5 tanh(u (a + b u^2 + c u^4)), coefficients fitted to
+// the exact normal CDF (max |error| 4.9e-5 on Phi, 5.6e-5 on gelu -- two orders below the bf16
+// rounding of the stored result); phi through ex2.  11 instructions, 2 of them MUFU, per element:
+// the GELU epilogue is instruction-issue bound (profiles/r1b_gemm_gelu_ncu_summary.txt).
 __device__ __forceinline__ void gelu_and_grad(float u, float& h, float& g) {
-  const float e = exp2f(-0.72134752044448170f * u * u);            // exp(-u^2 / 2)
-  const float t = __fdividef(1.0f, fmaf(0.23164189463f, fabsf(u), 1.0f));   // p / sqrt(2) = 0.3275911 / 1.41421356
-  float q = fmaf(1.061405429f, t, -1.453152027f);
-  q = fmaf(q, t, 1.421413741f);
-  q = fmaf(q, t, -0.284496736f);
-  q = fmaf(q, t, 0.254829592f);
-  q = 0.5f * q * t * e;                                             // 0.5 * (1 - erf(|u| / sqrt 2))
-  const float cdf = u >= 0.f ? 1.0f - q : q;
+  const float s = u * u;
+  float e, t;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-0.72134752044448170f * s));          // exp(-u^2 / 2)
+  const float arg = u * fmaf(s, fmaf(s, -3.55393957e-04f, 3.69307910e-02f), 7.97735401e-01f);
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(arg));
+  const float cdf = fmaf(0.5f, t, 0.5f);
   h = u * cdf;
   g = fmaf(u * 0.3989422804014327f, e, cdf);
 }

@@ -61,7 +61,7 @@ struct GemmArgs {
 };
 
 template <int A_MN, int B_MN, int MODE>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmD /* fp32 reduce target only */, const GemmArgs p) {
   extern __shared__ uint8_t smem_raw[];
@@ -82,7 +82,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int num_n = (p.N + BN - 1) / BN;
   const int kb_total = (p.K + BK - 1) / BK;
   const int kb_per_split = (kb_total + p.k_splits - 1) / p.k_splits;
-  const int num_items = num_m * num_n * p.k_splits;
+  // A cluster is a pair of CTAs working on two vertically adjacent tiles (same n_blk, m_blk = 2*pair +
+  // rank): they need the same B tile, so each loads half of it and TMA-multicasts it to both --
+  // 32 KB instead of 48 KB of L2 traffic per CTA and k-block.  (The K <= 1024 GEMMs of this model
+  // sit on the L2 throughput cap, not on the tensor pipe: profiles/r1b_gemm_l2_note.txt.)
+  const int num_mp = (num_m + 1) / 2;
+  const int num_items = num_mp * num_n * p.k_splits;        // per cluster
+  const uint32_t crank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -90,7 +97,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tma_prefetch_desc(&tmD);
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], 2);          // released by the MMA warps of BOTH CTAs (the peer writes here too)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
@@ -101,6 +108,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 1) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();                       // the peer's barriers exist before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -109,28 +117,32 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      for (int item = cluster_id; item < num_items; item += num_clusters) {
         const int n_blk = item % num_n;
-        const int m_blk = (item / num_n) % num_m;
-        const int split = item / (num_n * num_m);
+        const int m_blk = 2 * ((item / num_n) % num_mp) + int(crank);   // may be >= num_m (ghost tile: zero fill)
+        const int split = item / (num_n * num_mp);
         const int kb0 = split * kb_per_split;
         const int kb1 = min(kb_total, kb0 + kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sA = s_stage + stage * STAGE_BYTES;
           uint8_t* sB = sA + A_STAGE_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+          mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);      // own A + both halves of B
           if (A_MN) {
 #pragma unroll
             for (int c = 0; c < BM / 64; ++c) tma_load_2d(sA + c * (BK * 128), &tmA, &full_bar[stage], m_blk * BM + c * 64, kb * BK);
           } else {
             tma_load_2d(sA, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
           }
-          if (B_MN) {
+          if (B_MN) {               // this CTA's half of B: two of the four 64-column chunks
 #pragma unroll
-            for (int c = 0; c < BN / 64; ++c) tma_load_2d(sB + c * (BK * 128), &tmB, &full_bar[stage], n_blk * BN + c * 64, kb * BK);
-          } else {
-            tma_load_2d(sB, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
+            for (int cc = 0; cc < BN / 128; ++cc) {
+              const int c = int(crank) * (BN / 128) + cc;
+              tma_load_2d_mcast(sB + c * (BK * 128), &tmB, &full_bar[stage], n_blk * BN + c * 64, kb * BK, 0x3);
+            }
+          } else {                  // rows [crank*128, +128) of the 256-row B tile
+            tma_load_2d_mcast(sB + int(crank) * (B_STAGE_BYTES / 2), &tmB, &full_bar[stage], kb * BK,
+                              n_blk * BN + int(crank) * (BN / 2), 0x3);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -144,8 +156,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-        const int split = item / (num_n * num_m);
+      for (int item = cluster_id; item < num_items; item += num_clusters) {
+        const int split = item / (num_n * num_mp);
         const int kb0 = split * kb_per_split;
         const int kb1 = min(kb_total, kb0 + kb_per_split);
         mbar_wait(&acc_empty[acc], acc_phase ^ 1);
@@ -164,7 +176,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                         : umma_smem_desc(sB + kk * 32, 16, 1024);
             umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);     // smem slot reusable once these MMAs retire
+          umma_commit_mcast(&empty_bar[stage], 0x3);   // slot reusable (in both CTAs) once these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(&acc_full[acc]);          // accumulator complete
@@ -185,9 +197,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // coalesced access pattern of a 32-row x 64-col bf16 chunk: instruction i of lane l touches
     // row 4*i + l/8, 16-byte column group l%8  (8 lanes = one 128-byte line)
     const int crow = lane >> 3, cchunk = lane & 7;
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+    for (int item = cluster_id; item < num_items; item += num_clusters) {
       const int n_blk = item % num_n;
-      const int m_blk = (item / num_n) % num_m;
+      const int m_blk = 2 * ((item / num_n) % num_mp) + int(crank);
       const int row0 = m_blk * BM + wq * 32;
       const int col0 = n_blk * BN + chalf * (BN / 2);
       const bool row_ok = (row0 + lane) < p.M;
@@ -245,20 +257,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         auto do_chunk = [&](const int c, auto aux_sel) {
           constexpr int kAuxSel = decltype(aux_sel)::value;   // which prefetched aux register set to consume
           const int cbase = col0 + c * 64;
-          uint32_t auxw[has_aux ? 32 : 1];
           if constexpr (has_aux) {
             __syncwarp();                                 // earlier readers of my_buf are done
 #pragma unroll
             for (int i = 0; i < 8; ++i)
               *reinterpret_cast<uint4*>(my_buf + sw128_offset(4 * i + crow, cchunk)) = auxr[kAuxSel][i];
-            __syncwarp();
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const uint4 q = *reinterpret_cast<const uint4*>(my_buf + sw128_offset(lane, j));
-              auxw[4 * j] = q.x; auxw[4 * j + 1] = q.y; auxw[4 * j + 2] = q.z; auxw[4 * j + 3] = q.w;
-            }
           }
-          __syncwarp();                                   // my_buf may be overwritten with the output now
+          __syncwarp();     // aux staged (each lane then only touches its own row: reads aux, writes output)
           uint32_t out2w[MODE == kBiasGelu ? 32 : 1];     // second output of the GELU mode (gelu'(u))
           // the 64 columns are processed as two halves of 32 (rolled, except in the two-output mode
           // whose second output has to stay in registers) to keep the code I-cache resident
@@ -280,6 +285,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
               for (int j = 0; j < 32; ++j) bv[j] = 0.f;
             }
+            uint32_t auxw[has_aux ? 16 : 1];             // this row's aux for the 32 columns of this half
+            if constexpr (has_aux) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint4 q = *reinterpret_cast<const uint4*>(my_buf + sw128_offset(lane, half * 4 + j));
+                auxw[4 * j] = q.x; auxw[4 * j + 1] = q.y; auxw[4 * j + 2] = q.z; auxw[4 * j + 3] = q.w;
+              }
+            }
             tmem_ld_wait();
             uint32_t outw[16];
 #pragma unroll
@@ -287,7 +300,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               float a0 = __uint_as_float(v[2 * j]) + bv[2 * j];
               float a1 = __uint_as_float(v[2 * j + 1]) + bv[2 * j + 1];
               if constexpr (MODE == kBiasRes) {
-                const float2 r = unpack_bf16(auxw[half * 16 + j]);
+                const float2 r = unpack_bf16(auxw[j]);
                 a0 += r.x; a1 += r.y;
               } else if constexpr (MODE == kBiasGelu) {
                 float g0, g1;
@@ -295,7 +308,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 gelu_and_grad(a1, a1, g1);
                 out2w[half * 16 + j] = pack_bf16(g0, g1);
               } else if constexpr (MODE == kMulAux) {
-                const float2 u = unpack_bf16(auxw[half * 16 + j]);
+                const float2 u = unpack_bf16(auxw[j]);
                 a0 *= u.x; a1 *= u.y;
               }
               outw[j] = pack_bf16(a0, a1);
@@ -364,6 +377,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();                       // the peer may still multicast into / arrive on this CTA until here
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
@@ -376,8 +390,9 @@ int launch_mode(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
   auto kern = gemm_kernel<A_MN, B_MN, MODE>;
   STSWIN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   const int num_m = (args.M + BM - 1) / BM, num_n = (args.N + BN - 1) / BN;
-  const int items = num_m * num_n * args.k_splits;
-  const int grid = items < num_sms() ? items : num_sms();
+  const int items = ((num_m + 1) / 2) * num_n * args.k_splits;        // work items of a CTA pair
+  const int max_clusters = num_sms() / 2;
+  const int grid = 2 * (items < max_clusters ? items : max_clusters);
   kern<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, tmD, args);
   STSWIN_CUDA(cudaGetLastError());
   return kOk;
@@ -426,7 +441,7 @@ int gemm_bf16(const void* A, int a_major, long lda, const void* B, int b_major, 
     else              { dims[0] = M; dims[1] = K; box[0] = 64; box[1] = BK; }
     str[0] = (uint64_t)lda * 2;
     if ((rc = make_tmap(&tmA, TmapDtype::BF16, 2, A, dims, str, box, true)) != kOk) return rc;
-    if (b_major == 0) { dims[0] = K; dims[1] = N; box[0] = BK; box[1] = BN; }
+    if (b_major == 0) { dims[0] = K; dims[1] = N; box[0] = BK; box[1] = BN / 2; }   // each CTA of a pair loads half
     else              { dims[0] = N; dims[1] = K; box[0] = 64; box[1] = BK; }
     str[0] = (uint64_t)ldb * 2;
     if ((rc = make_tmap(&tmB, TmapDtype::BF16, 2, B, dims, str, box, true)) != kOk) return rc;
