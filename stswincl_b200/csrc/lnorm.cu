@@ -140,13 +140,18 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
       }
     }
   };
+  constexpr bool PREFETCH = NV <= 4;      // NV = 8 (PatchMerging rows of 2048) would spill with two rows live
   long row = (long)blockIdx.x * LN_WARPS + warp;
-  if (row < M) load_row(row, cd, cx, cr, c_mu, c_rs);
+  if (PREFETCH && row < M) load_row(row, cd, cx, cr, c_mu, c_rs);
   while (row < M) {
     const long nxt = row + stride;
-    uint4 nd[NV], nx[NV], nr[NV];
+    uint4 nd[PREFETCH ? NV : 1], nx[PREFETCH ? NV : 1], nr[PREFETCH ? NV : 1];
     float n_mu = 0.f, n_rs = 0.f;
-    if (nxt < M) load_row(nxt, nd, nx, nr, n_mu, n_rs);
+    if constexpr (PREFETCH) {
+      if (nxt < M) load_row(nxt, nd, nx, nr, n_mu, n_rs);
+    } else {
+      load_row(row, cd, cx, cr, c_mu, c_rs);
+    }
     const float mu = c_mu, rs = c_rs;
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -198,9 +203,11 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
         *reinterpret_cast<uint4*>(row_ptr(dx, row, vi, Ctot, pg)) = make_uint4(wo[0], wo[1], wo[2], wo[3]);
       }
     }
+    if constexpr (PREFETCH) {
 #pragma unroll
-    for (int i = 0; i < NV; ++i) { cd[i] = nd[i]; cx[i] = nx[i]; cr[i] = nr[i]; }
-    c_mu = n_mu; c_rs = n_rs;
+      for (int i = 0; i < NV; ++i) { cd[i] = nd[i]; cx[i] = nx[i]; cr[i] = nr[i]; }
+      c_mu = n_mu; c_rs = n_rs;
+    }
     row = nxt;
   }
   // CTA-level column reduction, one quantity at a time through s_red[LN_WARPS][Ctot]

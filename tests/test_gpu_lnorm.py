@@ -12,7 +12,7 @@ def _mk(shape, seed, scale=1.0, shift=0.0):
     return (torch.randn(*shape, generator=g) * scale + shift).to(torch.bfloat16)
 
 
-@pytest.mark.parametrize("M,C", [(1000, 512), (4096, 1024), (300, 128), (777, 256), (512, 2048)])
+@pytest.mark.parametrize("M,C", [(1000, 512), (4096, 1024), (300, 128), (777, 256), (512, 2048), (1234, 384), (163840, 512), (9, 64)])
 def test_layernorm_fwd_bwd(M, C):
     from oracle import swin_oracle as so
     from stswincl_b200 import ops
