@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--clips", type=int, default=8, help="clips per GPU per step (reference recipe: batch 8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="do not capture the step in a CUDA graph")
     return ap.parse_args()
 
 
@@ -158,8 +159,8 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(clips):
-    return {"workload": "configs[1]: Swin head train step (SwinTransformerLayerv5 dim 512, 64x80 tokens, 4 heads; "
+def workload_config(clips, graph=None):
+    return {"cuda_graph": graph, "workload": "configs[1]: Swin head train step (SwinTransformerLayerv5 dim 512, 64x80 tokens, 4 heads; "
                         "fwd+bwd+Adam) on EndoVis18-shaped OS-8 features, bf16",
             "clips_per_gpu": clips, "frames_per_clip": T, "feature_shape": [clips, T, DIM, RES[0], RES[1]],
             "optimizer": "torch.optim.Adam(fused=True) on the 96.6M Swin-head parameters",
@@ -192,7 +193,7 @@ def run_ours(args):
     if world > 1:
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True,
                                                         bucket_cap_mb=64, broadcast_buffers=False)
-    opt = torch.optim.Adam(model.parameters(), lr=3e-5, fused=True)
+    opt = torch.optim.Adam(model.parameters(), lr=3e-5, fused=True, capturable=True)
     B = args.clips
     g = torch.Generator(device=dev).manual_seed(1 + rank)
     x_dev = torch.relu(torch.randn(B, T, DIM, RES[0], RES[1], generator=g, device=dev)).to(torch.bfloat16)
@@ -229,9 +230,45 @@ def run_ours(args):
     for _ in range(args.warmup):
         step(x_dev)
     launches0 = ops.LAUNCHES
+    step(x_dev)
+    launches_per_step = ops.LAUNCHES - launches0
+
+    # The step has no host synchronisation and static shapes, so the whole forward + backward +
+    # optimizer step is captured once into a CUDA graph and replayed (single GPU; DDP steps run eagerly).
+    graph, static_x, static_loss = None, None, None
+    if world == 1 and not args.no_graph:
+        try:
+            static_x = x_dev.clone()
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    step(static_x)
+            torch.cuda.current_stream().wait_stream(side)
+            opt.zero_grad(set_to_none=True)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_loss = step(static_x)
+            graph.replay()
+            torch.cuda.synchronize()
+        except Exception as e:                      # capture is an optimisation of the harness, not of the product
+            print(f"bench.py: CUDA graph capture failed ({type(e).__name__}: {e}); timing eager steps", file=sys.stderr)
+            graph = None
+            torch.cuda.synchronize()
+
+    def run_step(x):
+        if graph is None:
+            return step(x)
+        if x is not static_x:
+            static_x.copy_(x, non_blocking=True)
+        graph.replay()
+        return static_loss
+
+    for _ in range(2):
+        run_step(x_dev)
     with ClockSampler(local) as clk:
-        ms_step = timed(lambda i: step(x_dev), args.steps)
-    launches = ops.LAUNCHES - launches0
+        ms_step = timed(lambda i: run_step(static_x if graph is not None else x_dev), args.steps)
+    launches = launches_per_step * args.steps
     clocks = clk.summary()
 
     # ---- end to end: pinned host features -> H2D (copy stream, double buffered) -> step -> loss.item()
@@ -255,7 +292,7 @@ def run_ours(args):
             prefetch(0)
         prefetch(i + 1)                      # next step's features travel while this step computes
         torch.cuda.current_stream().wait_event(ready[b])
-        loss = step(bufs[b])
+        loss = run_step(bufs[b])
         consumed[b].record(torch.cuda.current_stream())
         return loss.item()                   # D2H read of the step's result
 
@@ -306,7 +343,7 @@ def run_ours(args):
         line = {"metric": METRIC, "value": frames / (ms_step * 1e-3), "unit": "frames/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": workload_config(B), "clocks": clocks,
+                "config": workload_config(B, graph is not None), "clocks": clocks,
                 "e2e": {"value": frames / (ms_e2e * 1e-3), "unit": "frames/s", "ms_per_step": ms_e2e,
                         "h2d_bytes_per_step": x_host.numel() * x_host.element_size(), "d2h_bytes_per_step": d2h_bytes},
                 "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,

@@ -154,6 +154,20 @@ def test_full_size_block_vs_oracle():
     assert rel_err(y.cpu(), ref) < TOL
 
 
+def test_cadis_shaped_block_vs_oracle():
+    """Config 5: CaDIS-shaped crop 512x960 -> 64x120 tokens, shifted block, 8 heads."""
+    from oracle import swin_oracle as so
+    from stswincl_b200 import swin
+    dim, res, heads, ws, shift = 512, (64, 120), 8, 8, 4
+    params = so.make_block_params(dim, res, heads, ws, shift, seed=79)
+    m = _load(swin.SwinTransformerBlock(dim, res, heads, window_size=ws, shift_size=shift), params)
+    x = so.make_features(80, 1, 2, res[0] * res[1], dim)
+    ref = so.swin_block(x.to(torch.bfloat16).float(), params, res, heads, ws, shift)
+    y = m(x.cuda())
+    torch.cuda.synchronize()
+    assert rel_err(y.cpu(), ref) < TOL
+
+
 def test_cpu_tensor_raises():
     from stswincl_b200 import swin
     from stswincl_b200._lib import StswinError

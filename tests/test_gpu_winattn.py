@@ -23,6 +23,12 @@ CASES = [
     (3, 1, 8, 12, 128, 2, 4, 2),
     (1, 2, 64, 80, 512, 4, 8, 4),     # the real stage-1 geometry
     (1, 2, 32, 40, 1024, 4, 4, 2),    # the real stage-2 geometry
+    # config 5 (CaDIS-shaped 512x960 crop -> 64x120 tokens): window / head-count sweep
+    (1, 2, 64, 120, 512, 4, 8, 4),    # hd 128
+    (1, 2, 64, 120, 512, 8, 8, 4),    # hd 64
+    (1, 2, 64, 120, 512, 8, 4, 2),    # ws 4: 480 windows, 4 per tile
+    (1, 1, 64, 120, 512, 4, 8, 0),    # T = 1
+    (1, 2, 32, 60, 1024, 4, 4, 2),    # stage 2 of the same crop
 ]
 
 
@@ -68,3 +74,20 @@ def test_winattn_bwd_matches_oracle(case):
     assert rel_err(d_qkv.float().cpu(), q32.grad) < TOL_BF16
     assert rel_err(d_table.cpu(), t32.grad) < TOL_BF16
     assert rel_err(colsum.cpu(), q32.grad.sum((0, 1, 2))) < TOL_BF16
+
+
+@pytest.mark.parametrize("kw,msg", [
+    (dict(C=512, nH=16, ws=8, shift=4), "head_dim 32"),          # config-5 corner: 16 heads at C=512
+    (dict(C=512, nH=4, ws=7, shift=3, H=56, W=84), "tokens per window"),   # ws=7 -> 98 tokens
+    (dict(C=512, nH=4, ws=8, shift=3), "shift 3"),
+    (dict(C=512, nH=4, ws=8, shift=4, H=60), "multiples of the window size"),
+])
+def test_unsupported_geometry_fails_loudly(kw, msg):
+    """No silent fallback: shapes outside the kernels' envelope raise with a reason."""
+    from stswincl_b200 import ops
+    from stswincl_b200._lib import StswinError
+    H, W, C, nH, ws, shift = kw.get("H", 64), kw.get("W", 80), kw["C"], kw["nH"], kw["ws"], kw["shift"]
+    qkv = torch.zeros(1, 2, H * W, 3 * C, dtype=torch.bfloat16, device="cuda")
+    table = torch.zeros((2 * ws - 1) ** 2, nH, device="cuda")
+    with pytest.raises(StswinError, match=msg):
+        ops.winattn_fwd(qkv, table, H, W, nH, ws, shift)
