@@ -82,10 +82,15 @@ int stswin_gemm_bf16(const void* A, int a_major, int64_t lda,
  *   lse2       [stswin_winattn_lse_elems(...)] fp32 workspace written by fwd, read by bwd
  *   shift      0 or ws/2.  T*ws*ws must be 16, 32, 64 or 128; C/nH a multiple of 64, <= 256.
  *   qk_scale   multiplier of q (WindowAttention's `qk_scale`, :79); <= 0 selects (C/nH)^-0.5
+ *   mask       optional dense additive mask [mask_windows, N, N] fp32 (N = ws*ws), the `mask` argument of
+ *              WindowAttention.forward (:127-131): window w uses mask[w % mask_windows], tiled over the
+ *              frame pair.  NULL for the normal case -- the block's shift mask is a closed form of
+ *              (H, W, ws, shift) and is rebuilt in-kernel.
  */
 int64_t stswin_winattn_lse_elems(int B, int T, int H, int W, int C, int nH, int ws);
 int stswin_winattn_fwd(const void* qkv, const float* bias_table, void* out, float* lse2,
-                       int B, int T, int H, int W, int C, int nH, int ws, int shift, float qk_scale, void* stream);
+                       int B, int T, int H, int W, int C, int nH, int ws, int shift, float qk_scale,
+                       const float* mask, int mask_windows, void* stream);
 /* Backward of the same op sequence (what autograd derives for swin_512.py:119-138 + :210-231).
  *   d_out        [B, T, H, W, C]  bf16  gradient w.r.t. `out`
  *   d_qkv        [B, T, H, W, 3C] bf16  written (every element)
@@ -94,7 +99,8 @@ int stswin_winattn_fwd(const void* qkv, const float* bias_table, void* out, floa
  */
 int stswin_winattn_bwd(const void* qkv, const float* bias_table, const float* lse2, const void* d_out,
                        void* d_qkv, float* d_bias_table, float* d_qkv_colsum,
-                       int B, int T, int H, int W, int C, int nH, int ws, int shift, float qk_scale, void* stream);
+                       int B, int T, int H, int W, int C, int nH, int ws, int shift, float qk_scale,
+                       const float* mask, int mask_windows, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * LayerNorm (eps inside the rsqrt, fp32 statistics) over rows of `row_len` bf16 channels.

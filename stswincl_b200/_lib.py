@@ -79,8 +79,8 @@ SIGNATURES = {
     "stswin_last_error": ([], ctypes.c_char_p),
     "stswin_set_device": ([_i], ctypes.c_int),
     "stswin_winattn_lse_elems": ([_i] * 7, ctypes.c_int64),
-    "stswin_winattn_fwd": ([_vp, _fp, _vp, _fp] + [_i] * 8 + [ctypes.c_float, _vp], ctypes.c_int),
-    "stswin_winattn_bwd": ([_vp, _fp, _fp, _vp, _vp, _fp, _fp] + [_i] * 8 + [ctypes.c_float, _vp], ctypes.c_int),
+    "stswin_winattn_fwd": ([_vp, _fp, _vp, _fp] + [_i] * 8 + [ctypes.c_float, _fp, _i, _vp], ctypes.c_int),
+    "stswin_winattn_bwd": ([_vp, _fp, _fp, _vp, _vp, _fp, _fp] + [_i] * 8 + [ctypes.c_float, _fp, _i, _vp], ctypes.c_int),
     "stswin_layernorm_fwd": ([_vp, _fp, _fp, _vp, _fp, _fp, _i64, _i, ctypes.c_float, _i, _i, _i, _i, _vp], ctypes.c_int),
     "stswin_layernorm_bwd": ([_vp, _vp, _fp, _fp, _fp, _vp, _vp, _fp, _fp, _fp, _i64, _i, _i, _i, _i, _i, _vp], ctypes.c_int),
     "stswin_transpose": ([_vp, _i, _vp, _i, _i64, _i, _i, _vp], ctypes.c_int),

@@ -159,13 +159,31 @@ def regression_loss(q, k, adj1, adj2, adj3, neg3, label_patch1, label_patch2, la
 
 
 def consistency_loss_tail(pred_1, pred_2, proj_1_ng, proj_2_ng, proj_adj1_ng, proj_adj2_ng, proj_adj3_ng, proj_neg3_ng,
-                          mask_1, mask_2, mask_3, mask_4, mask_5, mask_6, class_num, *, normalize: bool = False):
+                          mask_1, mask_2, mask_3, mask_4, mask_5, mask_6, class_num, *, normalize: bool = False,
+                          cross_rank_negatives: bool = False, group=None):
     """``ConsistencyLoss.forward`` after ``self.pixpro(...)`` (:584-597): nearest label down-sampling
     to the embedding resolution, then the symmetric sum of two ``regression_loss`` calls; the four
-    shared key sets are prepared once."""
+    shared key sets are prepared once.
+
+    ``cross_rank_negatives=True`` (an EXTENSION of the reference, SURVEY D5 / C3 -- parity unpinned,
+    checked against the oracle's own generalisation): the four shared key sets and their labels are
+    all-gathered over ``group`` and the other ranks' copies are appended as extra key sets, so the
+    inter-video negatives span every rank.  With one rank it is the reference loss."""
     H, W = pred_1.shape[-2:]
     m = [downsample_labels(x, H, W) for x in (mask_1, mask_2, mask_3, mask_4, mask_5, mask_6)]
     cache: dict = {}
     shared, shared_l = [proj_adj1_ng, proj_adj2_ng, proj_adj3_ng, proj_neg3_ng], m[2:]
+    if cross_rank_negatives:
+        import torch.distributed as tdist
+        from . import dist as sdist
+        if tdist.is_available() and tdist.is_initialized() and tdist.get_world_size(group) > 1:
+            world = tdist.get_world_size(group)
+            gk = sdist.gather_key_sets([k.detach().to(_BF16).contiguous() for k in shared], group)
+            gl = sdist.gather_key_sets([l.to(torch.uint8).contiguous() for l in shared_l], group)
+            # gather_key_sets returns, per input, [own, others...]: keep own sets first, then every other rank's
+            own_k, own_l = gk[0::world], gl[0::world]
+            oth_k = [t for i in range(len(shared)) for t in gk[i * world + 1:(i + 1) * world]]
+            oth_l = [t for i in range(len(shared)) for t in gl[i * world + 1:(i + 1) * world]]
+            shared, shared_l = list(own_k) + oth_k, list(own_l) + oth_l
     return (pixel_contrast_loss(pred_1, [proj_2_ng, *shared], m[0], [m[1], *shared_l], class_num, normalize=normalize, _cache=cache)
             + pixel_contrast_loss(pred_2, [proj_1_ng, *shared], m[1], [m[0], *shared_l], class_num, normalize=normalize, _cache=cache))

@@ -23,16 +23,16 @@ int64_t stswin_winattn_lse_elems(int B, int T, int H, int W, int C, int nH, int 
   return stswin::winattn_lse_elems(B, T, H, W, C, nH, ws);
 }
 int stswin_winattn_fwd(const void* qkv, const float* bias_table, void* out, float* lse2, int B, int T, int H, int W,
-                       int C, int nH, int ws, int shift, float qk_scale, void* stream) {
-  return stswin::winattn_fwd(qkv, bias_table, out, lse2, B, T, H, W, C, nH, ws, shift, qk_scale,
+                       int C, int nH, int ws, int shift, float qk_scale, const float* mask, int mask_windows, void* stream) {
+  return stswin::winattn_fwd(qkv, bias_table, out, lse2, B, T, H, W, C, nH, ws, shift, qk_scale, mask, mask_windows,
                              static_cast<cudaStream_t>(stream));
 }
 
 int stswin_winattn_bwd(const void* qkv, const float* bias_table, const float* lse2, const void* d_out, void* d_qkv,
                        float* d_bias_table, float* d_qkv_colsum, int B, int T, int H, int W, int C, int nH, int ws,
-                       int shift, float qk_scale, void* stream) {
+                       int shift, float qk_scale, const float* mask, int mask_windows, void* stream) {
   return stswin::winattn_bwd(qkv, bias_table, lse2, d_out, d_qkv, d_bias_table, d_qkv_colsum, B, T, H, W, C, nH, ws,
-                             shift, qk_scale, static_cast<cudaStream_t>(stream));
+                             shift, qk_scale, mask, mask_windows, static_cast<cudaStream_t>(stream));
 }
 
 int stswin_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,

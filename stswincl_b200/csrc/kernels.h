@@ -10,10 +10,10 @@ int gemm_bf16(const void* A, int a_major, long lda, const void* B, int b_major, 
               int k_splits, cudaStream_t stream);
 
 int winattn_fwd(const void* qkv, const float* bias_table, void* out, float* lse2, int B, int T, int H, int W, int C,
-                int nH, int ws, int shift, float qk_scale, cudaStream_t stream);
+                int nH, int ws, int shift, float qk_scale, const float* mask, int mask_windows, cudaStream_t stream);
 int winattn_bwd(const void* qkv, const float* bias_table, const float* lse2, const void* d_out, void* d_qkv,
                 float* d_table, float* d_qkv_colsum, int B, int T, int H, int W, int C, int nH, int ws, int shift,
-                float qk_scale, cudaStream_t stream);
+                float qk_scale, const float* mask, int mask_windows, cudaStream_t stream);
 long winattn_lse_elems(int B, int T, int H, int W, int C, int nH, int ws);
 
 int layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, long M,

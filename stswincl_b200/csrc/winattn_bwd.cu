@@ -250,11 +250,14 @@ winattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, itp ^= 1) {
       const int tile = item / gm.nH;
       const RowGeom rg = row_geom(gm, tile, row);
-      if (grp == 0) s_lut[row] = uint32_t(rg.rr * (2 * gm.ws - 1) + rg.cc) | (uint32_t(rg.id) << 8);
+      if (grp == 0) s_lut[row] = uint32_t(rg.rr * (2 * gm.ws - 1) + rg.cc) | (uint32_t(rg.id) << 8) |
+                                 (uint32_t(rg.rr * gm.ws + rg.cc) << 16);      // key | region id | spatial position
       named_bar_sync(1, 256);
       key_i = (rg.rr + gm.ws - 1) * (2 * gm.ws - 1) + rg.cc + gm.ws - 1;
       col0 = rg.g * L;
       const bool use_mask = rg.wraps;
+      // dense mask row of this query token (stand-alone WindowAttention with an explicit mask tensor)
+      const float* mask_row = gm.mask ? gm.mask + ((size_t)(rg.gw % gm.mask_nw) * gm.N + (rg.rr * gm.ws + rg.cc)) * gm.N : nullptr;
 
       if (softmax_role) {
         const float lse_i = lse2[(size_t)item * 128 + rg.canon];
@@ -280,7 +283,8 @@ winattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid
                 const int jj = j8 * 8 + 2 * h + e;
                 const uint32_t lj = s_lut[col0 + cb * CH + jj];
                 float x = fmaf(__uint_as_float(v[jj]), gm.scale_log2e, s_tab[key_i - int(lj & 0xff)]);
-                if (use_mask && (lj >> 8) != uint32_t(rg.id)) x += kMaskLog2e;
+                if (use_mask && ((lj >> 8) & 0xffu) != uint32_t(rg.id)) x += kMaskLog2e;
+          if (mask_row != nullptr) x = fmaf(__ldg(mask_row + (lj >> 16)), 1.4426950408889634f, x);
                 pv[e] = fast_exp2(x - lse_i);
                 delta = fmaf(pv[e], __uint_as_float(w[jj]), delta);
               }
@@ -410,13 +414,15 @@ int set_smem_bwd(K kern, int bytes) {
 // see include/stswin_b200.h : stswin_winattn_bwd
 int winattn_bwd(const void* qkv, const float* bias_table, const float* lse2, const void* d_out, void* d_qkv,
                 float* d_table, float* d_qkv_colsum, int B, int T, int H, int W, int C, int nH, int ws, int shift,
-                float qk_scale, cudaStream_t stream) {
+                float qk_scale, const float* mask, int mask_windows, cudaStream_t stream) {
   STSWIN_CHECK_ARG(qkv && bias_table && lse2 && d_out && d_qkv && d_table, "winattn_bwd: null pointer");
   WinGeom gm;
   int rc = fill_geom(&gm, B, T, H, W, C, nH, ws, shift);
   if (rc != kOk) return rc;
   gm.uniform_quad = 1;
   if (qk_scale > 0.f) { gm.scale = qk_scale; gm.scale_log2e = qk_scale * 1.4426950408889634f; }
+  STSWIN_CHECK_ARG(mask == nullptr || mask_windows > 0, "winattn: mask given with mask_windows <= 0");
+  gm.mask = mask; gm.mask_nw = mask_windows;
   CUtensorMap tq_full, tq_quad, td_full, td_quad;
   if ((rc = make_window_tmaps(&tq_full, &tq_quad, qkv, gm, 3 * C)) != kOk) return rc;
   if ((rc = make_window_tmaps(&td_full, &td_quad, d_out, gm, C)) != kOk) return rc;

@@ -20,6 +20,8 @@ struct WinGeom {
   int hd, N, L, G, nWh, nWw, nW, total_windows, num_tiles, nc;   // nc = hd / 64
   float scale_log2e;                                              // hd^-0.5 * log2(e)
   float scale;                                                    // hd^-0.5
+  const float* mask;  // optional dense additive mask [mask_nw, N, N] (WindowAttention.forward's `mask`
+  int mask_nw;        //   argument, swin_512.py:127-131), applied ON TOP of the closed-form shift mask; or null
   int uniform_quad;   // 1: every window of a shifted block is moved as four quadrant boxes (one token
                       //    order per launch; the backward kernel needs that to sum dS across tiles)
 };
@@ -29,6 +31,7 @@ struct RowGeom {
   int rr, cc;  // token coordinates inside its window (shifted frame)
   int id;      // shift-mask region id 0..8 (swin_512.py:173-184), 0 when unshifted
   int canon;   // g*L + t*N + rr*ws + cc : position in the reference's own window-token order
+  int gw;      // global window index b*nW + win (clamped for padding windows)
   long tok;    // index of the source token in the natural [B*T, H, W] order (roll + partition undone)
   bool wraps;  // window crosses the image border (the only windows with a non-zero mask)
   bool valid;  // false for rows of a padding window in the last tile
@@ -59,6 +62,7 @@ __device__ __forceinline__ RowGeom row_geom(const WinGeom& gm, int tile, int r) 
   o.valid = gw < gm.total_windows;
   if (!o.valid) gw = gm.total_windows - 1;
   int b, wh, ww, t;
+  o.gw = gw;
   window_coords(gm, gw, b, wh, ww, o.wraps);
   if (!quad_order(gm, o.wraps)) {
     t = rem / gm.N;

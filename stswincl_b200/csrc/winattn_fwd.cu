@@ -166,12 +166,15 @@ winattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, it_phase ^= 1) {
       const int tile = item / gm.nH, head = item - tile * gm.nH;
       const RowGeom rg = row_geom(gm, tile, row);
-      s_lut[row] = uint32_t(rg.rr * (2 * gm.ws - 1) + rg.cc) | (uint32_t(rg.id) << 8);
+      s_lut[row] = uint32_t(rg.rr * (2 * gm.ws - 1) + rg.cc) | (uint32_t(rg.id) << 8) |
+                                 (uint32_t(rg.rr * gm.ws + rg.cc) << 16);      // key | region id | spatial position
       for (int i = sm_tid; i < nbias; i += 128) s_tab[i] = __ldg(bias_table + i * gm.nH + head) * 1.4426950408889634f;
       named_bar_sync(1, 128);
       const int key_i = (rg.rr + gm.ws - 1) * (2 * gm.ws - 1) + rg.cc + gm.ws - 1;
       const int col0 = rg.g * L;
       const bool use_mask = rg.wraps;
+      // dense mask row of this query token (stand-alone WindowAttention with an explicit mask tensor)
+      const float* mask_row = gm.mask ? gm.mask + ((size_t)(rg.gw % gm.mask_nw) * gm.N + (rg.rr * gm.ws + rg.cc)) * gm.N : nullptr;
 
       mbar_wait(s_full, it_phase);
       tc_fence_after();
@@ -186,7 +189,8 @@ winattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid
         for (int jj = 0; jj < CH; ++jj) {
           const uint32_t lj = s_lut[col0 + cb * CH + jj];
           float x = fmaf(__uint_as_float(v[jj]), gm.scale_log2e, s_tab[key_i - int(lj & 0xff)]);
-          if (use_mask && (lj >> 8) != uint32_t(rg.id)) x += kMaskLog2e;
+          if (use_mask && ((lj >> 8) & 0xffu) != uint32_t(rg.id)) x += kMaskLog2e;
+          if (mask_row != nullptr) x = fmaf(__ldg(mask_row + (lj >> 16)), 1.4426950408889634f, x);
           s[cb * CH + jj] = x;
           mx = fmaxf(mx, x);
         }
@@ -292,6 +296,7 @@ int fill_geom(WinGeom* gm, int B, int T, int H, int W, int C, int nH, int ws, in
   gm->scale_log2e = 1.4426950408889634f / sqrtf((float)gm->hd);
   gm->scale = 1.0f / sqrtf((float)gm->hd);
   gm->uniform_quad = 0;
+  gm->mask = nullptr; gm->mask_nw = 0;
   return kOk;
 }
 
@@ -324,12 +329,14 @@ long winattn_lse_elems(int B, int T, int H, int W, int C, int nH, int ws) {
 
 // see include/stswin_b200.h : stswin_winattn_fwd
 int winattn_fwd(const void* qkv, const float* bias_table, void* out, float* lse2, int B, int T, int H, int W, int C,
-                int nH, int ws, int shift, float qk_scale, cudaStream_t stream) {
+                int nH, int ws, int shift, float qk_scale, const float* mask, int mask_windows, cudaStream_t stream) {
   STSWIN_CHECK_ARG(qkv && bias_table && out && lse2, "winattn_fwd: null pointer");
   WinGeom gm;
   int rc = fill_geom(&gm, B, T, H, W, C, nH, ws, shift);
   if (rc != kOk) return rc;
   if (qk_scale > 0.f) { gm.scale = qk_scale; gm.scale_log2e = qk_scale * 1.4426950408889634f; }
+  STSWIN_CHECK_ARG(mask == nullptr || mask_windows > 0, "winattn: mask given with mask_windows <= 0");
+  gm.mask = mask; gm.mask_nw = mask_windows;
   CUtensorMap tq_full, tq_quad, to_full, to_quad;
   if ((rc = make_window_tmaps(&tq_full, &tq_quad, qkv, gm, 3 * C)) != kOk) return rc;
   if ((rc = make_window_tmaps(&to_full, &to_quad, out, gm, C)) != kOk) return rc;

@@ -123,6 +123,14 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn_major: bool = False, b_mn_maj
     return out
 
 
+def _mask_windows(mask: Optional[torch.Tensor], ws: int) -> int:
+    if mask is None:
+        return 0
+    _req(mask, torch.float32, "mask")
+    assert mask.dim() == 3 and mask.shape[1] == ws * ws and mask.shape[2] == ws * ws and mask.is_contiguous()
+    return mask.shape[0]
+
+
 def winattn_lse_elems(B, T, H, W, C, nH, ws) -> int:
     n = _lib.load().stswin_winattn_lse_elems(B, T, H, W, C, nH, ws)
     if n < 0:
@@ -131,7 +139,7 @@ def winattn_lse_elems(B, T, H, W, C, nH, ws) -> int:
 
 
 def winattn_fwd(qkv: torch.Tensor, bias_table: torch.Tensor, H: int, W: int, num_heads: int, ws: int, shift: int,
-                out: Optional[torch.Tensor] = None, qk_scale: float = 0.0):
+                out: Optional[torch.Tensor] = None, qk_scale: float = 0.0, mask: Optional[torch.Tensor] = None):
     """qkv [B, T, H*W, 3C] bf16 (natural token order) -> (out [B, T, H*W, C] bf16, lse2 fp32).
     stswin_winattn_fwd: gather (roll+partition) / QK^T / bias+mask / softmax / PV / scatter."""
     _req(qkv, torch.bfloat16, "qkv"); _req(bias_table, torch.float32, "bias_table")
@@ -144,7 +152,8 @@ def winattn_fwd(qkv: torch.Tensor, bias_table: torch.Tensor, H: int, W: int, num
     lse2 = torch.empty(winattn_lse_elems(B, T, H, W, C, num_heads, ws), dtype=torch.float32, device=qkv.device)
     with _launch("winattn_fwd", 8.0 * C * B * T * L * 2, qkv):     # q,k,v in + o out, bf16
         st = _lib.load().stswin_winattn_fwd(qkv.data_ptr(), bias_table.data_ptr(), out.data_ptr(), lse2.data_ptr(),
-                                            B, T, H, W, C, num_heads, ws, shift, float(qk_scale), _stream(qkv))
+                                            B, T, H, W, C, num_heads, ws, shift, float(qk_scale),
+                                            _ptr(mask), _mask_windows(mask, ws), _stream(qkv))
     _lib.check(st, "stswin_winattn_fwd")
     return out, lse2
 
@@ -152,7 +161,7 @@ def winattn_fwd(qkv: torch.Tensor, bias_table: torch.Tensor, H: int, W: int, num
 def winattn_bwd(qkv: torch.Tensor, bias_table: torch.Tensor, lse2: torch.Tensor, d_out: torch.Tensor,
                 H: int, W: int, num_heads: int, ws: int, shift: int, d_table: torch.Tensor,
                 d_qkv_colsum: Optional[torch.Tensor] = None, d_qkv: Optional[torch.Tensor] = None,
-                qk_scale: float = 0.0) -> torch.Tensor:
+                qk_scale: float = 0.0, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Gradient of winattn_fwd: returns d_qkv [B,T,H*W,3C] bf16; accumulates into d_table (fp32
     [(2ws-1)^2, nH]) and, if given, into d_qkv_colsum (fp32 [3C])."""
     _req(qkv, torch.bfloat16, "qkv"); _req(d_out, torch.bfloat16, "d_out")
@@ -168,7 +177,8 @@ def winattn_bwd(qkv: torch.Tensor, bias_table: torch.Tensor, lse2: torch.Tensor,
     with _launch("winattn_bwd", 14.0 * C * B * T * L * 2, qkv):    # q,k,v,dO in + dq,dk,dv out, bf16
         st = _lib.load().stswin_winattn_bwd(qkv.data_ptr(), bias_table.data_ptr(), lse2.data_ptr(), d_out.data_ptr(),
                                             d_qkv.data_ptr(), d_table.data_ptr(), _ptr(d_qkv_colsum),
-                                            B, T, H, W, C, num_heads, ws, shift, float(qk_scale), _stream(qkv))
+                                            B, T, H, W, C, num_heads, ws, shift, float(qk_scale),
+                                            _ptr(mask), _mask_windows(mask, ws), _stream(qkv))
     _lib.check(st, "stswin_winattn_bwd")
     return d_qkv
 

@@ -87,16 +87,17 @@ class _AttentionFn(torch.autograd.Function):
     x [Bp, T, H*W, C] bf16.  Gradients for x, table, qkv.{weight,bias}, proj.{weight,bias}."""
 
     @staticmethod
-    def forward(ctx, x, table, w_qkv, b_qkv, w_proj, b_proj, geom):
+    def forward(ctx, x, table, w_qkv, b_qkv, w_proj, b_proj, geom, mask=None):
         H, W, nH, ws, shift, qk_scale = geom
         Bp, T, L, C = x.shape
         x2 = x.reshape(-1, C)
         wq, wp = w_qkv.to(_BF16), w_proj.to(_BF16)
         qkv = ops.gemm(x2, wq, bias=b_qkv)
-        attn, lse2 = ops.winattn_fwd(qkv.view(Bp, T, L, 3 * C), table, H, W, nH, ws, shift, qk_scale=qk_scale)
+        attn, lse2 = ops.winattn_fwd(qkv.view(Bp, T, L, 3 * C), table, H, W, nH, ws, shift, qk_scale=qk_scale, mask=mask)
         out = ops.gemm(attn.view(-1, C), wp, bias=b_proj)
         ctx.save_for_backward(x2, qkv, attn, lse2, table, wq, wp)
         ctx.geom = geom
+        ctx.mask = mask
         ctx.has_qkv_bias = b_qkv is not None
         return out.view(Bp, T, L, C)
 
@@ -113,11 +114,11 @@ class _AttentionFn(torch.autograd.Function):
         d_table = torch.zeros_like(table)
         d_bqkv = torch.zeros(3 * C, dtype=torch.float32, device=d2.device) if ctx.has_qkv_bias else None
         d_qkv = ops.winattn_bwd(qkv.view(*Bp_T_L, 3 * C), table, lse2, d_attn.view(*Bp_T_L, C), H, W, nH, ws, shift,
-                                d_table, d_bqkv, qk_scale=qk_scale)
+                                d_table, d_bqkv, qk_scale=qk_scale, mask=ctx.mask)
         dq2 = d_qkv.view(-1, 3 * C)
         d_x = ops.gemm(dq2, wq, b_mn_major=True)
         d_wqkv = _linear_wgrad(dq2, x2, wq.shape)
-        return d_x.view(*Bp_T_L, C), d_table, d_wqkv, d_bqkv, d_wproj, d_bproj, None
+        return d_x.view(*Bp_T_L, C), d_table, d_wqkv, d_bqkv, d_wproj, d_bproj, None, None
 
 
 class _BlockFn(torch.autograd.Function):
@@ -252,8 +253,9 @@ class WindowAttention(nn.Module):
     """swin_512.py:73-141.  ``forward(x_v [B_, T, N, C], mask=None) -> [B_, T, N, C]``.
 
     Called stand-alone, every window is attended independently (it is treated as a ws x ws image
-    with one un-shifted window).  An explicit ``mask`` tensor is accepted only through
-    ``SwinTransformerBlock`` (which passes geometry instead of the dense mask)."""
+    with one un-shifted window); an explicit ``mask`` [nW, N, N] is added to the logits of window
+    ``b_ % nW`` exactly as at :127-131.  ``SwinTransformerBlock`` does not go through this path: its
+    kernels rebuild the shift mask from the geometry."""
 
     def __init__(self, dim, window_size, num_heads, qkv_bias=True, qk_scale=None, attn_drop=0., proj_drop=0.):
         super().__init__()
@@ -281,17 +283,16 @@ class WindowAttention(nn.Module):
         return 0.0 if abs(self.scale - default) < 1e-12 else float(self.scale)
 
     def forward(self, x_v, mask=None):
-        if mask is not None:
-            raise NotImplementedError(
-                "stand-alone WindowAttention with a dense mask tensor is not implemented; use "
-                "SwinTransformerBlock, whose kernels rebuild the shift mask from the geometry")
         B_, T, N, C = x_v.shape
+        if mask is not None:
+            assert mask.shape[1:] == (N, N) and B_ % mask.shape[0] == 0, "mask must be [nW, N, N] with B_ a multiple of nW"
+            mask = mask.detach().to(device=x_v.device, dtype=torch.float32).contiguous()
         ws = self.window_size[0]
         assert N == ws * ws and C == self.dim, "input feature has wrong size"
         in_dtype = x_v.dtype
         geom = (ws, ws, self.num_heads, ws, 0, self._qk_scale_arg())
         out = _AttentionFn.apply(_as_tokens_bf16(x_v).contiguous(), self.relative_position_bias_table,
-                                 self.qkv.weight, self.qkv.bias, self.proj.weight, self.proj.bias, geom)
+                                 self.qkv.weight, self.qkv.bias, self.proj.weight, self.proj.bias, geom, mask)
         return out if in_dtype == _BF16 else out.to(in_dtype)
 
 

@@ -119,6 +119,32 @@ def test_thirteen_key_sets_chunked_launches():
     assert rel_err(q.grad.cpu(), q_ref.grad) < TOL
 
 
+def test_cross_rank_negatives_single_rank_is_reference_loss():
+    """C3 extension: with world_size 1 the gathered form must equal the reference tail."""
+    import torch.distributed as dist
+    from oracle import loss_oracle as lo
+    from stswincl_b200 import contrast
+    g = _g()
+    N, C, H, W, K = 2, 64, 8, 14, 12
+    full = lo.make_label_maps(76, 6, N, 64, 112, K, coarse=(4, 7))
+    ds = [torch.nn.functional.interpolate(m, size=[H, W], mode="nearest") for m in full]
+    emb = lo.make_embeddings(77, ds, C, K)
+    pred_1, pred_2 = emb[0], lo.make_embeddings(78, ds[1:2], C, K)[0]
+    proj_1, proj_2 = lo.make_embeddings(79, ds[0:1], C, K)[0], emb[1]
+    c = lambda t: t.cuda()
+    created = False
+    if not dist.is_initialized():
+        dist.init_process_group("gloo", init_method="tcp://127.0.0.1:29577", rank=0, world_size=1)
+        created = True
+    try:
+        tail = contrast.consistency_loss_tail(c(pred_1), c(pred_2), c(proj_1), c(proj_2), c(emb[2]), c(emb[3]), c(emb[4]),
+                                              c(emb[5]), *[c(m) for m in full], K, cross_rank_negatives=True)
+    finally:
+        if created:
+            dist.destroy_process_group()
+    assert abs(float(tail) - float(g["tail_loss"])) < TOL * abs(float(g["tail_loss"]))
+
+
 def test_out_of_range_label_raises_and_cpu_raises():
     from oracle import make_goldens as mg
     from stswincl_b200 import contrast

@@ -75,8 +75,28 @@ def test_attention_module_standalone_unmasked():
     y = m(x.cuda())
     assert y.dtype == torch.float32
     assert rel_err(y.cpu(), ref) < TOL
-    with pytest.raises(NotImplementedError):
-        m(x.cuda(), mask=torch.zeros(6, 16, 16).cuda())
+
+
+@pytest.mark.parametrize("case", [("a0", 128, 4, 2, 2, (8, 12), 2, 2), ("a2", 256, 8, 2, 2, (16, 24), 4, 1)], ids=lambda c: c[0])
+def test_attention_module_with_dense_mask_vs_reference_golden(case):
+    """WindowAttention.forward(x_windows, mask=attn_mask) called exactly like the reference's block calls it
+    (swin_512.py:221): windows in, windows out, the dense {0,-100} mask tensor as an argument."""
+    from oracle import index_oracle as ix, swin_oracle as so
+    from stswincl_b200 import swin
+    tag, dim, ws, heads, T, (H, W), shift, B = case
+    g = _g("swin_attention.npz")
+    nW, N = (H // ws) * (W // ws), ws * ws
+    m = _load(swin.WindowAttention(dim, (ws, ws), heads), so.make_attention_params(dim, ws, heads, seed=11))
+    x = (so.make_features(21, B * nW, T, N, dim) - 0.4).cuda().requires_grad_(True)
+    w = (so.make_features(22, B * nW, T, N, dim) - 0.4).cuda()
+    mask = torch.from_numpy(ix.shift_attn_mask(H, W, ws, shift)).cuda()
+    y = m(x, mask=mask)
+    (y * w).sum().backward()
+    torch.cuda.synchronize()
+    assert rel_err(y.cpu(), g[f"{tag}_y"]) < TOL
+    assert rel_err(x.grad.cpu(), g[f"{tag}_dx"]) < TOL
+    assert rel_err(m.relative_position_bias_table.grad.cpu(), g[f"{tag}_d_relative_position_bias_table"]) < TOL
+    assert rel_err(m.qkv.bias.grad.cpu(), g[f"{tag}_d_qkv.bias"]) < TOL
 
 
 BLOCK_CASES = [("b0", 128, (16, 24), 2, 8, 0, 2, 1), ("b1", 128, (16, 24), 2, 8, 4, 2, 1),
