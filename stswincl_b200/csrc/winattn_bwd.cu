@@ -52,7 +52,7 @@ constexpr int SMEM_BYTES =
     1024 + (NRH + NRL) * SLOT_BYTES + 2 * PD_BYTES + 128 * 4 + 2 * (TAB_MAX + 1) * 4 + 2 * 128 * 4 + 256;
 constexpr float kMaskLog2e = -100.0f * 1.4426950408889634f;
 
-template <int L>
+template <int L, int SHT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 winattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid_constant__ CUtensorMap tm_qkv_quad,
                    const __grid_constant__ CUtensorMap tm_do_full, const __grid_constant__ CUtensorMap tm_do_quad,
@@ -83,9 +83,10 @@ winattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_items = gm.num_tiles * gm.nH;
+  const int num_items = gm.num_tiles * gm.ngrp;     // work item = (tile, head group)
   const int nc = gm.nc;
-  const int head = blockIdx.x % gm.nH;          // constant per CTA: gridDim.x % nH == 0
+  const int hg = blockIdx.x % gm.ngrp;          // head group, constant per CTA: gridDim.x % ngrp == 0
+  constexpr int SH = SHT;                       // heads per group (2 when head_dim is 32)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_qkv_full);
@@ -140,8 +141,8 @@ winattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid
       if (++slot == nslot) { slot = 0; phase ^= 1; }
     };
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-      const int tile = item / gm.nH;
-      const int hq = head * gm.hd;
+      const int tile = item / gm.ngrp;
+      const int hq = hg * gm.gch;
       if (ring_h) {
         for (int c = 0; c < nc; ++c) {
           load(tile, false, 0 * gm.C + hq + c * 64);   // Q_c
@@ -164,61 +165,62 @@ winattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid
       constexpr uint32_t idesc_kn = umma_idesc_bf16(128, 64, 0, 1);    // dQ = dS K
       constexpr uint32_t idesc_nn = umma_idesc_bf16(128, 64, 1, 1);    // dV = P^T dO, dK = dS^T Q
       int slot = 0, slotl = 0;
-      uint32_t phase = 0, phasel = 0, itp = 0;
+      uint32_t phase = 0, phasel = 0, sub_phase = 0;
       uint32_t obp[2] = {0, 0};           // per output buffer: parity of its next use
       const uint32_t p_addr = smem_u32(s_p), ds_addr = smem_u32(s_ds);
-      auto next_slot = [&]() { if (++slot == NRH) { slot = 0; phase ^= 1; } };
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x, itp ^= 1) {
-        mbar_wait(sdp_free, itp ^ 1);
-        tc_fence_after();
-        for (int c = 0; c < nc; ++c) {
-          for (int pair = 0; pair < 2; ++pair) {     // (Q_c, K_c) -> S ; (dO_c, V_c) -> dP
-            const int sa = slot;
-            mbar_wait(&fullh[slot], phase);
-            next_slot();
-            const int sb = slot;
-            mbar_wait(&fullh[slot], phase);
-            next_slot();
-            tc_fence_after();
-            const uint32_t aa = smem_u32(s_ringh + sa * SLOT_BYTES), ba = smem_u32(s_ringh + sb * SLOT_BYTES);
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-              umma_bf16(pair == 0 ? tmem_S : tmem_dP, umma_smem_desc(aa + kk * 32, 16, 1024),
-                        umma_smem_desc(ba + kk * 32, 16, 1024), idesc_kk, (c > 0 || kk > 0) ? 1u : 0u);
-            umma_commit(&emptyh[sa]);
-            umma_commit(&emptyh[sb]);
-          }
-        }
-        umma_commit(sdp_full);
-
-        mbar_wait(pds_full, itp);
-        tc_fence_after();
-        for (int c = 0; c < nc; ++c) {
-          for (int o = 0; o < 3; ++o) {              // dV_c, dQ_c, dK_c
-            const int ob = (3 * c + o) & 1;      // output chunk k of a tile uses TMEM buffer k % 2
-            mbar_wait(&fulll[slotl], phasel);
-            mbar_wait(&obuf_free[ob], obp[ob] ^ 1);
-            tc_fence_after();
-            const uint32_t xa = smem_u32(s_ringl + slotl * SLOT_BYTES);
-            const uint32_t dst = tmem_out + ob * 64;
-#pragma unroll
-            for (int kk = 0; kk < 8; ++kk) {
-              const uint64_t bdesc = umma_smem_desc(xa + kk * 2048, SLOT_BYTES, 1024);   // [rows x 64ch], MN-major
-              if (o == 0)        // dV = P^T dO : A = P viewed MN-major (m = key), k = query
-                umma_bf16(dst, umma_smem_desc(p_addr + kk * 2048, SLOT_BYTES, 1024), bdesc, idesc_nn, kk > 0);
-              else if (o == 1)   // dQ = dS K   : A = dS K-major, k = key
-                umma_bf16(dst, umma_smem_desc(ds_addr + (kk >> 2) * SLOT_BYTES + (kk & 3) * 32, 16, 1024), bdesc,
-                          idesc_kn, kk > 0);
-              else               // dK = dS^T Q : A = dS viewed MN-major
-                umma_bf16(dst, umma_smem_desc(ds_addr + kk * 2048, SLOT_BYTES, 1024), bdesc, idesc_nn, kk > 0);
+      auto take_h = [&]() { const int sl = slot; mbar_wait(&fullh[slot], phase); if (++slot == NRH) { slot = 0; phase ^= 1; } return sl; };
+      auto take_l = [&]() { const int sl = slotl; mbar_wait(&fulll[slotl], phasel); if (++slotl == NRL) { slotl = 0; phasel ^= 1; } return sl; };
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        int sa[4][2], sb[4][2], sl3[4][3];          // ring slots of this item's chunks (held across sub-heads)
+        for (int sub = 0; sub < SH; ++sub, sub_phase ^= 1) {
+          mbar_wait(sdp_free, sub_phase ^ 1);
+          tc_fence_after();
+          // S and dP; with two heads per chunk only the sub-head's 32-channel K range (two k-steps)
+          const int k0 = (SH == 1) ? 0 : sub * 2, k1 = (SH == 1) ? 4 : sub * 2 + 2;
+          for (int c = 0; c < nc; ++c) {
+            for (int pair = 0; pair < 2; ++pair) {     // (Q_c, K_c) -> S ; (dO_c, V_c) -> dP
+              if (sub == 0) { sa[c][pair] = take_h(); sb[c][pair] = take_h(); }
+              tc_fence_after();
+              const uint32_t aa = smem_u32(s_ringh + sa[c][pair] * SLOT_BYTES), ba = smem_u32(s_ringh + sb[c][pair] * SLOT_BYTES);
+              for (int kk = k0; kk < k1; ++kk)
+                umma_bf16(pair == 0 ? tmem_S : tmem_dP, umma_smem_desc(aa + kk * 32, 16, 1024),
+                          umma_smem_desc(ba + kk * 32, 16, 1024), idesc_kk, (c > 0 || kk > k0) ? 1u : 0u);
+              if (sub == SH - 1) {
+                umma_commit(&emptyh[sa[c][pair]]);
+                umma_commit(&emptyh[sb[c][pair]]);
+              }
             }
-            umma_commit(&emptyl[slotl]);
-            umma_commit(&obuf_full[ob]);
-            obp[ob] ^= 1;
-            if (++slotl == NRL) { slotl = 0; phasel ^= 1; }
           }
+          umma_commit(sdp_full);
+
+          mbar_wait(pds_full, sub_phase);
+          tc_fence_after();
+          for (int c = 0; c < nc; ++c) {
+            for (int o = 0; o < 3; ++o) {              // dV_c, dQ_c, dK_c (whole 64-channel chunk)
+              const int ob = ((sub * nc + c) * 3 + o) & 1;   // output chunk k of a tile uses TMEM buffer k % 2
+              if (sub == 0) sl3[c][o] = take_l();
+              mbar_wait(&obuf_free[ob], obp[ob] ^ 1);
+              tc_fence_after();
+              const uint32_t xa = smem_u32(s_ringl + sl3[c][o] * SLOT_BYTES);
+              const uint32_t dst = tmem_out + ob * 64;
+#pragma unroll
+              for (int kk = 0; kk < 8; ++kk) {
+                const uint64_t bdesc = umma_smem_desc(xa + kk * 2048, SLOT_BYTES, 1024);   // [rows x 64ch], MN-major
+                if (o == 0)        // dV = P^T dO : A = P viewed MN-major (m = key), k = query
+                  umma_bf16(dst, umma_smem_desc(p_addr + kk * 2048, SLOT_BYTES, 1024), bdesc, idesc_nn, kk > 0);
+                else if (o == 1)   // dQ = dS K   : A = dS K-major, k = key
+                  umma_bf16(dst, umma_smem_desc(ds_addr + (kk >> 2) * SLOT_BYTES + (kk & 3) * 32, 16, 1024), bdesc,
+                            idesc_kn, kk > 0);
+                else               // dK = dS^T Q : A = dS viewed MN-major
+                  umma_bf16(dst, umma_smem_desc(ds_addr + kk * 2048, SLOT_BYTES, 1024), bdesc, idesc_nn, kk > 0);
+              }
+              if (sub == SH - 1) umma_commit(&emptyl[sl3[c][o]]);
+              umma_commit(&obuf_full[ob]);
+              obp[ob] ^= 1;
+            }
+          }
+          umma_commit(pds_free);
         }
-        umma_commit(pds_free);
       }
     }
   } else if (warp >= 4) {
@@ -229,10 +231,7 @@ winattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid
     const int cm_tid = threadIdx.x - 128;         // 0..255 over both groups
     const uint32_t t_lane = uint32_t(wq * 32) << 16;
     const int nbias = (2 * gm.ws - 1) * (2 * gm.ws - 1);
-    for (int i = cm_tid; i < nbias; i += 256) {
-      s_tab[i] = __ldg(bias_table + i * gm.nH + head) * 1.4426950408889634f;
-      s_bacc[i] = 0.f;
-    }
+    for (int i = cm_tid; i < nbias; i += 256) s_bacc[i] = 0.f;
     constexpr bool COLSPLIT = (L >= 64);          // both groups work on S / dP (alternate 32-column chunks)
     constexpr int CH = (L >= 32) ? 32 : 16;
     constexpr int NCHUNK = L / CH;                // chunks of the row's own window columns
@@ -241,17 +240,25 @@ winattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid
     // the other frame; quadrant order folds the two frames inside each 32-column quadrant block).
     constexpr int NACC = COLSPLIT ? 32 : L;
     const bool quad = gm.shift > 0;               // uniform_quad: one token order per launch
-    float bacc[NACC];
+    float bacc[SH][NACC];                         // one set per head of the group
 #pragma unroll
-    for (int k = 0; k < NACC; ++k) bacc[k] = 0.f;
+    for (int h = 0; h < SH; ++h)
+#pragma unroll
+      for (int k = 0; k < NACC; ++k) bacc[h][k] = 0.f;
     const bool softmax_role = COLSPLIT || grp == 0;
-    uint32_t itp = 0, ob_phase = 0;
+    uint32_t sub_phase = 0, ob_phase = 0;
     int key_i = 0, col0 = 0;
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x, itp ^= 1) {
-      const int tile = item / gm.nH;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      const int tile = item / gm.ngrp;
       const RowGeom rg = row_geom(gm, tile, row);
+#pragma unroll
+     for (int sub = 0; sub < SH; ++sub, sub_phase ^= 1) {
+      const int head = hg * SH + sub;
+      named_bar_sync(1, 256);                     // everybody is done with the previous LUT / bias table
       if (grp == 0) s_lut[row] = uint32_t(rg.rr * (2 * gm.ws - 1) + rg.cc) | (uint32_t(rg.id) << 8) |
                                  (uint32_t(rg.rr * gm.ws + rg.cc) << 16);      // key | region id | spatial position
+      if (SH > 1 || item == int(blockIdx.x))      // the head (and so the table) changes only when SH > 1
+        for (int i = cm_tid; i < nbias; i += 256) s_tab[i] = __ldg(bias_table + i * gm.nH + head) * 1.4426950408889634f;
       named_bar_sync(1, 256);
       key_i = (rg.rr + gm.ws - 1) * (2 * gm.ws - 1) + rg.cc + gm.ws - 1;
       col0 = rg.g * L;
@@ -260,9 +267,9 @@ winattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid
       const float* mask_row = gm.mask ? gm.mask + ((size_t)(rg.gw % gm.mask_nw) * gm.N + (rg.rr * gm.ws + rg.cc)) * gm.N : nullptr;
 
       if (softmax_role) {
-        const float lse_i = lse2[(size_t)item * 128 + rg.canon];
-        mbar_wait(sdp_full, itp);
-        mbar_wait(pds_free, itp ^ 1);
+        const float lse_i = lse2[((size_t)tile * gm.nH + head) * 128 + rg.canon];
+        mbar_wait(sdp_full, sub_phase);
+        mbar_wait(pds_free, sub_phase ^ 1);
         tc_fence_after();
         // pass 1: P = exp2(S2 - lse2) -> smem (bf16), delta = sum_j P dP
         float delta = 0.f;
@@ -324,10 +331,10 @@ winattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid
               if (COLSPLIT) {
                 // row-major order: chunk = (frame, half of the 64 positions) -> position j of that half
                 // quadrant order : chunk = quadrant, 16 positions x 2 frames  -> (which quadrant)*16 + j%16
-                if (quad && L == 128) { bacc[ci * 16 + (j & 15)] += d0; bacc[ci * 16 + ((j + 1) & 15)] += d1; }
-                else                  { bacc[j] += d0; bacc[j + 1] += d1; }
+                if (quad && L == 128) { bacc[sub][ci * 16 + (j & 15)] += d0; bacc[sub][ci * 16 + ((j + 1) & 15)] += d1; }
+                else                  { bacc[sub][j] += d0; bacc[sub][j + 1] += d1; }
               } else {
-                bacc[ci * CH + j] += d0; bacc[ci * CH + j + 1] += d1;
+                bacc[sub][ci * CH + j] += d0; bacc[sub][ci * CH + j + 1] += d1;
               }
             }
             *reinterpret_cast<uint4*>(s_ds + off) = make_uint4(dk[0], dk[1], dk[2], dk[3]);
@@ -339,60 +346,75 @@ winattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid
         mbar_arrive(pds_full);          // P / dS visible to the tensor core
       }
 
-      // ---- drain dV_c, dQ_c, dK_c : TMEM -> bf16 -> this row's 128-byte line of d_qkv
+      // ---- drain dV_c, dQ_c, dK_c : TMEM -> bf16 -> this row's line of d_qkv
       //      (window_reverse + inverse roll = the token index of the row).  Output chunk k of the tile
-      //      lands in TMEM buffer k % 2, which is group (k % 2)'s to drain.
-      __nv_bfloat16* row_out = d_qkv + rg.tok * (3 * gm.C) + head * gm.hd;
-      for (int k = grp; k < 3 * nc; k += 2) {
-        const int c = k / 3, o = k - 3 * c;
+      //      lands in TMEM buffer k % 2, which is group (k % 2)'s to drain.  With two heads per chunk
+      //      (SH == 2) only columns [sub*32, +32) of the product belong to this sub-head.
+      __nv_bfloat16* row_out = d_qkv + rg.tok * (3 * gm.C) + hg * gm.gch;
+      for (int k = sub * nc * 3 + ((sub * nc * 3 + grp) & 1); k < (sub + 1) * nc * 3; k += 2) {
+        if ((k & 1) != grp) continue;
+        const int c = (k / 3) - sub * nc, o = k % 3;
         const int which = (o == 0) ? 2 : (o == 1 ? 0 : 1);
         const float m2 = !rg.valid ? 0.f : (o == 0 ? 1.0f : gm.scale);
         mbar_wait(&obuf_full[grp], ob_phase);
         ob_phase ^= 1;
         tc_fence_after();
+        constexpr int OW = (SH == 1) ? 64 : 32;         // valid output columns
         float a[64];
         {
           uint32_t v0[32], v1[32];
-          tmem_ld32(tmem_out + grp * 64 + t_lane, v0);
-          tmem_ld32(tmem_out + grp * 64 + t_lane + 32, v1);
+          tmem_ld32(tmem_out + grp * 64 + t_lane + (SH == 1 ? 0 : sub * 32), v0);
+          if (SH == 1) tmem_ld32(tmem_out + grp * 64 + t_lane + 32, v1);
           tmem_ld_wait();
 #pragma unroll
-          for (int q = 0; q < 32; ++q) { a[q] = __uint_as_float(v0[q]) * m2; a[32 + q] = __uint_as_float(v1[q]) * m2; }
+          for (int q = 0; q < 32; ++q) { a[q] = __uint_as_float(v0[q]) * m2; a[32 + q] = (SH == 1) ? __uint_as_float(v1[q]) * m2 : 0.f; }
         }
         tc_fence_before();
         mbar_arrive(&obuf_free[grp]);
-        const int ch0 = which * gm.C + c * 64;
+        const int ch0 = which * gm.C + c * 64 + (SH == 1 ? 0 : sub * 32);
         if (rg.valid) {
           uint4* dst = reinterpret_cast<uint4*>(row_out + ch0);
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
+          for (int j = 0; j < OW / 8; ++j)
             dst[j] = make_uint4(pack_bf16(a[8 * j], a[8 * j + 1]), pack_bf16(a[8 * j + 2], a[8 * j + 3]),
                                 pack_bf16(a[8 * j + 4], a[8 * j + 5]), pack_bf16(a[8 * j + 6], a[8 * j + 7]));
         }
         if (d_colsum != nullptr) {
-          warp_colsum64(a, lane);          // lane l: columns 2l, 2l+1 summed over this warp's 32 rows
-          atomicAdd(d_colsum + ch0 + head * gm.hd + 2 * lane, a[0]);
-          atomicAdd(d_colsum + ch0 + head * gm.hd + 2 * lane + 1, a[1]);
+          if (SH == 1) {
+            warp_colsum64(a, lane);          // lane l: columns 2l, 2l+1 summed over this warp's 32 rows
+            atomicAdd(d_colsum + ch0 + hg * gm.gch + 2 * lane, a[0]);
+            atomicAdd(d_colsum + ch0 + hg * gm.gch + 2 * lane + 1, a[1]);
+          } else {
+            warp_colsum64(a, lane);          // upper 32 values are zero: lanes 0-15 hold the 32 column sums
+            if (lane < 16) {
+              atomicAdd(d_colsum + ch0 + hg * gm.gch + 2 * lane, a[0]);
+              atomicAdd(d_colsum + ch0 + hg * gm.gch + 2 * lane + 1, a[1]);
+            }
+          }
         }
       }
-      // a tile has 3*nc output chunks; when that is odd the groups' buffer parities drift apart by design
-      // (each group tracks its own phase), nothing to do here.
+     }   // sub
     }
-    // ---- bias-table gradient: bin the per-row running sums by relative position, once per CTA
-    named_bar_sync(1, 256);
-    if (softmax_role) {
+    // ---- bias-table gradient: bin the per-row running sums by relative position, once per CTA and head
 #pragma unroll
-      for (int k = 0; k < NACC; ++k) {
-        // a column of this row's window that accumulator k stands for
-        int ck;
-        if (COLSPLIT) ck = (quad && L == 128) ? ((2 * (k >> 4) + grp) * 32 + (k & 15)) : (grp * 32 + k);
-        else          ck = k;
-        const uint32_t lj = s_lut[col0 + ck];
-        atomicAdd(&s_bacc[key_i - int(lj & 0xff)], bacc[k]);
+    for (int sub = 0; sub < SH; ++sub) {
+      named_bar_sync(1, 256);
+      for (int i = cm_tid; i < nbias; i += 256) s_bacc[i] = 0.f;
+      named_bar_sync(1, 256);
+      if (softmax_role) {
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) {
+          // a column of this row's window that accumulator k stands for
+          int ck;
+          if (COLSPLIT) ck = (quad && L == 128) ? ((2 * (k >> 4) + grp) * 32 + (k & 15)) : (grp * 32 + k);
+          else          ck = k;
+          const uint32_t lj = s_lut[col0 + ck];
+          atomicAdd(&s_bacc[key_i - int(lj & 0xff)], bacc[sub][k]);
+        }
       }
+      named_bar_sync(1, 256);
+      for (int i = cm_tid; i < nbias; i += 256) atomicAdd(d_table + i * gm.nH + hg * SH + sub, s_bacc[i]);
     }
-    named_bar_sync(1, 256);
-    for (int i = cm_tid; i < nbias; i += 256) atomicAdd(d_table + i * gm.nH + head, s_bacc[i]);
   }
 
   tc_fence_before();
@@ -427,16 +449,23 @@ int winattn_bwd(const void* qkv, const float* bias_table, const float* lse2, con
   if ((rc = make_window_tmaps(&tq_full, &tq_quad, qkv, gm, 3 * C)) != kOk) return rc;
   if ((rc = make_window_tmaps(&td_full, &td_quad, d_out, gm, C)) != kOk) return rc;
   STSWIN_CHECK_ARG((reinterpret_cast<uintptr_t>(d_qkv) & 15) == 0, "winattn_bwd: d_qkv must be 16-byte aligned");
-  const int items = gm.num_tiles * gm.nH;
+  const int items = gm.num_tiles * gm.ngrp;
   int grid = items < num_sms() ? items : num_sms();
-  grid -= grid % nH;                      // one head per CTA (items is a multiple of nH, so grid >= nH)
-  if (grid < nH) return set_error(kErrUnsupported, "winattn_bwd: num_heads %d exceeds the SM count", nH);
+  grid -= grid % gm.ngrp;                 // one head group per CTA (items is a multiple of ngrp, so grid >= ngrp)
+  if (grid < gm.ngrp) return set_error(kErrUnsupported, "winattn_bwd: %d head groups exceed the SM count", gm.ngrp);
 #define STSWIN_LAUNCH_BWD(LL)                                                                                      \
   case LL: {                                                                                                       \
-    if ((rc = set_smem_bwd(winattn_bwd_kernel<LL>, SMEM_BYTES)) != kOk) return rc;                                 \
-    winattn_bwd_kernel<LL><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(                                             \
-        tq_full, tq_quad, td_full, td_quad, static_cast<__nv_bfloat16*>(d_qkv), bias_table, lse2, d_table,         \
-        d_qkv_colsum, gm);                                                                                         \
+    if (gm.SH == 1) {                                                                                              \
+      if ((rc = set_smem_bwd(winattn_bwd_kernel<LL, 1>, SMEM_BYTES)) != kOk) return rc;                            \
+      winattn_bwd_kernel<LL, 1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(                                        \
+          tq_full, tq_quad, td_full, td_quad, static_cast<__nv_bfloat16*>(d_qkv), bias_table, lse2, d_table,       \
+          d_qkv_colsum, gm);                                                                                       \
+    } else {                                                                                                       \
+      if ((rc = set_smem_bwd(winattn_bwd_kernel<LL, 2>, SMEM_BYTES)) != kOk) return rc;                            \
+      winattn_bwd_kernel<LL, 2><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(                                        \
+          tq_full, tq_quad, td_full, td_quad, static_cast<__nv_bfloat16*>(d_qkv), bias_table, lse2, d_table,       \
+          d_qkv_colsum, gm);                                                                                       \
+    }                                                                                                              \
     break;                                                                                                         \
   }
   switch (gm.L) {

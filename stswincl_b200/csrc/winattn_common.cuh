@@ -17,7 +17,11 @@ namespace stswin {
 
 struct WinGeom {
   int B, T, H, W, C, nH, ws, shift;
-  int hd, N, L, G, nWh, nWw, nW, total_windows, num_tiles, nc;   // nc = hd / 64
+  int hd, N, L, G, nWh, nWw, nW, total_windows, num_tiles, nc;   // nc = 64-channel chunks per head group
+  int SH, ngrp, gch;   // head_dim >= 64: SH = 1, a "head group" is one head (gch = hd channels).
+                       // head_dim 32  : SH = 2 heads share one 64-channel chunk (gch = 64); S / dP use
+                       // the head's 32-channel K sub-range of the chunk, the output products run over
+                       // the whole chunk and only the head's own 32 columns are kept.
   float scale_log2e;                                              // hd^-0.5 * log2(e)
   float scale;                                                    // hd^-0.5
   const float* mask;  // optional dense additive mask [mask_nw, N, N] (WindowAttention.forward's `mask`

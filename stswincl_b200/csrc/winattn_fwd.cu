@@ -51,12 +51,14 @@ winattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid
   uint64_t* p_full = s_full + 2;
   uint64_t* o_full = s_full + 3;
   uint64_t* o_free = s_full + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 5);
+  uint64_t* pv_done = s_full + 5;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 6);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_items = gm.num_tiles * gm.nH;
+  const int num_items = gm.num_tiles * gm.ngrp;     // work item = (tile, head group)
   const int nc = gm.nc;
+  const int SH = gm.SH;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_qkv_full);
@@ -72,6 +74,7 @@ winattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid
     mbar_init(p_full, 128);
     mbar_init(o_full, 1);
     mbar_init(o_free, 128);
+    mbar_init(pv_done, 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -83,14 +86,14 @@ winattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_S = tmem_base;          // 128 columns
-  const uint32_t tmem_O = tmem_base + 128;    // hd columns (<= 256)
+  const uint32_t tmem_O = tmem_base + 128;    // nc*64 columns (<= 256), or SH*64 when two heads share a chunk
 
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer
     int slot = 0;
     uint32_t phase = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-      const int tile = item / gm.nH, head = item - tile * gm.nH;
+      const int tile = item / gm.ngrp, hg = item - tile * gm.ngrp;
       for (int step = 0; step < 3 * nc; ++step) {
         // order: Q0 K0 Q1 K1 ... then V0 V1 ...
         int which, c;
@@ -99,7 +102,7 @@ winattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid
         mbar_wait(&empty_bar[slot], phase ^ 1);
         if (lane == 0) mbar_arrive_expect_tx(&full_bar[slot], SLOT_BYTES);
         __syncwarp();
-        tile_boxes<true>(gm, tile, which * gm.C + head * gm.hd + c * 64, s_ring + slot * SLOT_BYTES, &tm_qkv_full,
+        tile_boxes<true>(gm, tile, which * gm.C + hg * gm.gch + c * 64, s_ring + slot * SLOT_BYTES, &tm_qkv_full,
                          &tm_qkv_quad, &full_bar[slot], lane);
         if (++slot == NSLOT) { slot = 0; phase ^= 1; }
       }
@@ -111,45 +114,51 @@ winattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);
       int slot = 0;
       uint32_t phase = 0;
-      uint32_t it_phase = 0;
+      uint32_t it_phase = 0, sub_phase = 0;      // per item / per (item, sub-head)
       const uint32_t p_addr = smem_u32(s_p);
+      auto take_slot = [&]() {                   // wait for the next ring slot in program order
+        const int sl = slot;
+        mbar_wait(&full_bar[slot], phase);
+        if (++slot == NSLOT) { slot = 0; phase ^= 1; }
+        return sl;
+      };
       for (int item = blockIdx.x; item < num_items; item += gridDim.x, it_phase ^= 1) {
-        // S = Q K^T
-        mbar_wait(s_free, it_phase ^ 1);
-        tc_fence_after();
-        for (int c = 0; c < nc; ++c) {
-          const int slot_q = slot;
-          mbar_wait(&full_bar[slot], phase);
-          if (++slot == NSLOT) { slot = 0; phase ^= 1; }
-          const int slot_k = slot;
-          mbar_wait(&full_bar[slot], phase);
-          if (++slot == NSLOT) { slot = 0; phase ^= 1; }
+        int sq[4], sk[4], sv[4];                 // ring slots of this item's chunks (nc <= 4)
+        for (int sub = 0; sub < SH; ++sub, sub_phase ^= 1) {
+          // S = Q K^T (for SH == 2: over the 32-channel K sub-range of sub-head `sub`)
+          mbar_wait(s_free, sub_phase ^ 1);
           tc_fence_after();
-          const uint32_t qa = smem_u32(s_ring + slot_q * SLOT_BYTES), ka = smem_u32(s_ring + slot_k * SLOT_BYTES);
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            umma_bf16(tmem_S, umma_smem_desc(qa + kk * 32, 16, 1024), umma_smem_desc(ka + kk * 32, 16, 1024), idesc_s,
-                      (c > 0 || kk > 0) ? 1u : 0u);
-          umma_commit(&empty_bar[slot_q]);
-          umma_commit(&empty_bar[slot_k]);
-        }
-        umma_commit(s_full);
-        // O = P V
-        mbar_wait(p_full, it_phase);
-        mbar_wait(o_free, it_phase ^ 1);
-        tc_fence_after();
-        for (int c = 0; c < nc; ++c) {
-          mbar_wait(&full_bar[slot], phase);
-          tc_fence_after();
-          const uint32_t va = smem_u32(s_ring + slot * SLOT_BYTES);
-#pragma unroll
-          for (int kk = 0; kk < 8; ++kk) {
-            const uint64_t adesc = umma_smem_desc(p_addr + (kk >> 2) * SLOT_BYTES + (kk & 3) * 32, 16, 1024);
-            const uint64_t bdesc = umma_smem_desc(va + kk * 2048, SLOT_BYTES, 1024);
-            umma_bf16(tmem_O + c * 64, adesc, bdesc, idesc_o, kk > 0 ? 1u : 0u);
+          for (int c = 0; c < nc; ++c) {
+            if (sub == 0) { sq[c] = take_slot(); sk[c] = take_slot(); }
+            tc_fence_after();
+            const uint32_t qa = smem_u32(s_ring + sq[c] * SLOT_BYTES), ka = smem_u32(s_ring + sk[c] * SLOT_BYTES);
+            const int k0 = (SH == 1) ? 0 : sub * 2, k1 = (SH == 1) ? 4 : sub * 2 + 2;
+            for (int kk = k0; kk < k1; ++kk)
+              umma_bf16(tmem_S, umma_smem_desc(qa + kk * 32, 16, 1024), umma_smem_desc(ka + kk * 32, 16, 1024), idesc_s,
+                        (c > 0 || kk > k0) ? 1u : 0u);
+            if (sub == SH - 1) {                 // last reader of these chunks
+              umma_commit(&empty_bar[sq[c]]);
+              umma_commit(&empty_bar[sk[c]]);
+            }
           }
-          umma_commit(&empty_bar[slot]);
-          if (++slot == NSLOT) { slot = 0; phase ^= 1; }
+          umma_commit(s_full);
+          // O = P V  (SH == 2: the whole 64-column chunk; the epilogue keeps the sub-head's own 32 columns)
+          mbar_wait(p_full, sub_phase);
+          if (sub == 0) mbar_wait(o_free, it_phase ^ 1);
+          tc_fence_after();
+          for (int c = 0; c < nc; ++c) {
+            if (sub == 0) sv[c] = take_slot();
+            tc_fence_after();
+            const uint32_t va = smem_u32(s_ring + sv[c] * SLOT_BYTES);
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+              const uint64_t adesc = umma_smem_desc(p_addr + (kk >> 2) * SLOT_BYTES + (kk & 3) * 32, 16, 1024);
+              const uint64_t bdesc = umma_smem_desc(va + kk * 2048, SLOT_BYTES, 1024);
+              umma_bf16(tmem_O + (SH == 1 ? c : sub) * 64, adesc, bdesc, idesc_o, kk > 0 ? 1u : 0u);
+            }
+            if (sub == SH - 1) umma_commit(&empty_bar[sv[c]]);
+          }
+          umma_commit(pv_done);                  // P may be overwritten
         }
         umma_commit(o_full);
       }
@@ -161,11 +170,15 @@ winattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid
     const int sm_tid = threadIdx.x - 64;      // 0..127
     const uint32_t t_lane = uint32_t(wq * 32) << 16;
     const int nbias = (2 * gm.ws - 1) * (2 * gm.ws - 1);
-    uint32_t it_phase = 0;
+    uint32_t it_phase = 0, sub_phase = 0;
     int stg_sel = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x, it_phase ^= 1) {
-      const int tile = item / gm.nH, head = item - tile * gm.nH;
+      const int tile = item / gm.ngrp, hg = item - tile * gm.ngrp;
       const RowGeom rg = row_geom(gm, tile, row);
+      float inv_sub[2] = {1.f, 1.f};
+     for (int sub = 0; sub < SH; ++sub, sub_phase ^= 1) {
+      const int head = hg * SH + sub;
+      named_bar_sync(1, 128);                  // everybody is done with the previous LUT / bias table
       s_lut[row] = uint32_t(rg.rr * (2 * gm.ws - 1) + rg.cc) | (uint32_t(rg.id) << 8) |
                                  (uint32_t(rg.rr * gm.ws + rg.cc) << 16);      // key | region id | spatial position
       for (int i = sm_tid; i < nbias; i += 128) s_tab[i] = __ldg(bias_table + i * gm.nH + head) * 1.4426950408889634f;
@@ -176,7 +189,7 @@ winattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid
       // dense mask row of this query token (stand-alone WindowAttention with an explicit mask tensor)
       const float* mask_row = gm.mask ? gm.mask + ((size_t)(rg.gw % gm.mask_nw) * gm.N + (rg.rr * gm.ws + rg.cc)) * gm.N : nullptr;
 
-      mbar_wait(s_full, it_phase);
+      mbar_wait(s_full, sub_phase);
       tc_fence_after();
       float s[L];
       float mx = -INFINITY;
@@ -199,6 +212,7 @@ winattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid
       tc_fence_before();
       mbar_arrive(s_free);
 
+      mbar_wait(pv_done, sub_phase ^ 1);        // the previous P V product has finished reading P
       float sum = 0.f;
 #pragma unroll
       for (int j8 = 0; j8 < L / 8; ++j8) {
@@ -219,16 +233,20 @@ winattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid
       }
       fence_proxy_async_smem();
       mbar_arrive(p_full);
-      const float inv = 1.0f / sum;
-      lse2[(size_t)item * 128 + rg.canon] = mx + log2f(sum);
+      inv_sub[sub] = 1.0f / sum;
+      lse2[((size_t)tile * gm.nH + head) * 128 + rg.canon] = mx + log2f(sum);
+     }
 
       // ---- epilogue: O * (1/sum) -> bf16 -> staging -> TMA store at the un-rolled coordinates
       mbar_wait(o_full, it_phase);
       tc_fence_after();
       for (int c = 0; c < nc; ++c) {
         uint32_t v0[32], v1[32];
-        tmem_ld32(tmem_O + t_lane + c * 64, v0);
-        tmem_ld32(tmem_O + t_lane + c * 64 + 32, v1);
+        // SH == 1: columns [c*64, +64) of this head.  SH == 2: columns [0,32) of sub-head 0's product
+        // and columns [32,64) of sub-head 1's product (each product spans the whole 64-channel chunk).
+        const float inv = inv_sub[0], inv1 = inv_sub[SH - 1];
+        tmem_ld32(tmem_O + t_lane + (SH == 1 ? c * 64 : 0), v0);
+        tmem_ld32(tmem_O + t_lane + (SH == 1 ? c * 64 + 32 : 64 + 32), v1);
         tmem_ld_wait();
         if (c == nc - 1) {
           tc_fence_before();
@@ -245,16 +263,16 @@ winattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid
           q.z = pack_bf16(__uint_as_float(v0[8 * j + 4]) * inv, __uint_as_float(v0[8 * j + 5]) * inv);
           q.w = pack_bf16(__uint_as_float(v0[8 * j + 6]) * inv, __uint_as_float(v0[8 * j + 7]) * inv);
           *reinterpret_cast<uint4*>(stg + sw128_offset(row, j)) = q;
-          q.x = pack_bf16(__uint_as_float(v1[8 * j + 0]) * inv, __uint_as_float(v1[8 * j + 1]) * inv);
-          q.y = pack_bf16(__uint_as_float(v1[8 * j + 2]) * inv, __uint_as_float(v1[8 * j + 3]) * inv);
-          q.z = pack_bf16(__uint_as_float(v1[8 * j + 4]) * inv, __uint_as_float(v1[8 * j + 5]) * inv);
-          q.w = pack_bf16(__uint_as_float(v1[8 * j + 6]) * inv, __uint_as_float(v1[8 * j + 7]) * inv);
+          q.x = pack_bf16(__uint_as_float(v1[8 * j + 0]) * inv1, __uint_as_float(v1[8 * j + 1]) * inv1);
+          q.y = pack_bf16(__uint_as_float(v1[8 * j + 2]) * inv1, __uint_as_float(v1[8 * j + 3]) * inv1);
+          q.z = pack_bf16(__uint_as_float(v1[8 * j + 4]) * inv1, __uint_as_float(v1[8 * j + 5]) * inv1);
+          q.w = pack_bf16(__uint_as_float(v1[8 * j + 6]) * inv1, __uint_as_float(v1[8 * j + 7]) * inv1);
           *reinterpret_cast<uint4*>(stg + sw128_offset(row, 4 + j)) = q;
         }
         fence_proxy_async_smem();
         named_bar_sync(1, 128);
         if (sm_tid < 32) {                             // warp 2 issues the scatter, one box per lane
-          tile_boxes<false>(gm, tile, head * gm.hd + c * 64, stg, &tm_out_full, &tm_out_quad, nullptr, lane);
+          tile_boxes<false>(gm, tile, hg * gm.gch + c * 64, stg, &tm_out_full, &tm_out_quad, nullptr, lane);
           tma_commit_group();
         }
         stg_sel ^= 1;
@@ -281,8 +299,8 @@ int fill_geom(WinGeom* gm, int B, int T, int H, int W, int C, int nH, int ws, in
   gm->hd = C / nH;
   gm->N = ws * ws;
   gm->L = T * ws * ws;
-  if (gm->hd % 64 != 0 || gm->hd > 256)
-    return set_error(kErrUnsupported, "winattn: head_dim %d unsupported (need a multiple of 64, <= 256)", gm->hd);
+  if (!((gm->hd % 64 == 0 && gm->hd <= 256) || (gm->hd == 32 && nH % 2 == 0)))
+    return set_error(kErrUnsupported, "winattn: head_dim %d unsupported (need 32 or a multiple of 64, <= 256)", gm->hd);
   if (gm->L > 128 || 128 % gm->L != 0 || gm->L < 16)
     return set_error(kErrUnsupported, "winattn: T*ws*ws = %d tokens per window unsupported (need 16, 32, 64 or 128)", gm->L);
   if (!(shift == 0 || (ws % 2 == 0 && shift == ws / 2)))
@@ -292,7 +310,10 @@ int fill_geom(WinGeom* gm, int B, int T, int H, int W, int C, int nH, int ws, in
   gm->nWh = H / ws; gm->nWw = W / ws; gm->nW = gm->nWh * gm->nWw;
   gm->total_windows = B * gm->nW;
   gm->num_tiles = (gm->total_windows + gm->G - 1) / gm->G;
-  gm->nc = gm->hd / 64;
+  gm->SH = gm->hd >= 64 ? 1 : 64 / gm->hd;
+  gm->ngrp = nH / gm->SH;
+  gm->gch = gm->SH * gm->hd;
+  gm->nc = gm->gch / 64;
   gm->scale_log2e = 1.4426950408889634f / sqrtf((float)gm->hd);
   gm->scale = 1.0f / sqrtf((float)gm->hd);
   gm->uniform_quad = 0;
@@ -340,7 +361,7 @@ int winattn_fwd(const void* qkv, const float* bias_table, void* out, float* lse2
   CUtensorMap tq_full, tq_quad, to_full, to_quad;
   if ((rc = make_window_tmaps(&tq_full, &tq_quad, qkv, gm, 3 * C)) != kOk) return rc;
   if ((rc = make_window_tmaps(&to_full, &to_quad, out, gm, C)) != kOk) return rc;
-  const int items = gm.num_tiles * gm.nH;
+  const int items = gm.num_tiles * gm.ngrp;
   const int grid = items < num_sms() ? items : num_sms();
 #define STSWIN_LAUNCH_FWD(LL)                                                                                       \
   case LL: {                                                                                                        \

@@ -29,6 +29,12 @@ CASES = [
     (1, 2, 64, 120, 512, 8, 4, 2),    # ws 4: 480 windows, 4 per tile
     (1, 1, 64, 120, 512, 4, 8, 0),    # T = 1
     (1, 2, 32, 60, 1024, 4, 4, 2),    # stage 2 of the same crop
+    # head_dim 32 (16 heads at C=512): two heads share a 64-channel chunk
+    (2, 2, 16, 24, 128, 4, 8, 4),
+    (2, 2, 16, 24, 128, 4, 8, 0),
+    (1, 2, 8, 12, 256, 8, 4, 2),
+    (3, 1, 8, 12, 64, 2, 4, 2),
+    (1, 2, 64, 120, 512, 16, 8, 4),
 ]
 
 
@@ -77,7 +83,7 @@ def test_winattn_bwd_matches_oracle(case):
 
 
 @pytest.mark.parametrize("kw,msg", [
-    (dict(C=512, nH=16, ws=8, shift=4), "head_dim 32"),          # config-5 corner: 16 heads at C=512
+    (dict(C=256, nH=16, ws=8, shift=4), "head_dim 16"),
     (dict(C=512, nH=4, ws=7, shift=3, H=56, W=84), "tokens per window"),   # ws=7 -> 98 tokens
     (dict(C=512, nH=4, ws=8, shift=3), "shift 3"),
     (dict(C=512, nH=4, ws=8, shift=4, H=60), "multiples of the window size"),
