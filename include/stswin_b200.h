@@ -80,7 +80,8 @@ int stswin_gemm_bf16(const void* A, int a_major, int64_t lda,
  *              position index :88-99 and the shift mask :171-192 are closed forms in-kernel)
  *   out        [B, T, H, W, C] bf16, same token order
  *   lse2       [stswin_winattn_lse_elems(...)] fp32 workspace written by fwd, read by bwd
- *   shift      0 or ws/2.  T*ws*ws must be 16, 32, 64 or 128; C/nH = 32 or a multiple of 64, <= 256.
+ *   shift      0 <= shift < ws (the reference uses 0 and ws/2).  ws <= 8 and T*ws*ws <= 128 (any value,
+ *              e.g. 98 for ws 7); H, W multiples of ws; C/nH = 32 or a multiple of 64, <= 256.
  *   qk_scale   multiplier of q (WindowAttention's `qk_scale`, :79); <= 0 selects (C/nH)^-0.5
  *   mask       optional dense additive mask [mask_windows, N, N] fp32 (N = ws*ws), the `mask` argument of
  *              WindowAttention.forward (:127-131): window w uses mask[w % mask_windows], tiled over the

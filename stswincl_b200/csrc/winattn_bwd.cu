@@ -38,7 +38,7 @@
 namespace stswin {
 
 int fill_geom(WinGeom* gm, int B, int T, int H, int W, int C, int nH, int ws, int shift);
-int make_window_tmaps(CUtensorMap* full, CUtensorMap* quad, const void* base, const WinGeom& gm, int channels);
+int make_window_tmaps(WinMaps* maps, const void* base, const WinGeom& gm, int channels);
 
 namespace {
 
@@ -49,13 +49,16 @@ constexpr int PD_BYTES = 2 * SLOT_BYTES;       // [128 x 128] bf16 as two K-majo
 constexpr int TAB_MAX = 15 * 15;
 constexpr int NUM_THREADS = 384;               // warp 0 producer H, 1 MMA, 2 producer L, 3 idle, 4-7 / 8-11 compute groups A / B
 constexpr int SMEM_BYTES =
-    1024 + (NRH + NRL) * SLOT_BYTES + 2 * PD_BYTES + 128 * 4 + 2 * (TAB_MAX + 1) * 4 + 2 * 128 * 4 + 256;
+    1024 + (NRH + NRL) * SLOT_BYTES + 2 * PD_BYTES + 128 * 4 + 3 * (TAB_MAX + 1) * 4 + 2 * 128 * 4 + 256;
 constexpr float kMaskLog2e = -100.0f * 1.4426950408889634f;
 
-template <int L, int SHT>
+// GEN (only with L = 128): windows of gm.L tokens with gm.L not a power of two, or rectangles of unequal
+// size (shift != ws/2): every thread walks the whole 128-column row and keeps the columns tagged with its
+// own window; the bias-table gradient then goes through shared-memory atomics instead of the per-column
+// register sums (whose column -> position fold relies on the regular power-of-two orders).
+template <int L, int SHT, bool GEN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-winattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid_constant__ CUtensorMap tm_qkv_quad,
-                   const __grid_constant__ CUtensorMap tm_do_full, const __grid_constant__ CUtensorMap tm_do_quad,
+winattn_bwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant__ WinMaps tm_do,
                    __nv_bfloat16* __restrict__ d_qkv, const float* __restrict__ bias_table, const float* __restrict__ lse2, float* __restrict__ d_table,
                    float* __restrict__ d_colsum, const WinGeom gm) {
   extern __shared__ uint8_t smem_raw[];
@@ -66,8 +69,8 @@ winattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid
   uint8_t* s_ds = s_p + PD_BYTES;
   uint32_t* s_lut = reinterpret_cast<uint32_t*>(s_ds + PD_BYTES);
   float* s_tab = reinterpret_cast<float*>(s_lut + 128);
-  float* s_bacc = s_tab + TAB_MAX + 1;
-  float* s_delta = s_bacc + TAB_MAX + 1;          // [2][128] partial row sums of the two compute groups
+  float* s_bacc = s_tab + TAB_MAX + 1;            // [2][TAB_MAX + 1]: one bin array per head of the group
+  float* s_delta = s_bacc + 2 * (TAB_MAX + 1);          // [2][128] partial row sums of the two compute groups
   uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(s_delta + 256) + 7) & ~uintptr_t(7));
   uint64_t* fullh = bars;
   uint64_t* emptyh = fullh + NRH;
@@ -89,10 +92,8 @@ winattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid
   constexpr int SH = SHT;                       // heads per group (2 when head_dim is 32)
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tm_qkv_full);
-    tma_prefetch_desc(&tm_qkv_quad);
-    tma_prefetch_desc(&tm_do_full);
-    tma_prefetch_desc(&tm_do_quad);
+    tma_prefetch_desc(&tm_qkv.full);
+    tma_prefetch_desc(&tm_do.full);
     for (int i = 0; i < NRH; ++i) {
       mbar_init(&fullh[i], 1);
       mbar_init(&emptyh[i], 1);
@@ -112,8 +113,10 @@ winattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
-  // P / dS: entries outside a row's own window stay zero.
-  for (int i = threadIdx.x; i < 2 * PD_BYTES / 16; i += NUM_THREADS) reinterpret_cast<uint4*>(s_p)[i] = make_uint4(0, 0, 0, 0);
+  // P / dS: entries outside a row's own window stay zero.  Rings: the padding rows of a tile (general
+  // mode) are never written by TMA and must read as zero.
+  for (int i = threadIdx.x; i < ((NRH + NRL) * SLOT_BYTES + 2 * PD_BYTES) / 16; i += NUM_THREADS)
+    reinterpret_cast<uint4*>(s_ringh)[i] = make_uint4(0, 0, 0, 0);
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -134,10 +137,9 @@ winattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid
     uint32_t phase = 0;
     auto load = [&](int tile, bool from_do, int ch0) {
       mbar_wait(&emptyb[slot], phase ^ 1);
-      if (lane == 0) mbar_arrive_expect_tx(&fullb[slot], SLOT_BYTES);
+      if (lane == 0) mbar_arrive_expect_tx(&fullb[slot], chunk_tx_bytes(gm));
       __syncwarp();
-      tile_boxes<true>(gm, tile, ch0, ring + slot * SLOT_BYTES, from_do ? &tm_do_full : &tm_qkv_full,
-                       from_do ? &tm_do_quad : &tm_qkv_quad, &fullb[slot], lane);
+      tile_boxes<true>(gm, tile, ch0, ring + slot * SLOT_BYTES, from_do ? &tm_do : &tm_qkv, &fullb[slot], lane);
       if (++slot == nslot) { slot = 0; phase ^= 1; }
     };
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
@@ -231,7 +233,7 @@ winattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid
     const int cm_tid = threadIdx.x - 128;         // 0..255 over both groups
     const uint32_t t_lane = uint32_t(wq * 32) << 16;
     const int nbias = (2 * gm.ws - 1) * (2 * gm.ws - 1);
-    for (int i = cm_tid; i < nbias; i += 256) s_bacc[i] = 0.f;
+    for (int i = cm_tid; i < 2 * (TAB_MAX + 1); i += 256) s_bacc[i] = 0.f;
     constexpr bool COLSPLIT = (L >= 64);          // both groups work on S / dP (alternate 32-column chunks)
     constexpr int CH = (L >= 32) ? 32 : 16;
     constexpr int NCHUNK = L / CH;                // chunks of the row's own window columns
@@ -255,19 +257,21 @@ winattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid
      for (int sub = 0; sub < SH; ++sub, sub_phase ^= 1) {
       const int head = hg * SH + sub;
       named_bar_sync(1, 256);                     // everybody is done with the previous LUT / bias table
+      // key | region id | spatial position | window tag (g + 1, 0 for a padding row)
+      const uint32_t my_tag = rg.inrange ? uint32_t(rg.g + 1) : 0u;
       if (grp == 0) s_lut[row] = uint32_t(rg.rr * (2 * gm.ws - 1) + rg.cc) | (uint32_t(rg.id) << 8) |
-                                 (uint32_t(rg.rr * gm.ws + rg.cc) << 16);      // key | region id | spatial position
+                                 (uint32_t(rg.rr * gm.ws + rg.cc) << 16) | (my_tag << 24);
       if (SH > 1 || item == int(blockIdx.x))      // the head (and so the table) changes only when SH > 1
         for (int i = cm_tid; i < nbias; i += 256) s_tab[i] = __ldg(bias_table + i * gm.nH + head) * 1.4426950408889634f;
       named_bar_sync(1, 256);
       key_i = (rg.rr + gm.ws - 1) * (2 * gm.ws - 1) + rg.cc + gm.ws - 1;
-      col0 = rg.g * L;
+      col0 = GEN ? 0 : rg.g * L;
       const bool use_mask = rg.wraps;
       // dense mask row of this query token (stand-alone WindowAttention with an explicit mask tensor)
       const float* mask_row = gm.mask ? gm.mask + ((size_t)(rg.gw % gm.mask_nw) * gm.N + (rg.rr * gm.ws + rg.cc)) * gm.N : nullptr;
 
       if (softmax_role) {
-        const float lse_i = lse2[((size_t)tile * gm.nH + head) * 128 + rg.canon];
+        const float lse_i = (GEN && !rg.inrange) ? 0.f : lse2[((size_t)tile * gm.nH + head) * 128 + rg.canon];
         mbar_wait(sdp_full, sub_phase);
         mbar_wait(pds_free, sub_phase ^ 1);
         tc_fence_after();
@@ -291,8 +295,10 @@ winattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid
                 const uint32_t lj = s_lut[col0 + cb * CH + jj];
                 float x = fmaf(__uint_as_float(v[jj]), gm.scale_log2e, s_tab[key_i - int(lj & 0xff)]);
                 if (use_mask && ((lj >> 8) & 0xffu) != uint32_t(rg.id)) x += kMaskLog2e;
-          if (mask_row != nullptr) x = fmaf(__ldg(mask_row + (lj >> 16)), 1.4426950408889634f, x);
+                if (mask_row != nullptr) x = fmaf(__ldg(mask_row + ((lj >> 16) & 0xffu)), 1.4426950408889634f, x);
                 pv[e] = fast_exp2(x - lse_i);
+                // general geometry: columns of another window (or padding) of this tile do not attend
+                if (GEN && ((lj >> 24) != my_tag || my_tag == 0u)) pv[e] = 0.f;
                 delta = fmaf(pv[e], __uint_as_float(w[jj]), delta);
               }
               pk[h] = pack_bf16(pv[0], pv[1]);
@@ -328,7 +334,12 @@ winattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid
               const float d1 = rg.valid ? pf.y * (__uint_as_float(w[j8 * 8 + 2 * h + 1]) - delta) : 0.f;
               dk[h] = pack_bf16(d0, d1);
               const int j = j8 * 8 + 2 * h;          // column inside the chunk, compile-time after unrolling
-              if (COLSPLIT) {
+              if (GEN) {
+                // irregular order: no static column -> position map, go through the shared bins
+                const uint32_t l0 = s_lut[col0 + cb * CH + j], l1 = s_lut[col0 + cb * CH + j + 1];
+                if (d0 != 0.f) atomicAdd(&s_bacc[sub * (TAB_MAX + 1) + key_i - int(l0 & 0xff)], d0);
+                if (d1 != 0.f) atomicAdd(&s_bacc[sub * (TAB_MAX + 1) + key_i - int(l1 & 0xff)], d1);
+              } else if (COLSPLIT) {
                 // row-major order: chunk = (frame, half of the 64 positions) -> position j of that half
                 // quadrant order : chunk = quadrant, 16 positions x 2 frames  -> (which quadrant)*16 + j%16
                 if (quad && L == 128) { bacc[sub][ci * 16 + (j & 15)] += d0; bacc[sub][ci * 16 + ((j + 1) & 15)] += d1; }
@@ -396,12 +407,10 @@ winattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid
      }   // sub
     }
     // ---- bias-table gradient: bin the per-row running sums by relative position, once per CTA and head
+    named_bar_sync(1, 256);
+    if (!GEN && softmax_role) {
 #pragma unroll
-    for (int sub = 0; sub < SH; ++sub) {
-      named_bar_sync(1, 256);
-      for (int i = cm_tid; i < nbias; i += 256) s_bacc[i] = 0.f;
-      named_bar_sync(1, 256);
-      if (softmax_role) {
+      for (int sub = 0; sub < SH; ++sub)
 #pragma unroll
         for (int k = 0; k < NACC; ++k) {
           // a column of this row's window that accumulator k stands for
@@ -409,11 +418,13 @@ winattn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid
           if (COLSPLIT) ck = (quad && L == 128) ? ((2 * (k >> 4) + grp) * 32 + (k & 15)) : (grp * 32 + k);
           else          ck = k;
           const uint32_t lj = s_lut[col0 + ck];
-          atomicAdd(&s_bacc[key_i - int(lj & 0xff)], bacc[sub][k]);
+          atomicAdd(&s_bacc[sub * (TAB_MAX + 1) + key_i - int(lj & 0xff)], bacc[sub][k]);
         }
-      }
-      named_bar_sync(1, 256);
-      for (int i = cm_tid; i < nbias; i += 256) atomicAdd(d_table + i * gm.nH + hg * SH + sub, s_bacc[i]);
+    }
+    named_bar_sync(1, 256);
+    for (int i = cm_tid; i < SH * nbias; i += 256) {
+      const int sub = i / nbias, bin = i - sub * nbias;
+      atomicAdd(d_table + bin * gm.nH + hg * SH + sub, s_bacc[sub * (TAB_MAX + 1) + bin]);
     }
   }
 
@@ -445,36 +456,32 @@ int winattn_bwd(const void* qkv, const float* bias_table, const float* lse2, con
   if (qk_scale > 0.f) { gm.scale = qk_scale; gm.scale_log2e = qk_scale * 1.4426950408889634f; }
   STSWIN_CHECK_ARG(mask == nullptr || mask_windows > 0, "winattn: mask given with mask_windows <= 0");
   gm.mask = mask; gm.mask_nw = mask_windows;
-  CUtensorMap tq_full, tq_quad, td_full, td_quad;
-  if ((rc = make_window_tmaps(&tq_full, &tq_quad, qkv, gm, 3 * C)) != kOk) return rc;
-  if ((rc = make_window_tmaps(&td_full, &td_quad, d_out, gm, C)) != kOk) return rc;
+  if (gm.shift > 0 && gm.ra != gm.rb) gm.general = 1;     // unequal rectangles: no static column -> position fold
+  WinMaps tq, td;
+  if ((rc = make_window_tmaps(&tq, qkv, gm, 3 * C)) != kOk) return rc;
+  if ((rc = make_window_tmaps(&td, d_out, gm, C)) != kOk) return rc;
   STSWIN_CHECK_ARG((reinterpret_cast<uintptr_t>(d_qkv) & 15) == 0, "winattn_bwd: d_qkv must be 16-byte aligned");
   const int items = gm.num_tiles * gm.ngrp;
   int grid = items < num_sms() ? items : num_sms();
   grid -= grid % gm.ngrp;                 // one head group per CTA (items is a multiple of ngrp, so grid >= ngrp)
   if (grid < gm.ngrp) return set_error(kErrUnsupported, "winattn_bwd: %d head groups exceed the SM count", gm.ngrp);
-#define STSWIN_LAUNCH_BWD(LL)                                                                                      \
-  case LL: {                                                                                                       \
-    if (gm.SH == 1) {                                                                                              \
-      if ((rc = set_smem_bwd(winattn_bwd_kernel<LL, 1>, SMEM_BYTES)) != kOk) return rc;                            \
-      winattn_bwd_kernel<LL, 1><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(                                        \
-          tq_full, tq_quad, td_full, td_quad, static_cast<__nv_bfloat16*>(d_qkv), bias_table, lse2, d_table,       \
-          d_qkv_colsum, gm);                                                                                       \
-    } else {                                                                                                       \
-      if ((rc = set_smem_bwd(winattn_bwd_kernel<LL, 2>, SMEM_BYTES)) != kOk) return rc;                            \
-      winattn_bwd_kernel<LL, 2><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(                                        \
-          tq_full, tq_quad, td_full, td_quad, static_cast<__nv_bfloat16*>(d_qkv), bias_table, lse2, d_table,       \
-          d_qkv_colsum, gm);                                                                                       \
-    }                                                                                                              \
-    break;                                                                                                         \
+#define STSWIN_LAUNCH_BWD(LL, SS, GG)                                                                          \
+  {                                                                                                            \
+    if ((rc = set_smem_bwd(winattn_bwd_kernel<LL, SS, GG>, SMEM_BYTES)) != kOk) return rc;                     \
+    winattn_bwd_kernel<LL, SS, GG><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(                                 \
+        tq, td, static_cast<__nv_bfloat16*>(d_qkv), bias_table, lse2, d_table, d_qkv_colsum, gm);              \
   }
-  switch (gm.L) {
-    STSWIN_LAUNCH_BWD(16)
-    STSWIN_LAUNCH_BWD(32)
-    STSWIN_LAUNCH_BWD(64)
-    STSWIN_LAUNCH_BWD(128)
-    default: return set_error(kErrUnsupported, "winattn_bwd: L=%d", gm.L);
+#define STSWIN_LAUNCH_BWD_L(LL, GG)                         \
+  {                                                         \
+    if (gm.SH == 1) STSWIN_LAUNCH_BWD(LL, 1, GG)            \
+    else STSWIN_LAUNCH_BWD(LL, 2, GG)                       \
   }
+  if (gm.general) STSWIN_LAUNCH_BWD_L(128, true)
+  else if (gm.L == 16) STSWIN_LAUNCH_BWD_L(16, false)
+  else if (gm.L == 32) STSWIN_LAUNCH_BWD_L(32, false)
+  else if (gm.L == 64) STSWIN_LAUNCH_BWD_L(64, false)
+  else STSWIN_LAUNCH_BWD_L(128, false)
+#undef STSWIN_LAUNCH_BWD_L
 #undef STSWIN_LAUNCH_BWD
   STSWIN_CUDA(cudaGetLastError());
   return kOk;

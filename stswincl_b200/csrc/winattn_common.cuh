@@ -1,6 +1,7 @@
 // Geometry shared by the window-attention forward and backward kernels.
 //
-// A "tile" is 128 token rows = G consecutive windows of L = T*ws*ws tokens each (G = 128/L).
+// A "tile" is 128 token rows = G consecutive windows of L = T*ws*ws tokens each (G = 128/L, rounded
+// down; when L does not divide 128 the last rows of the tile are padding and stay zero).
 // Work item = (tile, head).  Each operand chunk is [128 rows x 64 channels] bf16 in the
 // 128B-swizzled K-major layout, filled by TMA boxes taken straight from the un-rolled,
 // un-partitioned [B, T, H, W, channels] tensor: the cyclic shift and the window partition
@@ -24,6 +25,9 @@ struct WinGeom {
                        // the whole chunk and only the head's own 32 columns are kept.
   float scale_log2e;                                              // hd^-0.5 * log2(e)
   float scale;                                                    // hd^-0.5
+  int ra, rb;         // a shifted window that wraps is moved as 2x2 rectangles of (ws-shift | shift) rows x columns
+  int roff[5];        // first tile row of rectangle k inside its window's L rows (roff[4] = L)
+  int general;        // 1: L is not 16/32/64/128 -> kernels run their "whole row + window tag" path
   const float* mask;  // optional dense additive mask [mask_nw, N, N] (WindowAttention.forward's `mask`
   int mask_nw;        //   argument, swin_512.py:127-131), applied ON TOP of the closed-form shift mask; or null
   int uniform_quad;   // 1: every window of a shifted block is moved as four quadrant boxes (one token
@@ -38,7 +42,13 @@ struct RowGeom {
   int gw;      // global window index b*nW + win (clamped for padding windows)
   long tok;    // index of the source token in the natural [B*T, H, W] order (roll + partition undone)
   bool wraps;  // window crosses the image border (the only windows with a non-zero mask)
-  bool valid;  // false for rows of a padding window in the last tile
+  bool valid;  // false for rows of a padding window in the last tile, and for padding rows
+  bool inrange; // false for the padding rows r >= G*L of a tile (general mode only)
+};
+
+struct WinMaps {     // tensor maps over one [B*T, H, W, channels] tensor
+  CUtensorMap full;      // box = whole window (ws x ws x T)
+  CUtensorMap rect[4];   // boxes of the 2x2 rectangle decomposition of a wrapping window
 };
 
 __device__ __forceinline__ bool quad_order(const WinGeom& gm, bool wraps) {
@@ -57,14 +67,22 @@ __device__ __forceinline__ int region_band(int p, int extent, int ws, int shift)
   return (p >= extent - ws ? 1 : 0) + (p >= extent - shift ? 1 : 0);
 }
 
+// rectangle k (0..3) of the 2x2 decomposition: offsets / extents along h (k>>1) and w (k&1)
+__device__ __forceinline__ void rect_dims(const WinGeom& gm, int k, int& h_off, int& w_off, int& h_ext, int& w_ext) {
+  h_off = (k >> 1) ? gm.ra : 0;  h_ext = (k >> 1) ? gm.rb : gm.ra;
+  w_off = (k & 1) ? gm.ra : 0;   w_ext = (k & 1) ? gm.rb : gm.ra;
+}
+
 // geometry of tile row r of tile `tile`
 __device__ __forceinline__ RowGeom row_geom(const WinGeom& gm, int tile, int r) {
   RowGeom o;
   o.g = r / gm.L;
-  const int rem = r - o.g * gm.L;
+  o.inrange = o.g < gm.G;
+  if (!o.inrange) o.g = gm.G - 1;
+  const int rem = o.inrange ? r - o.g * gm.L : 0;
   int gw = tile * gm.G + o.g;
-  o.valid = gw < gm.total_windows;
-  if (!o.valid) gw = gm.total_windows - 1;
+  o.valid = o.inrange && gw < gm.total_windows;
+  if (gw > gm.total_windows - 1) gw = gm.total_windows - 1;
   int b, wh, ww, t;
   o.gw = gw;
   window_coords(gm, gw, b, wh, ww, o.wraps);
@@ -74,13 +92,15 @@ __device__ __forceinline__ RowGeom row_geom(const WinGeom& gm, int tile, int r) 
     o.rr = pos / gm.ws;
     o.cc = pos - o.rr * gm.ws;
   } else {
-    const int hw = gm.ws >> 1, qn = gm.L >> 2, qs = gm.N >> 2;
-    const int q = rem / qn;
-    const int r2 = rem - q * qn;
-    t = r2 / qs;
-    const int p = r2 - t * qs;
-    o.rr = (q >> 1) * hw + p / hw;
-    o.cc = (q & 1) * hw + p % hw;
+    int k = 0;
+    while (k < 3 && rem >= gm.roff[k + 1]) ++k;
+    int h_off, w_off, h_ext, w_ext;
+    rect_dims(gm, k, h_off, w_off, h_ext, w_ext);
+    const int r2 = rem - gm.roff[k], area = h_ext * w_ext;
+    t = r2 / area;
+    const int p = r2 - t * area;
+    o.rr = h_off + p / w_ext;
+    o.cc = w_off + p % w_ext;
   }
   o.canon = o.g * gm.L + t * gm.N + o.rr * gm.ws + o.cc;
   {
@@ -98,10 +118,8 @@ __device__ __forceinline__ RowGeom row_geom(const WinGeom& gm, int tile, int r) 
 //   ch0 : first channel of the chunk in the global tensor
 // Called by all 32 lanes of one warp; box k of the chunk is issued by lane k % 32.
 template <bool LOAD>
-__device__ __forceinline__ void tile_boxes(const WinGeom& gm, int tile, int ch0, uint8_t* buf,
-                                           const CUtensorMap* tm_full, const CUtensorMap* tm_quad, uint64_t* bar,
-                                           int lane) {
-  const int hw = gm.ws >> 1;
+__device__ __forceinline__ void tile_boxes(const WinGeom& gm, int tile, int ch0, uint8_t* buf, const WinMaps* tm,
+                                           uint64_t* bar, int lane) {
   for (int k = lane; k < gm.G * 4; k += 32) {
     const int g = k >> 2, q = k & 3;
     int gw = tile * gm.G + g;
@@ -116,17 +134,22 @@ __device__ __forceinline__ void tile_boxes(const WinGeom& gm, int tile, int ch0,
     if (!quad_order(gm, wraps)) {
       if (q != 0) continue;
       const int w0 = ww * gm.ws + gm.shift, h0 = wh * gm.ws + gm.shift;
-      if (LOAD) tma_load_4d(dst, tm_full, bar, ch0, w0, h0, b * gm.T);
-      else      tma_store_4d(tm_full, dst, ch0, w0, h0, b * gm.T);
+      if (LOAD) tma_load_4d(dst, &tm->full, bar, ch0, w0, h0, b * gm.T);
+      else      tma_store_4d(&tm->full, dst, ch0, w0, h0, b * gm.T);
     } else {
-      const int h0 = (wh * gm.ws + gm.shift + (q >> 1) * hw) % gm.H;
-      const int w0 = (ww * gm.ws + gm.shift + (q & 1) * hw) % gm.W;
-      uint8_t* d = dst + q * (gm.L >> 2) * 128;
-      if (LOAD) tma_load_4d(d, tm_quad, bar, ch0, w0, h0, b * gm.T);
-      else      tma_store_4d(tm_quad, d, ch0, w0, h0, b * gm.T);
+      int h_off, w_off, h_ext, w_ext;
+      rect_dims(gm, q, h_off, w_off, h_ext, w_ext);
+      const int h0 = (wh * gm.ws + gm.shift + h_off) % gm.H;
+      const int w0 = (ww * gm.ws + gm.shift + w_off) % gm.W;
+      uint8_t* d = dst + gm.roff[q] * 128;
+      if (LOAD) tma_load_4d(d, &tm->rect[q], bar, ch0, w0, h0, b * gm.T);
+      else      tma_store_4d(&tm->rect[q], d, ch0, w0, h0, b * gm.T);
     }
   }
 }
+
+// bytes one chunk load brings in (only the G*L real rows of the 128-row buffer)
+__device__ __forceinline__ uint32_t chunk_tx_bytes(const WinGeom& gm) { return uint32_t(gm.G * gm.L) * 128u; }
 
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;

@@ -30,10 +30,12 @@ constexpr int NUM_THREADS = 192;
 constexpr int SMEM_BYTES = 1024 + NSLOT * SLOT_BYTES + P_BYTES + STG_BYTES + 128 * 4 + TAB_MAX * 4 + 256;
 constexpr float kMaskLog2e = -100.0f * 1.4426950408889634f;
 
-template <int L>
+// L   : window columns a thread walks (16/32/64/128).  GEN (only with L = 128): the tile holds G windows of
+//       gm.L tokens with gm.L not a power of two (e.g. 7x7x2 = 98); every thread then walks the whole
+//       128-column row and keeps only the columns tagged with its own window.
+template <int L, bool GEN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-winattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid_constant__ CUtensorMap tm_qkv_quad,
-                   const __grid_constant__ CUtensorMap tm_out_full, const __grid_constant__ CUtensorMap tm_out_quad,
+winattn_fwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant__ WinMaps tm_out,
                    const float* __restrict__ bias_table, float* __restrict__ lse2, const WinGeom gm) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -61,10 +63,8 @@ winattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid
   const int SH = gm.SH;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tm_qkv_full);
-    tma_prefetch_desc(&tm_qkv_quad);
-    tma_prefetch_desc(&tm_out_full);
-    tma_prefetch_desc(&tm_out_quad);
+    tma_prefetch_desc(&tm_qkv.full);
+    tma_prefetch_desc(&tm_out.full);
     for (int i = 0; i < NSLOT; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -78,8 +78,10 @@ winattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
-  // P buffer: entries outside a row's own window stay zero for the whole kernel
-  for (int i = threadIdx.x; i < P_BYTES / 16; i += NUM_THREADS) reinterpret_cast<uint4*>(s_p)[i] = make_uint4(0, 0, 0, 0);
+  // P buffer: entries outside a row's own window stay zero for the whole kernel.  Ring: the padding
+  // rows of a tile (general mode) are never written by TMA and must read as zero.
+  for (int i = threadIdx.x; i < (NSLOT * SLOT_BYTES + P_BYTES) / 16; i += NUM_THREADS)
+    reinterpret_cast<uint4*>(s_ring)[i] = make_uint4(0, 0, 0, 0);
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -100,10 +102,10 @@ winattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid
         if (step < 2 * nc) { which = step & 1; c = step >> 1; }
         else               { which = 2; c = step - 2 * nc; }
         mbar_wait(&empty_bar[slot], phase ^ 1);
-        if (lane == 0) mbar_arrive_expect_tx(&full_bar[slot], SLOT_BYTES);
+        if (lane == 0) mbar_arrive_expect_tx(&full_bar[slot], chunk_tx_bytes(gm));
         __syncwarp();
-        tile_boxes<true>(gm, tile, which * gm.C + hg * gm.gch + c * 64, s_ring + slot * SLOT_BYTES, &tm_qkv_full,
-                         &tm_qkv_quad, &full_bar[slot], lane);
+        tile_boxes<true>(gm, tile, which * gm.C + hg * gm.gch + c * 64, s_ring + slot * SLOT_BYTES, &tm_qkv,
+                         &full_bar[slot], lane);
         if (++slot == NSLOT) { slot = 0; phase ^= 1; }
       }
     }
@@ -179,12 +181,14 @@ winattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid
      for (int sub = 0; sub < SH; ++sub, sub_phase ^= 1) {
       const int head = hg * SH + sub;
       named_bar_sync(1, 128);                  // everybody is done with the previous LUT / bias table
+      // key | region id | spatial position | window tag (g + 1, 0 for a padding row)
+      const uint32_t my_tag = rg.inrange ? uint32_t(rg.g + 1) : 0u;
       s_lut[row] = uint32_t(rg.rr * (2 * gm.ws - 1) + rg.cc) | (uint32_t(rg.id) << 8) |
-                                 (uint32_t(rg.rr * gm.ws + rg.cc) << 16);      // key | region id | spatial position
+                   (uint32_t(rg.rr * gm.ws + rg.cc) << 16) | (my_tag << 24);
       for (int i = sm_tid; i < nbias; i += 128) s_tab[i] = __ldg(bias_table + i * gm.nH + head) * 1.4426950408889634f;
       named_bar_sync(1, 128);
       const int key_i = (rg.rr + gm.ws - 1) * (2 * gm.ws - 1) + rg.cc + gm.ws - 1;
-      const int col0 = rg.g * L;
+      const int col0 = GEN ? 0 : rg.g * L;
       const bool use_mask = rg.wraps;
       // dense mask row of this query token (stand-alone WindowAttention with an explicit mask tensor)
       const float* mask_row = gm.mask ? gm.mask + ((size_t)(rg.gw % gm.mask_nw) * gm.N + (rg.rr * gm.ws + rg.cc)) * gm.N : nullptr;
@@ -203,7 +207,8 @@ winattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid
           const uint32_t lj = s_lut[col0 + cb * CH + jj];
           float x = fmaf(__uint_as_float(v[jj]), gm.scale_log2e, s_tab[key_i - int(lj & 0xff)]);
           if (use_mask && ((lj >> 8) & 0xffu) != uint32_t(rg.id)) x += kMaskLog2e;
-          if (mask_row != nullptr) x = fmaf(__ldg(mask_row + (lj >> 16)), 1.4426950408889634f, x);
+          if (mask_row != nullptr) x = fmaf(__ldg(mask_row + ((lj >> 16) & 0xffu)), 1.4426950408889634f, x);
+          if (GEN && (lj >> 24) != my_tag) x = -1.0e30f;        // another window's column, or padding
           s[cb * CH + jj] = x;
           mx = fmaxf(mx, x);
         }
@@ -219,8 +224,9 @@ winattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid
         uint32_t w[4];
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
-          const float p0 = fast_exp2(s[j8 * 8 + 2 * h] - mx);
-          const float p1 = fast_exp2(s[j8 * 8 + 2 * h + 1] - mx);
+          float p0 = fast_exp2(s[j8 * 8 + 2 * h] - mx);
+          float p1 = fast_exp2(s[j8 * 8 + 2 * h + 1] - mx);
+          if (GEN && !rg.inrange) { p0 = 0.f; p1 = 0.f; }          // padding row: keep P finite and empty
           // accumulate what the tensor core will actually see (bf16-rounded probabilities)
           const uint32_t pk = pack_bf16(p0, p1);
           const float2 pr = unpack_bf16(pk);
@@ -233,8 +239,8 @@ winattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid
       }
       fence_proxy_async_smem();
       mbar_arrive(p_full);
-      inv_sub[sub] = 1.0f / sum;
-      lse2[((size_t)tile * gm.nH + head) * 128 + rg.canon] = mx + log2f(sum);
+      inv_sub[sub] = (GEN && !rg.inrange) ? 0.f : 1.0f / sum;
+      if (!GEN || rg.inrange) lse2[((size_t)tile * gm.nH + head) * 128 + rg.canon] = mx + log2f(sum);
      }
 
       // ---- epilogue: O * (1/sum) -> bf16 -> staging -> TMA store at the un-rolled coordinates
@@ -272,7 +278,7 @@ winattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv_full, const __grid
         fence_proxy_async_smem();
         named_bar_sync(1, 128);
         if (sm_tid < 32) {                             // warp 2 issues the scatter, one box per lane
-          tile_boxes<false>(gm, tile, hg * gm.gch + c * 64, stg, &tm_out_full, &tm_out_quad, nullptr, lane);
+          tile_boxes<false>(gm, tile, hg * gm.gch + c * 64, stg, &tm_out, nullptr, lane);
           tma_commit_group();
         }
         stg_sel ^= 1;
@@ -301,11 +307,12 @@ int fill_geom(WinGeom* gm, int B, int T, int H, int W, int C, int nH, int ws, in
   gm->L = T * ws * ws;
   if (!((gm->hd % 64 == 0 && gm->hd <= 256) || (gm->hd == 32 && nH % 2 == 0)))
     return set_error(kErrUnsupported, "winattn: head_dim %d unsupported (need 32 or a multiple of 64, <= 256)", gm->hd);
-  if (gm->L > 128 || 128 % gm->L != 0 || gm->L < 16)
-    return set_error(kErrUnsupported, "winattn: T*ws*ws = %d tokens per window unsupported (need 16, 32, 64 or 128)", gm->L);
-  if (!(shift == 0 || (ws % 2 == 0 && shift == ws / 2)))
-    return set_error(kErrUnsupported, "winattn: shift %d unsupported (need 0 or window_size/2 = %d)", shift, ws / 2);
+  if (gm->L > 128 || gm->L < 1)
+    return set_error(kErrUnsupported, "winattn: T*ws*ws = %d tokens per window unsupported (need <= 128)", gm->L);
+  if (shift < 0 || shift >= ws)
+    return set_error(kErrInvalidArg, "winattn: shift %d must be in [0, window_size = %d)", shift, ws);
   if (ws > 8) return set_error(kErrUnsupported, "winattn: window size %d > 8 unsupported", ws);
+  gm->general = !(gm->L == 16 || gm->L == 32 || gm->L == 64 || gm->L == 128);
   gm->G = 128 / gm->L;
   gm->nWh = H / ws; gm->nWw = W / ws; gm->nW = gm->nWh * gm->nWw;
   gm->total_windows = B * gm->nW;
@@ -316,24 +323,35 @@ int fill_geom(WinGeom* gm, int B, int T, int H, int W, int C, int nH, int ws, in
   gm->nc = gm->gch / 64;
   gm->scale_log2e = 1.4426950408889634f / sqrtf((float)gm->hd);
   gm->scale = 1.0f / sqrtf((float)gm->hd);
+  gm->ra = ws - shift; gm->rb = shift;
+  {
+    int off = 0;
+    for (int k = 0; k < 4; ++k) {
+      gm->roff[k] = off;
+      off += ((k >> 1) ? gm->rb : gm->ra) * ((k & 1) ? gm->rb : gm->ra) * T;
+    }
+    gm->roff[4] = off;       // == L
+  }
   gm->uniform_quad = 0;
   gm->mask = nullptr; gm->mask_nw = 0;
   return kOk;
 }
 
-// tensor maps over a [B*T, H, W, channels] bf16 tensor: full-window box and quadrant box
-int make_window_tmaps(CUtensorMap* full, CUtensorMap* quad, const void* base, const WinGeom& gm, int channels) {
+// tensor maps over a [B*T, H, W, channels] bf16 tensor: whole-window box and the four rectangle boxes
+int make_window_tmaps(WinMaps* maps, const void* base, const WinGeom& gm, int channels) {
   uint64_t dims[4] = {(uint64_t)channels, (uint64_t)gm.W, (uint64_t)gm.H, (uint64_t)gm.B * gm.T};
   uint64_t str[3] = {(uint64_t)channels * 2, (uint64_t)gm.W * channels * 2, (uint64_t)gm.H * gm.W * channels * 2};
   uint32_t box_full[4] = {64, (uint32_t)gm.ws, (uint32_t)gm.ws, (uint32_t)gm.T};
-  int rc = make_tmap(full, TmapDtype::BF16, 4, base, dims, str, box_full, true);
+  int rc = make_tmap(&maps->full, TmapDtype::BF16, 4, base, dims, str, box_full, true);
   if (rc != kOk) return rc;
-  *quad = *full;
-  if (gm.shift > 0) {
-    uint32_t box_quad[4] = {64, (uint32_t)gm.ws / 2, (uint32_t)gm.ws / 2, (uint32_t)gm.T};
-    rc = make_tmap(quad, TmapDtype::BF16, 4, base, dims, str, box_quad, true);
+  for (int k = 0; k < 4; ++k) {
+    maps->rect[k] = maps->full;
+    if (gm.shift > 0) {
+      uint32_t box[4] = {64, (uint32_t)((k & 1) ? gm.rb : gm.ra), (uint32_t)((k >> 1) ? gm.rb : gm.ra), (uint32_t)gm.T};
+      if ((rc = make_tmap(&maps->rect[k], TmapDtype::BF16, 4, base, dims, str, box, true)) != kOk) return rc;
+    }
   }
-  return rc;
+  return kOk;
 }
 
 template <typename K>
@@ -358,25 +376,21 @@ int winattn_fwd(const void* qkv, const float* bias_table, void* out, float* lse2
   if (qk_scale > 0.f) { gm.scale = qk_scale; gm.scale_log2e = qk_scale * 1.4426950408889634f; }
   STSWIN_CHECK_ARG(mask == nullptr || mask_windows > 0, "winattn: mask given with mask_windows <= 0");
   gm.mask = mask; gm.mask_nw = mask_windows;
-  CUtensorMap tq_full, tq_quad, to_full, to_quad;
-  if ((rc = make_window_tmaps(&tq_full, &tq_quad, qkv, gm, 3 * C)) != kOk) return rc;
-  if ((rc = make_window_tmaps(&to_full, &to_quad, out, gm, C)) != kOk) return rc;
+  WinMaps tq, to;
+  if ((rc = make_window_tmaps(&tq, qkv, gm, 3 * C)) != kOk) return rc;
+  if ((rc = make_window_tmaps(&to, out, gm, C)) != kOk) return rc;
   const int items = gm.num_tiles * gm.ngrp;
   const int grid = items < num_sms() ? items : num_sms();
-#define STSWIN_LAUNCH_FWD(LL)                                                                                       \
-  case LL: {                                                                                                        \
-    if ((rc = set_smem(winattn_fwd_kernel<LL>, SMEM_BYTES)) != kOk) return rc;                                      \
-    winattn_fwd_kernel<LL><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tq_full, tq_quad, to_full, to_quad, bias_table, \
-                                                                      lse2, gm);                                    \
-    break;                                                                                                          \
+#define STSWIN_LAUNCH_FWD(LL, GG)                                                                              \
+  {                                                                                                            \
+    if ((rc = set_smem(winattn_fwd_kernel<LL, GG>, SMEM_BYTES)) != kOk) return rc;                             \
+    winattn_fwd_kernel<LL, GG><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tq, to, bias_table, lse2, gm);       \
   }
-  switch (gm.L) {
-    STSWIN_LAUNCH_FWD(16)
-    STSWIN_LAUNCH_FWD(32)
-    STSWIN_LAUNCH_FWD(64)
-    STSWIN_LAUNCH_FWD(128)
-    default: return set_error(kErrUnsupported, "winattn_fwd: L=%d", gm.L);
-  }
+  if (gm.general) STSWIN_LAUNCH_FWD(128, true)
+  else if (gm.L == 16) STSWIN_LAUNCH_FWD(16, false)
+  else if (gm.L == 32) STSWIN_LAUNCH_FWD(32, false)
+  else if (gm.L == 64) STSWIN_LAUNCH_FWD(64, false)
+  else STSWIN_LAUNCH_FWD(128, false)
 #undef STSWIN_LAUNCH_FWD
   STSWIN_CUDA(cudaGetLastError());
   return kOk;

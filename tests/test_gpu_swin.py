@@ -188,6 +188,29 @@ def test_cadis_shaped_block_vs_oracle():
     assert rel_err(y.cpu(), ref) < TOL
 
 
+def test_window7_block_fwd_bwd_vs_oracle():
+    """Config 5 corner: 7x7 windows, shift 3, on a 56x84-token crop (98-token windows, unequal rectangles)."""
+    from oracle import swin_oracle as so
+    from stswincl_b200 import swin
+    dim, res, heads, ws, shift = 256, (28, 42), 4, 7, 3
+    params = so.make_block_params(dim, res, heads, ws, shift, seed=81)
+    m = _load(swin.SwinTransformerBlock(dim, res, heads, window_size=ws, shift_size=shift), params)
+    x = so.make_features(82, 1, 2, res[0] * res[1], dim)
+    w = so.make_features(83, 1, 2, res[0] * res[1], dim) - 0.4
+    leaf = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and k != "attn_mask" else v) for k, v in params.items()}
+    xr = x.to(torch.bfloat16).float().requires_grad_(True)
+    ref = so.swin_block(xr, leaf, res, heads, ws, shift)
+    (ref * w).sum().backward()
+    xg = x.cuda().requires_grad_(True)
+    y = m(xg)
+    (y * w.cuda()).sum().backward()
+    torch.cuda.synchronize()
+    assert rel_err(y.cpu(), ref) < TOL
+    assert rel_err(xg.grad.cpu(), xr.grad) < TOL
+    assert rel_err(m.attn.relative_position_bias_table.grad.cpu(), leaf["attn.relative_position_bias_table"].grad) < TOL
+    assert rel_err(m.attn.qkv.bias.grad.cpu(), leaf["attn.qkv.bias"].grad) < TOL
+
+
 def test_cpu_tensor_raises():
     from stswincl_b200 import swin
     from stswincl_b200._lib import StswinError

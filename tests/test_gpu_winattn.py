@@ -35,6 +35,17 @@ CASES = [
     (1, 2, 8, 12, 256, 8, 4, 2),
     (3, 1, 8, 12, 64, 2, 4, 2),
     (1, 2, 64, 120, 512, 16, 8, 4),
+    # irregular geometry: 7x7 windows (98 or 49 tokens, padding rows in the tile), shifts other than ws/2,
+    # small windows with many per tile
+    (2, 2, 14, 21, 128, 2, 7, 3),
+    (2, 2, 14, 21, 128, 2, 7, 0),
+    (3, 1, 14, 21, 128, 2, 7, 3),     # T=1: two 49-token windows per tile, odd window count
+    (1, 2, 56, 84, 512, 4, 7, 3),     # config 5: ws 7 on the 56x84 crop
+    (1, 2, 56, 84, 512, 16, 7, 3),    # ... with 16 heads (head_dim 32)
+    (2, 2, 16, 24, 128, 2, 8, 3),     # unequal rectangles (5 | 3)
+    (2, 2, 8, 12, 128, 2, 4, 1),
+    (2, 2, 9, 12, 64, 1, 3, 1),       # 18-token windows, 7 per tile
+    (1, 2, 10, 15, 128, 2, 5, 2),     # 50-token windows
 ]
 
 
@@ -84,8 +95,8 @@ def test_winattn_bwd_matches_oracle(case):
 
 @pytest.mark.parametrize("kw,msg", [
     (dict(C=256, nH=16, ws=8, shift=4), "head_dim 16"),
-    (dict(C=512, nH=4, ws=7, shift=3, H=56, W=84), "tokens per window"),   # ws=7 -> 98 tokens
-    (dict(C=512, nH=4, ws=8, shift=3), "shift 3"),
+    (dict(C=512, nH=4, ws=16, shift=0), "tokens per window"),    # 16x16x2 = 512 tokens
+    (dict(C=512, nH=4, ws=8, shift=8), "shift 8"),
     (dict(C=512, nH=4, ws=8, shift=4, H=60), "multiples of the window size"),
 ])
 def test_unsupported_geometry_fails_loudly(kw, msg):
