@@ -19,6 +19,12 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// First 1024-byte aligned address inside a dynamic shared-memory array.  Written as base + offset
+// (not an integer round trip) so the compiler keeps the shared address space and emits LDS / STS.
+__device__ __forceinline__ uint8_t* align_smem_1024(uint8_t* raw) {
+  return raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u);
+}
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred = 0;
   asm volatile(

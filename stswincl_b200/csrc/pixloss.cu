@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1)
 pixloss_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ SetMaps tm_k, const SetPtrs lk,
                    const PixFwdArgs p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = align_smem_1024(smem_raw);
   uint8_t* s_a = smem;                                   // nkb k-blocks of the query tile (<= 4 x 16 KB)
   uint8_t* s_b = s_a + 4 * KB_BYTES;                     // ring
   uint8_t* s_lk = s_b + PF_STAGES * KB_BYTES;            // labels of the key set, padded to a tile multiple
@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(PB_THREADS, 1)
 pixloss_bwd_kernel(const __grid_constant__ SetMaps tm_k, const __grid_constant__ CUtensorMap tm_dq, const SetPtrs lk,
                    const PixBwdArgs p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = align_smem_1024(smem_raw);
   const int b_stage_bytes = p.C * 128;
   uint8_t* s_gen = smem;
   uint8_t* s_b = s_gen + PB_GEN * 16384;

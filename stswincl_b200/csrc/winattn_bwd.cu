@@ -62,7 +62,7 @@ winattn_bwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant
                    __nv_bfloat16* __restrict__ d_qkv, const float* __restrict__ bias_table, const float* __restrict__ lse2, float* __restrict__ d_table,
                    float* __restrict__ d_colsum, const WinGeom gm) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = align_smem_1024(smem_raw);
   uint8_t* s_ringh = smem;
   uint8_t* s_ringl = s_ringh + NRH * SLOT_BYTES;
   uint8_t* s_p = s_ringl + NRL * SLOT_BYTES;
@@ -71,7 +71,8 @@ winattn_bwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant
   float* s_tab = reinterpret_cast<float*>(s_lut + 128);
   float* s_bacc = s_tab + TAB_MAX + 1;            // [2][TAB_MAX + 1]: one bin array per head of the group
   float* s_delta = s_bacc + 2 * (TAB_MAX + 1);          // [2][128] partial row sums of the two compute groups
-  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(s_delta + 256) + 7) & ~uintptr_t(7));
+  static_assert(((128 + 3 * (TAB_MAX + 1) + 256) * 4) % 8 == 0, "mbarriers need 8-byte alignment");
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_delta + 256);
   uint64_t* fullh = bars;
   uint64_t* emptyh = fullh + NRH;
   uint64_t* fulll = emptyh + NRH;

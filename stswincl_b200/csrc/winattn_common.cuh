@@ -16,6 +16,19 @@
 
 namespace stswin {
 
+// Timeline tracing for tools/trace_attn.py (debug builds with -DSTSWIN_TRACE only): CTA 0 records
+// clock64() at named points of its first 64 work items.
+#ifdef STSWIN_TRACE
+#define STSWIN_TRACE_DECL(name) __device__ long long* name = nullptr;
+#define WTRACE(sym, it, id)                                                           \
+  do {                                                                                \
+    if (blockIdx.x == 0 && (it) < 64 && sym != nullptr) sym[(it) * 16 + (id)] = clock64(); \
+  } while (0)
+#else
+#define STSWIN_TRACE_DECL(name)
+#define WTRACE(sym, it, id) do { } while (0)
+#endif
+
 struct WinGeom {
   int B, T, H, W, C, nH, ws, shift;
   int hd, N, L, G, nWh, nWw, nW, total_windows, num_tiles, nc;   // nc = 64-channel chunks per head group

@@ -14,6 +14,9 @@
 //
 // CTA = 6 warps: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 softmax + epilogue
 // (thread <-> tile row <-> TMEM lane).  Operand chunks stream through a ring of 16 KB slots.
+#include <cstdlib>
+#include <type_traits>
+
 #include "winattn_common.cuh"
 #include "host_util.h"
 
@@ -29,23 +32,38 @@ constexpr int TAB_MAX = 15 * 15;               // (2*ws-1)^2 for ws <= 8
 constexpr int NUM_THREADS = 192;
 constexpr int SMEM_BYTES = 1024 + NSLOT * SLOT_BYTES + P_BYTES + STG_BYTES + 128 * 4 + TAB_MAX * 4 + 256;
 constexpr float kMaskLog2e = -100.0f * 1.4426950408889634f;
+STSWIN_TRACE_DECL(g_trace_fwd)
 
 // L   : window columns a thread walks (16/32/64/128).  GEN (only with L = 128): the tile holds G windows of
 //       gm.L tokens with gm.L not a power of two (e.g. 7x7x2 = 98); every thread then walks the whole
 //       128-column row and keeps only the columns tagged with its own window.
-template <int L, bool GEN>
+//
+// WS > 0 selects the fast softmax for the shipped geometries (L = T*WS*WS, whole launch in one token
+// order, or one order per window: see ORDER below).  The
+// column -> (relative-position key, quadrant) map is then a compile-time function of the column,
+// so the bias is one LDS at an immediate offset and the shift mask is one additive constant per
+// quadrant.  WS == 0 is the generic path (look-up table per column: dense mask, L = 16, GEN).
+template <int L, int WS, bool QUAD>
+__host__ __device__ constexpr int col_key(int j) {
+  constexpr int W1 = WS > 0 ? WS : 1, N = W1 * W1, HW = W1 > 1 ? W1 / 2 : 1, QL = L / 4;
+  if (!QUAD) return ((j % N) / W1) * (2 * W1 - 1) + (j % N) % W1;
+  const int q = j / QL, p = (j % QL) % (HW * HW);
+  return ((q >> 1) * HW + p / HW) * (2 * W1 - 1) + (q & 1) * HW + p % HW;
+}
+
+template <int L, int WS, int ORDER, bool GEN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 winattn_fwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant__ WinMaps tm_out,
                    const float* __restrict__ bias_table, float* __restrict__ lse2, const WinGeom gm) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = align_smem_1024(smem_raw);
   uint8_t* s_ring = smem;
   uint8_t* s_p = s_ring + NSLOT * SLOT_BYTES;
   uint8_t* s_stg = s_p + P_BYTES;
   uint32_t* s_lut = reinterpret_cast<uint32_t*>(s_stg + STG_BYTES);     // [128] key | id<<8
   float* s_tab = reinterpret_cast<float*>(s_lut + 128);                 // [TAB_MAX] bias * log2e for this head
+  static_assert(((128 + TAB_MAX + 1) * 4) % 8 == 0, "mbarriers need 8-byte alignment");
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_tab + TAB_MAX + 1);
-  bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(bars) + 7) & ~uintptr_t(7));
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + NSLOT;
   uint64_t* s_full = bars + 2 * NSLOT;
@@ -94,7 +112,8 @@ winattn_fwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant
     // ---------------------------------------------------------------- TMA producer
     int slot = 0;
     uint32_t phase = 0;
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+    int itl = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++itl) {
       const int tile = item / gm.ngrp, hg = item - tile * gm.ngrp;
       for (int step = 0; step < 3 * nc; ++step) {
         // order: Q0 K0 Q1 K1 ... then V0 V1 ...
@@ -102,6 +121,8 @@ winattn_fwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant
         if (step < 2 * nc) { which = step & 1; c = step >> 1; }
         else               { which = 2; c = step - 2 * nc; }
         mbar_wait(&empty_bar[slot], phase ^ 1);
+        if (lane == 0 && step == 0) WTRACE(g_trace_fwd, itl, 0);
+        if (lane == 0 && step == 3 * nc - 1) WTRACE(g_trace_fwd, itl, 1);
         if (lane == 0) mbar_arrive_expect_tx(&full_bar[slot], chunk_tx_bytes(gm));
         __syncwarp();
         tile_boxes<true>(gm, tile, which * gm.C + hg * gm.gch + c * 64, s_ring + slot * SLOT_BYTES, &tm_qkv,
@@ -124,7 +145,8 @@ winattn_fwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant
         if (++slot == NSLOT) { slot = 0; phase ^= 1; }
         return sl;
       };
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x, it_phase ^= 1) {
+      int itl = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, it_phase ^= 1, ++itl) {
         int sq[4], sk[4], sv[4];                 // ring slots of this item's chunks (nc <= 4)
         for (int sub = 0; sub < SH; ++sub, sub_phase ^= 1) {
           // S = Q K^T (for SH == 2: over the 32-channel K sub-range of sub-head `sub`)
@@ -132,6 +154,7 @@ winattn_fwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant
           tc_fence_after();
           for (int c = 0; c < nc; ++c) {
             if (sub == 0) { sq[c] = take_slot(); sk[c] = take_slot(); }
+            if (c == nc - 1) WTRACE(g_trace_fwd, itl, 13);
             tc_fence_after();
             const uint32_t qa = smem_u32(s_ring + sq[c] * SLOT_BYTES), ka = smem_u32(s_ring + sk[c] * SLOT_BYTES);
             const int k0 = (SH == 1) ? 0 : sub * 2, k1 = (SH == 1) ? 4 : sub * 2 + 2;
@@ -144,12 +167,15 @@ winattn_fwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant
             }
           }
           umma_commit(s_full);
+          WTRACE(g_trace_fwd, itl, 2);
           // O = P V  (SH == 2: the whole 64-column chunk; the epilogue keeps the sub-head's own 32 columns)
           mbar_wait(p_full, sub_phase);
           if (sub == 0) mbar_wait(o_free, it_phase ^ 1);
           tc_fence_after();
+          WTRACE(g_trace_fwd, itl, 3);
           for (int c = 0; c < nc; ++c) {
             if (sub == 0) sv[c] = take_slot();
+            if (c == nc - 1) WTRACE(g_trace_fwd, itl, 14);
             tc_fence_after();
             const uint32_t va = smem_u32(s_ring + sv[c] * SLOT_BYTES);
 #pragma unroll
@@ -161,6 +187,7 @@ winattn_fwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant
             if (sub == SH - 1) umma_commit(&empty_bar[sv[c]]);
           }
           umma_commit(pv_done);                  // P may be overwritten
+          WTRACE(g_trace_fwd, itl, 4);
         }
         umma_commit(o_full);
       }
@@ -174,8 +201,11 @@ winattn_fwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant
     const int nbias = (2 * gm.ws - 1) * (2 * gm.ws - 1);
     uint32_t it_phase = 0, sub_phase = 0;
     int stg_sel = 0;
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x, it_phase ^= 1) {
+    int itl = 0;
+    const bool tr = (threadIdx.x == 64);
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x, it_phase ^= 1, ++itl) {
       const int tile = item / gm.ngrp, hg = item - tile * gm.ngrp;
+      if (tr) WTRACE(g_trace_fwd, itl, 5);
       const RowGeom rg = row_geom(gm, tile, row);
       float inv_sub[2] = {1.f, 1.f};
      for (int sub = 0; sub < SH; ++sub, sub_phase ^= 1) {
@@ -193,11 +223,80 @@ winattn_fwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant
       // dense mask row of this query token (stand-alone WindowAttention with an explicit mask tensor)
       const float* mask_row = gm.mask ? gm.mask + ((size_t)(rg.gw % gm.mask_nw) * gm.N + (rg.rr * gm.ws + rg.cc)) * gm.N : nullptr;
 
+      if (tr) WTRACE(g_trace_fwd, itl, 6);
       mbar_wait(s_full, sub_phase);
       tc_fence_after();
+      if (tr) WTRACE(g_trace_fwd, itl, 7);
       float s[L];
       float mx = -INFINITY;
+      float sum = 0.f;
       constexpr int CH = (L >= 32) ? 32 : 16;
+      if constexpr (WS > 0) {
+        // ---- fast path: compile-time column map, instantiated per token order of the row's window
+        auto softmax_fast = [&](auto quad_tag) {
+          constexpr bool QUAD = decltype(quad_tag)::value;
+          constexpr int QL = L / 4, NQ = QUAD ? 4 : 1;
+          const float* tp = s_tab + key_i;
+          float mq[NQ];
+#pragma unroll
+          for (int q = 0; q < NQ; ++q) mq[q] = -INFINITY;
+#pragma unroll
+          for (int cb = 0; cb < L / CH; ++cb) {
+            uint32_t v[32];
+            tmem_ld_row_chunk<L>(tmem_S, t_lane, col0, cb, wq, lane, v);
+#pragma unroll
+            for (int jj = 0; jj < CH; ++jj) {
+              const int j = cb * CH + jj;
+              const float x = fmaf(__uint_as_float(v[jj]), gm.scale_log2e, tp[-col_key<L, WS, QUAD>(j)]);
+              s[j] = x;
+              mq[QUAD ? j / QL : 0] = fmaxf(mq[QUAD ? j / QL : 0], x);
+            }
+          }
+          // S is in registers: the next item's QK^T may overwrite TMEM now
+          tc_fence_before();
+          mbar_arrive(s_free);
+          if (tr) WTRACE(g_trace_fwd, itl, 8);
+          // shift mask (swin_512.py:171-192): a window of the last window row / column holds two bands
+          // per wrapping axis; tokens of different bands get -100.  In quadrant order the band pair
+          // of a token IS its quadrant, so the mask is one additive constant per quadrant of columns.
+          float nq[NQ];
+          if constexpr (QUAD) {
+            const int q_i = (rg.rr >= WS / 2 ? 2 : 0) | (rg.cc >= WS / 2 ? 1 : 0);
+            const int wm = (rg.id >= 3 ? 2 : 0) | (rg.id % 3 != 0 ? 1 : 0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              nq[q] = ((q ^ q_i) & wm) ? kMaskLog2e : 0.f;
+              mx = fmaxf(mx, mq[q] + nq[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) nq[q] -= mx;
+          } else {
+            mx = mq[0];
+            nq[0] = -mx;
+          }
+          mbar_wait(pv_done, sub_phase ^ 1);        // the previous P V product has finished reading P
+          if (tr) WTRACE(g_trace_fwd, itl, 9);
+#pragma unroll
+          for (int j8 = 0; j8 < L / 8; ++j8) {
+            uint32_t w[4];
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+              const int j = j8 * 8 + 2 * h;
+              const float p0 = fast_exp2(s[j] + nq[QUAD ? j / QL : 0]);
+              const float p1 = fast_exp2(s[j + 1] + nq[QUAD ? (j + 1) / QL : 0]);
+              sum += p0 + p1;
+              w[h] = pack_bf16(p0, p1);
+            }
+            const int col = col0 + j8 * 8;
+            *reinterpret_cast<uint4*>(s_p + (col >> 6) * SLOT_BYTES + sw128_offset(row, (col & 63) >> 3)) =
+                make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        };
+        // ORDER 0: unshifted block, row-major.  1: every window in quadrant order.  2: only the windows
+        // that wrap (a warp never straddles two windows for L >= 32, so the branch is warp-uniform).
+        if (ORDER == 0 || (ORDER == 2 && !rg.wraps)) softmax_fast(std::false_type{});
+        else                                         softmax_fast(std::true_type{});
+      } else {
 #pragma unroll
       for (int cb = 0; cb < L / CH; ++cb) {
         uint32_t v[32];
@@ -218,7 +317,6 @@ winattn_fwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant
       mbar_arrive(s_free);
 
       mbar_wait(pv_done, sub_phase ^ 1);        // the previous P V product has finished reading P
-      float sum = 0.f;
 #pragma unroll
       for (int j8 = 0; j8 < L / 8; ++j8) {
         uint32_t w[4];
@@ -227,18 +325,17 @@ winattn_fwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant
           float p0 = fast_exp2(s[j8 * 8 + 2 * h] - mx);
           float p1 = fast_exp2(s[j8 * 8 + 2 * h + 1] - mx);
           if (GEN && !rg.inrange) { p0 = 0.f; p1 = 0.f; }          // padding row: keep P finite and empty
-          // accumulate what the tensor core will actually see (bf16-rounded probabilities)
-          const uint32_t pk = pack_bf16(p0, p1);
-          const float2 pr = unpack_bf16(pk);
-          sum += pr.x + pr.y;
-          w[h] = pk;
+          sum += p0 + p1;
+          w[h] = pack_bf16(p0, p1);
         }
         const int col = col0 + j8 * 8;
         *reinterpret_cast<uint4*>(s_p + (col >> 6) * SLOT_BYTES + sw128_offset(row, (col & 63) >> 3)) =
             make_uint4(w[0], w[1], w[2], w[3]);
       }
+      }
       fence_proxy_async_smem();
       mbar_arrive(p_full);
+      if (tr) WTRACE(g_trace_fwd, itl, 10);
       inv_sub[sub] = (GEN && !rg.inrange) ? 0.f : 1.0f / sum;
       if (!GEN || rg.inrange) lse2[((size_t)tile * gm.nH + head) * 128 + rg.canon] = mx + log2f(sum);
      }
@@ -246,6 +343,7 @@ winattn_fwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant
       // ---- epilogue: O * (1/sum) -> bf16 -> staging -> TMA store at the un-rolled coordinates
       mbar_wait(o_full, it_phase);
       tc_fence_after();
+      if (tr) WTRACE(g_trace_fwd, itl, 11);
       for (int c = 0; c < nc; ++c) {
         uint32_t v0[32], v1[32];
         // SH == 1: columns [c*64, +64) of this head.  SH == 2: columns [0,32) of sub-head 0's product
@@ -281,8 +379,10 @@ winattn_fwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant
           tile_boxes<false>(gm, tile, hg * gm.gch + c * 64, stg, &tm_out, nullptr, lane);
           tma_commit_group();
         }
+        if (tr && c == 0) WTRACE(g_trace_fwd, itl, 15);
         stg_sel ^= 1;
       }
+      if (tr) WTRACE(g_trace_fwd, itl, 12);
     }
     if (sm_tid < 32) tma_wait_group<0>();
   }
@@ -366,6 +466,12 @@ long winattn_lse_elems(int B, int T, int H, int W, int C, int nH, int ws) {
   return (long)gm.num_tiles * gm.nH * 128;
 }
 
+#ifdef STSWIN_TRACE
+extern "C" int stswin_debug_trace_fwd(long long* buf) {
+  return cudaMemcpyToSymbol(g_trace_fwd, &buf, sizeof(buf)) == cudaSuccess ? 0 : -1;
+}
+#endif
+
 // see include/stswin_b200.h : stswin_winattn_fwd
 int winattn_fwd(const void* qkv, const float* bias_table, void* out, float* lse2, int B, int T, int H, int W, int C,
                 int nH, int ws, int shift, float qk_scale, const float* mask, int mask_windows, cudaStream_t stream) {
@@ -376,21 +482,36 @@ int winattn_fwd(const void* qkv, const float* bias_table, void* out, float* lse2
   if (qk_scale > 0.f) { gm.scale = qk_scale; gm.scale_log2e = qk_scale * 1.4426950408889634f; }
   STSWIN_CHECK_ARG(mask == nullptr || mask_windows > 0, "winattn: mask given with mask_windows <= 0");
   gm.mask = mask; gm.mask_nw = mask_windows;
+  gm.uniform_quad = (gm.L == 128 && !gm.general) ? 1 : gm.uniform_quad;
+  if (const char* e = getenv("STSWIN_FWD_UNIFORM")) gm.uniform_quad = atoi(e);   // TEMP experiment
   WinMaps tq, to;
   if ((rc = make_window_tmaps(&tq, qkv, gm, 3 * C)) != kOk) return rc;
   if ((rc = make_window_tmaps(&to, out, gm, C)) != kOk) return rc;
   const int items = gm.num_tiles * gm.ngrp;
   const int grid = items < num_sms() ? items : num_sms();
-#define STSWIN_LAUNCH_FWD(LL, GG)                                                                              \
+#define STSWIN_LAUNCH_FWD(LL, WW, QQ, GG)                                                                      \
   {                                                                                                            \
-    if ((rc = set_smem(winattn_fwd_kernel<LL, GG>, SMEM_BYTES)) != kOk) return rc;                             \
-    winattn_fwd_kernel<LL, GG><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tq, to, bias_table, lse2, gm);       \
+    if ((rc = set_smem(winattn_fwd_kernel<LL, WW, QQ, GG>, SMEM_BYTES)) != kOk) return rc;                     \
+    winattn_fwd_kernel<LL, WW, QQ, GG><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tq, to, bias_table, lse2, gm); \
   }
-  if (gm.general) STSWIN_LAUNCH_FWD(128, true)
-  else if (gm.L == 16) STSWIN_LAUNCH_FWD(16, false)
-  else if (gm.L == 32) STSWIN_LAUNCH_FWD(32, false)
-  else if (gm.L == 64) STSWIN_LAUNCH_FWD(64, false)
-  else STSWIN_LAUNCH_FWD(128, false)
+  // fast softmax: the shipped geometries (ws 8 or 4, 1 or 2 frames per window, shift 0 or ws/2, no dense mask)
+  const bool fast = !gm.general && mask == nullptr && (shift == 0 || 2 * shift == ws) &&
+                    ((ws == 8 && (gm.L == 128 || gm.L == 64)) || (ws == 4 && gm.L == 32));
+  // token order of a shifted block: small windows keep one box per interior window (16 tiny quadrant
+  // boxes per chunk cost more than they save); 128-token windows use one order for the whole launch
+  const int order = shift == 0 ? 0 : (gm.uniform_quad ? 1 : 2);
+  if (gm.general) STSWIN_LAUNCH_FWD(128, 0, 0, true)
+  else if (fast && gm.L == 128 && order == 0) STSWIN_LAUNCH_FWD(128, 8, 0, false)
+  else if (fast && gm.L == 128 && order == 1) STSWIN_LAUNCH_FWD(128, 8, 1, false)
+  else if (fast && gm.L == 128) STSWIN_LAUNCH_FWD(128, 8, 2, false)
+  else if (fast && gm.L == 64 && order == 0) STSWIN_LAUNCH_FWD(64, 8, 0, false)
+  else if (fast && gm.L == 64) STSWIN_LAUNCH_FWD(64, 8, 2, false)
+  else if (fast && gm.L == 32 && order == 0) STSWIN_LAUNCH_FWD(32, 4, 0, false)
+  else if (fast && gm.L == 32) STSWIN_LAUNCH_FWD(32, 4, 2, false)
+  else if (gm.L == 16) STSWIN_LAUNCH_FWD(16, 0, 0, false)
+  else if (gm.L == 32) STSWIN_LAUNCH_FWD(32, 0, 0, false)
+  else if (gm.L == 64) STSWIN_LAUNCH_FWD(64, 0, 0, false)
+  else STSWIN_LAUNCH_FWD(128, 0, 0, false)
 #undef STSWIN_LAUNCH_FWD
   STSWIN_CUDA(cudaGetLastError());
   return kOk;

@@ -150,7 +150,7 @@ def winattn_fwd(qkv: torch.Tensor, bias_table: torch.Tensor, H: int, W: int, num
     if out is None:
         out = torch.empty((B, T, L, C), dtype=torch.bfloat16, device=qkv.device)
     lse2 = torch.empty(winattn_lse_elems(B, T, H, W, C, num_heads, ws), dtype=torch.float32, device=qkv.device)
-    with _launch("winattn_fwd", 8.0 * C * B * T * L * 2, qkv):     # q,k,v in + o out, bf16
+    with _launch("winattn_fwd", 8.0 * C * B * T * L, qkv):     # bytes: q,k,v in + o out, bf16 = 8*C per token
         st = _lib.load().stswin_winattn_fwd(qkv.data_ptr(), bias_table.data_ptr(), out.data_ptr(), lse2.data_ptr(),
                                             B, T, H, W, C, num_heads, ws, shift, float(qk_scale),
                                             _ptr(mask), _mask_windows(mask, ws), _stream(qkv))
@@ -174,7 +174,7 @@ def winattn_bwd(qkv: torch.Tensor, bias_table: torch.Tensor, lse2: torch.Tensor,
         d_qkv = torch.empty_like(qkv)
     if d_qkv_colsum is not None:
         _req(d_qkv_colsum, torch.float32, "d_qkv_colsum"); assert d_qkv_colsum.numel() == C3
-    with _launch("winattn_bwd", 14.0 * C * B * T * L * 2, qkv):    # q,k,v,dO in + dq,dk,dv out, bf16
+    with _launch("winattn_bwd", 14.0 * C * B * T * L, qkv):    # bytes: q,k,v,dO in + dq,dk,dv out, bf16 = 14*C per token
         st = _lib.load().stswin_winattn_bwd(qkv.data_ptr(), bias_table.data_ptr(), lse2.data_ptr(), d_out.data_ptr(),
                                             d_qkv.data_ptr(), d_table.data_ptr(), _ptr(d_qkv_colsum),
                                             B, T, H, W, C, num_heads, ws, shift, float(qk_scale),
