@@ -43,6 +43,7 @@ struct WinGeom {
   int general;        // 1: L is not 16/32/64/128 -> kernels run their "whole row + window tag" path
   const float* mask;  // optional dense additive mask [mask_nw, N, N] (WindowAttention.forward's `mask`
   int mask_nw;        //   argument, swin_512.py:127-131), applied ON TOP of the closed-form shift mask; or null
+  unsigned long long mg_nW, mg_nWw;   // ceil(2^32 / nW), ceil(2^32 / nWw): exact division of window indices by multiply-shift
   int uniform_quad;   // 1: every window of a shifted block is moved as four quadrant boxes (one token
                       //    order per launch; the backward kernel needs that to sum dS across tiles)
 };
@@ -127,6 +128,52 @@ __device__ __forceinline__ RowGeom row_geom(const WinGeom& gm, int tile, int r) 
   return o;
 }
 
+// n / d for 0 <= n * d < 2^32 with mg = ceil(2^32 / d) (checked on the host in fill_geom)
+__device__ __forceinline__ int fast_div(int n, unsigned long long mg) {
+  return int((static_cast<unsigned long long>(static_cast<unsigned>(n)) * mg) >> 32);
+}
+
+// row_geom for the shipped geometries: L, ws compile-time (shifts instead of divisions), shift 0 or ws/2.
+// ORDER 0: row-major.  1: every window in quadrant order.  2: quadrant order for the windows that wrap.
+template <int L, int WS, int ORDER>
+__device__ __forceinline__ RowGeom row_geom_fast(const WinGeom& gm, int tile, int r) {
+  constexpr int N = WS * WS, G = 128 / L, HW = WS / 2, QL = L / 4;
+  RowGeom o;
+  o.g = r / L;
+  o.inrange = true;
+  const int rem = r % L;
+  int gw = tile * G + o.g;
+  o.valid = gw < gm.total_windows;
+  if (gw > gm.total_windows - 1) gw = gm.total_windows - 1;
+  o.gw = gw;
+  const int b = fast_div(gw, gm.mg_nW), win = gw - b * gm.nW;
+  const int wh = fast_div(win, gm.mg_nWw), ww = win - wh * gm.nWw;
+  o.wraps = ORDER != 0 && (wh == gm.nWh - 1 || ww == gm.nWw - 1);
+  int t;
+  if (ORDER == 0 || (ORDER == 2 && !o.wraps)) {
+    t = rem / N;
+    const int pos = rem % N;
+    o.rr = pos / WS;
+    o.cc = pos % WS;
+  } else {
+    const int q = rem / QL, r2 = rem % QL;
+    t = r2 / (HW * HW);
+    const int p = r2 % (HW * HW);
+    o.rr = (q >> 1) * HW + p / HW;
+    o.cc = (q & 1) * HW + p % HW;
+  }
+  o.canon = o.g * L + t * N + o.rr * WS + o.cc;
+  const int shift = ORDER == 0 ? 0 : HW;
+  int hs = wh * WS + o.rr + shift, wsrc = ww * WS + o.cc + shift;
+  if (hs >= gm.H) hs -= gm.H;
+  if (wsrc >= gm.W) wsrc -= gm.W;
+  o.tok = ((long)(b * gm.T + t) * gm.H + hs) * gm.W + wsrc;
+  o.id = 0;
+  if (ORDER != 0)
+    o.id = 3 * region_band(wh * WS + o.rr, gm.H, WS, HW) + region_band(ww * WS + o.cc, gm.W, WS, HW);
+  return o;
+}
+
 // Issue the TMA boxes that fill (LOAD) or drain (STORE) one [128 x 64ch] chunk buffer for `tile`.
 //   ch0 : first channel of the chunk in the global tensor
 // Called by all 32 lanes of one warp; box k of the chunk is issued by lane k % 32.
@@ -196,6 +243,27 @@ __device__ __forceinline__ void tmem_ld_row_chunk(uint32_t tmem_mat, uint32_t t_
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] = v[j + 16];
     }
+  }
+}
+
+// Write a block held one row per lane ([32 rows] x [NB x 16 bytes]) to global memory with whole-line
+// stores: the rows go through a per-warp 4 KB staging area (128B-swizzled, conflict-free both ways) and
+// come back 8 lanes per row, so one store instruction covers 4 complete 128-byte lines instead of 32
+// partial ones (a row-per-lane st.global is bound by the LSU: 32 lines per instruction).
+//   rowp[i] : global address of the block's first byte for row i*4 + lane/8, or nullptr to skip the row
+template <int NB>
+__device__ __forceinline__ void warp_store_rows(uint8_t* stage, const uint4 (&vals)[NB], uint8_t* const (&rowp)[8],
+                                                int lane) {
+  __syncwarp();                      // the previous block has been read out
+#pragma unroll
+  for (int j = 0; j < NB; ++j) *reinterpret_cast<uint4*>(stage + sw128_offset(lane, j)) = vals[j];
+  __syncwarp();
+  const int ch = lane & 7;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = i * 4 + (lane >> 3);
+    if (ch < NB && rowp[i] != nullptr)
+      *reinterpret_cast<uint4*>(rowp[i] + ch * 16) = *reinterpret_cast<const uint4*>(stage + sw128_offset(r, ch));
   }
 }
 

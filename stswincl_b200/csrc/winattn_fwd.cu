@@ -12,9 +12,11 @@
 // Output out [B, T, H, W, C]  bf16 (same token order), lse2 [num_tiles, nH, 128] fp32
 //        (base-2 log-sum-exp of every tile row, consumed by the backward kernel).
 //
-// CTA = 6 warps: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 softmax + epilogue
-// (thread <-> tile row <-> TMEM lane).  Operand chunks stream through a ring of 16 KB slots.
-#include <cstdlib>
+// CTA = 3 warpgroups: warp 0 TMA producer, warp 1 MMA issuer (warp-uniform control flow, one
+// elected lane issues), warps 4-7 softmax, warps 8-11 epilogue (thread <-> tile row <-> TMEM lane in
+// both; a softmax and an epilogue warp share each SM sub-partition, so the MUFU-heavy softmax of
+// item k overlaps the TMEM / store-heavy drain of item k-1).  Operand chunks stream through a ring
+// of 16 KB slots.  The tensor core runs one item ahead: S(k+1) is issued before P V(k).
 #include <type_traits>
 
 #include "winattn_common.cuh"
@@ -24,13 +26,15 @@ namespace stswin {
 
 namespace {
 
-constexpr int NSLOT = 9;
+constexpr int NQK = 6;                         // ring of Q / K chunks (consumed by S = Q K^T)
+constexpr int NV = 4;                          // ring of V chunks (consumed by O = P V)
+constexpr int NSLOT = NQK + NV;
 constexpr int SLOT_BYTES = 128 * 128;          // 128 rows x 64 bf16
 constexpr int P_BYTES = 2 * SLOT_BYTES;        // P [128 x 128] bf16 as two K-major halves
-constexpr int STG_BYTES = 2 * SLOT_BYTES;      // two output staging chunks
+constexpr int STG_BYTES = 4 * 4096;             // per-warp output transposition areas (epilogue warps)
 constexpr int TAB_MAX = 15 * 15;               // (2*ws-1)^2 for ws <= 8
-constexpr int NUM_THREADS = 192;
-constexpr int SMEM_BYTES = 1024 + NSLOT * SLOT_BYTES + P_BYTES + STG_BYTES + 128 * 4 + TAB_MAX * 4 + 256;
+constexpr int NUM_THREADS = 384;               // warpgroup 0: producer, MMA issuer (+2 idle); 1: softmax; 2: epilogue
+constexpr int SMEM_BYTES = 1024 + NSLOT * SLOT_BYTES + P_BYTES + STG_BYTES + 128 * 4 + 2 * (TAB_MAX + 1) * 4 + 512 * 4 + 256;
 constexpr float kMaskLog2e = -100.0f * 1.4426950408889634f;
 STSWIN_TRACE_DECL(g_trace_fwd)
 
@@ -53,18 +57,19 @@ __host__ __device__ constexpr int col_key(int j) {
 
 template <int L, int WS, int ORDER, bool GEN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-winattn_fwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant__ WinMaps tm_out,
+winattn_fwd_kernel(const __grid_constant__ WinMaps tm_qkv, __nv_bfloat16* __restrict__ out,
                    const float* __restrict__ bias_table, float* __restrict__ lse2, const WinGeom gm) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_smem_1024(smem_raw);
   uint8_t* s_ring = smem;
   uint8_t* s_p = s_ring + NSLOT * SLOT_BYTES;
-  uint8_t* s_stg = s_p + P_BYTES;
-  uint32_t* s_lut = reinterpret_cast<uint32_t*>(s_stg + STG_BYTES);     // [128] key | id<<8
-  float* s_tab = reinterpret_cast<float*>(s_lut + 128);                 // [TAB_MAX] bias * log2e for this head
-  static_assert(((128 + TAB_MAX + 1) * 4) % 8 == 0, "mbarriers need 8-byte alignment");
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_tab + TAB_MAX + 1);
-  uint64_t* full_bar = bars;
+  uint8_t* s_stage = s_p + P_BYTES;                                      // 4 warps x 4 KB output transposition
+  uint32_t* s_lut = reinterpret_cast<uint32_t*>(s_stage + STG_BYTES);    // [128] key | id<<8 | pos<<16 | tag<<24
+  float* s_tab = reinterpret_cast<float*>(s_lut + 128);                   // [2][TAB_MAX + 1] bias * log2e per head of the group
+  float* s_inv = s_tab + 2 * (TAB_MAX + 1);                               // [2 item parities][2 heads][128] 1 / rowsum
+  static_assert(((128 + 2 * (TAB_MAX + 1) + 512) * 4) % 8 == 0, "mbarriers need 8-byte alignment");
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_inv + 512);
+  uint64_t* full_bar = bars;                  // [NSLOT]: Q/K ring slots first, then the V ring slots
   uint64_t* empty_bar = bars + NSLOT;
   uint64_t* s_full = bars + 2 * NSLOT;
   uint64_t* s_free = s_full + 1;
@@ -72,17 +77,23 @@ winattn_fwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant
   uint64_t* o_full = s_full + 3;
   uint64_t* o_free = s_full + 4;
   uint64_t* pv_done = s_full + 5;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 6);
+  uint64_t* inv_full = s_full + 6;            // [2] 1/rowsum of every head of an item published (per item parity)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 8);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_items = gm.num_tiles * gm.ngrp;     // work item = (tile, head group)
   const int nc = gm.nc;
   const int SH = gm.SH;
+  const int hg = blockIdx.x % gm.ngrp;              // constant per CTA: gridDim.x % ngrp == 0
+  const int n_local = (num_items - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);   // items of this CTA
+  const int n_units = n_local * SH;                 // unit = (item, head of the group)
+  // One head per group: S of item k+1 is issued before P V of item k (the softmax of k+1 then never
+  // waits for a tensor-core round trip).
+  const bool lag = (SH == 1);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_qkv.full);
-    tma_prefetch_desc(&tm_out.full);
     for (int i = 0; i < NSLOT; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -93,6 +104,8 @@ winattn_fwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant
     mbar_init(o_full, 1);
     mbar_init(o_free, 128);
     mbar_init(pv_done, 1);
+    mbar_init(&inv_full[0], 128);
+    mbar_init(&inv_full[1], 128);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -100,6 +113,14 @@ winattn_fwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant
   // rows of a tile (general mode) are never written by TMA and must read as zero.
   for (int i = threadIdx.x; i < (NSLOT * SLOT_BYTES + P_BYTES) / 16; i += NUM_THREADS)
     reinterpret_cast<uint4*>(s_ring)[i] = make_uint4(0, 0, 0, 0);
+  // bias table(s) of this CTA's head group, pre-scaled by log2(e)
+  {
+    const int nbias = (2 * gm.ws - 1) * (2 * gm.ws - 1);
+    for (int i = threadIdx.x; i < SH * nbias; i += NUM_THREADS) {
+      const int sub = i / nbias, k = i - sub * nbias;
+      s_tab[sub * (TAB_MAX + 1) + k] = __ldg(bias_table + k * gm.nH + hg * SH + sub) * 1.4426950408889634f;
+    }
+  }
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -108,125 +129,147 @@ winattn_fwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant
   const uint32_t tmem_S = tmem_base;          // 128 columns
   const uint32_t tmem_O = tmem_base + 128;    // nc*64 columns (<= 256), or SH*64 when two heads share a chunk
 
-  if (warp == 0) {
-    // ---------------------------------------------------------------- TMA producer
+  // register budget per warpgroup (setmaxnreg): the softmax warps hold a whole 128-column row in registers
+  if (warp < 4) {
+   asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+   if (warp == 0 || warp == 2) {
+    // ---------------------------------------------------------------- TMA producers
+    // warp 0 feeds the Q/K ring (Q0 K0 Q1 K1 ... per item), warp 2 the V ring: two independent rings,
+    // so a V chunk waiting for its P never holds back the Q/K chunks of the next item (with one
+    // shared ring the slot dependencies formed a loop of two HBM latencies per two items).
+    const bool is_v = (warp == 2);
+    const int nslot = is_v ? NV : NQK;
+    uint8_t* ring = s_ring + (is_v ? NQK * SLOT_BYTES : 0);
+    uint64_t* fullb = full_bar + (is_v ? NQK : 0);
+    uint64_t* emptyb = empty_bar + (is_v ? NQK : 0);
     int slot = 0;
     uint32_t phase = 0;
-    int itl = 0;
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++itl) {
-      const int tile = item / gm.ngrp, hg = item - tile * gm.ngrp;
-      for (int step = 0; step < 3 * nc; ++step) {
-        // order: Q0 K0 Q1 K1 ... then V0 V1 ...
-        int which, c;
-        if (step < 2 * nc) { which = step & 1; c = step >> 1; }
-        else               { which = 2; c = step - 2 * nc; }
-        mbar_wait(&empty_bar[slot], phase ^ 1);
-        if (lane == 0 && step == 0) WTRACE(g_trace_fwd, itl, 0);
-        if (lane == 0 && step == 3 * nc - 1) WTRACE(g_trace_fwd, itl, 1);
-        if (lane == 0) mbar_arrive_expect_tx(&full_bar[slot], chunk_tx_bytes(gm));
+    for (int k = 0; k < n_local; ++k) {
+      const int item = int(blockIdx.x) + k * int(gridDim.x);
+      const int tile = item / gm.ngrp;
+      if (lane == 0) WTRACE(g_trace_fwd, k, is_v ? 1 : 0);
+      for (int step = 0; step < (is_v ? nc : 2 * nc); ++step) {
+        const int which = is_v ? 2 : (step & 1), c = is_v ? step : (step >> 1);
+        mbar_wait(&emptyb[slot], phase ^ 1);
+        if (lane == 0) mbar_arrive_expect_tx(&fullb[slot], chunk_tx_bytes(gm));
         __syncwarp();
-        tile_boxes<true>(gm, tile, which * gm.C + hg * gm.gch + c * 64, s_ring + slot * SLOT_BYTES, &tm_qkv,
-                         &full_bar[slot], lane);
-        if (++slot == NSLOT) { slot = 0; phase ^= 1; }
+        tile_boxes<true>(gm, tile, which * gm.C + hg * gm.gch + c * 64, ring + slot * SLOT_BYTES, &tm_qkv,
+                         &fullb[slot], lane);
+        if (++slot == nslot) { slot = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1) {
+   } else if (warp == 1) {
     // ---------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
-      constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);
-      int slot = 0;
-      uint32_t phase = 0;
-      uint32_t it_phase = 0, sub_phase = 0;      // per item / per (item, sub-head)
-      const uint32_t p_addr = smem_u32(s_p);
-      auto take_slot = [&]() {                   // wait for the next ring slot in program order
-        const int sl = slot;
-        mbar_wait(&full_bar[slot], phase);
-        if (++slot == NSLOT) { slot = 0; phase ^= 1; }
-        return sl;
-      };
-      int itl = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x, it_phase ^= 1, ++itl) {
-        int sq[4], sk[4], sv[4];                 // ring slots of this item's chunks (nc <= 4)
-        for (int sub = 0; sub < SH; ++sub, sub_phase ^= 1) {
-          // S = Q K^T (for SH == 2: over the 32-channel K sub-range of sub-head `sub`)
-          mbar_wait(s_free, sub_phase ^ 1);
-          tc_fence_after();
-          for (int c = 0; c < nc; ++c) {
-            if (sub == 0) { sq[c] = take_slot(); sk[c] = take_slot(); }
-            if (c == nc - 1) WTRACE(g_trace_fwd, itl, 13);
-            tc_fence_after();
-            const uint32_t qa = smem_u32(s_ring + sq[c] * SLOT_BYTES), ka = smem_u32(s_ring + sk[c] * SLOT_BYTES);
-            const int k0 = (SH == 1) ? 0 : sub * 2, k1 = (SH == 1) ? 4 : sub * 2 + 2;
-            for (int kk = k0; kk < k1; ++kk)
-              umma_bf16(tmem_S, umma_smem_desc(qa + kk * 32, 16, 1024), umma_smem_desc(ka + kk * 32, 16, 1024), idesc_s,
-                        (c > 0 || kk > k0) ? 1u : 0u);
-            if (sub == SH - 1) {                 // last reader of these chunks
-              umma_commit(&empty_bar[sq[c]]);
-              umma_commit(&empty_bar[sk[c]]);
-            }
-          }
-          umma_commit(s_full);
-          WTRACE(g_trace_fwd, itl, 2);
-          // O = P V  (SH == 2: the whole 64-column chunk; the epilogue keeps the sub-head's own 32 columns)
-          mbar_wait(p_full, sub_phase);
-          if (sub == 0) mbar_wait(o_free, it_phase ^ 1);
-          tc_fence_after();
-          WTRACE(g_trace_fwd, itl, 3);
-          for (int c = 0; c < nc; ++c) {
-            if (sub == 0) sv[c] = take_slot();
-            if (c == nc - 1) WTRACE(g_trace_fwd, itl, 14);
-            tc_fence_after();
-            const uint32_t va = smem_u32(s_ring + sv[c] * SLOT_BYTES);
-#pragma unroll
-            for (int kk = 0; kk < 8; ++kk) {
-              const uint64_t adesc = umma_smem_desc(p_addr + (kk >> 2) * SLOT_BYTES + (kk & 3) * 32, 16, 1024);
-              const uint64_t bdesc = umma_smem_desc(va + kk * 2048, SLOT_BYTES, 1024);
-              umma_bf16(tmem_O + (SH == 1 ? c : sub) * 64, adesc, bdesc, idesc_o, kk > 0 ? 1u : 0u);
-            }
-            if (sub == SH - 1) umma_commit(&empty_bar[sv[c]]);
-          }
-          umma_commit(pv_done);                  // P may be overwritten
-          WTRACE(g_trace_fwd, itl, 4);
+    // The whole warp runs the control flow (so slot indices and descriptors stay in uniform registers);
+    // one elected lane issues the tcgen05 instructions.
+    const bool leader = elect_one();
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
+    constexpr uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);
+    const uint32_t p_addr = smem_u32(s_p), ring_addr = smem_u32(s_ring);
+    uint32_t seq_qk = 0, seq_v = 0, base_qk = 0, base_v = 0;     // running chunk counters of the two rings
+    auto issue_S = [&](int u) {            // S = Q K^T (SH == 2: over the 32-channel K sub-range of head `sub`)
+      const int sub = (SH == 1) ? 0 : (u & 1);
+      mbar_wait(s_free, (u & 1) ^ 1);      // pass 1 of the previous unit has S in registers
+      tc_fence_after();
+      if (sub == 0) { base_qk = seq_qk; seq_qk += 2 * nc; }
+      const int k0 = (SH == 1) ? 0 : sub * 2, k1 = (SH == 1) ? 4 : sub * 2 + 2;
+      for (int c = 0; c < nc; ++c) {
+        const uint32_t nq = base_qk + 2 * c, nk = nq + 1;
+        const uint32_t sq = nq % NQK, sk = nk % NQK;
+        if (sub == 0) {
+          mbar_wait(&full_bar[sq], (nq / NQK) & 1);
+          mbar_wait(&full_bar[sk], (nk / NQK) & 1);
         }
-        umma_commit(o_full);
+        tc_fence_after();
+        const uint32_t qa = ring_addr + sq * SLOT_BYTES, ka = ring_addr + sk * SLOT_BYTES;
+        if (leader) {
+          for (int kk = k0; kk < k1; ++kk)
+            umma_bf16(tmem_S, umma_smem_desc(qa + kk * 32, 16, 1024), umma_smem_desc(ka + kk * 32, 16, 1024), idesc_s,
+                      (c > 0 || kk > k0) ? 1u : 0u);
+          if (sub == SH - 1) {               // last reader of these chunks
+            umma_commit(&empty_bar[sq]);
+            umma_commit(&empty_bar[sk]);
+          }
+        }
+      }
+      if (leader) {
+        umma_commit(s_full);
+        WTRACE(g_trace_fwd, (SH == 1 ? u : u >> 1), 2);
+      }
+      __syncwarp();
+    };
+    auto issue_PV = [&](int u) {           // O = P V (SH == 2: whole 64-column chunk; the epilogue keeps the head's own 32)
+      const int sub = (SH == 1) ? 0 : (u & 1);
+      const int k = (SH == 1) ? u : (u >> 1);
+      mbar_wait(p_full, u & 1);
+      if (sub == 0) {
+        mbar_wait(o_free, (k & 1) ^ 1);    // the previous item's O has been drained
+        base_v = seq_v; seq_v += nc;
+      }
+      tc_fence_after();
+      if (leader) WTRACE(g_trace_fwd, k, 3);
+      for (int c = 0; c < nc; ++c) {
+        const uint32_t nv = base_v + c, sv = NQK + nv % NV;
+        if (sub == 0) mbar_wait(&full_bar[sv], (nv / NV) & 1);
+        tc_fence_after();
+        const uint32_t va = ring_addr + sv * SLOT_BYTES;
+        if (leader) {
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {
+            const uint64_t adesc = umma_smem_desc(p_addr + (kk >> 2) * SLOT_BYTES + (kk & 3) * 32, 16, 1024);
+            const uint64_t bdesc = umma_smem_desc(va + kk * 2048, SLOT_BYTES, 1024);
+            umma_bf16(tmem_O + (SH == 1 ? c : sub) * 64, adesc, bdesc, idesc_o, kk > 0 ? 1u : 0u);
+          }
+          if (sub == SH - 1) umma_commit(&empty_bar[sv]);
+        }
+      }
+      if (leader) {
+        umma_commit(pv_done);              // P may be overwritten
+        if (sub == SH - 1) umma_commit(o_full);
+        WTRACE(g_trace_fwd, k, 4);
+      }
+      __syncwarp();
+    };
+    if (lag) {
+      if (n_units > 0) issue_S(0);
+      for (int u = 0; u < n_units; ++u) {
+        if (u + 1 < n_units) issue_S(u + 1);
+        issue_PV(u);
+      }
+    } else {
+      for (int u = 0; u < n_units; ++u) {
+        issue_S(u);
+        issue_PV(u);
       }
     }
-  } else {
-    // ---------------------------------------------------------------- softmax + epilogue
+   }
+  } else if (warp < 8) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    // ---------------------------------------------------------------- softmax warps (group A)
+    // thread <-> tile row <-> TMEM lane.  Per unit: S -> registers (+ bias, mask), row max, P = exp2(.)
+    // -> smem (bf16) for the P V product; 1/rowsum goes to smem for the epilogue warps.
     const int wq = warp & 3;
-    const int row = wq * 32 + lane;           // tile row == TMEM lane
-    const int sm_tid = threadIdx.x - 64;      // 0..127
+    const int row = wq * 32 + lane;
     const uint32_t t_lane = uint32_t(wq * 32) << 16;
-    const int nbias = (2 * gm.ws - 1) * (2 * gm.ws - 1);
-    uint32_t it_phase = 0, sub_phase = 0;
-    int stg_sel = 0;
-    int itl = 0;
-    const bool tr = (threadIdx.x == 64);
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x, it_phase ^= 1, ++itl) {
-      const int tile = item / gm.ngrp, hg = item - tile * gm.ngrp;
-      if (tr) WTRACE(g_trace_fwd, itl, 5);
-      const RowGeom rg = row_geom(gm, tile, row);
-      float inv_sub[2] = {1.f, 1.f};
-     for (int sub = 0; sub < SH; ++sub, sub_phase ^= 1) {
+    const bool tr = (threadIdx.x == 128);
+    (void)tr;
+    RowGeom rg;
+    int key_i = 0, col0 = 0;
+    for (int u = 0; u < n_units; ++u) {
+      const int sub = (SH == 1) ? 0 : (u & 1);
+      const int k = (SH == 1) ? u : (u >> 1);
+      const int item = int(blockIdx.x) + k * int(gridDim.x);
+      const int tile = item / gm.ngrp;
       const int head = hg * SH + sub;
-      named_bar_sync(1, 128);                  // everybody is done with the previous LUT / bias table
-      // key | region id | spatial position | window tag (g + 1, 0 for a padding row)
-      const uint32_t my_tag = rg.inrange ? uint32_t(rg.g + 1) : 0u;
-      s_lut[row] = uint32_t(rg.rr * (2 * gm.ws - 1) + rg.cc) | (uint32_t(rg.id) << 8) |
-                   (uint32_t(rg.rr * gm.ws + rg.cc) << 16) | (my_tag << 24);
-      for (int i = sm_tid; i < nbias; i += 128) s_tab[i] = __ldg(bias_table + i * gm.nH + head) * 1.4426950408889634f;
-      named_bar_sync(1, 128);
-      const int key_i = (rg.rr + gm.ws - 1) * (2 * gm.ws - 1) + rg.cc + gm.ws - 1;
-      const int col0 = GEN ? 0 : rg.g * L;
-      const bool use_mask = rg.wraps;
-      // dense mask row of this query token (stand-alone WindowAttention with an explicit mask tensor)
-      const float* mask_row = gm.mask ? gm.mask + ((size_t)(rg.gw % gm.mask_nw) * gm.N + (rg.rr * gm.ws + rg.cc)) * gm.N : nullptr;
-
-      if (tr) WTRACE(g_trace_fwd, itl, 6);
-      mbar_wait(s_full, sub_phase);
-      tc_fence_after();
-      if (tr) WTRACE(g_trace_fwd, itl, 7);
+      if (sub == 0) {
+        if (tr) WTRACE(g_trace_fwd, k, 5);
+        if constexpr (WS > 0) rg = row_geom_fast<L, WS, ORDER>(gm, tile, row);
+        else                  rg = row_geom(gm, tile, row);
+        key_i = (rg.rr + gm.ws - 1) * (2 * gm.ws - 1) + rg.cc + gm.ws - 1;
+        col0 = GEN ? 0 : rg.g * L;
+        if (tr) WTRACE(g_trace_fwd, k, 6);
+      }
+      const float* tab = s_tab + sub * (TAB_MAX + 1);
       float s[L];
       float mx = -INFINITY;
       float sum = 0.f;
@@ -236,10 +279,13 @@ winattn_fwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant
         auto softmax_fast = [&](auto quad_tag) {
           constexpr bool QUAD = decltype(quad_tag)::value;
           constexpr int QL = L / 4, NQ = QUAD ? 4 : 1;
-          const float* tp = s_tab + key_i;
+          const float* tp = tab + key_i;
           float mq[NQ];
 #pragma unroll
           for (int q = 0; q < NQ; ++q) mq[q] = -INFINITY;
+          mbar_wait(s_full, u & 1);
+          tc_fence_after();
+          if (tr) WTRACE(g_trace_fwd, k, 7);
 #pragma unroll
           for (int cb = 0; cb < L / CH; ++cb) {
             uint32_t v[32];
@@ -252,10 +298,10 @@ winattn_fwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant
               mq[QUAD ? j / QL : 0] = fmaxf(mq[QUAD ? j / QL : 0], x);
             }
           }
-          // S is in registers: the next item's QK^T may overwrite TMEM now
+          // S is in registers: the next unit's QK^T may overwrite TMEM now
           tc_fence_before();
           mbar_arrive(s_free);
-          if (tr) WTRACE(g_trace_fwd, itl, 8);
+          if (tr) WTRACE(g_trace_fwd, k, 8);
           // shift mask (swin_512.py:171-192): a window of the last window row / column holds two bands
           // per wrapping axis; tokens of different bands get -100.  In quadrant order the band pair
           // of a token IS its quadrant, so the mask is one additive constant per quadrant of columns.
@@ -274,8 +320,8 @@ winattn_fwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant
             mx = mq[0];
             nq[0] = -mx;
           }
-          mbar_wait(pv_done, sub_phase ^ 1);        // the previous P V product has finished reading P
-          if (tr) WTRACE(g_trace_fwd, itl, 9);
+          mbar_wait(pv_done, (u & 1) ^ 1);        // the previous P V product has finished reading P
+          if (tr) WTRACE(g_trace_fwd, k, 9);
 #pragma unroll
           for (int j8 = 0; j8 < L / 8; ++j8) {
             uint32_t w[4];
@@ -292,63 +338,100 @@ winattn_fwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant
                 make_uint4(w[0], w[1], w[2], w[3]);
           }
         };
-        // ORDER 0: unshifted block, row-major.  1: every window in quadrant order.  2: only the windows
-        // that wrap (a warp never straddles two windows for L >= 32, so the branch is warp-uniform).
+        // a warp never straddles two windows for L >= 32, so the branch is warp-uniform
         if (ORDER == 0 || (ORDER == 2 && !rg.wraps)) softmax_fast(std::false_type{});
         else                                         softmax_fast(std::true_type{});
       } else {
+        // ---- generic path: per-column look-up table (any order, dense mask, window tags)
+        named_bar_sync(1, 128);                  // everybody is done with the previous LUT
+        const uint32_t my_tag = rg.inrange ? uint32_t(rg.g + 1) : 0u;
+        s_lut[row] = uint32_t(rg.rr * (2 * gm.ws - 1) + rg.cc) | (uint32_t(rg.id) << 8) |
+                     (uint32_t(rg.rr * gm.ws + rg.cc) << 16) | (my_tag << 24);
+        named_bar_sync(1, 128);
+        const bool use_mask = rg.wraps;
+        // dense mask row of this query token (stand-alone WindowAttention with an explicit mask tensor)
+        const float* mask_row =
+            gm.mask ? gm.mask + ((size_t)(rg.gw % gm.mask_nw) * gm.N + (rg.rr * gm.ws + rg.cc)) * gm.N : nullptr;
+        mbar_wait(s_full, u & 1);
+        tc_fence_after();
 #pragma unroll
-      for (int cb = 0; cb < L / CH; ++cb) {
-        uint32_t v[32];
-        tmem_ld_row_chunk<L>(tmem_S, t_lane, col0, cb, wq, lane, v);
+        for (int cb = 0; cb < L / CH; ++cb) {
+          uint32_t v[32];
+          tmem_ld_row_chunk<L>(tmem_S, t_lane, col0, cb, wq, lane, v);
 #pragma unroll
-        for (int jj = 0; jj < CH; ++jj) {
-          const uint32_t lj = s_lut[col0 + cb * CH + jj];
-          float x = fmaf(__uint_as_float(v[jj]), gm.scale_log2e, s_tab[key_i - int(lj & 0xff)]);
-          if (use_mask && ((lj >> 8) & 0xffu) != uint32_t(rg.id)) x += kMaskLog2e;
-          if (mask_row != nullptr) x = fmaf(__ldg(mask_row + ((lj >> 16) & 0xffu)), 1.4426950408889634f, x);
-          if (GEN && (lj >> 24) != my_tag) x = -1.0e30f;        // another window's column, or padding
-          s[cb * CH + jj] = x;
-          mx = fmaxf(mx, x);
+          for (int jj = 0; jj < CH; ++jj) {
+            const uint32_t lj = s_lut[col0 + cb * CH + jj];
+            float x = fmaf(__uint_as_float(v[jj]), gm.scale_log2e, tab[key_i - int(lj & 0xff)]);
+            if (use_mask && ((lj >> 8) & 0xffu) != uint32_t(rg.id)) x += kMaskLog2e;
+            if (mask_row != nullptr) x = fmaf(__ldg(mask_row + ((lj >> 16) & 0xffu)), 1.4426950408889634f, x);
+            if (GEN && (lj >> 24) != my_tag) x = -1.0e30f;        // another window's column, or padding
+            s[cb * CH + jj] = x;
+            mx = fmaxf(mx, x);
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(s_free);
+        mbar_wait(pv_done, (u & 1) ^ 1);
+#pragma unroll
+        for (int j8 = 0; j8 < L / 8; ++j8) {
+          uint32_t w[4];
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            float p0 = fast_exp2(s[j8 * 8 + 2 * h] - mx);
+            float p1 = fast_exp2(s[j8 * 8 + 2 * h + 1] - mx);
+            if (GEN && !rg.inrange) { p0 = 0.f; p1 = 0.f; }          // padding row: keep P finite and empty
+            sum += p0 + p1;
+            w[h] = pack_bf16(p0, p1);
+          }
+          const int col = col0 + j8 * 8;
+          *reinterpret_cast<uint4*>(s_p + (col >> 6) * SLOT_BYTES + sw128_offset(row, (col & 63) >> 3)) =
+              make_uint4(w[0], w[1], w[2], w[3]);
         }
       }
-      // S is in registers: the next item's QK^T may overwrite TMEM now
-      tc_fence_before();
-      mbar_arrive(s_free);
-
-      mbar_wait(pv_done, sub_phase ^ 1);        // the previous P V product has finished reading P
-#pragma unroll
-      for (int j8 = 0; j8 < L / 8; ++j8) {
-        uint32_t w[4];
-#pragma unroll
-        for (int h = 0; h < 4; ++h) {
-          float p0 = fast_exp2(s[j8 * 8 + 2 * h] - mx);
-          float p1 = fast_exp2(s[j8 * 8 + 2 * h + 1] - mx);
-          if (GEN && !rg.inrange) { p0 = 0.f; p1 = 0.f; }          // padding row: keep P finite and empty
-          sum += p0 + p1;
-          w[h] = pack_bf16(p0, p1);
-        }
-        const int col = col0 + j8 * 8;
-        *reinterpret_cast<uint4*>(s_p + (col >> 6) * SLOT_BYTES + sw128_offset(row, (col & 63) >> 3)) =
-            make_uint4(w[0], w[1], w[2], w[3]);
-      }
-      }
+      // 1/rowsum for the epilogue warps: slot (item parity, head of the group), read after p_full
+      s_inv[((k & 1) * 2 + sub) * 128 + row] = (GEN && !rg.inrange) ? 0.f : 1.0f / sum;
+      if (sub == SH - 1) mbar_arrive(&inv_full[k & 1]);
       fence_proxy_async_smem();
       mbar_arrive(p_full);
-      if (tr) WTRACE(g_trace_fwd, itl, 10);
-      inv_sub[sub] = (GEN && !rg.inrange) ? 0.f : 1.0f / sum;
+      if (tr) WTRACE(g_trace_fwd, k, 10);
       if (!GEN || rg.inrange) lse2[((size_t)tile * gm.nH + head) * 128 + rg.canon] = mx + log2f(sum);
-     }
-
-      // ---- epilogue: O * (1/sum) -> bf16 -> staging -> TMA store at the un-rolled coordinates
-      mbar_wait(o_full, it_phase);
+    }
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 160;");
+    // ---------------------------------------------------------------- epilogue warps (group B)
+    // drain O of every item: O * (1/rowsum) -> bf16 -> whole 128-byte lines of `out` at the un-rolled
+    // token index of each row (window_reverse + inverse roll, swin_512.py:224-231)
+    const int wq = warp & 3;
+    const int row = wq * 32 + lane;
+    const uint32_t t_lane = uint32_t(wq * 32) << 16;
+    uint8_t* stage = s_stage + (warp - 8) * 4096;
+    const bool tr = (threadIdx.x == 256);
+    (void)tr;
+    for (int k = 0; k < n_local; ++k) {
+      const int item = int(blockIdx.x) + k * int(gridDim.x);
+      const int tile = item / gm.ngrp;
+      RowGeom rg;
+      if constexpr (WS > 0) rg = row_geom_fast<L, WS, ORDER>(gm, tile, row);
+      else                  rg = row_geom(gm, tile, row);
+      const long tok = rg.valid ? rg.tok : -1;
+      uint8_t* rowp[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const long t = __shfl_sync(0xffffffffu, tok, i * 4 + (lane >> 3));
+        rowp[i] = t < 0 ? nullptr : reinterpret_cast<uint8_t*>(out + t * gm.C + hg * gm.gch);
+      }
+      // 1/rowsum of every head of this item (the softmax warps cannot overwrite the slot before the
+      // P V of item k+1 starts, which waits for this warp's o_free)
+      mbar_wait(&inv_full[k & 1], (k >> 1) & 1);
+      const float inv0 = s_inv[((k & 1) * 2 + 0) * 128 + row];
+      const float inv1 = s_inv[((k & 1) * 2 + (SH - 1)) * 128 + row];
+      mbar_wait(o_full, k & 1);
       tc_fence_after();
-      if (tr) WTRACE(g_trace_fwd, itl, 11);
+      if (tr) WTRACE(g_trace_fwd, k, 11);
       for (int c = 0; c < nc; ++c) {
         uint32_t v0[32], v1[32];
-        // SH == 1: columns [c*64, +64) of this head.  SH == 2: columns [0,32) of sub-head 0's product
-        // and columns [32,64) of sub-head 1's product (each product spans the whole 64-channel chunk).
-        const float inv = inv_sub[0], inv1 = inv_sub[SH - 1];
+        // SH == 1: columns [c*64, +64) of this head.  SH == 2: columns [0,32) of head 0's product
+        // and columns [32,64) of head 1's product (each product spans the whole 64-channel chunk).
         tmem_ld32(tmem_O + t_lane + (SH == 1 ? c * 64 : 0), v0);
         tmem_ld32(tmem_O + t_lane + (SH == 1 ? c * 64 + 32 : 64 + 32), v1);
         tmem_ld_wait();
@@ -356,35 +439,25 @@ winattn_fwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant
           tc_fence_before();
           mbar_arrive(o_free);
         }
-        uint8_t* stg = s_stg + stg_sel * SLOT_BYTES;
-        if (sm_tid < 32) tma_wait_group_read<1>();     // the stores that last used this buffer have drained
-        named_bar_sync(1, 128);
+        uint4 vals[8];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          uint4 q;
-          q.x = pack_bf16(__uint_as_float(v0[8 * j + 0]) * inv, __uint_as_float(v0[8 * j + 1]) * inv);
-          q.y = pack_bf16(__uint_as_float(v0[8 * j + 2]) * inv, __uint_as_float(v0[8 * j + 3]) * inv);
-          q.z = pack_bf16(__uint_as_float(v0[8 * j + 4]) * inv, __uint_as_float(v0[8 * j + 5]) * inv);
-          q.w = pack_bf16(__uint_as_float(v0[8 * j + 6]) * inv, __uint_as_float(v0[8 * j + 7]) * inv);
-          *reinterpret_cast<uint4*>(stg + sw128_offset(row, j)) = q;
-          q.x = pack_bf16(__uint_as_float(v1[8 * j + 0]) * inv1, __uint_as_float(v1[8 * j + 1]) * inv1);
-          q.y = pack_bf16(__uint_as_float(v1[8 * j + 2]) * inv1, __uint_as_float(v1[8 * j + 3]) * inv1);
-          q.z = pack_bf16(__uint_as_float(v1[8 * j + 4]) * inv1, __uint_as_float(v1[8 * j + 5]) * inv1);
-          q.w = pack_bf16(__uint_as_float(v1[8 * j + 6]) * inv1, __uint_as_float(v1[8 * j + 7]) * inv1);
-          *reinterpret_cast<uint4*>(stg + sw128_offset(row, 4 + j)) = q;
+          vals[j] = make_uint4(pack_bf16(__uint_as_float(v0[8 * j + 0]) * inv0, __uint_as_float(v0[8 * j + 1]) * inv0),
+                               pack_bf16(__uint_as_float(v0[8 * j + 2]) * inv0, __uint_as_float(v0[8 * j + 3]) * inv0),
+                               pack_bf16(__uint_as_float(v0[8 * j + 4]) * inv0, __uint_as_float(v0[8 * j + 5]) * inv0),
+                               pack_bf16(__uint_as_float(v0[8 * j + 6]) * inv0, __uint_as_float(v0[8 * j + 7]) * inv0));
+          vals[4 + j] = make_uint4(pack_bf16(__uint_as_float(v1[8 * j + 0]) * inv1, __uint_as_float(v1[8 * j + 1]) * inv1),
+                                   pack_bf16(__uint_as_float(v1[8 * j + 2]) * inv1, __uint_as_float(v1[8 * j + 3]) * inv1),
+                                   pack_bf16(__uint_as_float(v1[8 * j + 4]) * inv1, __uint_as_float(v1[8 * j + 5]) * inv1),
+                                   pack_bf16(__uint_as_float(v1[8 * j + 6]) * inv1, __uint_as_float(v1[8 * j + 7]) * inv1));
         }
-        fence_proxy_async_smem();
-        named_bar_sync(1, 128);
-        if (sm_tid < 32) {                             // warp 2 issues the scatter, one box per lane
-          tile_boxes<false>(gm, tile, hg * gm.gch + c * 64, stg, &tm_out, nullptr, lane);
-          tma_commit_group();
-        }
-        if (tr && c == 0) WTRACE(g_trace_fwd, itl, 15);
-        stg_sel ^= 1;
+        uint8_t* rp[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rp[i] = rowp[i] ? rowp[i] + c * 128 : nullptr;
+        warp_store_rows<8>(stage, vals, rp, lane);
       }
-      if (tr) WTRACE(g_trace_fwd, itl, 12);
+      if (tr) WTRACE(g_trace_fwd, k, 12);
     }
-    if (sm_tid < 32) tma_wait_group<0>();
   }
 
   tc_fence_before();
@@ -434,6 +507,11 @@ int fill_geom(WinGeom* gm, int B, int T, int H, int W, int C, int nH, int ws, in
   }
   gm->uniform_quad = 0;
   gm->mask = nullptr; gm->mask_nw = 0;
+  // exact multiply-shift division of window indices (row_geom_fast)
+  if ((unsigned long long)gm->total_windows * (unsigned long long)gm->nW >= (1ull << 32))
+    return set_error(kErrUnsupported, "winattn: %d windows exceed the supported index range", gm->total_windows);
+  gm->mg_nW = ((1ull << 32) + gm->nW - 1) / gm->nW;
+  gm->mg_nWw = ((1ull << 32) + gm->nWw - 1) / gm->nWw;
   return kOk;
 }
 
@@ -482,23 +560,22 @@ int winattn_fwd(const void* qkv, const float* bias_table, void* out, float* lse2
   if (qk_scale > 0.f) { gm.scale = qk_scale; gm.scale_log2e = qk_scale * 1.4426950408889634f; }
   STSWIN_CHECK_ARG(mask == nullptr || mask_windows > 0, "winattn: mask given with mask_windows <= 0");
   gm.mask = mask; gm.mask_nw = mask_windows;
-  gm.uniform_quad = (gm.L == 128 && !gm.general) ? 1 : gm.uniform_quad;
-  if (const char* e = getenv("STSWIN_FWD_UNIFORM")) gm.uniform_quad = atoi(e);   // TEMP experiment
-  WinMaps tq, to;
+  STSWIN_CHECK_ARG((reinterpret_cast<uintptr_t>(out) & 15) == 0, "winattn_fwd: out must be 16-byte aligned");
+  WinMaps tq;
   if ((rc = make_window_tmaps(&tq, qkv, gm, 3 * C)) != kOk) return rc;
-  if ((rc = make_window_tmaps(&to, out, gm, C)) != kOk) return rc;
   const int items = gm.num_tiles * gm.ngrp;
-  const int grid = items < num_sms() ? items : num_sms();
+  int grid = items < num_sms() ? items : num_sms();
+  grid -= grid % gm.ngrp;                 // every CTA keeps one head group (its bias tables live in smem)
 #define STSWIN_LAUNCH_FWD(LL, WW, QQ, GG)                                                                      \
   {                                                                                                            \
     if ((rc = set_smem(winattn_fwd_kernel<LL, WW, QQ, GG>, SMEM_BYTES)) != kOk) return rc;                     \
-    winattn_fwd_kernel<LL, WW, QQ, GG><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tq, to, bias_table, lse2, gm); \
+    winattn_fwd_kernel<LL, WW, QQ, GG><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tq, static_cast<__nv_bfloat16*>(out), bias_table, lse2, gm); \
   }
   // fast softmax: the shipped geometries (ws 8 or 4, 1 or 2 frames per window, shift 0 or ws/2, no dense mask)
   const bool fast = !gm.general && mask == nullptr && (shift == 0 || 2 * shift == ws) &&
                     ((ws == 8 && (gm.L == 128 || gm.L == 64)) || (ws == 4 && gm.L == 32));
-  // token order of a shifted block: small windows keep one box per interior window (16 tiny quadrant
-  // boxes per chunk cost more than they save); 128-token windows use one order for the whole launch
+  // token order of a shifted block: quadrant order only for the windows that wrap (one box per
+  // interior window measured faster than four quadrant boxes for every window, at every L)
   const int order = shift == 0 ? 0 : (gm.uniform_quad ? 1 : 2);
   if (gm.general) STSWIN_LAUNCH_FWD(128, 0, 0, true)
   else if (fast && gm.L == 128 && order == 0) STSWIN_LAUNCH_FWD(128, 8, 0, false)

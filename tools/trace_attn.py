@@ -32,7 +32,7 @@ assert fn(buf.data_ptr()) == 0
 if which == "fwd":
     ops.winattn_fwd(qkv, table, H, W, nH, ws, shift)
     names = ["ld_first", "ld_last", "S_issued", "PV_begin", "PV_issued", "item_start", "geom_done", "S_ready",
-             "pass1_done", "P_free", "pass2_done", "O_ready", "epi_done", "QK_landed", "V_landed", "epi_c0"]
+             "pass1_done", "P_free", "pass2_done", "O_ready", "epi_done"]
 else:
     ops.winattn_bwd(qkv, table, lse, do, H, W, nH, ws, shift, dt)
     names = ["ldH_first", "ldH_last", "ldL_first", "ldL_last", "SdP_issued", "out_begin", "out_issued", "item_start",
