@@ -31,6 +31,8 @@
 // launch uses ONE token order (gm.uniform_quad) and every CTA sees ONE head (grid % nH == 0).
 // (A first version accumulated bf16 dS on the tensor core through an identity tile; its rounding
 // noise reached 6% of the gradient for a 6-window batch.)
+#include <type_traits>
+
 #include "winattn_common.cuh"
 #include "host_util.h"
 #include "kernels.h"
@@ -42,21 +44,22 @@ int make_window_tmaps(WinMaps* maps, const void* base, const WinGeom& gm, int ch
 
 namespace {
 
-constexpr int NRH = 6;                         // ring H: first-pass chunks, streamed from HBM
+constexpr int NRH = 5;                         // ring H: first-pass chunks, streamed from HBM
 constexpr int NRL = 3;                         // ring L: second-pass chunks, re-read from L2
 constexpr int SLOT_BYTES = 128 * 128;
 constexpr int PD_BYTES = 2 * SLOT_BYTES;       // [128 x 128] bf16 as two K-major halves
+constexpr int STG_BYTES = 8 * 2048;            // per-warp output transposition areas (drain warps)
 constexpr int TAB_MAX = 15 * 15;
-constexpr int NUM_THREADS = 384;               // warp 0 producer H, 1 MMA, 2 producer L, 3 idle, 4-7 / 8-11 compute groups A / B
-constexpr int SMEM_BYTES =
-    1024 + (NRH + NRL) * SLOT_BYTES + 2 * PD_BYTES + 128 * 4 + 3 * (TAB_MAX + 1) * 4 + 2 * 128 * 4 + 256;
+constexpr int NUM_THREADS = 512;               // warpgroup 0: producers H / L, MMA issuer; 1: softmax backward; 2, 3: drain
+constexpr int SMEM_BYTES = 1024 + (NRH + NRL) * SLOT_BYTES + 2 * PD_BYTES + STG_BYTES + 128 * 4 +
+                           4 * (TAB_MAX + 1) * 4 + 256;
 constexpr float kMaskLog2e = -100.0f * 1.4426950408889634f;
+STSWIN_TRACE_DECL(g_trace_bwd)
 
-// GEN (only with L = 128): windows of gm.L tokens with gm.L not a power of two, or rectangles of unequal
-// size (shift != ws/2): every thread walks the whole 128-column row and keeps the columns tagged with its
-// own window; the bias-table gradient then goes through shared-memory atomics instead of the per-column
-// register sums (whose column -> position fold relies on the regular power-of-two orders).
-template <int L, int SHT, bool GEN>
+// L, GEN as in the forward kernel.  WS > 0: fast path for the shipped geometries (compile-time column
+// maps; the bias-table gradient is summed in registers).  ORDER: 0 unshifted (row-major), 2 shifted
+// (quadrant order for the windows that wrap).  SHT: heads per 64-channel group (2 when head_dim is 32).
+template <int L, int WS, int ORDER, int SHT, bool GEN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 winattn_bwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant__ WinMaps tm_do,
                    __nv_bfloat16* __restrict__ d_qkv, const float* __restrict__ bias_table, const float* __restrict__ lse2, float* __restrict__ d_table,
@@ -67,23 +70,25 @@ winattn_bwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant
   uint8_t* s_ringl = s_ringh + NRH * SLOT_BYTES;
   uint8_t* s_p = s_ringl + NRL * SLOT_BYTES;
   uint8_t* s_ds = s_p + PD_BYTES;
-  uint32_t* s_lut = reinterpret_cast<uint32_t*>(s_ds + PD_BYTES);
-  float* s_tab = reinterpret_cast<float*>(s_lut + 128);
-  float* s_bacc = s_tab + TAB_MAX + 1;            // [2][TAB_MAX + 1]: one bin array per head of the group
-  float* s_delta = s_bacc + 2 * (TAB_MAX + 1);          // [2][128] partial row sums of the two compute groups
-  static_assert(((128 + 3 * (TAB_MAX + 1) + 256) * 4) % 8 == 0, "mbarriers need 8-byte alignment");
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_delta + 256);
+  uint8_t* s_stage = s_ds + PD_BYTES;
+  uint32_t* s_lut = reinterpret_cast<uint32_t*>(s_stage + STG_BYTES);
+  float* s_tab = reinterpret_cast<float*>(s_lut + 128);   // [2][TAB_MAX + 1] bias * log2e, one table per head of the group
+  float* s_bacc = s_tab + 2 * (TAB_MAX + 1);              // [2][TAB_MAX + 1] bias-table gradient bins of this CTA
+  static_assert(((128 + 4 * (TAB_MAX + 1)) * 4) % 8 == 0, "mbarriers need 8-byte alignment");
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bacc + 2 * (TAB_MAX + 1));
   uint64_t* fullh = bars;
   uint64_t* emptyh = fullh + NRH;
   uint64_t* fulll = emptyh + NRH;
   uint64_t* emptyl = fulll + NRL;
-  uint64_t* sdp_full = emptyl + NRL;
-  uint64_t* sdp_free = sdp_full + 1;
-  uint64_t* pds_full = sdp_full + 2;
-  uint64_t* pds_free = sdp_full + 3;
-  uint64_t* obuf_full = sdp_full + 4;   // [2]
-  uint64_t* obuf_free = sdp_full + 6;   // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sdp_full + 8);
+  uint64_t* sdp_full = emptyl + NRL;    // S and dP of a unit complete (tensor core)
+  uint64_t* s_free = sdp_full + 1;      // S read out (after pass 1)
+  uint64_t* dp_free = sdp_full + 2;     // [2] dP buffer read out (after pass 2)
+  uint64_t* pds_full = sdp_full + 4;    // P and dS of a unit in shared memory
+  uint64_t* p_free = sdp_full + 5;      // the dV products have read P
+  uint64_t* ds_free = sdp_full + 6;     // the dQ / dK products have read dS
+  uint64_t* obuf_full = sdp_full + 7;   // [2]
+  uint64_t* obuf_free = sdp_full + 9;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sdp_full + 11);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -91,6 +96,9 @@ winattn_bwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant
   const int nc = gm.nc;
   const int hg = blockIdx.x % gm.ngrp;          // head group, constant per CTA: gridDim.x % ngrp == 0
   constexpr int SH = SHT;                       // heads per group (2 when head_dim is 32)
+  const int n_local = (num_items - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
+  const int n_units = n_local * SH;             // unit = (item, head of the group)
+  const int nbias = (2 * gm.ws - 1) * (2 * gm.ws - 1);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_qkv.full);
@@ -104,9 +112,12 @@ winattn_bwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant
       mbar_init(&emptyl[i], 1);
     }
     mbar_init(sdp_full, 1);
-    mbar_init(sdp_free, (L >= 64) ? 256 : 128);     // every thread that reads S / dP
-    mbar_init(pds_full, (L >= 64) ? 256 : 128);     // every thread that writes P / dS
-    mbar_init(pds_free, 1);
+    mbar_init(s_free, 128);
+    mbar_init(&dp_free[0], 128);
+    mbar_init(&dp_free[1], 128);
+    mbar_init(pds_full, 128);
+    mbar_init(p_free, 1);
+    mbar_init(ds_free, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&obuf_full[i], 1);
       mbar_init(&obuf_free[i], 128);
@@ -118,17 +129,26 @@ winattn_bwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant
   // mode) are never written by TMA and must read as zero.
   for (int i = threadIdx.x; i < ((NRH + NRL) * SLOT_BYTES + 2 * PD_BYTES) / 16; i += NUM_THREADS)
     reinterpret_cast<uint4*>(s_ringh)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = threadIdx.x; i < 2 * (TAB_MAX + 1); i += NUM_THREADS) s_bacc[i] = 0.f;
+  for (int i = threadIdx.x; i < SH * nbias; i += NUM_THREADS) {
+    const int sub = i / nbias, k = i - sub * nbias;
+    s_tab[sub * (TAB_MAX + 1) + k] = __ldg(bias_table + k * gm.nH + hg * SH + sub) * 1.4426950408889634f;
+  }
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base;
-  const uint32_t tmem_dP = tmem_base + 128;
-  const uint32_t tmem_out = tmem_base + 256;    // two 64-column output accumulators
+  const uint32_t tmem_S = tmem_base;            // 128 columns
+  const uint32_t tmem_dP = tmem_base + 128;     // two 128-column buffers (units alternate)
+  const uint32_t tmem_out = tmem_base + 384;    // two 64-column output accumulators
 
-  if (warp == 0 || warp == 2) {
+  if (warp < 4) {
+   asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+   if (warp == 0 || warp == 2) {
     // ---------------------------------------------------------------- TMA producers (all lanes issue boxes)
+    // ring H (warp 0): per 64-channel chunk c: Q_c K_c dO_c V_c      -> S, dP
+    // ring L (warp 2): dO_0.. (dV), then per c: K_c (dQ_c) Q_c (dK_c) -> re-read from L2
     const bool ring_h = (warp == 0);
     uint8_t* ring = ring_h ? s_ringh : s_ringl;
     uint64_t* fullb = ring_h ? fullh : fulll;
@@ -143,9 +163,11 @@ winattn_bwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant
       tile_boxes<true>(gm, tile, ch0, ring + slot * SLOT_BYTES, from_do ? &tm_do : &tm_qkv, &fullb[slot], lane);
       if (++slot == nslot) { slot = 0; phase ^= 1; }
     };
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+    for (int k = 0; k < n_local; ++k) {
+      const int item = int(blockIdx.x) + k * int(gridDim.x);
       const int tile = item / gm.ngrp;
       const int hq = hg * gm.gch;
+      if (lane == 0) WTRACE(g_trace_bwd, k, ring_h ? 0 : 2);
       if (ring_h) {
         for (int c = 0; c < nc; ++c) {
           load(tile, false, 0 * gm.C + hq + c * 64);   // Q_c
@@ -154,136 +176,278 @@ winattn_bwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant
           load(tile, false, 2 * gm.C + hq + c * 64);   // V_c
         }
       } else {
+        for (int c = 0; c < nc; ++c) load(tile, true, hq + c * 64);   // dO_c -> dV_c
         for (int c = 0; c < nc; ++c) {
-          load(tile, true, hq + c * 64);               // dO_c -> dV_c
           load(tile, false, 1 * gm.C + hq + c * 64);   // K_c  -> dQ_c
           load(tile, false, 0 * gm.C + hq + c * 64);   // Q_c  -> dK_c
         }
       }
+      if (lane == 0) WTRACE(g_trace_bwd, k, ring_h ? 1 : 3);
     }
-  } else if (warp == 1) {
+   } else if (warp == 1) {
     // ---------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc_kk = umma_idesc_bf16(128, 128, 0, 0);   // S, dP
-      constexpr uint32_t idesc_kn = umma_idesc_bf16(128, 64, 0, 1);    // dQ = dS K
-      constexpr uint32_t idesc_nn = umma_idesc_bf16(128, 64, 1, 1);    // dV = P^T dO, dK = dS^T Q
-      int slot = 0, slotl = 0;
-      uint32_t phase = 0, phasel = 0, sub_phase = 0;
-      uint32_t obp[2] = {0, 0};           // per output buffer: parity of its next use
-      const uint32_t p_addr = smem_u32(s_p), ds_addr = smem_u32(s_ds);
-      auto take_h = [&]() { const int sl = slot; mbar_wait(&fullh[slot], phase); if (++slot == NRH) { slot = 0; phase ^= 1; } return sl; };
-      auto take_l = [&]() { const int sl = slotl; mbar_wait(&fulll[slotl], phasel); if (++slotl == NRL) { slotl = 0; phasel ^= 1; } return sl; };
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-        int sa[4][2], sb[4][2], sl3[4][3];          // ring slots of this item's chunks (held across sub-heads)
-        for (int sub = 0; sub < SH; ++sub, sub_phase ^= 1) {
-          mbar_wait(sdp_free, sub_phase ^ 1);
-          tc_fence_after();
-          // S and dP; with two heads per chunk only the sub-head's 32-channel K range (two k-steps)
-          const int k0 = (SH == 1) ? 0 : sub * 2, k1 = (SH == 1) ? 4 : sub * 2 + 2;
-          for (int c = 0; c < nc; ++c) {
-            for (int pair = 0; pair < 2; ++pair) {     // (Q_c, K_c) -> S ; (dO_c, V_c) -> dP
-              if (sub == 0) { sa[c][pair] = take_h(); sb[c][pair] = take_h(); }
-              tc_fence_after();
-              const uint32_t aa = smem_u32(s_ringh + sa[c][pair] * SLOT_BYTES), ba = smem_u32(s_ringh + sb[c][pair] * SLOT_BYTES);
-              for (int kk = k0; kk < k1; ++kk)
-                umma_bf16(pair == 0 ? tmem_S : tmem_dP, umma_smem_desc(aa + kk * 32, 16, 1024),
-                          umma_smem_desc(ba + kk * 32, 16, 1024), idesc_kk, (c > 0 || kk > k0) ? 1u : 0u);
-              if (sub == SH - 1) {
-                umma_commit(&emptyh[sa[c][pair]]);
-                umma_commit(&emptyh[sb[c][pair]]);
-              }
-            }
-          }
-          umma_commit(sdp_full);
-
-          mbar_wait(pds_full, sub_phase);
-          tc_fence_after();
-          for (int c = 0; c < nc; ++c) {
-            for (int o = 0; o < 3; ++o) {              // dV_c, dQ_c, dK_c (whole 64-channel chunk)
-              const int ob = ((sub * nc + c) * 3 + o) & 1;   // output chunk k of a tile uses TMEM buffer k % 2
-              if (sub == 0) sl3[c][o] = take_l();
-              mbar_wait(&obuf_free[ob], obp[ob] ^ 1);
-              tc_fence_after();
-              const uint32_t xa = smem_u32(s_ringl + sl3[c][o] * SLOT_BYTES);
-              const uint32_t dst = tmem_out + ob * 64;
+    // warp-uniform control flow (descriptors stay in uniform registers); one elected lane issues.
+    const bool leader = elect_one();
+    constexpr uint32_t idesc_kk = umma_idesc_bf16(128, 128, 0, 0);   // S, dP
+    constexpr uint32_t idesc_kn = umma_idesc_bf16(128, 64, 0, 1);    // dQ = dS K
+    constexpr uint32_t idesc_nn = umma_idesc_bf16(128, 64, 1, 1);    // dV = P^T dO, dK = dS^T Q
+    const uint32_t p_addr = smem_u32(s_p), ds_addr = smem_u32(s_ds);
+    const uint32_t rh_addr = smem_u32(s_ringh), rl_addr = smem_u32(s_ringl);
+    uint32_t seq_h = 0, seq_l = 0, base_h = 0, base_l = 0;   // running chunk counters of the two rings
+    uint32_t nout = 0;                                        // output products issued so far (buffer = nout & 1)
+    auto issue_SdP = [&](int u) {
+      const int sub = (SH == 1) ? 0 : (u & 1);
+      const int b = u & 1;                                    // dP buffer of this unit
+      mbar_wait(s_free, (u & 1) ^ 1);                         // pass 1 of the previous unit has read S
+      mbar_wait(&dp_free[b], ((u >> 1) & 1) ^ 1);             // pass 2 of unit u-2 has read this dP buffer
+      tc_fence_after();
+      if (sub == 0) { base_h = seq_h; seq_h += 4 * nc; }
+      // with two heads per chunk only the head's 32-channel K range (two k-steps)
+      const int k0 = (SH == 1) ? 0 : sub * 2, k1 = (SH == 1) ? 4 : sub * 2 + 2;
+      for (int c = 0; c < nc; ++c) {
 #pragma unroll
-              for (int kk = 0; kk < 8; ++kk) {
-                const uint64_t bdesc = umma_smem_desc(xa + kk * 2048, SLOT_BYTES, 1024);   // [rows x 64ch], MN-major
-                if (o == 0)        // dV = P^T dO : A = P viewed MN-major (m = key), k = query
-                  umma_bf16(dst, umma_smem_desc(p_addr + kk * 2048, SLOT_BYTES, 1024), bdesc, idesc_nn, kk > 0);
-                else if (o == 1)   // dQ = dS K   : A = dS K-major, k = key
-                  umma_bf16(dst, umma_smem_desc(ds_addr + (kk >> 2) * SLOT_BYTES + (kk & 3) * 32, 16, 1024), bdesc,
-                            idesc_kn, kk > 0);
-                else               // dK = dS^T Q : A = dS viewed MN-major
-                  umma_bf16(dst, umma_smem_desc(ds_addr + kk * 2048, SLOT_BYTES, 1024), bdesc, idesc_nn, kk > 0);
-              }
-              if (sub == SH - 1) umma_commit(&emptyl[sl3[c][o]]);
-              umma_commit(&obuf_full[ob]);
-              obp[ob] ^= 1;
+        for (int pair = 0; pair < 2; ++pair) {     // (Q_c, K_c) -> S ; (dO_c, V_c) -> dP
+          const uint32_t na = base_h + 4 * c + 2 * pair, nb = na + 1;
+          const uint32_t sa = na % NRH, sb = nb % NRH;
+          if (sub == 0) {
+            mbar_wait(&fullh[sa], (na / NRH) & 1);
+            mbar_wait(&fullh[sb], (nb / NRH) & 1);
+          }
+          tc_fence_after();
+          const uint32_t aa = rh_addr + sa * SLOT_BYTES, ba = rh_addr + sb * SLOT_BYTES;
+          if (leader) {
+            for (int kk = k0; kk < k1; ++kk)
+              umma_bf16(pair == 0 ? tmem_S : tmem_dP + b * 128, umma_smem_desc(aa + kk * 32, 16, 1024),
+                        umma_smem_desc(ba + kk * 32, 16, 1024), idesc_kk, (c > 0 || kk > k0) ? 1u : 0u);
+            if (sub == SH - 1) {
+              umma_commit(&emptyh[sa]);
+              umma_commit(&emptyh[sb]);
             }
           }
-          umma_commit(pds_free);
         }
       }
-    }
-  } else if (warp >= 4) {
-    // ---------------------------------------------------------------- softmax-backward + epilogue (2 groups)
-    const int grp = (warp - 4) >> 2;              // 0: warps 4-7, 1: warps 8-11
-    const int wq = warp & 3;                      // TMEM lane quarter
-    const int row = wq * 32 + lane;
-    const int cm_tid = threadIdx.x - 128;         // 0..255 over both groups
-    const uint32_t t_lane = uint32_t(wq * 32) << 16;
-    const int nbias = (2 * gm.ws - 1) * (2 * gm.ws - 1);
-    for (int i = cm_tid; i < 2 * (TAB_MAX + 1); i += 256) s_bacc[i] = 0.f;
-    constexpr bool COLSPLIT = (L >= 64);          // both groups work on S / dP (alternate 32-column chunks)
-    constexpr int CH = (L >= 32) ? 32 : 16;
-    constexpr int NCHUNK = L / CH;                // chunks of the row's own window columns
-    // running sums over tiles of dS[row, key position], one accumulator per key position this
-    // thread sees.  L = 128: chunks cb and cb+2 of a thread hold the same positions (row-major order:
-    // the other frame; quadrant order folds the two frames inside each 32-column quadrant block).
-    constexpr int NACC = COLSPLIT ? 32 : L;
-    const bool quad = gm.shift > 0;               // uniform_quad: one token order per launch
-    float bacc[SH][NACC];                         // one set per head of the group
-#pragma unroll
-    for (int h = 0; h < SH; ++h)
-#pragma unroll
-      for (int k = 0; k < NACC; ++k) bacc[h][k] = 0.f;
-    const bool softmax_role = COLSPLIT || grp == 0;
-    uint32_t sub_phase = 0, ob_phase = 0;
-    int key_i = 0, col0 = 0;
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-      const int tile = item / gm.ngrp;
-      const RowGeom rg = row_geom(gm, tile, row);
-#pragma unroll
-     for (int sub = 0; sub < SH; ++sub, sub_phase ^= 1) {
-      const int head = hg * SH + sub;
-      named_bar_sync(1, 256);                     // everybody is done with the previous LUT / bias table
-      // key | region id | spatial position | window tag (g + 1, 0 for a padding row)
-      const uint32_t my_tag = rg.inrange ? uint32_t(rg.g + 1) : 0u;
-      if (grp == 0) s_lut[row] = uint32_t(rg.rr * (2 * gm.ws - 1) + rg.cc) | (uint32_t(rg.id) << 8) |
-                                 (uint32_t(rg.rr * gm.ws + rg.cc) << 16) | (my_tag << 24);
-      if (SH > 1 || item == int(blockIdx.x))      // the head (and so the table) changes only when SH > 1
-        for (int i = cm_tid; i < nbias; i += 256) s_tab[i] = __ldg(bias_table + i * gm.nH + head) * 1.4426950408889634f;
-      named_bar_sync(1, 256);
-      key_i = (rg.rr + gm.ws - 1) * (2 * gm.ws - 1) + rg.cc + gm.ws - 1;
-      col0 = GEN ? 0 : rg.g * L;
-      const bool use_mask = rg.wraps;
-      // dense mask row of this query token (stand-alone WindowAttention with an explicit mask tensor)
-      const float* mask_row = gm.mask ? gm.mask + ((size_t)(rg.gw % gm.mask_nw) * gm.N + (rg.rr * gm.ws + rg.cc)) * gm.N : nullptr;
-
-      if (softmax_role) {
-        const float lse_i = (GEN && !rg.inrange) ? 0.f : lse2[((size_t)tile * gm.nH + head) * 128 + rg.canon];
-        mbar_wait(sdp_full, sub_phase);
-        mbar_wait(pds_free, sub_phase ^ 1);
+      if (leader) {
+        umma_commit(sdp_full);
+        WTRACE(g_trace_bwd, (SH == 1 ? u : u >> 1), 4);
+      }
+      __syncwarp();
+    };
+    auto issue_out = [&](int u) {
+      const int sub = (SH == 1) ? 0 : (u & 1);
+      mbar_wait(pds_full, u & 1);
+      tc_fence_after();
+      if (leader) WTRACE(g_trace_bwd, (SH == 1 ? u : u >> 1), 5);
+      if (sub == 0) { base_l = seq_l; seq_l += 3 * nc; }
+      // products in ring-L order: dV_0 .. dV_{nc-1}, then dQ_c, dK_c per chunk (whole 64-channel chunks)
+      for (int n = 0; n < 3 * nc; ++n) {
+        const int o = n < nc ? 0 : 1 + ((n - nc) & 1);        // 0: dV, 1: dQ, 2: dK
+        const uint32_t nl = base_l + n, sl = nl % NRL;
+        const uint32_t ob = nout & 1;
+        if (sub == 0) mbar_wait(&fulll[sl], (nl / NRL) & 1);
+        mbar_wait(&obuf_free[ob], ((nout >> 1) & 1) ^ 1);     // the drain warps have emptied this accumulator
         tc_fence_after();
-        // pass 1: P = exp2(S2 - lse2) -> smem (bf16), delta = sum_j P dP
-        float delta = 0.f;
+        const uint32_t xa = rl_addr + sl * SLOT_BYTES;
+        const uint32_t dst = tmem_out + ob * 64;
+        if (leader) {
 #pragma unroll
-        for (int ci = 0; ci < (COLSPLIT ? NCHUNK / 2 : NCHUNK); ++ci) {
-          const int cb = COLSPLIT ? 2 * ci + grp : ci;
+          for (int kk = 0; kk < 8; ++kk) {
+            const uint64_t bdesc = umma_smem_desc(xa + kk * 2048, SLOT_BYTES, 1024);   // [rows x 64ch], MN-major
+            if (o == 0)        // dV = P^T dO : A = P viewed MN-major (m = key), k = query
+              umma_bf16(dst, umma_smem_desc(p_addr + kk * 2048, SLOT_BYTES, 1024), bdesc, idesc_nn, kk > 0);
+            else if (o == 1)   // dQ = dS K   : A = dS K-major, k = key
+              umma_bf16(dst, umma_smem_desc(ds_addr + (kk >> 2) * SLOT_BYTES + (kk & 3) * 32, 16, 1024), bdesc,
+                        idesc_kn, kk > 0);
+            else               // dK = dS^T Q : A = dS viewed MN-major
+              umma_bf16(dst, umma_smem_desc(ds_addr + kk * 2048, SLOT_BYTES, 1024), bdesc, idesc_nn, kk > 0);
+          }
+          if (sub == SH - 1) umma_commit(&emptyl[sl]);
+          umma_commit(&obuf_full[ob]);
+          if (n == nc - 1) umma_commit(p_free);               // P may be overwritten by the next unit's pass 1
+        }
+        ++nout;
+      }
+      if (leader) {
+        umma_commit(ds_free);                                 // dS may be overwritten by the next unit's pass 2
+        WTRACE(g_trace_bwd, (SH == 1 ? u : u >> 1), 6);
+      }
+      __syncwarp();
+    };
+    // S / dP of unit u+1 are issued before the output products of unit u: they run on the tensor
+    // core while the softmax-backward warps are in pass 2 of unit u.
+    if (n_units > 0) issue_SdP(0);
+    for (int u = 0; u < n_units; ++u) {
+      if (u + 1 < n_units) issue_SdP(u + 1);
+      issue_out(u);
+    }
+   }
+  } else if (warp < 8) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    // ---------------------------------------------------------------- softmax-backward warps (group A)
+    // thread <-> tile row <-> TMEM lane.  pass 1: P = exp2(S2 - lse2) -> smem, delta = sum_j P dP.
+    // pass 2: dS = P o (dP - delta) -> smem, bias-table gradient sums.
+    const int wq = warp & 3;
+    const int row = wq * 32 + lane;
+    const int cm_tid = threadIdx.x - 128;
+    const uint32_t t_lane = uint32_t(wq * 32) << 16;
+    const bool tr = (threadIdx.x == 128);
+    (void)tr;
+    constexpr int CH = (L >= 32) ? 32 : 16;
+    constexpr int NCHUNK = L / CH;
+    // fast path with one head per group: per-row running sums of dS over every item of this CTA, one per
+    // key position (the TxT tiling folds onto the same entry).  They are binned by relative position
+    // whenever the row's own position changes (token order switch) and at the end of the kernel.
+    constexpr bool REG_BACC = (WS > 0 && SH == 1);
+    constexpr int NPOS = REG_BACC ? WS * WS : 1;
+    float bacc[NPOS];
+#pragma unroll
+    for (int i = 0; i < NPOS; ++i) bacc[i] = 0.f;
+    int bacc_key = -1;                       // key_i the sums in bacc belong to (-1: empty)
+    auto flush_bacc = [&]() {
+      if constexpr (REG_BACC) {
+        if (bacc_key >= 0) {
+#pragma unroll
+          for (int pos = 0; pos < NPOS; ++pos) {
+            const int key = (pos / WS) * (2 * WS - 1) + pos % WS;
+            if (bacc[pos] != 0.f) atomicAdd(&s_bacc[bacc_key - key], bacc[pos]);
+            bacc[pos] = 0.f;
+          }
+        }
+      }
+    };
+    RowGeom rg;
+    int key_i = 0, col0 = 0;
+    for (int u = 0; u < n_units; ++u) {
+      const int sub = (SH == 1) ? 0 : (u & 1);
+      const int k = (SH == 1) ? u : (u >> 1);
+      const int item = int(blockIdx.x) + k * int(gridDim.x);
+      const int tile = item / gm.ngrp;
+      const int head = hg * SH + sub;
+      const uint32_t tmem_dPu = tmem_dP + (u & 1) * 128;
+      if (sub == 0) {
+        if (tr) WTRACE(g_trace_bwd, k, 7);
+        if constexpr (WS > 0) rg = row_geom_fast<L, WS, ORDER>(gm, tile, row);
+        else                  rg = row_geom(gm, tile, row);
+        key_i = (rg.rr + gm.ws - 1) * (2 * gm.ws - 1) + rg.cc + gm.ws - 1;
+        col0 = GEN ? 0 : rg.g * L;
+        if constexpr (REG_BACC) {
+          if (key_i != bacc_key) { flush_bacc(); bacc_key = key_i; }
+        }
+      }
+      const float* tab = s_tab + sub * (TAB_MAX + 1);
+      float* bins = s_bacc + sub * (TAB_MAX + 1);
+      const float lse_i = (GEN && !rg.inrange) ? 0.f : lse2[((size_t)tile * gm.nH + head) * 128 + rg.canon];
+      float delta = 0.f;
+
+      if constexpr (WS > 0) {
+        // ---- fast path: compile-time column map, instantiated per token order of the row's window
+        auto softmax_bwd_fast = [&](auto quad_tag) {
+          constexpr bool QUAD = decltype(quad_tag)::value;
+          constexpr int QL = L / 4;
+          const float* tp = tab + key_i;
+          // shift mask: one additive constant per quadrant of columns (see the forward kernel); folded with -lse
+          float nq[4];
+          if constexpr (QUAD) {
+            const int q_i = (rg.rr >= WS / 2 ? 2 : 0) | (rg.cc >= WS / 2 ? 1 : 0);
+            const int wm = (rg.id >= 3 ? 2 : 0) | (rg.id % 3 != 0 ? 1 : 0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) nq[q] = (((q ^ q_i) & wm) ? kMaskLog2e : 0.f) - lse_i;
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) nq[q] = -lse_i;
+          }
+          mbar_wait(sdp_full, u & 1);
+          tc_fence_after();
+          if (tr) WTRACE(g_trace_bwd, k, 8);
+          // pass 1
+#pragma unroll
+          for (int cb = 0; cb < NCHUNK; ++cb) {
+            uint32_t v[32], w[32];
+            tmem_ld_row_chunk<L>(tmem_S, t_lane, col0, cb, wq, lane, v);
+            tmem_ld_row_chunk<L>(tmem_dPu, t_lane, col0, cb, wq, lane, w);
+            if (cb == 0) {
+              mbar_wait(p_free, (u & 1) ^ 1);                  // the previous unit's dV products have read P
+              if (tr) WTRACE(g_trace_bwd, k, 13);
+            }
+#pragma unroll
+            for (int j8 = 0; j8 < CH / 8; ++j8) {
+              uint32_t pk[4];
+#pragma unroll
+              for (int h = 0; h < 4; ++h) {
+                float pv[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                  const int jj = j8 * 8 + 2 * h + e, j = cb * CH + jj;
+                  const float x = fmaf(__uint_as_float(v[jj]), gm.scale_log2e, tp[-col_key<L, WS, QUAD>(j)]);
+                  pv[e] = fast_exp2(x + nq[QUAD ? j / QL : 0]);
+                  delta = fmaf(pv[e], __uint_as_float(w[jj]), delta);
+                }
+                pk[h] = pack_bf16(pv[0], pv[1]);
+              }
+              const int col = col0 + cb * CH + j8 * 8;
+              *reinterpret_cast<uint4*>(s_p + (col >> 6) * SLOT_BYTES + sw128_offset(row, (col & 63) >> 3)) =
+                  make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+          }
+          tc_fence_before();
+          mbar_arrive(s_free);            // S may be overwritten by the next unit
+          if (tr) WTRACE(g_trace_bwd, k, 9);
+          // pass 2
+          mbar_wait(ds_free, (u & 1) ^ 1);                     // the previous unit's dQ / dK products have read dS
+          if (tr) WTRACE(g_trace_bwd, k, 14);
+#pragma unroll
+          for (int cb = 0; cb < NCHUNK; ++cb) {
+            uint32_t w[32];
+            tmem_ld_row_chunk<L>(tmem_dPu, t_lane, col0, cb, wq, lane, w);
+#pragma unroll
+            for (int j8 = 0; j8 < CH / 8; ++j8) {
+              const int col = col0 + cb * CH + j8 * 8;
+              const uint32_t off = (col >> 6) * SLOT_BYTES + sw128_offset(row, (col & 63) >> 3);
+              const uint4 pq = *reinterpret_cast<const uint4*>(s_p + off);
+              const uint32_t pw[4] = {pq.x, pq.y, pq.z, pq.w};
+              uint32_t dk[4];
+#pragma unroll
+              for (int h = 0; h < 4; ++h) {
+                const int jj = j8 * 8 + 2 * h, j = cb * CH + jj;
+                const float2 pf = unpack_bf16(pw[h]);
+                // rows of a padding window hold filler data: keep them out of the bias-table sum
+                const float d0 = rg.valid ? pf.x * (__uint_as_float(w[jj]) - delta) : 0.f;
+                const float d1 = rg.valid ? pf.y * (__uint_as_float(w[jj + 1]) - delta) : 0.f;
+                dk[h] = pack_bf16(d0, d1);
+                if constexpr (REG_BACC) {
+                  bacc[col_pos<L, WS, QUAD>(j)] += d0;
+                  bacc[col_pos<L, WS, QUAD>(j + 1)] += d1;
+                } else {
+                  if (d0 != 0.f) atomicAdd(&bins[key_i - col_key<L, WS, QUAD>(j)], d0);
+                  if (d1 != 0.f) atomicAdd(&bins[key_i - col_key<L, WS, QUAD>(j + 1)], d1);
+                }
+              }
+              *reinterpret_cast<uint4*>(s_ds + off) = make_uint4(dk[0], dk[1], dk[2], dk[3]);
+            }
+          }
+        };
+        // a warp never straddles two windows for L >= 32, so the branch is warp-uniform
+        if (ORDER == 0 || (ORDER == 2 && !rg.wraps)) softmax_bwd_fast(std::false_type{});
+        else                                         softmax_bwd_fast(std::true_type{});
+      } else {
+        // ---- generic path: per-column look-up table (any order, dense mask, window tags); the
+        //      bias-table gradient goes through the shared bins (no static column -> position map)
+        named_bar_sync(1, 128);                     // everybody is done with the previous LUT
+        const uint32_t my_tag = rg.inrange ? uint32_t(rg.g + 1) : 0u;
+        s_lut[row] = uint32_t(rg.rr * (2 * gm.ws - 1) + rg.cc) | (uint32_t(rg.id) << 8) |
+                     (uint32_t(rg.rr * gm.ws + rg.cc) << 16) | (my_tag << 24);
+        named_bar_sync(1, 128);
+        const bool use_mask = rg.wraps;
+        // dense mask row of this query token (stand-alone WindowAttention with an explicit mask tensor)
+        const float* mask_row =
+            gm.mask ? gm.mask + ((size_t)(rg.gw % gm.mask_nw) * gm.N + (rg.rr * gm.ws + rg.cc)) * gm.N : nullptr;
+        mbar_wait(sdp_full, u & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int cb = 0; cb < NCHUNK; ++cb) {
           uint32_t v[32], w[32];
           tmem_ld_row_chunk<L>(tmem_S, t_lane, col0, cb, wq, lane, v);
-          tmem_ld_row_chunk<L>(tmem_dP, t_lane, col0, cb, wq, lane, w);
+          tmem_ld_row_chunk<L>(tmem_dPu, t_lane, col0, cb, wq, lane, w);
+          if (cb == 0) mbar_wait(p_free, (u & 1) ^ 1);
 #pragma unroll
           for (int j8 = 0; j8 < CH / 8; ++j8) {
             uint32_t pk[4];
@@ -294,7 +458,7 @@ winattn_bwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant
               for (int e = 0; e < 2; ++e) {
                 const int jj = j8 * 8 + 2 * h + e;
                 const uint32_t lj = s_lut[col0 + cb * CH + jj];
-                float x = fmaf(__uint_as_float(v[jj]), gm.scale_log2e, s_tab[key_i - int(lj & 0xff)]);
+                float x = fmaf(__uint_as_float(v[jj]), gm.scale_log2e, tab[key_i - int(lj & 0xff)]);
                 if (use_mask && ((lj >> 8) & 0xffu) != uint32_t(rg.id)) x += kMaskLog2e;
                 if (mask_row != nullptr) x = fmaf(__ldg(mask_row + ((lj >> 16) & 0xffu)), 1.4426950408889634f, x);
                 pv[e] = fast_exp2(x - lse_i);
@@ -309,17 +473,13 @@ winattn_bwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant
                 make_uint4(pk[0], pk[1], pk[2], pk[3]);
           }
         }
-        if (COLSPLIT) {                            // row sum = own half + the other group's half
-          s_delta[grp * 128 + row] = delta;
-          named_bar_sync(2, 256);
-          delta += s_delta[(grp ^ 1) * 128 + row];
-        }
-        // pass 2: dS = P o (dP - delta) -> smem (bf16)
+        tc_fence_before();
+        mbar_arrive(s_free);
+        mbar_wait(ds_free, (u & 1) ^ 1);
 #pragma unroll
-        for (int ci = 0; ci < (COLSPLIT ? NCHUNK / 2 : NCHUNK); ++ci) {
-          const int cb = COLSPLIT ? 2 * ci + grp : ci;
+        for (int cb = 0; cb < NCHUNK; ++cb) {
           uint32_t w[32];
-          tmem_ld_row_chunk<L>(tmem_dP, t_lane, col0, cb, wq, lane, w);
+          tmem_ld_row_chunk<L>(tmem_dPu, t_lane, col0, cb, wq, lane, w);
 #pragma unroll
           for (int j8 = 0; j8 < CH / 8; ++j8) {
             const int col = col0 + cb * CH + j8 * 8;
@@ -329,103 +489,106 @@ winattn_bwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant
             uint32_t dk[4];
 #pragma unroll
             for (int h = 0; h < 4; ++h) {
+              const int jj = j8 * 8 + 2 * h;
               const float2 pf = unpack_bf16(pw[h]);
-              // rows of a padding window hold filler data: keep them out of the bias-table sum
-              const float d0 = rg.valid ? pf.x * (__uint_as_float(w[j8 * 8 + 2 * h]) - delta) : 0.f;
-              const float d1 = rg.valid ? pf.y * (__uint_as_float(w[j8 * 8 + 2 * h + 1]) - delta) : 0.f;
+              const float d0 = rg.valid ? pf.x * (__uint_as_float(w[jj]) - delta) : 0.f;
+              const float d1 = rg.valid ? pf.y * (__uint_as_float(w[jj + 1]) - delta) : 0.f;
               dk[h] = pack_bf16(d0, d1);
-              const int j = j8 * 8 + 2 * h;          // column inside the chunk, compile-time after unrolling
-              if (GEN) {
-                // irregular order: no static column -> position map, go through the shared bins
-                const uint32_t l0 = s_lut[col0 + cb * CH + j], l1 = s_lut[col0 + cb * CH + j + 1];
-                if (d0 != 0.f) atomicAdd(&s_bacc[sub * (TAB_MAX + 1) + key_i - int(l0 & 0xff)], d0);
-                if (d1 != 0.f) atomicAdd(&s_bacc[sub * (TAB_MAX + 1) + key_i - int(l1 & 0xff)], d1);
-              } else if (COLSPLIT) {
-                // row-major order: chunk = (frame, half of the 64 positions) -> position j of that half
-                // quadrant order : chunk = quadrant, 16 positions x 2 frames  -> (which quadrant)*16 + j%16
-                if (quad && L == 128) { bacc[sub][ci * 16 + (j & 15)] += d0; bacc[sub][ci * 16 + ((j + 1) & 15)] += d1; }
-                else                  { bacc[sub][j] += d0; bacc[sub][j + 1] += d1; }
-              } else {
-                bacc[sub][ci * CH + j] += d0; bacc[sub][ci * CH + j + 1] += d1;
-              }
+              const uint32_t l0 = s_lut[col0 + cb * CH + jj], l1 = s_lut[col0 + cb * CH + jj + 1];
+              if (d0 != 0.f) atomicAdd(&bins[key_i - int(l0 & 0xff)], d0);
+              if (d1 != 0.f) atomicAdd(&bins[key_i - int(l1 & 0xff)], d1);
             }
             *reinterpret_cast<uint4*>(s_ds + off) = make_uint4(dk[0], dk[1], dk[2], dk[3]);
           }
         }
-        tc_fence_before();
-        mbar_arrive(sdp_free);          // S / dP may be overwritten by the next tile
-        fence_proxy_async_smem();
-        mbar_arrive(pds_full);          // P / dS visible to the tensor core
       }
-
-      // ---- drain dV_c, dQ_c, dK_c : TMEM -> bf16 -> this row's line of d_qkv
-      //      (window_reverse + inverse roll = the token index of the row).  Output chunk k of the tile
-      //      lands in TMEM buffer k % 2, which is group (k % 2)'s to drain.  With two heads per chunk
-      //      (SH == 2) only columns [sub*32, +32) of the product belong to this sub-head.
-      __nv_bfloat16* row_out = d_qkv + rg.tok * (3 * gm.C) + hg * gm.gch;
-      for (int k = sub * nc * 3 + ((sub * nc * 3 + grp) & 1); k < (sub + 1) * nc * 3; k += 2) {
-        if ((k & 1) != grp) continue;
-        const int c = (k / 3) - sub * nc, o = k % 3;
-        const int which = (o == 0) ? 2 : (o == 1 ? 0 : 1);
-        const float m2 = !rg.valid ? 0.f : (o == 0 ? 1.0f : gm.scale);
-        mbar_wait(&obuf_full[grp], ob_phase);
-        ob_phase ^= 1;
-        tc_fence_after();
-        constexpr int OW = (SH == 1) ? 64 : 32;         // valid output columns
-        float a[64];
-        {
-          uint32_t v0[32], v1[32];
-          tmem_ld32(tmem_out + grp * 64 + t_lane + (SH == 1 ? 0 : sub * 32), v0);
-          if (SH == 1) tmem_ld32(tmem_out + grp * 64 + t_lane + 32, v1);
-          tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&dp_free[u & 1]);     // this dP buffer may be overwritten (by unit u+2)
+      fence_proxy_async_smem();
+      mbar_arrive(pds_full);            // P / dS visible to the tensor core
+      if (tr) WTRACE(g_trace_bwd, k, 10);
+    }
+    // ---- bias-table gradient: bin what is left in registers, then one global atomic per bin, CTA and head
+    flush_bacc();
+    named_bar_sync(1, 128);
+    for (int i = cm_tid; i < SH * nbias; i += 128) {
+      const int sub = i / nbias, bin = i - sub * nbias;
+      atomicAdd(d_table + bin * gm.nH + hg * SH + sub, s_bacc[sub * (TAB_MAX + 1) + bin]);
+    }
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 112;");
+    // ---------------------------------------------------------------- drain warps (groups B0 / B1)
+    // Output product n of the CTA lands in TMEM accumulator n % 2, which is group (n % 2)'s to drain:
+    // TMEM -> bf16 -> 64-byte row segments of d_qkv at the row's token (window_reverse + inverse roll
+    // = the token index of the row), plus the qkv-bias gradient column sums.  32 columns at a time.
+    const int bg = (warp - 8) >> 2;               // 0: warps 8-11, 1: warps 12-15
+    const int wq = warp & 3;
+    const int row = wq * 32 + lane;
+    const uint32_t t_lane = uint32_t(wq * 32) << 16;
+    uint8_t* stage = s_stage + (warp - 8) * 2048;
+    const bool tr = (threadIdx.x == 256);
+    (void)tr;
+    uint32_t nout = 0;                            // products of the CTA so far
+    for (int k = 0; k < n_local; ++k) {
+      const int item = int(blockIdx.x) + k * int(gridDim.x);
+      const int tile = item / gm.ngrp;
+      RowGeom rg;
+      if constexpr (WS > 0) rg = row_geom_fast<L, WS, ORDER>(gm, tile, row);
+      else                  rg = row_geom(gm, tile, row);
+      const long tok = rg.valid ? rg.tok : -1;
+      uint8_t* rowp[4];
 #pragma unroll
-          for (int q = 0; q < 32; ++q) { a[q] = __uint_as_float(v0[q]) * m2; a[32 + q] = (SH == 1) ? __uint_as_float(v1[q]) * m2 : 0.f; }
-        }
-        tc_fence_before();
-        mbar_arrive(&obuf_free[grp]);
-        const int ch0 = which * gm.C + c * 64 + (SH == 1 ? 0 : sub * 32);
-        if (rg.valid) {
-          uint4* dst = reinterpret_cast<uint4*>(row_out + ch0);
+      for (int i = 0; i < 4; ++i) {
+        const long t = __shfl_sync(0xffffffffu, tok, i * 8 + (lane >> 2));
+        rowp[i] = t < 0 ? nullptr : reinterpret_cast<uint8_t*>(d_qkv + t * (3 * gm.C) + hg * gm.gch);
+      }
+#pragma unroll 1
+      for (int sub = 0; sub < SH; ++sub) {
+#pragma unroll 1
+        for (int n = 0; n < 3 * nc; ++n, ++nout) {
+          if (int(nout & 1) != bg) continue;
+          const int o = n < nc ? 0 : 1 + ((n - nc) & 1);        // 0: dV, 1: dQ, 2: dK
+          const int c = n < nc ? n : ((n - nc) >> 1);
+          const int which = (o == 0) ? 2 : (o == 1 ? 0 : 1);
+          const float m2 = !rg.valid ? 0.f : (o == 0 ? 1.0f : gm.scale);
+          mbar_wait(&obuf_full[bg], (nout >> 1) & 1);
+          tc_fence_after();
+          if (tr && n == 0) WTRACE(g_trace_bwd, k, 11);
+          // two heads per chunk (SH == 2): only columns [sub*32, +32) of the product belong to this head
+          constexpr int NHALF = (SH == 1) ? 2 : 1;
 #pragma unroll
-          for (int j = 0; j < OW / 8; ++j)
-            dst[j] = make_uint4(pack_bf16(a[8 * j], a[8 * j + 1]), pack_bf16(a[8 * j + 2], a[8 * j + 3]),
-                                pack_bf16(a[8 * j + 4], a[8 * j + 5]), pack_bf16(a[8 * j + 6], a[8 * j + 7]));
-        }
-        if (d_colsum != nullptr) {
-          if (SH == 1) {
-            warp_colsum64(a, lane);          // lane l: columns 2l, 2l+1 summed over this warp's 32 rows
-            atomicAdd(d_colsum + ch0 + hg * gm.gch + 2 * lane, a[0]);
-            atomicAdd(d_colsum + ch0 + hg * gm.gch + 2 * lane + 1, a[1]);
-          } else {
-            warp_colsum64(a, lane);          // upper 32 values are zero: lanes 0-15 hold the 32 column sums
-            if (lane < 16) {
-              atomicAdd(d_colsum + ch0 + hg * gm.gch + 2 * lane, a[0]);
-              atomicAdd(d_colsum + ch0 + hg * gm.gch + 2 * lane + 1, a[1]);
+          for (int half = 0; half < NHALF; ++half) {
+            const int cofs = (SH == 1) ? half * 32 : sub * 32;     // first column inside the 64-channel chunk
+            float a[32];
+            {
+              uint32_t v[32];
+              tmem_ld32(tmem_out + bg * 64 + t_lane + cofs, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int q = 0; q < 32; ++q) a[q] = __uint_as_float(v[q]) * m2;
+            }
+            if (half == NHALF - 1) {
+              tc_fence_before();
+              mbar_arrive(&obuf_free[bg]);
+            }
+            const int ch0 = which * gm.C + c * 64 + cofs;          // relative to the head group's first channel
+            uint4 vals[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              vals[j] = make_uint4(pack_bf16(a[8 * j], a[8 * j + 1]), pack_bf16(a[8 * j + 2], a[8 * j + 3]),
+                                   pack_bf16(a[8 * j + 4], a[8 * j + 5]), pack_bf16(a[8 * j + 6], a[8 * j + 7]));
+            uint8_t* rp[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) rp[i] = rowp[i] ? rowp[i] + ch0 * 2 : nullptr;
+            warp_store_rows_half(stage, vals, rp, lane);
+            if (d_colsum != nullptr) {
+              warp_colsum<32>(a, lane);        // lane l: column l summed over this warp's 32 rows
+              atomicAdd(d_colsum + ch0 + hg * gm.gch + lane, a[0]);
             }
           }
         }
       }
-     }   // sub
-    }
-    // ---- bias-table gradient: bin the per-row running sums by relative position, once per CTA and head
-    named_bar_sync(1, 256);
-    if (!GEN && softmax_role) {
-#pragma unroll
-      for (int sub = 0; sub < SH; ++sub)
-#pragma unroll
-        for (int k = 0; k < NACC; ++k) {
-          // a column of this row's window that accumulator k stands for
-          int ck;
-          if (COLSPLIT) ck = (quad && L == 128) ? ((2 * (k >> 4) + grp) * 32 + (k & 15)) : (grp * 32 + k);
-          else          ck = k;
-          const uint32_t lj = s_lut[col0 + ck];
-          atomicAdd(&s_bacc[sub * (TAB_MAX + 1) + key_i - int(lj & 0xff)], bacc[sub][k]);
-        }
-    }
-    named_bar_sync(1, 256);
-    for (int i = cm_tid; i < SH * nbias; i += 256) {
-      const int sub = i / nbias, bin = i - sub * nbias;
-      atomicAdd(d_table + bin * gm.nH + hg * SH + sub, s_bacc[sub * (TAB_MAX + 1) + bin]);
+      if (tr) WTRACE(g_trace_bwd, k, 12);
     }
   }
 
@@ -445,6 +608,12 @@ int set_smem_bwd(K kern, int bytes) {
 
 }  // namespace
 
+#ifdef STSWIN_TRACE
+extern "C" int stswin_debug_trace_bwd(long long* buf) {
+  return cudaMemcpyToSymbol(g_trace_bwd, &buf, sizeof(buf)) == cudaSuccess ? 0 : -1;
+}
+#endif
+
 // see include/stswin_b200.h : stswin_winattn_bwd
 int winattn_bwd(const void* qkv, const float* bias_table, const float* lse2, const void* d_out, void* d_qkv,
                 float* d_table, float* d_qkv_colsum, int B, int T, int H, int W, int C, int nH, int ws, int shift,
@@ -453,7 +622,6 @@ int winattn_bwd(const void* qkv, const float* bias_table, const float* lse2, con
   WinGeom gm;
   int rc = fill_geom(&gm, B, T, H, W, C, nH, ws, shift);
   if (rc != kOk) return rc;
-  gm.uniform_quad = 1;
   if (qk_scale > 0.f) { gm.scale = qk_scale; gm.scale_log2e = qk_scale * 1.4426950408889634f; }
   STSWIN_CHECK_ARG(mask == nullptr || mask_windows > 0, "winattn: mask given with mask_windows <= 0");
   gm.mask = mask; gm.mask_nw = mask_windows;
@@ -466,23 +634,33 @@ int winattn_bwd(const void* qkv, const float* bias_table, const float* lse2, con
   int grid = items < num_sms() ? items : num_sms();
   grid -= grid % gm.ngrp;                 // one head group per CTA (items is a multiple of ngrp, so grid >= ngrp)
   if (grid < gm.ngrp) return set_error(kErrUnsupported, "winattn_bwd: %d head groups exceed the SM count", gm.ngrp);
-#define STSWIN_LAUNCH_BWD(LL, SS, GG)                                                                          \
+#define STSWIN_LAUNCH_BWD(LL, WW, OO, SS, GG)                                                                  \
   {                                                                                                            \
-    if ((rc = set_smem_bwd(winattn_bwd_kernel<LL, SS, GG>, SMEM_BYTES)) != kOk) return rc;                     \
-    winattn_bwd_kernel<LL, SS, GG><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(                                 \
+    if ((rc = set_smem_bwd(winattn_bwd_kernel<LL, WW, OO, SS, GG>, SMEM_BYTES)) != kOk) return rc;             \
+    winattn_bwd_kernel<LL, WW, OO, SS, GG><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(                         \
         tq, td, static_cast<__nv_bfloat16*>(d_qkv), bias_table, lse2, d_table, d_qkv_colsum, gm);              \
   }
-#define STSWIN_LAUNCH_BWD_L(LL, GG)                         \
+#define STSWIN_LAUNCH_BWD_S(LL, WW, OO, GG)                 \
   {                                                         \
-    if (gm.SH == 1) STSWIN_LAUNCH_BWD(LL, 1, GG)            \
-    else STSWIN_LAUNCH_BWD(LL, 2, GG)                       \
+    if (gm.SH == 1) STSWIN_LAUNCH_BWD(LL, WW, OO, 1, GG)    \
+    else STSWIN_LAUNCH_BWD(LL, WW, OO, 2, GG)               \
   }
-  if (gm.general) STSWIN_LAUNCH_BWD_L(128, true)
-  else if (gm.L == 16) STSWIN_LAUNCH_BWD_L(16, false)
-  else if (gm.L == 32) STSWIN_LAUNCH_BWD_L(32, false)
-  else if (gm.L == 64) STSWIN_LAUNCH_BWD_L(64, false)
-  else STSWIN_LAUNCH_BWD_L(128, false)
-#undef STSWIN_LAUNCH_BWD_L
+  // fast path: the shipped geometries (ws 8 or 4, 1 or 2 frames per window, shift 0 or ws/2, no dense mask)
+  const bool fast = !gm.general && mask == nullptr && (shift == 0 || 2 * shift == ws) &&
+                    ((ws == 8 && (gm.L == 128 || gm.L == 64)) || (ws == 4 && gm.L == 32));
+  const bool shifted = shift > 0;
+  if (gm.general) STSWIN_LAUNCH_BWD_S(128, 0, 0, true)
+  else if (fast && gm.L == 128 && !shifted) STSWIN_LAUNCH_BWD_S(128, 8, 0, false)
+  else if (fast && gm.L == 128) STSWIN_LAUNCH_BWD_S(128, 8, 2, false)
+  else if (fast && gm.L == 64 && !shifted) STSWIN_LAUNCH_BWD_S(64, 8, 0, false)
+  else if (fast && gm.L == 64) STSWIN_LAUNCH_BWD_S(64, 8, 2, false)
+  else if (fast && gm.L == 32 && !shifted) STSWIN_LAUNCH_BWD_S(32, 4, 0, false)
+  else if (fast && gm.L == 32) STSWIN_LAUNCH_BWD_S(32, 4, 2, false)
+  else if (gm.L == 16) STSWIN_LAUNCH_BWD_S(16, 0, 0, false)
+  else if (gm.L == 32) STSWIN_LAUNCH_BWD_S(32, 0, 0, false)
+  else if (gm.L == 64) STSWIN_LAUNCH_BWD_S(64, 0, 0, false)
+  else STSWIN_LAUNCH_BWD_S(128, 0, 0, false)
+#undef STSWIN_LAUNCH_BWD_S
 #undef STSWIN_LAUNCH_BWD
   STSWIN_CUDA(cudaGetLastError());
   return kOk;

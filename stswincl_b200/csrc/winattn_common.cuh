@@ -128,6 +128,25 @@ __device__ __forceinline__ RowGeom row_geom(const WinGeom& gm, int tile, int r) 
   return o;
 }
 
+// Compile-time column maps of the shipped geometries (L = T*WS*WS tokens per window, shift 0 or WS/2).
+// Column j of a window's L columns, in row-major order (QUAD = false: t, row, column) or quadrant order
+// (QUAD = true: quadrant, t, row, column inside the quadrant):
+//   col_pos : spatial position rr*WS + cc of the token
+//   col_key : rr*(2*WS-1) + cc, so that key_i - col_key(j) indexes the relative-position bias table
+template <int L, int WS, bool QUAD>
+__host__ __device__ constexpr int col_pos(int j) {
+  constexpr int W1 = WS > 0 ? WS : 1, N = W1 * W1, HW = W1 > 1 ? W1 / 2 : 1, QL = L / 4;
+  if (!QUAD) return j % N;
+  const int q = j / QL, p = (j % QL) % (HW * HW);
+  return ((q >> 1) * HW + p / HW) * W1 + (q & 1) * HW + p % HW;
+}
+template <int L, int WS, bool QUAD>
+__host__ __device__ constexpr int col_key(int j) {
+  constexpr int W1 = WS > 0 ? WS : 1;
+  const int pos = col_pos<L, WS, QUAD>(j);
+  return (pos / W1) * (2 * W1 - 1) + pos % W1;
+}
+
 // n / d for 0 <= n * d < 2^32 with mg = ceil(2^32 / d) (checked on the host in fill_geom)
 __device__ __forceinline__ int fast_div(int n, unsigned long long mg) {
   return int((static_cast<unsigned long long>(static_cast<unsigned>(n)) * mg) >> 32);
@@ -267,12 +286,13 @@ __device__ __forceinline__ void warp_store_rows(uint8_t* stage, const uint4 (&va
   }
 }
 
-// Column sums over the 32 lanes of a warp for 64 per-lane values (lane = row): a butterfly that
-// halves the live values at every step (62 shuffles).  On return lane l holds the sums of
-// columns 2*l and 2*l+1 in a[0], a[1].
-__device__ __forceinline__ void warp_colsum64(float (&a)[64], int lane) {
+// Column sums over the 32 lanes of a warp for NV (32 or 64) per-lane values (lane = row): a butterfly
+// that halves the live values at every step (NV - NV/32 shuffles).  On return lane l holds the sums
+// of columns l*NV/32 .. in a[0 .. NV/32).
+template <int NV>
+__device__ __forceinline__ void warp_colsum(float (&a)[NV], int lane) {
 #pragma unroll
-  for (int n = 32, off = 16; n >= 2; n >>= 1, off >>= 1) {
+  for (int n = NV / 2, off = 16; off >= 1; n >>= 1, off >>= 1) {
     const bool hi = (lane & off) != 0;
 #pragma unroll
     for (int k = 0; k < n; ++k) {
@@ -280,6 +300,27 @@ __device__ __forceinline__ void warp_colsum64(float (&a)[64], int lane) {
       const float recv = __shfl_xor_sync(0xffffffffu, send, off);
       a[k] = (hi ? a[k + n] : a[k]) + recv;
     }
+  }
+}
+__device__ __forceinline__ void warp_colsum64(float (&a)[64], int lane) { warp_colsum<64>(a, lane); }
+
+// Same idea as warp_store_rows for a [32 rows] x [64 bytes] block (4 x 16 bytes per lane) through a
+// 2 KB staging area: the rows come back 4 lanes per row, one store instruction covers 8 rows x 64 bytes.
+//   rowp[i] : global address of the block's first byte for row i*8 + lane/4, or nullptr to skip the row
+__device__ __forceinline__ void warp_store_rows_half(uint8_t* stage, const uint4 (&vals)[4], uint8_t* const (&rowp)[4],
+                                                     int lane) {
+  __syncwarp();                      // the previous block has been read out
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    *reinterpret_cast<uint4*>(stage + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = vals[j];
+  __syncwarp();
+  const int ch = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = i * 8 + (lane >> 2);
+    if (rowp[i] != nullptr)
+      *reinterpret_cast<uint4*>(rowp[i] + ch * 16) =
+          *reinterpret_cast<const uint4*>(stage + r * 64 + ((ch ^ ((r >> 1) & 3)) << 4));
   }
 }
 

@@ -47,14 +47,6 @@ STSWIN_TRACE_DECL(g_trace_fwd)
 // column -> (relative-position key, quadrant) map is then a compile-time function of the column,
 // so the bias is one LDS at an immediate offset and the shift mask is one additive constant per
 // quadrant.  WS == 0 is the generic path (look-up table per column: dense mask, L = 16, GEN).
-template <int L, int WS, bool QUAD>
-__host__ __device__ constexpr int col_key(int j) {
-  constexpr int W1 = WS > 0 ? WS : 1, N = W1 * W1, HW = W1 > 1 ? W1 / 2 : 1, QL = L / 4;
-  if (!QUAD) return ((j % N) / W1) * (2 * W1 - 1) + (j % N) % W1;
-  const int q = j / QL, p = (j % QL) % (HW * HW);
-  return ((q >> 1) * HW + p / HW) * (2 * W1 - 1) + (q & 1) * HW + p % HW;
-}
-
 template <int L, int WS, int ORDER, bool GEN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 winattn_fwd_kernel(const __grid_constant__ WinMaps tm_qkv, __nv_bfloat16* __restrict__ out,

@@ -36,7 +36,7 @@ if which == "fwd":
 else:
     ops.winattn_bwd(qkv, table, lse, do, H, W, nH, ws, shift, dt)
     names = ["ldH_first", "ldH_last", "ldL_first", "ldL_last", "SdP_issued", "out_begin", "out_issued", "item_start",
-             "SdP_ready", "pass1_done", "pass2_done", "drain_done"]
+             "SdP_ready", "pass1_done", "pass2_done", "drain_beg", "drain_done", "P_free", "dS_free"]
 torch.cuda.synchronize()
 assert fn(0) == 0
 t = buf.view(64, NPT).cpu()
