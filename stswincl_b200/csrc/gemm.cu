@@ -150,8 +150,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // The whole warp runs the loop, one elected lane issues: with warp-uniform control flow the
+    // descriptors live in uniform registers.  (Issued from inside `if (lane == 0)` every tcgen05.mma was
+    // preceded by a serialised chain of R2UR moves, ~100 cycles per instruction: as long as the MMA itself.)
+    {
+      const bool leader = elect_one();
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
+      const uint32_t stage_base = smem_u32(s_stage);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -166,20 +171,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sA = smem_u32(s_stage + stage * STAGE_BYTES);
+          const uint32_t sA = stage_base + stage * STAGE_BYTES;
           const uint32_t sB = sA + A_STAGE_BYTES;
+          if (leader) {
 #pragma unroll
-          for (int kk = 0; kk < BK / 16; ++kk) {
-            const uint64_t adesc = A_MN ? umma_smem_desc(sA + kk * 2048, BK * 128, 1024)
-                                        : umma_smem_desc(sA + kk * 32, 16, 1024);
-            const uint64_t bdesc = B_MN ? umma_smem_desc(sB + kk * 2048, BK * 128, 1024)
-                                        : umma_smem_desc(sB + kk * 32, 16, 1024);
-            umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+            for (int kk = 0; kk < BK / 16; ++kk) {
+              const uint64_t adesc = A_MN ? umma_smem_desc(sA + kk * 2048, BK * 128, 1024)
+                                          : umma_smem_desc(sA + kk * 32, 16, 1024);
+              const uint64_t bdesc = B_MN ? umma_smem_desc(sB + kk * 2048, BK * 128, 1024)
+                                          : umma_smem_desc(sB + kk * 32, 16, 1024);
+              umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+            }
+            umma_commit_mcast(&empty_bar[stage], 0x3);   // slot reusable (in both CTAs) once these MMAs retire
           }
-          umma_commit_mcast(&empty_bar[stage], 0x3);   // slot reusable (in both CTAs) once these MMAs retire
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&acc_full[acc]);          // accumulator complete
+        if (leader) umma_commit(&acc_full[acc]);          // accumulator complete
+        __syncwarp();
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
