@@ -28,9 +28,9 @@ struct PmGeom {        // PatchMerging gather geometry (pm == 0: plain rows)
 };
 
 // pointer to the 8-element group `v` (0 .. Ctot/8) of logical row `row`
-template <typename T>
+template <bool PM, typename T>
 __device__ __forceinline__ T* row_ptr(T* base, long row, int v, int Ctot, const PmGeom& g) {
-  if (!g.pm) return base + row * Ctot + v * 8;
+  if (!PM) return base + row * Ctot + v * 8;
   const int H2 = g.H >> 1, W2 = g.W >> 1;
   const int per_img = H2 * W2;
   const long bt = row / per_img;
@@ -49,21 +49,63 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-template <int NV>   // NV = ceil(Ctot / 256): 16-byte groups per lane
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Both kernels stream rows through a per-warp ring in shared memory filled by cp.async (16 bytes per
+// lane and group, no registers held while a row is in flight): NSTG-1 rows ahead per warp keep
+// ~100 KB per SM in flight, which one-row-per-warp register kernels could not (they reached 41-55 % of
+// the HBM roofline).  A lane only ever reads back the 16-byte groups it copied itself, so
+// cp.async.wait_group is the only synchronisation the ring needs.
+template <int NV, int NSTG, bool PM>   // NV = ceil(Ctot / 256): 16-byte groups per lane; PM: PatchMerging gather
 __global__ void __launch_bounds__(LN_THREADS)
 ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
               __nv_bfloat16* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd, long M, int Ctot,
               float eps, PmGeom pg) {
+  extern __shared__ uint4 s_ring4[];     // [LN_WARPS][NSTG][Ctot / 8]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = Ctot >> 3;
-  for (long row = (long)blockIdx.x * LN_WARPS + warp; row < M; row += (long)gridDim.x * LN_WARPS) {
+  uint4* ring = s_ring4 + (size_t)warp * NSTG * nvec;
+  const long stride = (long)gridDim.x * LN_WARPS;
+  const long row0 = (long)blockIdx.x * LN_WARPS + warp;
+  auto issue = [&](long row, int stg) {
+    if (row < M) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int vi = lane + 32 * i;
+        if (vi < nvec) cp_async16(ring + stg * nvec + vi, row_ptr<PM>(x, row, vi, Ctot, pg));
+      }
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int s = 0; s < NSTG - 1; ++s) issue(row0 + s * stride, s);
+  // gamma / beta of this lane's columns stay in registers for every row of the warp
+  float gr[NV][8], br[NV][8];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int vi = lane + 32 * i;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      gr[i][k] = vi < nvec ? __ldg(gamma + vi * 8 + k) : 0.f;
+      br[i][k] = vi < nvec ? __ldg(beta + vi * 8 + k) : 0.f;
+    }
+  }
+  int stg = 0;
+  for (long row = row0; row < M; row += stride) {
+    issue(row + (NSTG - 1) * stride, stg == 0 ? NSTG - 1 : stg - 1);
+    cp_async_wait<NSTG - 1>();
     float v[NV][8];
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int vi = lane + 32 * i;
       if (vi < nvec) {
-        const uint4 q = __ldg(reinterpret_cast<const uint4*>(row_ptr(x, row, vi, Ctot, pg)));
+        const uint4 q = ring[stg * nvec + vi];
         const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -90,30 +132,32 @@ ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gam
     for (int i = 0; i < NV; ++i) {
       const int vi = lane + 32 * i;
       if (vi < nvec) {
-        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8));
-        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8 + 4));
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8));
-        const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8 + 4));
-        uint4 q;
-        q.x = pack_bf16((v[i][0] - mu) * rs * g0.x + b0.x, (v[i][1] - mu) * rs * g0.y + b0.y);
-        q.y = pack_bf16((v[i][2] - mu) * rs * g0.z + b0.z, (v[i][3] - mu) * rs * g0.w + b0.w);
-        q.z = pack_bf16((v[i][4] - mu) * rs * g1.x + b1.x, (v[i][5] - mu) * rs * g1.y + b1.y);
-        q.w = pack_bf16((v[i][6] - mu) * rs * g1.z + b1.z, (v[i][7] - mu) * rs * g1.w + b1.w);
-        *reinterpret_cast<uint4*>(y + row * Ctot + vi * 8) = q;      // output rows are always dense
+        const float nm = -mu * rs;
+        uint32_t w[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          w[k] = pack_bf16(fmaf(fmaf(v[i][2 * k], rs, nm), gr[i][2 * k], br[i][2 * k]),
+                           fmaf(fmaf(v[i][2 * k + 1], rs, nm), gr[i][2 * k + 1], br[i][2 * k + 1]));
+        *reinterpret_cast<uint4*>(y + row * Ctot + vi * 8) = make_uint4(w[0], w[1], w[2], w[3]);   // output rows are always dense
       }
     }
+    if (++stg == NSTG) stg = 0;
   }
+  cp_async_wait<0>();
 }
 
-template <int NV, bool COLSUM>
-__global__ void __launch_bounds__(LN_THREADS, (NV <= 2 ? 2 : 1))
+template <int NV, bool COLSUM, int NSTG, bool PM, bool RES>
+__global__ void __launch_bounds__(LN_THREADS)
 ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
               const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
               const __nv_bfloat16* __restrict__ dres, __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma,
               float* __restrict__ dbeta, float* __restrict__ dx_colsum, long M, int Ctot, PmGeom pg) {
-  extern __shared__ float s_red[];       // [LN_WARPS][Ctot] scratch for the column reductions
+  extern __shared__ uint4 s_ring4[];     // [LN_WARPS][NSTG][NARR][Ctot / 8]; reused as [LN_WARPS][Ctot] floats at the end
+  constexpr int NARR = RES ? 3 : 2;      // dy, x (, residual gradient)
+  float* s_red = reinterpret_cast<float*>(s_ring4);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = Ctot >> 3;
+  uint4* ring = s_ring4 + (size_t)warp * NSTG * NARR * nvec;
   float a_dg[NV][8], a_db[NV][8], a_cs[COLSUM ? NV : 1][8];
 #pragma unroll
   for (int i = 0; i < NV; ++i)
@@ -122,46 +166,50 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
       a_dg[i][k] = 0.f; a_db[i][k] = 0.f;
       if (COLSUM) a_cs[i][k] = 0.f;
     }
-  const bool has_res = dres != nullptr;
+  constexpr bool has_res = RES;
   const long stride = (long)gridDim.x * LN_WARPS;
-  // raw 16-byte groups of the row being processed, and of the next row (prefetched while this one
-  // is reduced: one row per warp is otherwise a single dependent load -> shuffle -> store chain)
-  uint4 cd[NV], cx[NV], cr[NV];
-  float c_mu = 0.f, c_rs = 0.f;
-  auto load_row = [&](long row, uint4 (&d)[NV], uint4 (&xx)[NV], uint4 (&r)[NV], float& mu, float& rs) {
-    mu = mean[row]; rs = rstd[row];
+  const long row0 = (long)blockIdx.x * LN_WARPS + warp;
+  auto issue = [&](long row, int stg) {
+    if (row < M) {
+      uint4* d = ring + stg * NARR * nvec;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int vi = lane + 32 * i;
-      if (vi < nvec) {
-        d[i] = __ldg(reinterpret_cast<const uint4*>(dy + row * Ctot + vi * 8));
-        xx[i] = __ldg(reinterpret_cast<const uint4*>(row_ptr(x, row, vi, Ctot, pg)));
-        if (has_res) r[i] = __ldg(reinterpret_cast<const uint4*>(dres + row * Ctot + vi * 8));
+      for (int i = 0; i < NV; ++i) {
+        const int vi = lane + 32 * i;
+        if (vi < nvec) {
+          cp_async16(d + vi, dy + row * Ctot + vi * 8);
+          cp_async16(d + nvec + vi, row_ptr<PM>(x, row, vi, Ctot, pg));
+          if (has_res) cp_async16(d + 2 * nvec + vi, dres + row * Ctot + vi * 8);
+        }
       }
     }
+    cp_async_commit();
   };
-  constexpr bool PREFETCH = NV <= 4;      // NV = 8 (PatchMerging rows of 2048) would spill with two rows live
-  long row = (long)blockIdx.x * LN_WARPS + warp;
-  if (PREFETCH && row < M) load_row(row, cd, cx, cr, c_mu, c_rs);
-  while (row < M) {
-    const long nxt = row + stride;
-    uint4 nd[PREFETCH ? NV : 1], nx[PREFETCH ? NV : 1], nr[PREFETCH ? NV : 1];
-    float n_mu = 0.f, n_rs = 0.f;
-    if constexpr (PREFETCH) {
-      if (nxt < M) load_row(nxt, nd, nx, nr, n_mu, n_rs);
-    } else {
-      load_row(row, cd, cx, cr, c_mu, c_rs);
-    }
-    const float mu = c_mu, rs = c_rs;
+#pragma unroll
+  for (int s = 0; s < NSTG - 1; ++s) issue(row0 + s * stride, s);
+  float gmr[NV][8];                      // gamma of this lane's columns
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int vi = lane + 32 * i;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) gmr[i][k] = vi < nvec ? __ldg(gamma + vi * 8 + k) : 0.f;
+  }
+  int stg = 0;
+  float n_mu = 0.f, n_rs = 0.f;
+  if (row0 < M) { n_mu = mean[row0]; n_rs = rstd[row0]; }
+  for (long row = row0; row < M; row += stride) {
+    issue(row + (NSTG - 1) * stride, stg == 0 ? NSTG - 1 : stg - 1);
+    const float mu = n_mu, rs = n_rs;
+    if (row + stride < M) { n_mu = mean[row + stride]; n_rs = rstd[row + stride]; }
+    cp_async_wait<NSTG - 1>();
+    const uint4* cur = ring + stg * NARR * nvec;
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int vi = lane + 32 * i;
       if (vi < nvec) {
-        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8));
-        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8 + 4));
-        const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-        const uint32_t wd[4] = {cd[i].x, cd[i].y, cd[i].z, cd[i].w}, wx[4] = {cx[i].x, cx[i].y, cx[i].z, cx[i].w};
+        const float (&gm)[8] = gmr[i];
+        const uint4 cd = cur[vi], cx = cur[nvec + vi];
+        const uint32_t wd[4] = {cd.x, cd.y, cd.z, cd.w}, wx[4] = {cx.x, cx.y, cx.z, cx.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const float2 fd = unpack_bf16(wd[k]), fx = unpack_bf16(wx[k]);
@@ -179,11 +227,12 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
     for (int i = 0; i < NV; ++i) {
       const int vi = lane + 32 * i;
       if (vi < nvec) {
-        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8));
-        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8 + 4));
-        const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-        const uint32_t wd[4] = {cd[i].x, cd[i].y, cd[i].z, cd[i].w}, wx[4] = {cx[i].x, cx[i].y, cx[i].z, cx[i].w};
-        const uint32_t wr[4] = {cr[i].x, cr[i].y, cr[i].z, cr[i].w};
+        const float (&gm)[8] = gmr[i];
+        const uint4 cd = cur[vi], cx = cur[nvec + vi];
+        const uint32_t wd[4] = {cd.x, cd.y, cd.z, cd.w}, wx[4] = {cx.x, cx.y, cx.z, cx.w};
+        uint4 cr = make_uint4(0, 0, 0, 0);
+        if (has_res) cr = cur[2 * nvec + vi];
+        const uint32_t wr[4] = {cr.x, cr.y, cr.z, cr.w};
         uint32_t wo[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -200,17 +249,13 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
             a_cs[i][2 * k] += fo.x; a_cs[i][2 * k + 1] += fo.y;
           }
         }
-        *reinterpret_cast<uint4*>(row_ptr(dx, row, vi, Ctot, pg)) = make_uint4(wo[0], wo[1], wo[2], wo[3]);
+        *reinterpret_cast<uint4*>(row_ptr<PM>(dx, row, vi, Ctot, pg)) = make_uint4(wo[0], wo[1], wo[2], wo[3]);
       }
     }
-    if constexpr (PREFETCH) {
-#pragma unroll
-      for (int i = 0; i < NV; ++i) { cd[i] = nd[i]; cx[i] = nx[i]; cr[i] = nr[i]; }
-      c_mu = n_mu; c_rs = n_rs;
-    }
-    row = nxt;
+    if (++stg == NSTG) stg = 0;
   }
-  // CTA-level column reduction, one quantity at a time through s_red[LN_WARPS][Ctot]
+  cp_async_wait<0>();
+  // CTA-level column reduction, one quantity at a time through s_red[LN_WARPS][Ctot] (the ring is idle now)
   auto flush = [&](float (&acc)[NV][8], float* out) {
     __syncthreads();
 #pragma unroll
@@ -253,12 +298,6 @@ __global__ void transpose_kernel(const TI* __restrict__ in, TO* __restrict__ out
   }
 }
 
-int ln_grid(long M) {
-  long want = (M + LN_WARPS - 1) / LN_WARPS;
-  long cap = (long)num_sms() * 8;
-  return (int)(want < cap ? want : cap);
-}
-
 int check_ln_shape(long M, int Ctot, int pm, int H, int W, int C) {
   STSWIN_CHECK_ARG(M > 0 && Ctot > 0, "layernorm: empty input");
   STSWIN_CHECK_ARG(Ctot % 8 == 0 && Ctot <= 2048, "layernorm: row length %d must be a multiple of 8 and <= 2048", Ctot);
@@ -280,14 +319,25 @@ int layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y,
   if (rc != kOk) return rc;
   PmGeom pg{pm, H, W, C};
   const int nv = (Ctot + 255) / 256;
-  const int grid = ln_grid(M);
   auto xb = static_cast<const __nv_bfloat16*>(x);
   auto yb = static_cast<__nv_bfloat16*>(y);
-#define STSWIN_LN_FWD(NV_) ln_fwd_kernel<NV_><<<grid, LN_THREADS, 0, stream>>>(xb, gamma, beta, yb, mean, rstd, M, Ctot, eps, pg)
-  if (nv <= 1) STSWIN_LN_FWD(1);
-  else if (nv <= 2) STSWIN_LN_FWD(2);
-  else if (nv <= 4) STSWIN_LN_FWD(4);
-  else STSWIN_LN_FWD(8);
+  const long want = (M + LN_WARPS - 1) / LN_WARPS;
+  // ring: LN_WARPS x NSTG rows of Ctot bf16; ~64 KB per CTA, as many CTAs per SM as fit
+#define STSWIN_LN_FWD(NV_, NSTG_, PM_)                                                                             \
+  do {                                                                                                          \
+    const int smem = LN_WARPS * NSTG_ * Ctot * 2;                                                               \
+    const int per_sm = smem <= 56 * 1024 ? 4 : (smem <= 112 * 1024 ? 2 : 1);                                    \
+    const int grid = (int)(want < (long)num_sms() * per_sm ? want : (long)num_sms() * per_sm);                  \
+    STSWIN_CUDA(cudaFuncSetAttribute(ln_fwd_kernel<NV_, NSTG_, PM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+    ln_fwd_kernel<NV_, NSTG_, PM_><<<grid, LN_THREADS, smem, stream>>>(xb, gamma, beta, yb, mean, rstd, M, Ctot, eps, pg); \
+  } while (0)
+  if (pm) {                      // PatchMerging rows: 4*C channels
+    if (nv <= 4) STSWIN_LN_FWD(4, 4, true);
+    else STSWIN_LN_FWD(8, 3, true);
+  } else if (nv <= 1) STSWIN_LN_FWD(1, 8, false);
+  else if (nv <= 2) STSWIN_LN_FWD(2, 6, false);
+  else if (nv <= 4) STSWIN_LN_FWD(4, 4, false);
+  else STSWIN_LN_FWD(8, 3, false);
 #undef STSWIN_LN_FWD
   STSWIN_CUDA(cudaGetLastError());
   return kOk;
@@ -303,29 +353,37 @@ int layernorm_bwd(const void* dy, const void* x, const float* mean, const float*
   STSWIN_CHECK_ARG(!(pm && dres), "layernorm_bwd: residual input is not supported together with the patch-merging scatter");
   PmGeom pg{pm, H, W, C};
   const int nv = (Ctot + 255) / 256;
-  long want = (M + LN_WARPS - 1) / LN_WARPS;
-  const int grid = (int)(want < num_sms() * 2 ? want : num_sms() * 2);   // 2 CTAs / SM when they fit; few column atomics
-  const int smem = LN_WARPS * Ctot * 4;
+  const long want = (M + LN_WARPS - 1) / LN_WARPS;
   auto dyb = static_cast<const __nv_bfloat16*>(dy);
   auto xb = static_cast<const __nv_bfloat16*>(x);
   auto rb = static_cast<const __nv_bfloat16*>(dres);
   auto dxb = static_cast<__nv_bfloat16*>(dx);
-#define STSWIN_LN_BWD(NV_)                                                                                         \
-  do {                                                                                                             \
-    if (dx_colsum) {                                                                                               \
-      STSWIN_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<NV_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-      ln_bwd_kernel<NV_, true><<<grid, LN_THREADS, smem, stream>>>(dyb, xb, mean, rstd, gamma, rb, dxb, dgamma, dbeta, \
-                                                                   dx_colsum, M, Ctot, pg);                        \
-    } else {                                                                                                       \
-      STSWIN_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<NV_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-      ln_bwd_kernel<NV_, false><<<grid, LN_THREADS, smem, stream>>>(dyb, xb, mean, rstd, gamma, rb, dxb, dgamma,   \
-                                                                    dbeta, dx_colsum, M, Ctot, pg);                \
-    }                                                                                                              \
+  // ring: LN_WARPS x NSTG x 3 rows of Ctot bf16 (dy, x, residual gradient); <= 2 CTAs per SM (few column atomics)
+#define STSWIN_LN_BWD_K(NV_, CS_, NSTG_, PM_, RES_)                                                                \
+  do {                                                                                                          \
+    const int smem = LN_WARPS * NSTG_ * (RES_ ? 3 : 2) * Ctot * 2;                                              \
+    const int per_sm = (smem <= 112 * 1024 && NV_ <= 2) ? 2 : 1;                                                \
+    const int grid = (int)(want < (long)num_sms() * per_sm ? want : (long)num_sms() * per_sm);                  \
+    STSWIN_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<NV_, CS_, NSTG_, PM_, RES_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+    ln_bwd_kernel<NV_, CS_, NSTG_, PM_, RES_><<<grid, LN_THREADS, smem, stream>>>(dyb, xb, mean, rstd, gamma, rb, dxb, dgamma, dbeta, \
+                                                                       dx_colsum, M, Ctot, pg);                 \
   } while (0)
-  if (nv <= 1) STSWIN_LN_BWD(1);
-  else if (nv <= 2) STSWIN_LN_BWD(2);
-  else if (nv <= 4) STSWIN_LN_BWD(4);
-  else STSWIN_LN_BWD(8);
+  // stages: with / without the residual-gradient row (3 / 2 arrays per stage)
+#define STSWIN_LN_BWD(NV_, NS_RES_, NS_NORES_, PM_)                                     \
+  do {                                                                                  \
+    if (dx_colsum && rb) STSWIN_LN_BWD_K(NV_, true, NS_RES_, PM_, true);                \
+    else if (dx_colsum) STSWIN_LN_BWD_K(NV_, true, NS_NORES_, PM_, false);              \
+    else if (rb) STSWIN_LN_BWD_K(NV_, false, NS_RES_, PM_, true);                       \
+    else STSWIN_LN_BWD_K(NV_, false, NS_NORES_, PM_, false);                            \
+  } while (0)
+  if (pm) {                      // no residual input with the patch-merging scatter (checked above)
+    if (nv <= 4) { if (dx_colsum) STSWIN_LN_BWD_K(4, true, 6, true, false); else STSWIN_LN_BWD_K(4, false, 6, true, false); }
+    else { if (dx_colsum) STSWIN_LN_BWD_K(8, true, 3, true, false); else STSWIN_LN_BWD_K(8, false, 3, true, false); }
+  } else if (nv <= 1) STSWIN_LN_BWD(1, 6, 8, false);
+  else if (nv <= 2) STSWIN_LN_BWD(2, 4, 6, false);
+  else if (nv <= 4) STSWIN_LN_BWD(4, 4, 6, false);
+  else STSWIN_LN_BWD(8, 2, 3, false);
+#undef STSWIN_LN_BWD_K
 #undef STSWIN_LN_BWD
   STSWIN_CUDA(cudaGetLastError());
   return kOk;

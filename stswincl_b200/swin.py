@@ -225,6 +225,51 @@ class _TransposeFn(torch.autograd.Function):
         return ops.transpose(g.contiguous(), ctx.in_dtype), None
 
 
+class _SplitMidFn(torch.autograd.Function):
+    """x [B, 4, L, C] -> (frames 1..2 as a contiguous [B, 2, L, C] copy, x itself).
+
+    Together with ``_PutMidFn`` this is ``x[:, 1:3]`` -> blocks -> ``cat([x[:, :1], y, x[:, 3:]])``
+    (swin_512.py:302-307, middle layer) without the cat kernel and without any zero-fill / add in the
+    backward: ``_PutMidFn.backward`` allocates the gradient of x and fills frames 0 and 3, this
+    backward fills frames 1..2 of that same buffer."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.shape, ctx.dtype = x.shape, x.dtype
+        xm = x[:, 1:3].contiguous()
+        return xm, x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, d_xm, d_pass):
+        if d_pass is None:
+            d_pass = torch.zeros(ctx.shape, dtype=ctx.dtype, device=d_xm.device)
+        if d_xm is not None:
+            d_pass[:, 1:3].copy_(d_xm)
+        else:
+            d_pass[:, 1:3].zero_()
+        return d_pass
+
+
+class _PutMidFn(torch.autograd.Function):
+    """(x_pass [B, 4, L, C], y [B, 2, L, C]) -> x_pass with frames 1..2 replaced by y."""
+
+    @staticmethod
+    def forward(ctx, x_pass, y):
+        out = torch.empty_like(x_pass)
+        out[:, 0].copy_(x_pass[:, 0])
+        out[:, 3].copy_(x_pass[:, 3])
+        out[:, 1:3].copy_(y)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        # frames 1..2 of d_pass are left for _SplitMidFn.backward to fill (a fresh buffer, never aliased)
+        d_pass = torch.empty_like(d_out)
+        d_pass[:, 0].copy_(d_out[:, 0])
+        d_pass[:, 3].copy_(d_out[:, 3])
+        return d_pass, d_out[:, 1:3].contiguous()
+
+
 def _as_tokens_bf16(x: torch.Tensor) -> torch.Tensor:
     if not x.is_cuda:
         raise StswinError("stswincl_b200 modules need CUDA tensors (no CPU path)")
@@ -410,8 +455,8 @@ class SwinTransformerLayerv5(nn.Module):
         if both_pairs:
             y = blk1.forward_tokens(blk0.forward_tokens(x.view(B * 2, 2, L, C)))
             return y.view(B, 4, L, C)
-        y = blk1.forward_tokens(blk0.forward_tokens(x[:, 1:3].contiguous()))
-        return torch.cat([x[:, 0:1], y, x[:, 3:4]], dim=1)
+        xm, x_pass = _SplitMidFn.apply(x)
+        return _PutMidFn.apply(x_pass, blk1.forward_tokens(blk0.forward_tokens(xm)))
 
     def forward(self, x_v):
         B, T, C, H, W = x_v.shape
