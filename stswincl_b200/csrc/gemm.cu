@@ -31,9 +31,9 @@ namespace {
 constexpr int BM = 128;
 constexpr int BN = 256;
 constexpr int BK = 64;
-constexpr int STAGES = 4;
-constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KB
-constexpr int B_STAGE_BYTES = BN * BK * 2;   // 32 KB
+constexpr int STAGES = 6;
+constexpr int A_STAGE_BYTES = BM * BK * 2;         // 16 KB: this CTA's 128 rows of the pair's 256-row A tile
+constexpr int B_STAGE_BYTES = (BN / 2) * BK * 2;   // 16 KB: this CTA's half of the 256-column B tile
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int EPI_WARPS = 8;
 constexpr int EPI_BUF_BYTES = 32 * 128;      // 32 rows x 128 B per epilogue warp
@@ -82,10 +82,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int num_n = (p.N + BN - 1) / BN;
   const int kb_total = (p.K + BK - 1) / BK;
   const int kb_per_split = (kb_total + p.k_splits - 1) / p.k_splits;
-  // A cluster is a pair of CTAs working on two vertically adjacent tiles (same n_blk, m_blk = 2*pair +
-  // rank): they need the same B tile, so each loads half of it and TMA-multicasts it to both --
-  // 32 KB instead of 48 KB of L2 traffic per CTA and k-block.  (The K <= 1024 GEMMs of this model
-  // sit on the L2 throughput cap, not on the tensor pipe: profiles/r1b_gemm_l2_note.txt.)
+  // A cluster is a pair of CTAs (two SMs of one TPC) that computes one 256 x 256 tile with
+  // tcgen05.mma.cta_group::2: CTA r holds rows [r*128, +128) of A and columns [r*128, +128) of B, the
+  // leader issues one M = 256 instruction for both tensor cores, each CTA accumulates its 128 rows
+  // in its own TMEM and runs its own epilogue.  Per CTA and k-block that is 32 KB of TMA fill and
+  // 8 KB of operand reads per MMA instead of 48 KB / 12 KB for two independent 128 x 256 tiles with a
+  // multicast B: the single-CTA version sat on the shared-memory bandwidth (fill + operand reads +
+  // epilogue staging ~ 220 B/clk against 128 B/clk) at 54 % tensor-pipe activity.
   const int num_mp = (num_m + 1) / 2;
   const int num_items = num_mp * num_n * p.k_splits;        // per cluster
   const uint32_t crank = cluster_ctarank();
@@ -96,16 +99,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmD);
     for (int i = 0; i < STAGES; ++i) {
-      mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 2);          // released by the MMA warps of BOTH CTAs (the peer writes here too)
+      mbar_init(&full_bar[i], 2);           // leader's copy is the live one: one arrive.expect_tx per CTA of the pair
+      mbar_init(&empty_bar[i], 1);          // multicast commit of the leader's MMA warp
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], EPI_WARPS);
+      mbar_init(&acc_empty[i], 2 * EPI_WARPS);    // leader's copy: the epilogue warps of both CTAs
     }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  if (warp == 1) tmem_alloc_2sm<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();                       // the peer's barriers exist before anything is multicast to them
@@ -127,22 +130,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sA = s_stage + stage * STAGE_BYTES;
           uint8_t* sB = sA + A_STAGE_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);      // own A + both halves of B
+          const uint32_t lfull = mapa_u32(&full_bar[stage], 0);      // the leader's barrier collects both CTAs' bytes
+          mbar_arrive_expect_tx_cluster(lfull, STAGE_BYTES);
           if (A_MN) {
 #pragma unroll
-            for (int c = 0; c < BM / 64; ++c) tma_load_2d(sA + c * (BK * 128), &tmA, &full_bar[stage], m_blk * BM + c * 64, kb * BK);
+            for (int c = 0; c < BM / 64; ++c) tma_load_2d_2sm(sA + c * (BK * 128), &tmA, lfull, m_blk * BM + c * 64, kb * BK);
           } else {
-            tma_load_2d(sA, &tmA, &full_bar[stage], kb * BK, m_blk * BM);
+            tma_load_2d_2sm(sA, &tmA, lfull, kb * BK, m_blk * BM);
           }
           if (B_MN) {               // this CTA's half of B: two of the four 64-column chunks
 #pragma unroll
-            for (int cc = 0; cc < BN / 128; ++cc) {
-              const int c = int(crank) * (BN / 128) + cc;
-              tma_load_2d_mcast(sB + c * (BK * 128), &tmB, &full_bar[stage], n_blk * BN + c * 64, kb * BK, 0x3);
-            }
+            for (int cc = 0; cc < BN / 128; ++cc)
+              tma_load_2d_2sm(sB + cc * (BK * 128), &tmB, lfull, n_blk * BN + (int(crank) * (BN / 128) + cc) * 64, kb * BK);
           } else {                  // rows [crank*128, +128) of the 256-row B tile
-            tma_load_2d_mcast(sB + int(crank) * (B_STAGE_BYTES / 2), &tmB, &full_bar[stage], kb * BK,
-                              n_blk * BN + int(crank) * (BN / 2), 0x3);
+            tma_load_2d_2sm(sB, &tmB, lfull, kb * BK, n_blk * BN + int(crank) * (BN / 2));
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -153,9 +154,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // The whole warp runs the loop, one elected lane issues: with warp-uniform control flow the
     // descriptors live in uniform registers.  (Issued from inside `if (lane == 0)` every tcgen05.mma was
     // preceded by a serialised chain of R2UR moves, ~100 cycles per instruction: as long as the MMA itself.)
-    {
+    if (crank == 0) {
       const bool leader = elect_one();
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN, A_MN, B_MN);
       const uint32_t stage_base = smem_u32(s_stage);
       int stage = 0;
       uint32_t phase = 0;
@@ -180,14 +181,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                           : umma_smem_desc(sA + kk * 32, 16, 1024);
               const uint64_t bdesc = B_MN ? umma_smem_desc(sB + kk * 2048, BK * 128, 1024)
                                           : umma_smem_desc(sB + kk * 32, 16, 1024);
-              umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+              umma_bf16_2sm(d_tmem, adesc, bdesc, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
             }
-            umma_commit_mcast(&empty_bar[stage], 0x3);   // slot reusable (in both CTAs) once these MMAs retire
+            umma_commit_2sm_mcast(&empty_bar[stage], 0x3);   // slot reusable (in both CTAs) once these MMAs retire
           }
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        if (leader) umma_commit(&acc_full[acc]);          // accumulator complete
+        if (leader) umma_commit_2sm_mcast(&acc_full[acc], 0x3);   // accumulator complete (both CTAs' epilogues)
         __syncwarp();
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
@@ -378,7 +379,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       // all TMEM reads of this accumulator are done -> hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(&acc_empty[acc], 0));   // the leader's MMA warp owns both accumulators
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (lane == 0) tma_wait_group<0>();
@@ -389,7 +390,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   cluster_sync_all();                       // the peer may still multicast into / arrive on this CTA until here
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<512>(tmem_base);
+    tmem_dealloc_2sm<512>(tmem_base);
   }
 }
 
