@@ -254,12 +254,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         // staged 32 x 64 chunk -> global, 128-byte lines
         auto store_staged = [&](__nv_bfloat16* dst, int cb) {
+          uint4 q[8];                  // all eight shared loads first: a load -> store chain per line serialises
+#pragma unroll
+          for (int i = 0; i < 8; ++i) q[i] = *reinterpret_cast<const uint4*>(my_buf + sw128_offset(4 * i + crow, cchunk));
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const int rl = 4 * i + crow;
-            const uint4 q = *reinterpret_cast<const uint4*>(my_buf + sw128_offset(rl, cchunk));
-            const int r = row0 + rl, n = cb + cchunk * 8;
-            if (r < p.M && n < p.N) *reinterpret_cast<uint4*>(dst + (size_t)r * p.ldd + n) = q;
+            const int r = row0 + 4 * i + crow, n = cb + cchunk * 8;
+            if (r < p.M && n < p.N) *reinterpret_cast<uint4*>(dst + (size_t)r * p.ldd + n) = q[i];
           }
         };
         mbar_wait(&acc_full[acc], acc_phase);

@@ -59,6 +59,23 @@ def test_gemm_epilogues(M, N, K):
     assert _rel(d.float(), acc * R.float()) < 1e-2
 
 
+def test_gemm_gelu_outliers():
+    """Pre-activations far outside the usual range (|u| up to ~60): GELU(u) -> u or 0 and GELU'(u) -> 1 or 0.
+    (The polynomial inside the tanh form changes sign beyond |u| ~ 11 unless u^2 is clamped.)"""
+    from stswincl_b200 import ops
+    M, N, K = 256, 256, 64
+    A = torch.zeros(M, K, dtype=torch.bfloat16, device="cuda")
+    B = torch.zeros(N, K, dtype=torch.bfloat16, device="cuda")
+    bias = torch.linspace(-60.0, 60.0, N, device="cuda")
+    dg = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    h = ops.gemm(A, B, mode=ops.EPI_BIAS_GELU, bias=bias, out2=dg)
+    u = bias.double().requires_grad_(True)
+    href = torch.nn.functional.gelu(u)
+    href.sum().backward()
+    assert (h.float() - href.detach().float()[None, :]).abs().max() < 0.26      # bf16 spacing at 60 is 0.25
+    assert (dg.float() - u.grad.float()[None, :]).abs().max() < 1e-2
+
+
 @pytest.mark.parametrize("M,N,K,splits", [(512, 512, 8192, 16), (1536, 512, 4096, 6), (200, 300, 1000, 3)])
 def test_gemm_wgrad_splitk(M, N, K, splits):
     """dW[M,N] += dy^T x : both operands stored [K, .] (MN-major), fp32 TMA add-reduction."""
