@@ -125,6 +125,12 @@ int stswin_layernorm_bwd(const void* dy, const void* x, const float* mean, const
  * (swin_512.py:314,319,326). */
 int stswin_transpose(const void* in, int in_is_f32, void* out, int out_is_f32, int64_t batch, int R, int Cc, void* stream);
 
+/* Batched strided copy: dst[b*dst_stride + i] = src[b*src_stride + i] for i < bytes, b < batches (all in bytes;
+ * pointers, strides and `bytes` multiples of 16).  Moves the frame slices of the middle Swin layer
+ * (x[:, 1:3] in, cat([x[:, :1], y, x[:, 3:]]) out, swin_512.py:302-307) at copy bandwidth. */
+int stswin_copy_strided(void* dst, int64_t dst_stride, const void* src, int64_t src_stride, int64_t bytes, int batches,
+                        void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Pixel-level contrastive loss (K7).  Replaces regression_loss / posMask / negMask of
  * pixcontrast_18/contrast/models/PixPro_swin_v5.py:48-129 and the F.normalize(dim=1) calls

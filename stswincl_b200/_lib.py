@@ -84,6 +84,7 @@ SIGNATURES = {
     "stswin_layernorm_fwd": ([_vp, _fp, _fp, _vp, _fp, _fp, _i64, _i, ctypes.c_float, _i, _i, _i, _i, _vp], ctypes.c_int),
     "stswin_layernorm_bwd": ([_vp, _vp, _fp, _fp, _fp, _vp, _vp, _fp, _fp, _fp, _i64, _i, _i, _i, _i, _i, _vp], ctypes.c_int),
     "stswin_transpose": ([_vp, _i, _vp, _i, _i64, _i, _i, _vp], ctypes.c_int),
+    "stswin_copy_strided": ([_vp, _i64, _vp, _i64, _i64, _i, _vp], ctypes.c_int),
     "stswin_pix_normalize": ([_vp, _i, _vp, _fp, _fp, _i, _i, _i, _i, _vp], ctypes.c_int),
     "stswin_pixloss_fwd": ([_vp, _vp, _vp, _vp, _i, _i, _i, _i, _fp, _fp, _fp, _vp], ctypes.c_int),
     "stswin_pixloss_bwd": ([_vp, _vp, _vp, _fp, _fp, _fp, _i, _i, _i, _i, _fp, _vp], ctypes.c_int),

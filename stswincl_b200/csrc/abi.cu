@@ -50,6 +50,10 @@ int stswin_transpose(const void* in, int in_is_f32, void* out, int out_is_f32, i
                      void* stream) {
   return stswin::transpose_cvt(in, in_is_f32, out, out_is_f32, batch, R, Cc, static_cast<cudaStream_t>(stream));
 }
+int stswin_copy_strided(void* dst, int64_t dst_stride, const void* src, int64_t src_stride, int64_t bytes, int batches,
+                        void* stream) {
+  return stswin::copy_strided(dst, dst_stride, src, src_stride, bytes, batches, static_cast<cudaStream_t>(stream));
+}
 
 int stswin_pix_normalize(const void* x, int x_is_f32, void* xn, float* inv_norm, float* ksum, int N, int C, int HW,
                          int do_normalize, void* stream) {

@@ -336,6 +336,56 @@ __device__ __forceinline__ void gelu_and_grad(float u, float& h, float& g) {
   const float da = fmaf(s, fmaf(s, 5.0f * c2, 3.0f * c1), c0);
   g = fmaf(0.5f * u * fmaf(-t, t, 1.0f), da, cdf);
 }
+// ---- packed fp32x2 arithmetic (FFMA2 / FMUL2 / FADD2 on sm_100): two lanes of work per issue slot
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// gelu_and_grad for two values at once (same approximation, packed arithmetic): u = acc + bias,
+// returns the packed bf16 pairs of GELU(u) and GELU'(u)
+__device__ __forceinline__ void gelu_and_grad_x2(float acc0, float acc1, float b0, float b1, uint32_t& h_bf16x2,
+                                                 uint32_t& g_bf16x2) {
+  constexpr float c0 = 7.97735401e-01f, c1 = 3.69307910e-02f, c2 = -3.55393957e-04f;
+  const uint64_t u = f2_add(f2_pack(acc0, acc1), f2_pack(b0, b1));
+  float s0, s1;
+  f2_unpack(f2_mul(u, u), s0, s1);
+  const uint64_t s = f2_pack(fminf(s0, 64.0f), fminf(s1, 64.0f));
+  const uint64_t p = f2_fma(s, f2_fma(s, f2_pack(c2, c2), f2_pack(c1, c1)), f2_pack(c0, c0));
+  float a0, a1, t0, t1;
+  f2_unpack(f2_mul(u, p), a0, a1);
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(a0));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(a1));
+  const uint64_t t = f2_pack(t0, t1);
+  const uint64_t cdf = f2_fma(t, f2_pack(0.5f, 0.5f), f2_pack(0.5f, 0.5f));
+  const uint64_t h = f2_mul(u, cdf);
+  const uint64_t da = f2_fma(s, f2_fma(s, f2_pack(5.0f * c2, 5.0f * c2), f2_pack(3.0f * c1, 3.0f * c1)), f2_pack(c0, c0));
+  const uint64_t w = f2_fma(t, t, f2_pack(-1.0f, -1.0f));                    // t^2 - 1
+  const uint64_t g = f2_fma(f2_mul(f2_mul(u, w), da), f2_pack(-0.5f, -0.5f), cdf);
+  float h0, h1, g0, g1;
+  f2_unpack(h, h0, h1);
+  f2_unpack(g, g0, g1);
+  h_bf16x2 = pack_bf16(h0, h1);
+  g_bf16x2 = pack_bf16(g0, g1);
+}
 // byte offset of 16-byte chunk `chunk` (0..7) of row `row` inside a 128B-swizzled tile whose
 // rows are 128 bytes and whose base is 1024-byte aligned (the pattern TMA and UMMA both use)
 __device__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t chunk) {

@@ -308,21 +308,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             uint32_t outw[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              float a0 = __uint_as_float(v[2 * j]) + bv[2 * j];
-              float a1 = __uint_as_float(v[2 * j + 1]) + bv[2 * j + 1];
-              if constexpr (MODE == kBiasRes) {
-                const float2 r = unpack_bf16(auxw[j]);
-                a0 += r.x; a1 += r.y;
-              } else if constexpr (MODE == kBiasGelu) {
-                float g0, g1;
-                gelu_and_grad(a0, a0, g0);
-                gelu_and_grad(a1, a1, g1);
-                out2w[half * 16 + j] = pack_bf16(g0, g1);
-              } else if constexpr (MODE == kMulAux) {
-                const float2 u = unpack_bf16(auxw[j]);
-                a0 *= u.x; a1 *= u.y;
+              if constexpr (MODE == kBiasGelu) {
+                gelu_and_grad_x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]), bv[2 * j], bv[2 * j + 1], outw[j],
+                                 out2w[half * 16 + j]);
+              } else {
+                float a0 = __uint_as_float(v[2 * j]) + bv[2 * j];
+                float a1 = __uint_as_float(v[2 * j + 1]) + bv[2 * j + 1];
+                if constexpr (MODE == kBiasRes) {
+                  const float2 r = unpack_bf16(auxw[j]);
+                  a0 += r.x; a1 += r.y;
+                } else if constexpr (MODE == kMulAux) {
+                  const float2 u = unpack_bf16(auxw[j]);
+                  a0 *= u.x; a1 *= u.y;
+                }
+                outw[j] = pack_bf16(a0, a1);
               }
-              outw[j] = pack_bf16(a0, a1);
             }
             if (!row_ok) {                               // rows past M (last tile only): keep them out of colsum
 #pragma unroll

@@ -22,6 +22,7 @@ int layernorm_bwd(const void* dy, const void* x, const float* mean, const float*
                   const void* dres, void* dx, float* dgamma, float* dbeta, float* dx_colsum, long M, int Ctot, int pm,
                   int H, int W, int C, cudaStream_t stream);
 int transpose_cvt(const void* in, int in_f32, void* out, int out_f32, long batch, int R, int Cc, cudaStream_t stream);
+int copy_strided(void* dst, long dst_stride, const void* src, long src_stride, long bytes, int batches, cudaStream_t stream);
 
 int pix_normalize(const void* x, int x_is_f32, void* xn, float* inv_norm, float* ksum, int N, int C, int HW,
                   int do_normalize, cudaStream_t stream);

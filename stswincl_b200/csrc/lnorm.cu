@@ -298,6 +298,20 @@ __global__ void transpose_kernel(const TI* __restrict__ in, TO* __restrict__ out
   }
 }
 
+// dst[b][i] = src[b][i], 16 bytes per access, four loads in flight per thread
+__global__ void __launch_bounds__(256)
+copy_strided_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src, long dst_stride16, long src_stride16, long n16) {
+  const uint4* s = src + (long)blockIdx.y * src_stride16;
+  uint4* d = dst + (long)blockIdx.y * dst_stride16;
+  const long step = (long)gridDim.x * blockDim.x;
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * step < n16; i += 4 * step) {
+    const uint4 a = __ldg(s + i), b = __ldg(s + i + step), c = __ldg(s + i + 2 * step), e = __ldg(s + i + 3 * step);
+    d[i] = a; d[i + step] = b; d[i + 2 * step] = c; d[i + 3 * step] = e;
+  }
+  for (; i < n16; i += step) d[i] = __ldg(s + i);
+}
+
 int check_ln_shape(long M, int Ctot, int pm, int H, int W, int C) {
   STSWIN_CHECK_ARG(M > 0 && Ctot > 0, "layernorm: empty input");
   STSWIN_CHECK_ARG(Ctot % 8 == 0 && Ctot <= 2048, "layernorm: row length %d must be a multiple of 8 and <= 2048", Ctot);
@@ -385,6 +399,25 @@ int layernorm_bwd(const void* dy, const void* x, const float* mean, const float*
   else STSWIN_LN_BWD(8, 2, 3, false);
 #undef STSWIN_LN_BWD_K
 #undef STSWIN_LN_BWD
+  STSWIN_CUDA(cudaGetLastError());
+  return kOk;
+}
+
+// see include/stswin_b200.h : stswin_copy_strided
+int copy_strided(void* dst, long dst_stride, const void* src, long src_stride, long bytes, int batches, cudaStream_t stream) {
+  STSWIN_CHECK_ARG(dst && src && bytes > 0 && batches > 0, "copy_strided: bad argument");
+  STSWIN_CHECK_ARG(batches <= 65535, "copy_strided: %d batches exceed gridDim.y", batches);
+  STSWIN_CHECK_ARG(((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src) | (uintptr_t)dst_stride |
+                     (uintptr_t)src_stride | (uintptr_t)bytes) & 15) == 0,
+                   "copy_strided: pointers, strides and size must be multiples of 16 bytes");
+  const long n16 = bytes / 16;
+  long per = (n16 + 256 * 4 - 1) / (256 * 4);                       // blocks that give every thread four vectors
+  const long cap = ((long)num_sms() * 8 + batches - 1) / batches;   // ~8 blocks per SM in total
+  if (per > cap) per = cap;
+  if (per < 1) per = 1;
+  dim3 grid((unsigned)per, (unsigned)batches);
+  copy_strided_kernel<<<grid, 256, 0, stream>>>(static_cast<uint4*>(dst), static_cast<const uint4*>(src), dst_stride / 16,
+                                                src_stride / 16, n16);
   STSWIN_CUDA(cudaGetLastError());
   return kOk;
 }

@@ -244,3 +244,18 @@ def transpose(x: torch.Tensor, out_dtype: torch.dtype) -> torch.Tensor:
                                           int(out_dtype == torch.float32), b, R, Cc, _stream(x))
     _lib.check(st, "stswin_transpose")
     return out
+
+
+def copy_frames(dst: torch.Tensor, src: torch.Tensor) -> None:
+    """dst[b] = src[b] for two [batch, ...] views whose trailing dims are dense (only the batch stride
+    may differ): the frame slices of the middle Swin layer (stswin_copy_strided)."""
+    assert dst.shape == src.shape and dst.dtype == src.dtype and dst.is_cuda and src.is_cuda
+    b = dst.shape[0]
+    inner = dst[0].numel() * dst.element_size()
+    assert dst[0].is_contiguous() and src[0].is_contiguous()
+    ds = dst.stride(0) * dst.element_size() if b > 1 else inner
+    ss = src.stride(0) * src.element_size() if b > 1 else inner
+    with _launch("copy", float(2 * b * inner), dst):
+        st = _lib.load().stswin_copy_strided(dst.data_ptr(), ds, src.data_ptr(), ss, inner, b, _stream(dst))
+    _lib.check(st, "stswin_copy_strided")
+

@@ -236,7 +236,9 @@ class _SplitMidFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x):
         ctx.shape, ctx.dtype = x.shape, x.dtype
-        xm = x[:, 1:3].contiguous()
+        B, _, L, C = x.shape
+        xm = torch.empty((B, 2, L, C), dtype=x.dtype, device=x.device)
+        ops.copy_frames(xm, x[:, 1:3])
         return xm, x.view_as(x)
 
     @staticmethod
@@ -244,7 +246,7 @@ class _SplitMidFn(torch.autograd.Function):
         if d_pass is None:
             d_pass = torch.zeros(ctx.shape, dtype=ctx.dtype, device=d_xm.device)
         if d_xm is not None:
-            d_pass[:, 1:3].copy_(d_xm)
+            ops.copy_frames(d_pass[:, 1:3], d_xm.contiguous())
         else:
             d_pass[:, 1:3].zero_()
         return d_pass
@@ -256,18 +258,22 @@ class _PutMidFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x_pass, y):
         out = torch.empty_like(x_pass)
-        out[:, 0].copy_(x_pass[:, 0])
-        out[:, 3].copy_(x_pass[:, 3])
-        out[:, 1:3].copy_(y)
+        ops.copy_frames(out[:, 0], x_pass[:, 0])
+        ops.copy_frames(out[:, 3], x_pass[:, 3])
+        ops.copy_frames(out[:, 1:3], y.contiguous())
         return out
 
     @staticmethod
     def backward(ctx, d_out):
         # frames 1..2 of d_pass are left for _SplitMidFn.backward to fill (a fresh buffer, never aliased)
+        d_out = d_out.contiguous()
         d_pass = torch.empty_like(d_out)
-        d_pass[:, 0].copy_(d_out[:, 0])
-        d_pass[:, 3].copy_(d_out[:, 3])
-        return d_pass, d_out[:, 1:3].contiguous()
+        ops.copy_frames(d_pass[:, 0], d_out[:, 0])
+        ops.copy_frames(d_pass[:, 3], d_out[:, 3])
+        B, _, L, C = d_out.shape
+        d_y = torch.empty((B, 2, L, C), dtype=d_out.dtype, device=d_out.device)
+        ops.copy_frames(d_y, d_out[:, 1:3])
+        return d_pass, d_y
 
 
 def _as_tokens_bf16(x: torch.Tensor) -> torch.Tensor:
