@@ -336,6 +336,13 @@ __device__ __forceinline__ void gelu_and_grad(float u, float& h, float& g) {
   const float da = fmaf(s, fmaf(s, 5.0f * c2, 3.0f * c1), c0);
   g = fmaf(0.5f * u * fmaf(-t, t, 1.0f), da, cdf);
 }
+// 256-bit global store (STG.256 on sm_100): a full 32-byte sector per lane and instruction
+__device__ __forceinline__ void st_global_v8(void* p, const uint32_t (&v)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+               "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+
 // ---- packed fp32x2 arithmetic (FFMA2 / FMUL2 / FADD2 on sm_100): two lanes of work per issue slot
 __device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
   uint64_t r;

@@ -14,21 +14,20 @@
 //
 // Streaming: operand chunks [128 rows x 64 ch] flow through 16 KB ring slots twice -- once from
 // HBM for S and dP (ring H, producer warp 0), once more from L2 for the three output products
-// (ring L, producer warp 6).  Two independent rings let the HBM loads of tile i+1 run while tile i
-// is still in its softmax-backward / second pass (a single ring serialised them: 46-60% of HBM
-// peak, profiles/r1_attn_bwd_ncu_summary.txt).  S, dP and two 64-column output accumulators live in
-// TMEM; outputs go TMEM -> registers -> global directly (each thread owns one token row and writes
-// its 128-byte line), so no staging buffer competes with the rings for shared memory.
-// The register-level work (softmax backward, output conversion, bias-gradient sums) is done by TWO
-// groups of four warps, i.e. two warps per SM sub-partition: with a single warp per sub-partition
-// every dependent instruction exposed its full latency and a tile took ~28k cycles.  For L >= 64
-// the groups take alternate 32-column chunks of S / dP (row sums are exchanged through shared
-// memory); the groups always alternate the 64-column output chunks (group g drains TMEM buffer g).  The bias-table gradient needs the sum of
-// dS over every tile this CTA processes: each thread (= query row) keeps N = ws*ws fp32 running
-// sums, one per key position (the TxT tiling folds onto the same entry), and bins them by relative
-// position once at the end of the kernel -- no per-element atomics in the main loop, and no bf16
-// rounding inside a sum that cancels heavily.  For that sum to be meaningful every tile of a
-// launch uses ONE token order (gm.uniform_quad) and every CTA sees ONE head (grid % nH == 0).
+// (ring L, producer warp 2).  (One shared in-order ring was tried twice: it chains the two passes into
+// one HBM/L2 latency after the other on the MMA warp's critical path.)  S, two dP buffers and two
+// 64-column output accumulators live in TMEM.
+// Four warpgroups (setmaxnreg): producers + MMA issuer (warp-uniform control flow, one elected lane
+// issues) / softmax-backward (one thread per tile row, 232 registers) / two drain groups that
+// alternate the output products (TMEM -> bf16 -> 256-bit stores to the row's own line of d_qkv:
+// the scatter is the row's token index, no staging buffer).
+// The bias-table gradient needs the sum of dS over every item this CTA processes: on the fast path
+// each softmax-backward thread (= query row) keeps N = ws*ws fp32 running sums, one per key position
+// (the TxT tiling folds onto the same entry), together with the row's N bias values, and bins them by
+// relative position into shared memory whenever the row's own position changes (windows that wrap
+// use quadrant token order, interior windows row-major) and at the end -- no per-element atomics in
+// the main loop and no bf16 rounding inside a sum that cancels heavily; every CTA sees ONE head
+// group (grid % ngrp == 0).  Generic / general paths: shared-memory atomics per element.
 // (A first version accumulated bf16 dS on the tensor core through an identity tile; its rounding
 // noise reached 6% of the gradient for a 6-window batch.)
 #include <type_traits>
@@ -44,14 +43,13 @@ int make_window_tmaps(WinMaps* maps, const void* base, const WinGeom& gm, int ch
 
 namespace {
 
-constexpr int NRH = 5;                         // ring H: first-pass chunks, streamed from HBM
+constexpr int NRH = 6;                         // ring H: first-pass chunks, streamed from HBM
 constexpr int NRL = 3;                         // ring L: second-pass chunks, re-read from L2
 constexpr int SLOT_BYTES = 128 * 128;
 constexpr int PD_BYTES = 2 * SLOT_BYTES;       // [128 x 128] bf16 as two K-major halves
-constexpr int STG_BYTES = 8 * 2048;            // per-warp output transposition areas (drain warps)
 constexpr int TAB_MAX = 15 * 15;
 constexpr int NUM_THREADS = 512;               // warpgroup 0: producers H / L, MMA issuer; 1: softmax backward; 2, 3: drain
-constexpr int SMEM_BYTES = 1024 + (NRH + NRL) * SLOT_BYTES + 2 * PD_BYTES + STG_BYTES + 128 * 4 +
+constexpr int SMEM_BYTES = 1024 + (NRH + NRL) * SLOT_BYTES + 2 * PD_BYTES + 128 * 4 +
                            4 * (TAB_MAX + 1) * 4 + 256;
 constexpr float kMaskLog2e = -100.0f * 1.4426950408889634f;
 STSWIN_TRACE_DECL(g_trace_bwd)
@@ -70,8 +68,7 @@ winattn_bwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant
   uint8_t* s_ringl = s_ringh + NRH * SLOT_BYTES;
   uint8_t* s_p = s_ringl + NRL * SLOT_BYTES;
   uint8_t* s_ds = s_p + PD_BYTES;
-  uint8_t* s_stage = s_ds + PD_BYTES;
-  uint32_t* s_lut = reinterpret_cast<uint32_t*>(s_stage + STG_BYTES);
+  uint32_t* s_lut = reinterpret_cast<uint32_t*>(s_ds + PD_BYTES);
   float* s_tab = reinterpret_cast<float*>(s_lut + 128);   // [2][TAB_MAX + 1] bias * log2e, one table per head of the group
   float* s_bacc = s_tab + 2 * (TAB_MAX + 1);              // [2][TAB_MAX + 1] bias-table gradient bins of this CTA
   static_assert(((128 + 4 * (TAB_MAX + 1)) * 4) % 8 == 0, "mbarriers need 8-byte alignment");
@@ -299,9 +296,10 @@ winattn_bwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant
     constexpr bool REG_BACC = (WS > 0 && SH == 1);
     constexpr int NPOS = REG_BACC ? WS * WS : 1;
     float bacc[NPOS];
+    float breg[NPOS];                        // bias * log2e of this row against every key position (same lifetime)
 #pragma unroll
-    for (int i = 0; i < NPOS; ++i) bacc[i] = 0.f;
-    int bacc_key = -1;                       // key_i the sums in bacc belong to (-1: empty)
+    for (int i = 0; i < NPOS; ++i) { bacc[i] = 0.f; breg[i] = 0.f; }
+    int bacc_key = -1;                       // key_i the sums in bacc / the values in breg belong to (-1: none)
     auto flush_bacc = [&]() {
       if constexpr (REG_BACC) {
         if (bacc_key >= 0) {
@@ -330,12 +328,19 @@ winattn_bwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant
         key_i = (rg.rr + gm.ws - 1) * (2 * gm.ws - 1) + rg.cc + gm.ws - 1;
         col0 = GEN ? 0 : rg.g * L;
         if constexpr (REG_BACC) {
-          if (key_i != bacc_key) { flush_bacc(); bacc_key = key_i; }
+          if (key_i != bacc_key) {           // the row's own position changed (token-order switch)
+            flush_bacc();
+            bacc_key = key_i;
+#pragma unroll
+            for (int pos = 0; pos < NPOS; ++pos) breg[pos] = s_tab[key_i - ((pos / WS) * (2 * WS - 1) + pos % WS)];
+          }
         }
       }
       const float* tab = s_tab + sub * (TAB_MAX + 1);
       float* bins = s_bacc + sub * (TAB_MAX + 1);
-      const float lse_i = (GEN && !rg.inrange) ? 0.f : lse2[((size_t)tile * gm.nH + head) * 128 + rg.canon];
+      // lse2 is indexed by the forward's tiling (natural window order): tile = window / G, row = (window % G)*L + ...
+      const float lse_i = (GEN && !rg.inrange) ? 0.f
+                          : lse2[((size_t)(rg.gw / gm.G) * gm.nH + head) * 128 + (rg.gw % gm.G) * gm.L + (rg.canon - rg.g * gm.L)];
       float delta = 0.f;
 
       if constexpr (WS > 0) {
@@ -362,8 +367,10 @@ winattn_bwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant
 #pragma unroll
           for (int cb = 0; cb < NCHUNK; ++cb) {
             uint32_t v[32], w[32];
-            tmem_ld_row_chunk<L>(tmem_S, t_lane, col0, cb, wq, lane, v);
-            tmem_ld_row_chunk<L>(tmem_dPu, t_lane, col0, cb, wq, lane, w);
+            static_assert(L >= 32, "fast path: 32-column chunks");
+            tmem_ld32(tmem_S + t_lane + col0 + cb * 32, v);    // both loads in flight, one wait
+            tmem_ld32(tmem_dPu + t_lane + col0 + cb * 32, w);
+            tmem_ld_wait();
             if (cb == 0) {
               mbar_wait(p_free, (u & 1) ^ 1);                  // the previous unit's dV products have read P
               if (tr) WTRACE(g_trace_bwd, k, 13);
@@ -377,7 +384,8 @@ winattn_bwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                   const int jj = j8 * 8 + 2 * h + e, j = cb * CH + jj;
-                  const float x = fmaf(__uint_as_float(v[jj]), gm.scale_log2e, tp[-col_key<L, WS, QUAD>(j)]);
+                  const float bias = REG_BACC ? breg[col_pos<L, WS, QUAD>(j)] : tp[-col_key<L, WS, QUAD>(j)];
+                  const float x = fmaf(__uint_as_float(v[jj]), gm.scale_log2e, bias);
                   pv[e] = fast_exp2(x + nq[QUAD ? j / QL : 0]);
                   delta = fmaf(pv[e], __uint_as_float(w[jj]), delta);
                 }
@@ -519,13 +527,14 @@ winattn_bwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant
     asm volatile("setmaxnreg.dec.sync.aligned.u32 112;");
     // ---------------------------------------------------------------- drain warps (groups B0 / B1)
     // Output product n of the CTA lands in TMEM accumulator n % 2, which is group (n % 2)'s to drain:
-    // TMEM -> bf16 -> 64-byte row segments of d_qkv at the row's token (window_reverse + inverse roll
-    // = the token index of the row), plus the qkv-bias gradient column sums.  32 columns at a time.
+    // TMEM -> bf16 -> the row's own line of d_qkv (window_reverse + inverse roll = the token index of
+    // the row) with 256-bit stores, one full 32-byte sector per lane and instruction: no shared-memory
+    // staging (the SM's shared-memory port is the scarce resource of this kernel), plus the qkv-bias
+    // gradient column sums.  32 columns at a time.
     const int bg = (warp - 8) >> 2;               // 0: warps 8-11, 1: warps 12-15
     const int wq = warp & 3;
     const int row = wq * 32 + lane;
     const uint32_t t_lane = uint32_t(wq * 32) << 16;
-    uint8_t* stage = s_stage + (warp - 8) * 2048;
     const bool tr = (threadIdx.x == 256);
     (void)tr;
     uint32_t nout = 0;                            // products of the CTA so far
@@ -535,13 +544,7 @@ winattn_bwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant
       RowGeom rg;
       if constexpr (WS > 0) rg = row_geom_fast<L, WS, ORDER>(gm, tile, row);
       else                  rg = row_geom(gm, tile, row);
-      const long tok = rg.valid ? rg.tok : -1;
-      uint8_t* rowp[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const long t = __shfl_sync(0xffffffffu, tok, i * 8 + (lane >> 2));
-        rowp[i] = t < 0 ? nullptr : reinterpret_cast<uint8_t*>(d_qkv + t * (3 * gm.C) + hg * gm.gch);
-      }
+      __nv_bfloat16* row_out = d_qkv + rg.tok * (3 * gm.C) + hg * gm.gch;
 #pragma unroll 1
       for (int sub = 0; sub < SH; ++sub) {
 #pragma unroll 1
@@ -572,15 +575,15 @@ winattn_bwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant
               mbar_arrive(&obuf_free[bg]);
             }
             const int ch0 = which * gm.C + c * 64 + cofs;          // relative to the head group's first channel
-            uint4 vals[4];
+            if (rg.valid) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              vals[j] = make_uint4(pack_bf16(a[8 * j], a[8 * j + 1]), pack_bf16(a[8 * j + 2], a[8 * j + 3]),
-                                   pack_bf16(a[8 * j + 4], a[8 * j + 5]), pack_bf16(a[8 * j + 6], a[8 * j + 7]));
-            uint8_t* rp[4];
+              for (int j = 0; j < 2; ++j) {
+                uint32_t w8[8];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) rp[i] = rowp[i] ? rowp[i] + ch0 * 2 : nullptr;
-            warp_store_rows_half(stage, vals, rp, lane);
+                for (int e = 0; e < 8; ++e) w8[e] = pack_bf16(a[16 * j + 2 * e], a[16 * j + 2 * e + 1]);
+                st_global_v8(row_out + ch0 + 16 * j, w8);
+              }
+            }
             if (d_colsum != nullptr) {
               warp_colsum<32>(a, lane);        // lane l: column l summed over this warp's 32 rows
               atomicAdd(d_colsum + ch0 + hg * gm.gch + lane, a[0]);
@@ -626,10 +629,11 @@ int winattn_bwd(const void* qkv, const float* bias_table, const float* lse2, con
   STSWIN_CHECK_ARG(mask == nullptr || mask_windows > 0, "winattn: mask given with mask_windows <= 0");
   gm.mask = mask; gm.mask_nw = mask_windows;
   if (gm.shift > 0 && gm.ra != gm.rb) gm.general = 1;     // unequal rectangles: no static column -> position fold
+  gm.perm = (gm.shift > 0 && gm.nWh > 1 && gm.nWw > 1) ? 1 : 0;   // interior windows first: one token-order switch per CTA
   WinMaps tq, td;
   if ((rc = make_window_tmaps(&tq, qkv, gm, 3 * C)) != kOk) return rc;
   if ((rc = make_window_tmaps(&td, d_out, gm, C)) != kOk) return rc;
-  STSWIN_CHECK_ARG((reinterpret_cast<uintptr_t>(d_qkv) & 15) == 0, "winattn_bwd: d_qkv must be 16-byte aligned");
+  STSWIN_CHECK_ARG((reinterpret_cast<uintptr_t>(d_qkv) & 31) == 0, "winattn_bwd: d_qkv must be 32-byte aligned");
   const int items = gm.num_tiles * gm.ngrp;
   int grid = items < num_sms() ? items : num_sms();
   grid -= grid % gm.ngrp;                 // one head group per CTA (items is a multiple of ngrp, so grid >= ngrp)

@@ -44,6 +44,7 @@ struct WinGeom {
   const float* mask;  // optional dense additive mask [mask_nw, N, N] (WindowAttention.forward's `mask`
   int mask_nw;        //   argument, swin_512.py:127-131), applied ON TOP of the closed-form shift mask; or null
   unsigned long long mg_nW, mg_nWw;   // ceil(2^32 / nW), ceil(2^32 / nWw): exact division of window indices by multiply-shift
+  int perm;           // 1: window indices are enumerated interior-windows-first (see window_coords)
   int uniform_quad;   // 1: every window of a shifted block is moved as four quadrant boxes (one token
                       //    order per launch; the backward kernel needs that to sum dS across tiles)
 };
@@ -53,7 +54,7 @@ struct RowGeom {
   int rr, cc;  // token coordinates inside its window (shifted frame)
   int id;      // shift-mask region id 0..8 (swin_512.py:173-184), 0 when unshifted
   int canon;   // g*L + t*N + rr*ws + cc : position in the reference's own window-token order
-  int gw;      // global window index b*nW + win (clamped for padding windows)
+  int gw;      // global window index b*nW + win in the natural order (clamped for padding windows)
   long tok;    // index of the source token in the natural [B*T, H, W] order (roll + partition undone)
   bool wraps;  // window crosses the image border (the only windows with a non-zero mask)
   bool valid;  // false for rows of a padding window in the last tile, and for padding rows
@@ -69,7 +70,32 @@ __device__ __forceinline__ bool quad_order(const WinGeom& gm, bool wraps) {
   return gm.uniform_quad ? (gm.shift > 0) : wraps;
 }
 
+// Window index -> (image, window row, window column).  With gm.perm the indices enumerate the interior
+// windows of every image first and the windows that wrap around the border (last window row / column
+// of a shifted block) after them: a CTA that walks its items in increasing order then changes token
+// order (row-major <-> quadrant) once instead of at every third item, which is what the backward
+// kernel's per-row register state (bias values, bias-gradient sums) wants.
 __device__ __forceinline__ void window_coords(const WinGeom& gm, int gw, int& b, int& wh, int& ww, bool& wraps) {
+  if (gm.perm) {
+    const int ni = (gm.nWh - 1) * (gm.nWw - 1);       // interior windows per image
+    const int n_int = gm.B * ni;
+    if (gw < n_int) {
+      b = gw / ni;
+      const int r = gw - b * ni;
+      wh = r / (gm.nWw - 1);
+      ww = r - wh * (gm.nWw - 1);
+      wraps = false;
+    } else {
+      const int nwr = gm.nWh + gm.nWw - 1;            // wrapping windows per image
+      int r = gw - n_int;
+      b = r / nwr;
+      r -= b * nwr;
+      if (r < gm.nWw) { wh = gm.nWh - 1; ww = r; }
+      else            { wh = r - gm.nWw; ww = gm.nWw - 1; }
+      wraps = gm.shift > 0;
+    }
+    return;
+  }
   b = gw / gm.nW;
   const int win = gw - b * gm.nW;
   wh = win / gm.nWw;
@@ -98,8 +124,8 @@ __device__ __forceinline__ RowGeom row_geom(const WinGeom& gm, int tile, int r) 
   o.valid = o.inrange && gw < gm.total_windows;
   if (gw > gm.total_windows - 1) gw = gm.total_windows - 1;
   int b, wh, ww, t;
-  o.gw = gw;
   window_coords(gm, gw, b, wh, ww, o.wraps);
+  o.gw = b * gm.nW + wh * gm.nWw + ww;        // the window's index in the natural (un-permuted) order
   if (!quad_order(gm, o.wraps)) {
     t = rem / gm.N;
     const int pos = rem - t * gm.N;
@@ -164,10 +190,17 @@ __device__ __forceinline__ RowGeom row_geom_fast(const WinGeom& gm, int tile, in
   int gw = tile * G + o.g;
   o.valid = gw < gm.total_windows;
   if (gw > gm.total_windows - 1) gw = gm.total_windows - 1;
-  o.gw = gw;
-  const int b = fast_div(gw, gm.mg_nW), win = gw - b * gm.nW;
-  const int wh = fast_div(win, gm.mg_nWw), ww = win - wh * gm.nWw;
-  o.wraps = ORDER != 0 && (wh == gm.nWh - 1 || ww == gm.nWw - 1);
+  int b, wh, ww;
+  if (gm.perm) {
+    window_coords(gm, gw, b, wh, ww, o.wraps);
+  } else {
+    b = fast_div(gw, gm.mg_nW);
+    const int win = gw - b * gm.nW;
+    wh = fast_div(win, gm.mg_nWw);
+    ww = win - wh * gm.nWw;
+    o.wraps = ORDER != 0 && (wh == gm.nWh - 1 || ww == gm.nWw - 1);
+  }
+  o.gw = b * gm.nW + wh * gm.nWw + ww;        // the window's index in the natural (un-permuted) order
   int t;
   if (ORDER == 0 || (ORDER == 2 && !o.wraps)) {
     t = rem / N;

@@ -498,6 +498,7 @@ int fill_geom(WinGeom* gm, int B, int T, int H, int W, int C, int nH, int ws, in
     gm->roff[4] = off;       // == L
   }
   gm->uniform_quad = 0;
+  gm->perm = 0;
   gm->mask = nullptr; gm->mask_nw = 0;
   // exact multiply-shift division of window indices (row_geom_fast)
   if ((unsigned long long)gm->total_windows * (unsigned long long)gm->nW >= (1ull << 32))
