@@ -58,6 +58,7 @@ int stswin_set_device(int device);
 #define STSWIN_EPI_BIAS_GELU 2     /* u = acc + bias ; D = gelu_erf(u) ; D2 = gelu_erf'(u) */
 #define STSWIN_EPI_MUL_AUX 3       /* D = acc * aux     (dgrad through GELU: aux = D2)  */
 #define STSWIN_EPI_F32_REDUCE 4    /* D(fp32) += acc, split-K                          */
+#define STSWIN_EPI_BIAS_GELU_FWD 5 /* D = gelu_erf(acc + bias)      (inference: no D2) */
 
 int stswin_gemm_bf16(const void* A, int a_major, int64_t lda,
                      const void* B, int b_major, int64_t ldb,

@@ -393,6 +393,23 @@ __device__ __forceinline__ void gelu_and_grad_x2(float acc0, float acc1, float b
   h_bf16x2 = pack_bf16(h0, h1);
   g_bf16x2 = pack_bf16(g0, g1);
 }
+// forward-only GELU of two values (inference: no derivative output)
+__device__ __forceinline__ uint32_t gelu_x2(float acc0, float acc1, float b0, float b1) {
+  constexpr float c0 = 7.97735401e-01f, c1 = 3.69307910e-02f, c2 = -3.55393957e-04f;
+  const uint64_t u = f2_add(f2_pack(acc0, acc1), f2_pack(b0, b1));
+  float s0, s1;
+  f2_unpack(f2_mul(u, u), s0, s1);
+  const uint64_t s = f2_pack(fminf(s0, 64.0f), fminf(s1, 64.0f));
+  const uint64_t p = f2_fma(s, f2_fma(s, f2_pack(c2, c2), f2_pack(c1, c1)), f2_pack(c0, c0));
+  float a0, a1, t0, t1;
+  f2_unpack(f2_mul(u, p), a0, a1);
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(a0));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(a1));
+  const uint64_t h = f2_mul(u, f2_fma(f2_pack(t0, t1), f2_pack(0.5f, 0.5f), f2_pack(0.5f, 0.5f)));
+  float h0, h1;
+  f2_unpack(h, h0, h1);
+  return pack_bf16(h0, h1);
+}
 // byte offset of 16-byte chunk `chunk` (0..7) of row `row` inside a 128B-swizzled tile whose
 // rows are 128 bytes and whose base is 1024-byte aligned (the pattern TMA and UMMA both use)
 __device__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t chunk) {

@@ -46,6 +46,7 @@ enum Mode : int {
   kBiasGelu = 2,    // u = acc + bias ; D = gelu(u) ; D2 = gelu'(u)
   kMulAux = 3,      // D = acc * aux
   kF32Reduce = 4,   // D(fp32) += acc          (split-K, TMA add-reduction)
+  kBiasGeluFwd = 5, // D = gelu(acc + bias)    (inference: no derivative output)
 };
 
 struct GemmArgs {
@@ -308,7 +309,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             uint32_t outw[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              if constexpr (MODE == kBiasGelu) {
+              if constexpr (MODE == kBiasGeluFwd) {
+                outw[j] = gelu_x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]), bv[2 * j], bv[2 * j + 1]);
+              } else if constexpr (MODE == kBiasGelu) {
                 gelu_and_grad_x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]), bv[2 * j], bv[2 * j + 1], outw[j],
                                  out2w[half * 16 + j]);
               } else {
@@ -416,6 +419,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tm
     case kBias: return launch_mode<A_MN, B_MN, kBias>(tmA, tmB, tmD, args, stream);
     case kBiasRes: return launch_mode<A_MN, B_MN, kBiasRes>(tmA, tmB, tmD, args, stream);
     case kBiasGelu: return launch_mode<A_MN, B_MN, kBiasGelu>(tmA, tmB, tmD, args, stream);
+    case kBiasGeluFwd: return launch_mode<A_MN, B_MN, kBiasGeluFwd>(tmA, tmB, tmD, args, stream);
     case kMulAux: return launch_mode<A_MN, B_MN, kMulAux>(tmA, tmB, tmD, args, stream);
     default: return launch_mode<A_MN, B_MN, kF32Reduce>(tmA, tmB, tmD, args, stream);
   }
@@ -428,7 +432,7 @@ int gemm_bf16(const void* A, int a_major, long lda, const void* B, int b_major, 
               const void* aux, long ld_aux, const float* bias, float* colsum, int M, int N, int K, int mode,
               int k_splits, cudaStream_t stream) {
   STSWIN_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
-  STSWIN_CHECK_ARG(mode >= kBias && mode <= kF32Reduce, "gemm: unknown epilogue mode %d", mode);
+  STSWIN_CHECK_ARG(mode >= kBias && mode <= kBiasGeluFwd, "gemm: unknown epilogue mode %d", mode);
   STSWIN_CHECK_ARG(a_major == 0 || a_major == 1, "gemm: a_major must be 0 or 1");
   STSWIN_CHECK_ARG(b_major == 0 || b_major == 1, "gemm: b_major must be 0 or 1");
   STSWIN_CHECK_ARG(!(a_major == 1 && b_major == 0), "gemm: (A MN-major, B K-major) is not instantiated");

@@ -12,7 +12,7 @@ import torch
 from . import _lib
 from ._lib import StswinError
 
-EPI_BIAS, EPI_BIAS_RES, EPI_BIAS_GELU, EPI_MUL_AUX, EPI_F32_REDUCE = 0, 1, 2, 3, 4
+EPI_BIAS, EPI_BIAS_RES, EPI_BIAS_GELU, EPI_MUL_AUX, EPI_F32_REDUCE, EPI_BIAS_GELU_FWD = 0, 1, 2, 3, 4, 5
 
 # ---------------------------------------------------------------------------------------------
 # launch accounting (bench.py): every C-ABI kernel launch is counted; with an EventProfiler

@@ -131,7 +131,8 @@ class _BlockFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, table, w_qkv, b_qkv, w_proj, b_proj, g1, be1, g2, be2, w_fc1, b_fc1, w_fc2, b_fc2, geom):
-        H, W, nH, ws, shift, qk_scale, eps = geom
+        H, W, nH, ws, shift, qk_scale, eps, infer = geom
+        geom = geom[:7]
         Bp, T, L, C = x.shape
         x2 = x.reshape(-1, C)
         wq, wp, w1, w2 = w_qkv.to(_BF16), w_proj.to(_BF16), w_fc1.to(_BF16), w_fc2.to(_BF16)
@@ -139,6 +140,13 @@ class _BlockFn(torch.autograd.Function):
         attn, lse2 = ops.winattn_fwd(qkv.view(Bp, T, L, 3 * C), table, H, W, nH, ws, shift, qk_scale=qk_scale)
         y = ops.gemm(attn.view(-1, C), wp, bias=b_proj, aux=x2, mode=ops.EPI_BIAS_RES)
         yn, mean2, rstd2 = ops.layernorm_fwd(y, g2, be2, eps)
+        if infer or not any(ctx.needs_input_grad):
+            # inference (no_grad key encoders of the pre-training model, evaluation): no gelu' output,
+            # nothing kept for a backward
+            h = ops.gemm(yn, w1, bias=b_fc1, mode=ops.EPI_BIAS_GELU_FWD)
+            z = ops.gemm(h, w2, bias=b_fc2, aux=y, mode=ops.EPI_BIAS_RES)
+            out, _, _ = ops.layernorm_fwd(z, g1, be1, eps)
+            return out.view(Bp, T, L, C)
         dgelu = torch.empty((x2.shape[0], w1.shape[0]), dtype=_BF16, device=x.device)   # gelu'(fc1 out), for the backward
         h = ops.gemm(yn, w1, bias=b_fc1, mode=ops.EPI_BIAS_GELU, out2=dgelu)
         z = ops.gemm(h, w2, bias=b_fc2, aux=y, mode=ops.EPI_BIAS_RES)
@@ -390,9 +398,12 @@ class SwinTransformerBlock(nn.Module):
     def forward_tokens(self, x: torch.Tensor) -> torch.Tensor:
         """bf16 in, bf16 out; no dtype round trip (used by the layer container)."""
         a, m = self.attn, self.mlp
+        # grad mode is decided here: inside autograd.Function.forward it always reads "disabled", and
+        # ctx.needs_input_grad ignores torch.no_grad()
+        infer = not torch.is_grad_enabled()
         return _BlockFn.apply(x, a.relative_position_bias_table, a.qkv.weight, a.qkv.bias, a.proj.weight, a.proj.bias,
                               self.norm1.weight, self.norm1.bias, self.norm2.weight, self.norm2.bias,
-                              m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias, self._geom())
+                              m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias, self._geom() + (infer,))
 
     def forward(self, x_v):
         H, W = self.input_resolution

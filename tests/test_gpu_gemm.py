@@ -54,6 +54,9 @@ def test_gemm_epilogues(M, N, K):
     assert _rel(h.float(), href.detach().float()) < 1e-2
     assert _rel(dg.float(), uref.grad.float()) < 1e-2
     assert _rel(cs, h.float().sum(0)) < 1e-3
+    # forward-only GELU (inference path)
+    h1 = ops.gemm(A, B, mode=ops.EPI_BIAS_GELU_FWD, bias=bias)
+    assert _rel(h1.float(), href.detach().float()) < 1e-2
     # multiply by aux (dgrad through GELU)
     d = ops.gemm(A, B, mode=ops.EPI_MUL_AUX, aux=R)
     assert _rel(d.float(), acc * R.float()) < 1e-2

@@ -174,6 +174,24 @@ def test_full_size_block_vs_oracle():
     assert rel_err(y.cpu(), ref) < TOL
 
 
+def test_block_inference_path_matches_training_path():
+    """Under no_grad (the six key-encoder passes of the pre-training model) the block takes the
+    forward-only GELU epilogue and keeps nothing for a backward: same output as the training forward."""
+    from oracle import swin_oracle as so
+    from stswincl_b200 import swin
+    dim, res, heads, ws, shift = 512, (32, 40), 4, 8, 4
+    params = so.make_block_params(dim, res, heads, ws, shift, seed=83)
+    m = _load(swin.SwinTransformerBlock(dim, res, heads, window_size=ws, shift_size=shift), params)
+    x = so.make_features(84, 2, 2, res[0] * res[1], dim).cuda()
+    y_train = m(x)
+    with torch.no_grad():
+        y_eval = m(x)
+    assert y_train.requires_grad and not y_eval.requires_grad
+    assert rel_err(y_eval.float().cpu(), y_train.detach().float().cpu()) < 5e-3
+    ref = so.swin_block(x.cpu().to(torch.bfloat16).float(), params, res, heads, ws, shift)
+    assert rel_err(y_eval.float().cpu(), ref) < TOL
+
+
 def test_cadis_shaped_block_vs_oracle():
     """Config 5: CaDIS-shaped crop 512x960 -> 64x120 tokens, shifted block, 8 heads."""
     from oracle import swin_oracle as so
