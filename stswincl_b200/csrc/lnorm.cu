@@ -312,6 +312,36 @@ copy_strided_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src, long
   for (; i < n16; i += step) d[i] = __ldg(s + i);
 }
 
+// bf16 [batch, R, Cc] -> [batch, Cc, R]: 64 x 64 tiles, 16-byte global accesses on both sides.
+// Each thread loads two 8-element row segments, scatters them transposed into shared memory
+// (row stride 72 elements: the eight 2-byte stores of a segment land in different banks for
+// neighbouring lanes) and reads two 8-element segments of the transposed tile back.
+__global__ void __launch_bounds__(256)
+transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int R, int Cc) {
+  __shared__ __align__(16) __nv_bfloat16 tile[64][72];     // tile[c][r]
+  const long b = blockIdx.z;
+  const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+  const __nv_bfloat16* ib = in + b * (long)R * Cc;
+  __nv_bfloat16* ob = out + b * (long)R * Cc;
+  const int t = threadIdx.x;
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    const int r = p * 32 + (t >> 3), cg = (t & 7) * 8;      // row of the tile, first of 8 columns
+    uint4 q = make_uint4(0, 0, 0, 0);
+    if (r0 + r < R && c0 + cg < Cc) q = __ldg(reinterpret_cast<const uint4*>(ib + (long)(r0 + r) * Cc + c0 + cg));
+    const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(&q);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) tile[cg + k][r] = e[k];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    const int c = p * 32 + (t >> 3), rg = (t & 7) * 8;
+    if (c0 + c < Cc && r0 + rg < R)
+      *reinterpret_cast<uint4*>(ob + (long)(c0 + c) * R + r0 + rg) = *reinterpret_cast<const uint4*>(&tile[c][rg]);
+  }
+}
+
 int check_ln_shape(long M, int Ctot, int pm, int H, int W, int C) {
   STSWIN_CHECK_ARG(M > 0 && Ctot > 0, "layernorm: empty input");
   STSWIN_CHECK_ARG(Ctot % 8 == 0 && Ctot <= 2048, "layernorm: row length %d must be a multiple of 8 and <= 2048", Ctot);
@@ -426,6 +456,13 @@ int copy_strided(void* dst, long dst_stride, const void* src, long src_stride, l
 int transpose_cvt(const void* in, int in_f32, void* out, int out_f32, long batch, int R, int Cc, cudaStream_t stream) {
   STSWIN_CHECK_ARG(in && out && batch > 0 && R > 0 && Cc > 0, "transpose: bad argument");
   STSWIN_CHECK_ARG(batch <= 65535, "transpose: batch %ld exceeds gridDim.z", batch);
+  if (!in_f32 && !out_f32 && R % 8 == 0 && Cc % 8 == 0 &&
+      ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
+    dim3 g64((Cc + 63) / 64, (R + 63) / 64, (unsigned)batch);
+    transpose_bf16_kernel<<<g64, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(in), static_cast<__nv_bfloat16*>(out), R, Cc);
+    STSWIN_CUDA(cudaGetLastError());
+    return kOk;
+  }
   dim3 grid((Cc + 31) / 32, (R + 31) / 32, (unsigned)batch), block(32, 8);
   if (in_f32 && out_f32)
     transpose_kernel<float, float><<<grid, block, 0, stream>>>(static_cast<const float*>(in), static_cast<float*>(out), R, Cc);

@@ -70,3 +70,14 @@ def test_transpose(dt_in, dt_out):
     torch.cuda.synchronize()
     ref = x.to(torch.bfloat16).float().transpose(1, 2) if torch.bfloat16 in (dt_in, dt_out) else x.transpose(1, 2)
     assert torch.equal(out.float().cpu(), ref.contiguous())
+
+
+@pytest.mark.parametrize("shape", [(3, 5120, 512), (2, 1280, 1024), (2, 200, 72), (1, 64, 64)])
+def test_transpose_bf16_vectorised(shape):
+    """bf16 -> bf16 with both extents multiples of 8 takes the 64x64-tile kernel (16-byte accesses); ragged tiles too."""
+    from stswincl_b200 import ops
+    x = torch.randn(*shape, generator=torch.Generator().manual_seed(1)).to(torch.bfloat16)
+    out = ops.transpose(x.cuda(), torch.bfloat16)
+    torch.cuda.synchronize()
+    assert torch.equal(out.cpu(), x.transpose(1, 2).contiguous())
+
