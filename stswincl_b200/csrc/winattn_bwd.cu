@@ -364,8 +364,17 @@ winattn_bwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant
           tc_fence_after();
           if (tr) WTRACE(g_trace_bwd, k, 8);
           // pass 1
+          // Row-major order with two frames per window: the columns of frame 1 repeat the key positions of
+          // frame 0, so the frame loop stays ROLLED (half the straight-line code: the unrolled 128-column
+          // body did not fit the instruction cache, 30 % of this warp's stall samples were instruction fetch).
+          constexpr bool ROLL_T = !QUAD && L == 128 && L == 2 * WS * WS;
+          constexpr int NOUT = ROLL_T ? 2 : 1, NIN = NCHUNK / NOUT;
+#pragma unroll 1
+          for (int to = 0; to < NOUT; ++to)
 #pragma unroll
-          for (int cb = 0; cb < NCHUNK; ++cb) {
+          for (int ci = 0; ci < NIN; ++ci) {
+            const int cb = to * NIN + ci;                      // chunk of the row (runtime when rolled)
+            const int jb = ROLL_T ? ci * CH : cb * CH;         // column the compile-time maps are evaluated at
             uint32_t v[32], w[32];
             static_assert(L >= 32, "fast path: 32-column chunks");
             tmem_ld32(tmem_S + t_lane + col0 + cb * 32, v);    // both loads in flight, one wait
@@ -383,7 +392,7 @@ winattn_bwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant
                 float pv[2];
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                  const int jj = j8 * 8 + 2 * h + e, j = cb * CH + jj;
+                  const int jj = j8 * 8 + 2 * h + e, j = jb + jj;
                   const float bias = REG_BACC ? breg[col_pos<L, WS, QUAD>(j)] : tp[-col_key<L, WS, QUAD>(j)];
                   const float x = fmaf(__uint_as_float(v[jj]), gm.scale_log2e, bias);
                   pv[e] = fast_exp2(x + nq[QUAD ? j / QL : 0]);
@@ -402,10 +411,15 @@ winattn_bwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant
           // pass 2
           mbar_wait(ds_free, (u & 1) ^ 1);                     // the previous unit's dQ / dK products have read dS
           if (tr) WTRACE(g_trace_bwd, k, 14);
+#pragma unroll 1
+          for (int to = 0; to < NOUT; ++to)
 #pragma unroll
-          for (int cb = 0; cb < NCHUNK; ++cb) {
+          for (int ci = 0; ci < NIN; ++ci) {
+            const int cb = to * NIN + ci;
+            const int jb = ROLL_T ? ci * CH : cb * CH;
             uint32_t w[32];
-            tmem_ld_row_chunk<L>(tmem_dPu, t_lane, col0, cb, wq, lane, w);
+            tmem_ld32(tmem_dPu + t_lane + col0 + cb * 32, w);
+            tmem_ld_wait();
 #pragma unroll
             for (int j8 = 0; j8 < CH / 8; ++j8) {
               const int col = col0 + cb * CH + j8 * 8;
@@ -415,7 +429,7 @@ winattn_bwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant
               uint32_t dk[4];
 #pragma unroll
               for (int h = 0; h < 4; ++h) {
-                const int jj = j8 * 8 + 2 * h, j = cb * CH + jj;
+                const int jj = j8 * 8 + 2 * h, j = jb + jj;
                 const float2 pf = unpack_bf16(pw[h]);
                 // rows of a padding window hold filler data: keep them out of the bias-table sum
                 const float d0 = rg.valid ? pf.x * (__uint_as_float(w[jj]) - delta) : 0.f;
@@ -559,8 +573,8 @@ winattn_bwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant
           if (tr && n == 0) WTRACE(g_trace_bwd, k, 11);
           // two heads per chunk (SH == 2): only columns [sub*32, +32) of the product belong to this head
           constexpr int NHALF = (SH == 1) ? 2 : 1;
-#pragma unroll
-          for (int half = 0; half < NHALF; ++half) {
+#pragma unroll 1
+          for (int half = 0; half < NHALF; ++half) {     // rolled: small code (instruction cache)
             const int cofs = (SH == 1) ? half * 32 : sub * 32;     // first column inside the 64-channel chunk
             float a[32];
             {
