@@ -43,8 +43,8 @@ int make_window_tmaps(WinMaps* maps, const void* base, const WinGeom& gm, int ch
 
 namespace {
 
-constexpr int NRH = 6;                         // ring H: first-pass chunks, streamed from HBM
-constexpr int NRL = 3;                         // ring L: second-pass chunks, re-read from L2
+constexpr int NRH = 5;                         // ring H: first-pass chunks, streamed from HBM
+constexpr int NRL = 4;                         // ring L: second-pass chunks, re-read from L2
 constexpr int SLOT_BYTES = 128 * 128;
 constexpr int PD_BYTES = 2 * SLOT_BYTES;       // [128 x 128] bf16 as two K-major halves
 constexpr int TAB_MAX = 15 * 15;
