@@ -363,29 +363,41 @@ winattn_bwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant
           mbar_wait(sdp_full, u & 1);
           tc_fence_after();
           if (tr) WTRACE(g_trace_bwd, k, 8);
+          // Both passes walk the row's L columns in pieces of CW columns.  With two frames per 8x8 window
+          // the columns of frame 1 repeat the key positions of frame 0 (row-major: 64 columns later;
+          // quadrant order: 16 columns later inside each 32-column quadrant), so the frame loop stays ROLLED
+          // and only half of the columns exist as straight-line code: the fully unrolled 128-column bodies did
+          // not fit the instruction cache (30 % of this warp's stall samples were instruction fetch).
+          constexpr bool ROLL = (L == 128 && WS == 8);
+          constexpr int CW = (ROLL && QUAD) ? 16 : 32;          // columns per piece (one TMEM load)
+          constexpr int NPIECE = ROLL ? (64 / CW) : NCHUNK;     // unrolled pieces per frame (ROLL) / per row
+          constexpr int NFR = ROLL ? 2 : 1;                     // rolled iterations
+          // piece pc of rolled iteration fr: first column in the row, and the column the compile-time maps use
+          auto piece_col = [](int fr, int pc) { return !ROLL ? pc * 32 : (QUAD ? pc * 32 + fr * 16 : fr * 64 + pc * 32); };
+          auto piece_map = [](int pc) { return (ROLL && QUAD) ? pc * 32 : pc * 32; };
+          static_assert(L >= 32, "fast path: 32-column chunks");
           // pass 1
-          // Row-major order with two frames per window: the columns of frame 1 repeat the key positions of
-          // frame 0, so the frame loop stays ROLLED (half the straight-line code: the unrolled 128-column
-          // body did not fit the instruction cache, 30 % of this warp's stall samples were instruction fetch).
-          constexpr bool ROLL_T = !QUAD && L == 128 && L == 2 * WS * WS;
-          constexpr int NOUT = ROLL_T ? 2 : 1, NIN = NCHUNK / NOUT;
 #pragma unroll 1
-          for (int to = 0; to < NOUT; ++to)
+          for (int fr = 0; fr < NFR; ++fr)
 #pragma unroll
-          for (int ci = 0; ci < NIN; ++ci) {
-            const int cb = to * NIN + ci;                      // chunk of the row (runtime when rolled)
-            const int jb = ROLL_T ? ci * CH : cb * CH;         // column the compile-time maps are evaluated at
-            uint32_t v[32], w[32];
-            static_assert(L >= 32, "fast path: 32-column chunks");
-            tmem_ld32(tmem_S + t_lane + col0 + cb * 32, v);    // both loads in flight, one wait
-            tmem_ld32(tmem_dPu + t_lane + col0 + cb * 32, w);
+          for (int pc = 0; pc < NPIECE; ++pc) {
+            const int cc0 = piece_col(fr, pc);                 // runtime when rolled
+            const int jb = piece_map(pc);                      // compile-time
+            uint32_t v[CW], w[CW];
+            if constexpr (CW == 32) {
+              tmem_ld32(tmem_S + t_lane + col0 + cc0, v);      // both loads in flight, one wait
+              tmem_ld32(tmem_dPu + t_lane + col0 + cc0, w);
+            } else {
+              tmem_ld16(tmem_S + t_lane + col0 + cc0, v);
+              tmem_ld16(tmem_dPu + t_lane + col0 + cc0, w);
+            }
             tmem_ld_wait();
-            if (cb == 0) {
+            if (fr == 0 && pc == 0) {
               mbar_wait(p_free, (u & 1) ^ 1);                  // the previous unit's dV products have read P
               if (tr) WTRACE(g_trace_bwd, k, 13);
             }
 #pragma unroll
-            for (int j8 = 0; j8 < CH / 8; ++j8) {
+            for (int j8 = 0; j8 < CW / 8; ++j8) {
               uint32_t pk[4];
 #pragma unroll
               for (int h = 0; h < 4; ++h) {
@@ -400,7 +412,7 @@ winattn_bwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant
                 }
                 pk[h] = pack_bf16(pv[0], pv[1]);
               }
-              const int col = col0 + cb * CH + j8 * 8;
+              const int col = col0 + cc0 + j8 * 8;
               *reinterpret_cast<uint4*>(s_p + (col >> 6) * SLOT_BYTES + sw128_offset(row, (col & 63) >> 3)) =
                   make_uint4(pk[0], pk[1], pk[2], pk[3]);
             }
@@ -412,17 +424,18 @@ winattn_bwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant
           mbar_wait(ds_free, (u & 1) ^ 1);                     // the previous unit's dQ / dK products have read dS
           if (tr) WTRACE(g_trace_bwd, k, 14);
 #pragma unroll 1
-          for (int to = 0; to < NOUT; ++to)
+          for (int fr = 0; fr < NFR; ++fr)
 #pragma unroll
-          for (int ci = 0; ci < NIN; ++ci) {
-            const int cb = to * NIN + ci;
-            const int jb = ROLL_T ? ci * CH : cb * CH;
-            uint32_t w[32];
-            tmem_ld32(tmem_dPu + t_lane + col0 + cb * 32, w);
+          for (int pc = 0; pc < NPIECE; ++pc) {
+            const int cc0 = piece_col(fr, pc);
+            const int jb = piece_map(pc);
+            uint32_t w[CW];
+            if constexpr (CW == 32) tmem_ld32(tmem_dPu + t_lane + col0 + cc0, w);
+            else                    tmem_ld16(tmem_dPu + t_lane + col0 + cc0, w);
             tmem_ld_wait();
 #pragma unroll
-            for (int j8 = 0; j8 < CH / 8; ++j8) {
-              const int col = col0 + cb * CH + j8 * 8;
+            for (int j8 = 0; j8 < CW / 8; ++j8) {
+              const int col = col0 + cc0 + j8 * 8;
               const uint32_t off = (col >> 6) * SLOT_BYTES + sw128_offset(row, (col & 63) >> 3);
               const uint4 pq = *reinterpret_cast<const uint4*>(s_p + off);
               const uint32_t pw[4] = {pq.x, pq.y, pq.z, pq.w};
