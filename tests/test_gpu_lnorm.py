@@ -81,3 +81,20 @@ def test_transpose_bf16_vectorised(shape):
     torch.cuda.synchronize()
     assert torch.equal(out.cpu(), x.transpose(1, 2).contiguous())
 
+
+def test_copy_frames_strided_batches():
+    """stswin_copy_strided: frame slices of a [B, 4, L, C] tensor in and out (the middle Swin layer's glue)."""
+    from stswincl_b200 import ops
+    x = torch.randn(3, 4, 37, 64, generator=torch.Generator().manual_seed(2)).to(torch.bfloat16).cuda()
+    mid = torch.empty(3, 2, 37, 64, dtype=torch.bfloat16, device="cuda")
+    ops.copy_frames(mid, x[:, 1:3])
+    assert torch.equal(mid, x[:, 1:3])
+    out = torch.zeros_like(x)
+    ops.copy_frames(out[:, 0], x[:, 0])
+    ops.copy_frames(out[:, 3], x[:, 3])
+    ops.copy_frames(out[:, 1:3], mid)
+    torch.cuda.synchronize()
+    assert torch.equal(out, x)
+    with pytest.raises(Exception):
+        ops.copy_frames(out[:, 0, :, 1:], x[:, 0, :, 1:])        # inner dims not dense
+
