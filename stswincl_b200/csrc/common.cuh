@@ -343,6 +343,29 @@ __device__ __forceinline__ void st_global_v8(void* p, const uint32_t (&v)[8]) {
                : "memory");
 }
 
+// Column sums over the 32 lanes of a warp for NV (32 or 64) per-lane values (lane = row): a butterfly
+// that halves the live values at every step (NV - NV/32 shuffles).  On return lane l holds the sums
+// of columns l*NV/32 .. in a[0 .. NV/32).
+template <int NV>
+__device__ __forceinline__ void warp_colsum(float (&a)[NV], int lane) {
+#pragma unroll
+  for (int n = NV / 2, off = 16; off >= 1; n >>= 1, off >>= 1) {
+    const bool hi = (lane & off) != 0;
+#pragma unroll
+    for (int k = 0; k < n; ++k) {
+      const float send = hi ? a[k] : a[k + n];
+      const float recv = __shfl_xor_sync(0xffffffffu, send, off);
+      a[k] = (hi ? a[k + n] : a[k]) + recv;
+    }
+  }
+}
+// 256-bit read-only global load (LDG.256)
+__device__ __forceinline__ void ld_global_nc_v8(const void* p, uint32_t (&v)[8]) {
+  asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "l"(p));
+}
+
 // ---- packed fp32x2 arithmetic (FFMA2 / FMUL2 / FADD2 on sm_100): two lanes of work per issue slot
 __device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
   uint64_t r;

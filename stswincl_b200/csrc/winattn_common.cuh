@@ -319,22 +319,6 @@ __device__ __forceinline__ void warp_store_rows(uint8_t* stage, const uint4 (&va
   }
 }
 
-// Column sums over the 32 lanes of a warp for NV (32 or 64) per-lane values (lane = row): a butterfly
-// that halves the live values at every step (NV - NV/32 shuffles).  On return lane l holds the sums
-// of columns l*NV/32 .. in a[0 .. NV/32).
-template <int NV>
-__device__ __forceinline__ void warp_colsum(float (&a)[NV], int lane) {
-#pragma unroll
-  for (int n = NV / 2, off = 16; off >= 1; n >>= 1, off >>= 1) {
-    const bool hi = (lane & off) != 0;
-#pragma unroll
-    for (int k = 0; k < n; ++k) {
-      const float send = hi ? a[k] : a[k + n];
-      const float recv = __shfl_xor_sync(0xffffffffu, send, off);
-      a[k] = (hi ? a[k + n] : a[k]) + recv;
-    }
-  }
-}
 __device__ __forceinline__ void warp_colsum64(float (&a)[64], int lane) { warp_colsum<64>(a, lane); }
 
 // Same idea as warp_store_rows for a [32 rows] x [64 bytes] block (4 x 16 bytes per lane) through a
