@@ -359,13 +359,6 @@ __device__ __forceinline__ void warp_colsum(float (&a)[NV], int lane) {
     }
   }
 }
-// 256-bit read-only global load (LDG.256)
-__device__ __forceinline__ void ld_global_nc_v8(const void* p, uint32_t (&v)[8]) {
-  asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-               : "l"(p));
-}
-
 // ---- packed fp32x2 arithmetic (FFMA2 / FMUL2 / FADD2 on sm_100): two lanes of work per issue slot
 __device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
   uint64_t r;

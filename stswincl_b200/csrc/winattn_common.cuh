@@ -319,28 +319,6 @@ __device__ __forceinline__ void warp_store_rows(uint8_t* stage, const uint4 (&va
   }
 }
 
-__device__ __forceinline__ void warp_colsum64(float (&a)[64], int lane) { warp_colsum<64>(a, lane); }
-
-// Same idea as warp_store_rows for a [32 rows] x [64 bytes] block (4 x 16 bytes per lane) through a
-// 2 KB staging area: the rows come back 4 lanes per row, one store instruction covers 8 rows x 64 bytes.
-//   rowp[i] : global address of the block's first byte for row i*8 + lane/4, or nullptr to skip the row
-__device__ __forceinline__ void warp_store_rows_half(uint8_t* stage, const uint4 (&vals)[4], uint8_t* const (&rowp)[4],
-                                                     int lane) {
-  __syncwarp();                      // the previous block has been read out
-#pragma unroll
-  for (int j = 0; j < 4; ++j)
-    *reinterpret_cast<uint4*>(stage + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = vals[j];
-  __syncwarp();
-  const int ch = lane & 3;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int r = i * 8 + (lane >> 2);
-    if (rowp[i] != nullptr)
-      *reinterpret_cast<uint4*>(rowp[i] + ch * 16) =
-          *reinterpret_cast<const uint4*>(stage + r * 64 + ((ch ^ ((r >> 1) & 3)) << 4));
-  }
-}
-
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
