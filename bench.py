@@ -324,8 +324,8 @@ def run_ours(args):
                 "frac": achieved / pk["tflops_sustained"], "traffic": traffic, "peak_source": pk["source"] + ", sustained",
                 "launches_timed": gsum["launches"], "avg_launch_ms": gsum["ms"] / gsum["launches"],
                 "share_of_step": round(gsum["ms"] / total_ms, 4), "family_time_shares": shares}
-    # secondary, HBM-bound: the window-attention core kernels
-    for k in ("winattn_fwd", "winattn_bwd"):
+    # secondary, HBM-bound: the window-attention core kernels and the row-wise / layout kernels
+    for k in ("winattn_fwd", "winattn_bwd", "layernorm_fwd", "layernorm_bwd", "transpose", "copy"):
         if k in fam:
             gbs = fam[k]["work"] / (fam[k]["ms"] * 1e-3) / 1e9
             roofline[k] = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
