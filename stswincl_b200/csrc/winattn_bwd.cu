@@ -347,12 +347,13 @@ winattn_bwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant
         // ---- fast path: compile-time column map, instantiated per token order of the row's window
         auto softmax_bwd_fast = [&](auto quad_tag) {
           constexpr bool QUAD = decltype(quad_tag)::value;
-          constexpr int QL = L / 4;
+          constexpr int LW = win_tokens<L, WS>();      // real columns of the window (98 of 128 for 7x7x2)
+          constexpr int RA = (WS + 1) / 2;             // rows / columns of the first rectangle pair
           const float* tp = tab + key_i;
           // shift mask: one additive constant per quadrant of columns (see the forward kernel); folded with -lse
           float nq[4];
           if constexpr (QUAD) {
-            const int q_i = (rg.rr >= WS / 2 ? 2 : 0) | (rg.cc >= WS / 2 ? 1 : 0);
+            const int q_i = (rg.rr >= RA ? 2 : 0) | (rg.cc >= RA ? 1 : 0);
             const int wm = (rg.id >= 3 ? 2 : 0) | (rg.id % 3 != 0 ? 1 : 0);
 #pragma unroll
             for (int q = 0; q < 4; ++q) nq[q] = (((q ^ q_i) & wm) ? kMaskLog2e : 0.f) - lse_i;
@@ -405,10 +406,14 @@ winattn_bwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                   const int jj = j8 * 8 + 2 * h + e, j = jb + jj;
-                  const float bias = REG_BACC ? breg[col_pos<L, WS, QUAD>(j)] : tp[-col_key<L, WS, QUAD>(j)];
-                  const float x = fmaf(__uint_as_float(v[jj]), gm.scale_log2e, bias);
-                  pv[e] = fast_exp2(x + nq[QUAD ? j / QL : 0]);
-                  delta = fmaf(pv[e], __uint_as_float(w[jj]), delta);
+                  pv[e] = 0.f;
+                  if (j < LW) {                        // compile-time: padding columns stay zero
+                    const float bias = REG_BACC ? breg[col_pos<L, WS, QUAD>(j)] : tp[-col_key<L, WS, QUAD>(j)];
+                    const float x = fmaf(__uint_as_float(v[jj]), gm.scale_log2e, bias);
+                    pv[e] = fast_exp2(x + nq[col_rect<L, WS, QUAD>(j)]);
+                    if (LW < L && !rg.inrange) pv[e] = 0.f;    // padding row of the slot
+                    delta = fmaf(pv[e], __uint_as_float(w[jj]), delta);
+                  }
                 }
                 pk[h] = pack_bf16(pv[0], pv[1]);
               }
@@ -449,11 +454,11 @@ winattn_bwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant
                 const float d1 = rg.valid ? pf.y * (__uint_as_float(w[jj + 1]) - delta) : 0.f;
                 dk[h] = pack_bf16(d0, d1);
                 if constexpr (REG_BACC) {
-                  bacc[col_pos<L, WS, QUAD>(j)] += d0;
-                  bacc[col_pos<L, WS, QUAD>(j + 1)] += d1;
+                  if (j < LW) bacc[col_pos<L, WS, QUAD>(j < LW ? j : 0)] += d0;
+                  if (j + 1 < LW) bacc[col_pos<L, WS, QUAD>(j + 1 < LW ? j + 1 : 0)] += d1;
                 } else {
-                  if (d0 != 0.f) atomicAdd(&bins[key_i - col_key<L, WS, QUAD>(j)], d0);
-                  if (d1 != 0.f) atomicAdd(&bins[key_i - col_key<L, WS, QUAD>(j + 1)], d1);
+                  if (j < LW && d0 != 0.f) atomicAdd(&bins[key_i - col_key<L, WS, QUAD>(j < LW ? j : 0)], d0);
+                  if (j + 1 < LW && d1 != 0.f) atomicAdd(&bins[key_i - col_key<L, WS, QUAD>(j + 1 < LW ? j + 1 : 0)], d1);
                 }
               }
               *reinterpret_cast<uint4*>(s_ds + off) = make_uint4(dk[0], dk[1], dk[2], dk[3]);
@@ -680,7 +685,11 @@ int winattn_bwd(const void* qkv, const float* bias_table, const float* lse2, con
   const bool fast = !gm.general && mask == nullptr && (shift == 0 || 2 * shift == ws) &&
                     ((ws == 8 && (gm.L == 128 || gm.L == 64)) || (ws == 4 && gm.L == 32));
   const bool shifted = shift > 0;
-  if (gm.general) STSWIN_LAUNCH_BWD_S(128, 0, 0, true)
+  // 7x7 windows with two frames (98 of the 128 tile rows) and shift 0 or 3: compile-time maps as well
+  const bool fast7 = mask == nullptr && ws == 7 && gm.L == 98 && (shift == 0 || shift == 3);
+  if (fast7 && !shifted) STSWIN_LAUNCH_BWD_S(128, 7, 0, false)
+  else if (fast7) STSWIN_LAUNCH_BWD_S(128, 7, 2, false)
+  else if (gm.general) STSWIN_LAUNCH_BWD_S(128, 0, 0, true)
   else if (fast && gm.L == 128 && !shifted) STSWIN_LAUNCH_BWD_S(128, 8, 0, false)
   else if (fast && gm.L == 128) STSWIN_LAUNCH_BWD_S(128, 8, 2, false)
   else if (fast && gm.L == 64 && !shifted) STSWIN_LAUNCH_BWD_S(64, 8, 0, false)

@@ -154,17 +154,42 @@ __device__ __forceinline__ RowGeom row_geom(const WinGeom& gm, int tile, int r) 
   return o;
 }
 
-// Compile-time column maps of the shipped geometries (L = T*WS*WS tokens per window, shift 0 or WS/2).
-// Column j of a window's L columns, in row-major order (QUAD = false: t, row, column) or quadrant order
-// (QUAD = true: quadrant, t, row, column inside the quadrant):
-//   col_pos : spatial position rr*WS + cc of the token
-//   col_key : rr*(2*WS-1) + cc, so that key_i - col_key(j) indexes the relative-position bias table
+// Compile-time column maps of the fast-path geometries.  WS is the window size; L the tile rows one
+// window slot spans (a power of two, <= 128); the window really holds LW = win_tokens<L, WS>() tokens:
+// LW = L for ws 8 / 4, and 98 of the 128 rows for 7x7 windows with two frames (rows / columns >= LW
+// are padding).  Shift is 0 or WS/2, so a window that wraps splits into 2x2 rectangles of
+// RA = ceil(WS/2) and RB = WS - RA rows / columns (quadrants when WS is even).
+// Column j (< LW) of a window, in row-major order (QUAD = false: t, row, column) or rectangle order
+// (QUAD = true: rectangle, t, row, column inside the rectangle):
+//   col_rect : rectangle index 0..3 (0 in row-major order)
+//   col_pos  : spatial position rr*WS + cc of the token
+//   col_key  : rr*(2*WS-1) + cc, so that key_i - col_key(j) indexes the relative-position bias table
+template <int L, int WS>
+__host__ __device__ constexpr int win_tokens() { return WS == 7 ? 98 : L; }
+template <int L, int WS>
+__host__ __device__ constexpr int rect_off(int k) {    // first column of rectangle k (k = 4: LW)
+  constexpr int W1 = WS > 0 ? WS : 1, T = win_tokens<L, WS>() / (W1 * W1) > 0 ? win_tokens<L, WS>() / (W1 * W1) : 1;
+  constexpr int RA = (W1 + 1) / 2, RB = W1 - RA;
+  int off = 0;
+  for (int q = 0; q < k; ++q) off += ((q >> 1) ? RB : RA) * ((q & 1) ? RB : RA) * T;
+  return off;
+}
+template <int L, int WS, bool QUAD>
+__host__ __device__ constexpr int col_rect(int j) {
+  // loop-free (the optimiser must fold this to a constant for every unrolled column)
+  constexpr int o1 = rect_off<L, WS>(1), o2 = rect_off<L, WS>(2), o3 = rect_off<L, WS>(3);
+  return QUAD ? (j >= o1 ? 1 : 0) + (j >= o2 ? 1 : 0) + (j >= o3 ? 1 : 0) : 0;
+}
 template <int L, int WS, bool QUAD>
 __host__ __device__ constexpr int col_pos(int j) {
-  constexpr int W1 = WS > 0 ? WS : 1, N = W1 * W1, HW = W1 > 1 ? W1 / 2 : 1, QL = L / 4;
+  constexpr int W1 = WS > 0 ? WS : 1, N = W1 * W1, RA = (W1 + 1) / 2, RB = W1 - RA;
+  constexpr int o1 = rect_off<L, WS>(1), o2 = rect_off<L, WS>(2), o3 = rect_off<L, WS>(3);
   if (!QUAD) return j % N;
-  const int q = j / QL, p = (j % QL) % (HW * HW);
-  return ((q >> 1) * HW + p / HW) * W1 + (q & 1) * HW + p % HW;
+  const int k = col_rect<L, WS, true>(j);
+  const int hext = (k >> 1) ? RB : RA, wext = (k & 1) ? RB : RA;
+  const int off = k == 0 ? 0 : (k == 1 ? o1 : (k == 2 ? o2 : o3));
+  const int p = (j - off) % (hext * wext);
+  return (((k >> 1) ? RA : 0) + p / wext) * W1 + ((k & 1) ? RA : 0) + p % wext;
 }
 template <int L, int WS, bool QUAD>
 __host__ __device__ constexpr int col_key(int j) {
@@ -178,17 +203,18 @@ __device__ __forceinline__ int fast_div(int n, unsigned long long mg) {
   return int((static_cast<unsigned long long>(static_cast<unsigned>(n)) * mg) >> 32);
 }
 
-// row_geom for the shipped geometries: L, ws compile-time (shifts instead of divisions), shift 0 or ws/2.
+// row_geom for the fast-path geometries: L, ws compile-time (shifts / constant divisions), shift 0 or ws/2.
 // ORDER 0: row-major.  1: every window in quadrant order.  2: quadrant order for the windows that wrap.
 template <int L, int WS, int ORDER>
 __device__ __forceinline__ RowGeom row_geom_fast(const WinGeom& gm, int tile, int r) {
-  constexpr int N = WS * WS, G = 128 / L, HW = WS / 2, QL = L / 4;
+  constexpr int N = WS * WS, G = 128 / L, LW = win_tokens<L, WS>(), RA = (WS + 1) / 2, RB = WS - RA;
   RowGeom o;
   o.g = r / L;
-  o.inrange = true;
-  const int rem = r % L;
+  const int rin = r % L;
+  o.inrange = rin < LW;                       // LW < L: the tail rows of the slot are padding
+  const int rem = o.inrange ? rin : 0;
   int gw = tile * G + o.g;
-  o.valid = gw < gm.total_windows;
+  o.valid = o.inrange && gw < gm.total_windows;
   if (gw > gm.total_windows - 1) gw = gm.total_windows - 1;
   int b, wh, ww;
   if (gm.perm) {
@@ -208,21 +234,25 @@ __device__ __forceinline__ RowGeom row_geom_fast(const WinGeom& gm, int tile, in
     o.rr = pos / WS;
     o.cc = pos % WS;
   } else {
-    const int q = rem / QL, r2 = rem % QL;
-    t = r2 / (HW * HW);
-    const int p = r2 % (HW * HW);
-    o.rr = (q >> 1) * HW + p / HW;
-    o.cc = (q & 1) * HW + p % HW;
+    int k = 0;
+#pragma unroll
+    for (int q = 1; q < 4; ++q) k += (rem >= rect_off<L, WS>(q)) ? 1 : 0;
+    const int hext = (k >> 1) ? RB : RA, wext = (k & 1) ? RB : RA, area = hext * wext;
+    const int r2 = rem - ((k == 0) ? 0 : (k == 1) ? rect_off<L, WS>(1) : (k == 2) ? rect_off<L, WS>(2) : rect_off<L, WS>(3));
+    t = r2 / area;
+    const int p = r2 - t * area;
+    o.rr = ((k >> 1) ? RA : 0) + p / wext;
+    o.cc = ((k & 1) ? RA : 0) + p % wext;
   }
-  o.canon = o.g * L + t * N + o.rr * WS + o.cc;
-  const int shift = ORDER == 0 ? 0 : HW;
+  o.canon = o.g * LW + t * N + o.rr * WS + o.cc;
+  const int shift = ORDER == 0 ? 0 : WS / 2;
   int hs = wh * WS + o.rr + shift, wsrc = ww * WS + o.cc + shift;
   if (hs >= gm.H) hs -= gm.H;
   if (wsrc >= gm.W) wsrc -= gm.W;
   o.tok = ((long)(b * gm.T + t) * gm.H + hs) * gm.W + wsrc;
   o.id = 0;
   if (ORDER != 0)
-    o.id = 3 * region_band(wh * WS + o.rr, gm.H, WS, HW) + region_band(ww * WS + o.cc, gm.W, WS, HW);
+    o.id = 3 * region_band(wh * WS + o.rr, gm.H, WS, WS / 2) + region_band(ww * WS + o.cc, gm.W, WS, WS / 2);
   return o;
 }
 

@@ -270,7 +270,9 @@ winattn_fwd_kernel(const __grid_constant__ WinMaps tm_qkv, __nv_bfloat16* __rest
         // ---- fast path: compile-time column map, instantiated per token order of the row's window
         auto softmax_fast = [&](auto quad_tag) {
           constexpr bool QUAD = decltype(quad_tag)::value;
-          constexpr int QL = L / 4, NQ = QUAD ? 4 : 1;
+          constexpr int NQ = QUAD ? 4 : 1;
+          constexpr int LW = win_tokens<L, WS>();      // real columns of the window (98 of 128 for 7x7x2)
+          constexpr int RA = (WS + 1) / 2;             // rows / columns of the first rectangle pair
           const float* tp = tab + key_i;
           float mq[NQ];
 #pragma unroll
@@ -285,9 +287,11 @@ winattn_fwd_kernel(const __grid_constant__ WinMaps tm_qkv, __nv_bfloat16* __rest
 #pragma unroll
             for (int jj = 0; jj < CH; ++jj) {
               const int j = cb * CH + jj;
-              const float x = fmaf(__uint_as_float(v[jj]), gm.scale_log2e, tp[-col_key<L, WS, QUAD>(j)]);
-              s[j] = x;
-              mq[QUAD ? j / QL : 0] = fmaxf(mq[QUAD ? j / QL : 0], x);
+              if (j < LW) {                            // compile-time: padding columns are never touched
+                const float x = fmaf(__uint_as_float(v[jj]), gm.scale_log2e, tp[-col_key<L, WS, QUAD>(j)]);
+                s[j] = x;
+                mq[col_rect<L, WS, QUAD>(j)] = fmaxf(mq[col_rect<L, WS, QUAD>(j)], x);
+              }
             }
           }
           // S is in registers: the next unit's QK^T may overwrite TMEM now
@@ -299,7 +303,7 @@ winattn_fwd_kernel(const __grid_constant__ WinMaps tm_qkv, __nv_bfloat16* __rest
           // of a token IS its quadrant, so the mask is one additive constant per quadrant of columns.
           float nq[NQ];
           if constexpr (QUAD) {
-            const int q_i = (rg.rr >= WS / 2 ? 2 : 0) | (rg.cc >= WS / 2 ? 1 : 0);
+            const int q_i = (rg.rr >= RA ? 2 : 0) | (rg.cc >= RA ? 1 : 0);
             const int wm = (rg.id >= 3 ? 2 : 0) | (rg.id % 3 != 0 ? 1 : 0);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -314,14 +318,16 @@ winattn_fwd_kernel(const __grid_constant__ WinMaps tm_qkv, __nv_bfloat16* __rest
           }
           mbar_wait(pv_done, (u & 1) ^ 1);        // the previous P V product has finished reading P
           if (tr) WTRACE(g_trace_fwd, k, 9);
+          if (LW < L && !rg.inrange) return;      // padding row of the slot: its P row stays zero
 #pragma unroll
-          for (int j8 = 0; j8 < L / 8; ++j8) {
+          for (int j8 = 0; j8 < (LW + 7) / 8; ++j8) {
             uint32_t w[4];
 #pragma unroll
             for (int h = 0; h < 4; ++h) {
               const int j = j8 * 8 + 2 * h;
-              const float p0 = fast_exp2(s[j] + nq[QUAD ? j / QL : 0]);
-              const float p1 = fast_exp2(s[j + 1] + nq[QUAD ? (j + 1) / QL : 0]);
+              float p0 = 0.f, p1 = 0.f;
+              if (j < LW) p0 = fast_exp2(s[j] + nq[col_rect<L, WS, QUAD>(j)]);
+              if (j + 1 < LW) p1 = fast_exp2(s[j + 1] + nq[col_rect<L, WS, QUAD>(j + 1)]);
               sum += p0 + p1;
               w[h] = pack_bf16(p0, p1);
             }
@@ -381,12 +387,12 @@ winattn_fwd_kernel(const __grid_constant__ WinMaps tm_qkv, __nv_bfloat16* __rest
         }
       }
       // 1/rowsum for the epilogue warps: slot (item parity, head of the group), read after p_full
-      s_inv[((k & 1) * 2 + sub) * 128 + row] = (GEN && !rg.inrange) ? 0.f : 1.0f / sum;
+      s_inv[((k & 1) * 2 + sub) * 128 + row] = !rg.inrange ? 0.f : 1.0f / sum;     // padding rows of a slot: nothing to scale
       if (sub == SH - 1) mbar_arrive(&inv_full[k & 1]);
       fence_proxy_async_smem();
       mbar_arrive(p_full);
       if (tr) WTRACE(g_trace_fwd, k, 10);
-      if (!GEN || rg.inrange) lse2[((size_t)tile * gm.nH + head) * 128 + rg.canon] = mx + log2f(sum);
+      if (rg.inrange) lse2[((size_t)tile * gm.nH + head) * 128 + rg.canon] = mx + log2f(sum);
     }
   } else {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 160;");
@@ -570,7 +576,11 @@ int winattn_fwd(const void* qkv, const float* bias_table, void* out, float* lse2
   // token order of a shifted block: quadrant order only for the windows that wrap (one box per
   // interior window measured faster than four quadrant boxes for every window, at every L)
   const int order = shift == 0 ? 0 : (gm.uniform_quad ? 1 : 2);
-  if (gm.general) STSWIN_LAUNCH_FWD(128, 0, 0, true)
+  // 7x7 windows with two frames (98 of the 128 tile rows) and shift 0 or 3: compile-time maps as well
+  const bool fast7 = gm.general && mask == nullptr && ws == 7 && gm.L == 98 && (shift == 0 || shift == 3);
+  if (fast7 && order == 0) STSWIN_LAUNCH_FWD(128, 7, 0, false)
+  else if (fast7) STSWIN_LAUNCH_FWD(128, 7, 2, false)
+  else if (gm.general) STSWIN_LAUNCH_FWD(128, 0, 0, true)
   else if (fast && gm.L == 128 && order == 0) STSWIN_LAUNCH_FWD(128, 8, 0, false)
   else if (fast && gm.L == 128 && order == 1) STSWIN_LAUNCH_FWD(128, 8, 1, false)
   else if (fast && gm.L == 128) STSWIN_LAUNCH_FWD(128, 8, 2, false)
