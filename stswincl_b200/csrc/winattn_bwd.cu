@@ -290,16 +290,28 @@ winattn_bwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant
     (void)tr;
     constexpr int CH = (L >= 32) ? 32 : 16;
     constexpr int NCHUNK = L / CH;
-    // fast path with one head per group: per-row running sums of dS over every item of this CTA, one per
-    // key position (the TxT tiling folds onto the same entry).  They are binned by relative position
-    // whenever the row's own position changes (token order switch) and at the end of the kernel.
-    constexpr bool REG_BACC = (WS > 0 && SH == 1);
+    // fast path: per-row running sums of dS over every item of this CTA, one per key position (the TxT
+    // tiling folds onto the same entry).  They are binned by relative position whenever the row's own
+    // position changes (token order switch) and at the end of the kernel.  Two heads per group (SH == 2):
+    // one set per head; the units alternate between the heads, so the two register arrays are SWAPPED
+    // after every unit and the code always addresses `bacc` (no dynamic register indexing, one body).
+    // The row's bias values are kept in registers too when there is one head per group.
+    constexpr bool REG_BACC = (WS > 0);
+    constexpr bool REG_BIAS = (WS > 0 && SH == 1);
     constexpr int NPOS = REG_BACC ? WS * WS : 1;
-    float bacc[NPOS];
-    float breg[NPOS];                        // bias * log2e of this row against every key position (same lifetime)
+    constexpr int NPOS2 = (REG_BACC && SH == 2) ? NPOS : 1;
+    constexpr int NBIAS = REG_BIAS ? NPOS : 1;
+    float bacc[NPOS];                        // sums of the head of the current unit
+    float bacc_o[NPOS2];                     // SH == 2: sums of the other head
+    float breg[NBIAS];                       // bias * log2e of this row against every key position
 #pragma unroll
-    for (int i = 0; i < NPOS; ++i) { bacc[i] = 0.f; breg[i] = 0.f; }
-    int bacc_key = -1;                       // key_i the sums in bacc / the values in breg belong to (-1: none)
+    for (int i = 0; i < NPOS; ++i) bacc[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < NPOS2; ++i) bacc_o[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < NBIAS; ++i) breg[i] = 0.f;
+    int bacc_key = -1;                       // key_i the sums / bias values belong to (-1: none)
+    // (called between items, i.e. with `bacc` = head 0 and `bacc_o` = head 1)
     auto flush_bacc = [&]() {
       if constexpr (REG_BACC) {
         if (bacc_key >= 0) {
@@ -308,6 +320,10 @@ winattn_bwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant
             const int key = (pos / WS) * (2 * WS - 1) + pos % WS;
             if (bacc[pos] != 0.f) atomicAdd(&s_bacc[bacc_key - key], bacc[pos]);
             bacc[pos] = 0.f;
+            if constexpr (SH == 2) {
+              if (bacc_o[pos] != 0.f) atomicAdd(&s_bacc[(TAB_MAX + 1) + bacc_key - key], bacc_o[pos]);
+              bacc_o[pos] = 0.f;
+            }
           }
         }
       }
@@ -331,8 +347,10 @@ winattn_bwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant
           if (key_i != bacc_key) {           // the row's own position changed (token-order switch)
             flush_bacc();
             bacc_key = key_i;
+            if constexpr (REG_BIAS) {
 #pragma unroll
-            for (int pos = 0; pos < NPOS; ++pos) breg[pos] = s_tab[key_i - ((pos / WS) * (2 * WS - 1) + pos % WS)];
+              for (int pos = 0; pos < NPOS; ++pos) breg[pos] = s_tab[key_i - ((pos / WS) * (2 * WS - 1) + pos % WS)];
+            }
           }
         }
       }
@@ -408,7 +426,7 @@ winattn_bwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant
                   const int jj = j8 * 8 + 2 * h + e, j = jb + jj;
                   pv[e] = 0.f;
                   if (j < LW) {                        // compile-time: padding columns stay zero
-                    const float bias = REG_BACC ? breg[col_pos<L, WS, QUAD>(j)] : tp[-col_key<L, WS, QUAD>(j)];
+                    const float bias = REG_BIAS ? breg[REG_BIAS ? col_pos<L, WS, QUAD>(j) : 0] : tp[-col_key<L, WS, QUAD>(j)];
                     const float x = fmaf(__uint_as_float(v[jj]), gm.scale_log2e, bias);
                     pv[e] = fast_exp2(x + nq[col_rect<L, WS, QUAD>(j)]);
                     if (LW < L && !rg.inrange) pv[e] = 0.f;    // padding row of the slot
@@ -547,6 +565,10 @@ winattn_bwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant
       fence_proxy_async_smem();
       mbar_arrive(pds_full);            // P / dS visible to the tensor core
       if (tr) WTRACE(g_trace_bwd, k, 10);
+      if constexpr (REG_BACC && SH == 2) {   // the next unit belongs to the other head
+#pragma unroll
+        for (int pos = 0; pos < NPOS; ++pos) { const float t = bacc[pos]; bacc[pos] = bacc_o[pos]; bacc_o[pos] = t; }
+      }
     }
     // ---- bias-table gradient: bin what is left in registers, then one global atomic per bin, CTA and head
     flush_bacc();
