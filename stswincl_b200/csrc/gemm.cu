@@ -31,12 +31,12 @@ namespace {
 constexpr int BM = 128;
 constexpr int BN = 256;
 constexpr int BK = 64;
-constexpr int STAGES = 6;
+constexpr int STAGES = 5;
 constexpr int A_STAGE_BYTES = BM * BK * 2;         // 16 KB: this CTA's 128 rows of the pair's 256-row A tile
 constexpr int B_STAGE_BYTES = (BN / 2) * BK * 2;   // 16 KB: this CTA's half of the 256-column B tile
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int EPI_WARPS = 8;
-constexpr int EPI_BUF_BYTES = 32 * 128;      // 32 rows x 128 B per epilogue warp
+constexpr int EPI_BUF_BYTES = 2 * 32 * 128;  // two 32-row x 128-byte staging tiles per epilogue warp (ping-pong)
 constexpr int NUM_THREADS = 32 * (2 + EPI_WARPS);
 constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + EPI_WARPS * EPI_BUF_BYTES + 256;
 
@@ -64,7 +64,8 @@ struct GemmArgs {
 template <int A_MN, int B_MN, int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-            const __grid_constant__ CUtensorMap tmD /* fp32 reduce target only */, const GemmArgs p) {
+            const __grid_constant__ CUtensorMap tmD /* D: bf16 [32 x 64] boxes, or the fp32 reduce target */,
+            const __grid_constant__ CUtensorMap tmD2 /* second output of the GELU mode */, const GemmArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_smem_1024(smem_raw);
   uint8_t* s_stage = smem;
@@ -99,6 +100,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmD);
+    tma_prefetch_desc(&tmD2);
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 2);           // leader's copy is the live one: one arrive.expect_tx per CTA of the pair
       mbar_init(&empty_bar[i], 1);          // multicast commit of the leader's MMA warp
@@ -201,7 +203,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int ew = warp - 2;                         // 0..7
     const int wq = warp & 3;                         // TMEM lane quarter
     const int chalf = ew >> 2;                       // column half of the tile
-    uint8_t* my_buf = s_out + ew * EPI_BUF_BYTES;    // one 32-row x 128-byte staging tile, reused
+    uint8_t* const my_bufs = s_out + ew * EPI_BUF_BYTES;   // two 32-row x 128-byte staging tiles
+    uint8_t* my_buf = my_bufs;
+    int chunk_no = 0;                                // chunks staged so far (selects the tile)
     constexpr bool has_aux = (MODE == kBiasRes || MODE == kMulAux);
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -253,15 +257,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                 : make_uint4(0, 0, 0, 0);
             }
         }
-        // staged 32 x 64 chunk -> global, 128-byte lines
-        auto store_staged = [&](__nv_bfloat16* dst, int cb) {
-          uint4 q[8];                  // all eight shared loads first: a load -> store chain per line serialises
-#pragma unroll
-          for (int i = 0; i < 8; ++i) q[i] = *reinterpret_cast<const uint4*>(my_buf + sw128_offset(4 * i + crow, cchunk));
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = row0 + 4 * i + crow, n = cb + cchunk * 8;
-            if (r < p.M && n < p.N) *reinterpret_cast<uint4*>(dst + (size_t)r * p.ldd + n) = q[i];
+        // staged 32 x 64 chunk -> global: one TMA box per warp and chunk (clipped at the matrix edge by the
+        // tensor map); the warp goes on while the TMA engine reads the tile
+        auto store_staged = [&](const CUtensorMap* tm, const uint8_t* buf, int cb) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (cb < p.N && row0 < p.M) tma_store_2d(tm, buf, cb, row0);
+            tma_commit_group();
           }
         };
         mbar_wait(&acc_full[acc], acc_phase);
@@ -269,8 +272,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         auto do_chunk = [&](const int c, auto aux_sel) {
           constexpr int kAuxSel = decltype(aux_sel)::value;   // which prefetched aux register set to consume
           const int cbase = col0 + c * 64;
+          // this chunk's staging tile; its previous TMA store (two chunks ago; the GELU mode's second
+          // output: one chunk ago) must have been read out
+          my_buf = my_bufs + (MODE == kBiasGelu ? 0 : (chunk_no & 1)) * (32 * 128);
+          ++chunk_no;
+          if (lane == 0) tma_wait_group_read<1>();
+          __syncwarp();
           if constexpr (has_aux) {
-            __syncwarp();                                 // earlier readers of my_buf are done
 #pragma unroll
             for (int i = 0; i < 8; ++i)
               *reinterpret_cast<uint4*>(my_buf + sw128_offset(4 * i + crow, cchunk)) = auxr[kAuxSel][i];
@@ -347,8 +355,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll 1
             for (int half = 0; half < 2; ++half) do_half(half);
           }
-          __syncwarp();
-          store_staged(p.D, cbase);
+          store_staged(&tmD, my_buf, cbase);
           if (p.colsum != nullptr) {
             // lane owns columns (2*lane, 2*lane+1) of this 64-wide chunk: sum the 32 staged rows
             float s0 = 0.f, s1 = 0.f;
@@ -363,13 +370,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (n + 1 < p.N) atomicAdd(p.colsum + n + 1, s1);
           }
           if constexpr (MODE == kBiasGelu) {
+            uint8_t* buf2 = my_bufs + 32 * 128;           // the second output has its own tile
+            if (lane == 0) tma_wait_group_read<1>();      // its store of the previous chunk (the D store above may be in flight)
             __syncwarp();
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              *reinterpret_cast<uint4*>(my_buf + sw128_offset(lane, j)) =
+              *reinterpret_cast<uint4*>(buf2 + sw128_offset(lane, j)) =
                   make_uint4(out2w[4 * j], out2w[4 * j + 1], out2w[4 * j + 2], out2w[4 * j + 3]);
-            __syncwarp();
-            store_staged(p.D2, cbase);
+            store_staged(&tmD2, buf2, cbase);
           }
         };
         if constexpr (has_aux) {       // unrolled: each chunk consumes its own prefetched registers
@@ -399,29 +407,29 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 }
 
 template <int A_MN, int B_MN, int MODE>
-int launch_mode(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const GemmArgs& args,
-           cudaStream_t stream) {
+int launch_mode(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const CUtensorMap& tmD2,
+                const GemmArgs& args, cudaStream_t stream) {
   auto kern = gemm_kernel<A_MN, B_MN, MODE>;
   STSWIN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   const int num_m = (args.M + BM - 1) / BM, num_n = (args.N + BN - 1) / BN;
   const int items = ((num_m + 1) / 2) * num_n * args.k_splits;        // work items of a CTA pair
   const int max_clusters = num_sms() / 2;
   const int grid = 2 * (items < max_clusters ? items : max_clusters);
-  kern<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, tmD, args);
+  kern<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, tmD, tmD2, args);
   STSWIN_CUDA(cudaGetLastError());
   return kOk;
 }
 
 template <int A_MN, int B_MN>
-int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const GemmArgs& args,
-           cudaStream_t stream) {
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const CUtensorMap& tmD2,
+           const GemmArgs& args, cudaStream_t stream) {
   switch (args.mode) {
-    case kBias: return launch_mode<A_MN, B_MN, kBias>(tmA, tmB, tmD, args, stream);
-    case kBiasRes: return launch_mode<A_MN, B_MN, kBiasRes>(tmA, tmB, tmD, args, stream);
-    case kBiasGelu: return launch_mode<A_MN, B_MN, kBiasGelu>(tmA, tmB, tmD, args, stream);
-    case kBiasGeluFwd: return launch_mode<A_MN, B_MN, kBiasGeluFwd>(tmA, tmB, tmD, args, stream);
-    case kMulAux: return launch_mode<A_MN, B_MN, kMulAux>(tmA, tmB, tmD, args, stream);
-    default: return launch_mode<A_MN, B_MN, kF32Reduce>(tmA, tmB, tmD, args, stream);
+    case kBias: return launch_mode<A_MN, B_MN, kBias>(tmA, tmB, tmD, tmD2, args, stream);
+    case kBiasRes: return launch_mode<A_MN, B_MN, kBiasRes>(tmA, tmB, tmD, tmD2, args, stream);
+    case kBiasGelu: return launch_mode<A_MN, B_MN, kBiasGelu>(tmA, tmB, tmD, tmD2, args, stream);
+    case kBiasGeluFwd: return launch_mode<A_MN, B_MN, kBiasGeluFwd>(tmA, tmB, tmD, tmD2, args, stream);
+    case kMulAux: return launch_mode<A_MN, B_MN, kMulAux>(tmA, tmB, tmD, tmD2, args, stream);
+    default: return launch_mode<A_MN, B_MN, kF32Reduce>(tmA, tmB, tmD, tmD2, args, stream);
   }
 }
 
@@ -447,7 +455,7 @@ int gemm_bf16(const void* A, int a_major, long lda, const void* B, int b_major, 
   // every split must own at least one k-block (an empty split would publish an unwritten accumulator)
   while (k_splits > 1 && (k_splits - 1) * ((kb_total + k_splits - 1) / k_splits) >= kb_total) --k_splits;
 
-  CUtensorMap tmA, tmB, tmD;
+  CUtensorMap tmA, tmB, tmD, tmD2;
   int rc;
   {
     uint64_t dims[2], str[1];
@@ -461,6 +469,7 @@ int gemm_bf16(const void* A, int a_major, long lda, const void* B, int b_major, 
     str[0] = (uint64_t)ldb * 2;
     if ((rc = make_tmap(&tmB, TmapDtype::BF16, 2, B, dims, str, box, true)) != kOk) return rc;
     tmD = tmA;
+    tmD2 = tmA;
     if (mode == kF32Reduce) {
       STSWIN_CHECK_ARG(ldd % 4 == 0, "gemm: fp32 ldd must be a multiple of 4");
       dims[0] = N; dims[1] = M;
@@ -473,13 +482,18 @@ int gemm_bf16(const void* A, int a_major, long lda, const void* B, int b_major, 
       if (mode == kBiasRes || mode == kMulAux)
         STSWIN_CHECK_ARG(ld_aux % 8 == 0 && (reinterpret_cast<uintptr_t>(aux) & 15) == 0,
                          "gemm: aux must be 16-byte aligned with ld_aux a multiple of 8");
+      // bf16 outputs leave through TMA: [32 rows x 64 columns] boxes of the 128B-swizzled staging tiles
+      dims[0] = N; dims[1] = M;
+      str[0] = (uint64_t)ldd * 2; box[0] = 64; box[1] = 32;
+      if ((rc = make_tmap(&tmD, TmapDtype::BF16, 2, D, dims, str, box, true)) != kOk) return rc;
+      if (D2 != nullptr && (rc = make_tmap(&tmD2, TmapDtype::BF16, 2, D2, dims, str, box, true)) != kOk) return rc;
     }
   }
   GemmArgs args{M, N, K, mode, k_splits, bias, colsum, static_cast<__nv_bfloat16*>(D), static_cast<__nv_bfloat16*>(D2),
                 static_cast<const __nv_bfloat16*>(aux), ldd, ld_aux};
-  if (a_major == 0 && b_major == 0) return launch<0, 0>(tmA, tmB, tmD, args, stream);
-  if (a_major == 0 && b_major == 1) return launch<0, 1>(tmA, tmB, tmD, args, stream);
-  return launch<1, 1>(tmA, tmB, tmD, args, stream);
+  if (a_major == 0 && b_major == 0) return launch<0, 0>(tmA, tmB, tmD, tmD2, args, stream);
+  if (a_major == 0 && b_major == 1) return launch<0, 1>(tmA, tmB, tmD, tmD2, args, stream);
+  return launch<1, 1>(tmA, tmB, tmD, tmD2, args, stream);
 }
 
 }  // namespace stswin
