@@ -160,6 +160,52 @@ int stswin_pixloss_bwd(const void* const* keys, const uint8_t* lq, const uint8_t
                        const float* ksum, const float* d_loss, int n_sets, int N, int C, int HW, float* dq32,
                        void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Training-step kernels either side of the two hot paths.
+ *
+ * OHEM cross-entropy.  Replaces OhemCELoss2D.forward (seg18/utils/losses.py:16-40): per-pixel
+ * cross_entropy(reduction='none', ignore_index) :33, the full descending sort :34 and the
+ * `loss[n_min] > thresh` branch :36-39, without the sort and without a host read:
+ *   more than n_min losses above thresh -> mean of the losses above thresh,
+ *   otherwise                           -> mean of the n_min largest (k-th value by a 3-pass radix select).
+ *   logits  [B, K, HW] fp32 (logits_is_f32) or bf16, class-major as the decoder emits (NCHW)
+ *   labels  [B, HW] int64; a label equal to ignore_index contributes loss 0 (and no gradient)
+ *   thresh  the loss threshold -log(0.7) of :26;   1 <= n_min < B*HW (:36 indexes loss[n_min])
+ *   loss_px [B*HW] fp32 per-pixel losses (kept for the backward);  ws: stswin_ohem_ws_bytes() bytes
+ *   loss    device scalar;  sel [4] fp32: {cut, gradient weight of a loss above cut, weight of a loss
+ *           equal to cut (ties at the n_min-th value share the remaining weight), unused}
+ * stswin_ohem_ce_bwd: d_logits (dtype of logits, every element written) =
+ *           weight(pixel) * (softmax - onehot) * d_loss   (d_loss: device scalar)
+ */
+int64_t stswin_ohem_ws_bytes(void);
+int stswin_ohem_ce_fwd(const void* logits, int logits_is_f32, const int64_t* labels, int B, int K, int64_t HW,
+                       int ignore_index, float thresh, int64_t n_min, float* loss_px, void* ws, float* loss, float* sel,
+                       void* stream);
+int stswin_ohem_ce_bwd(const void* logits, int logits_is_f32, const int64_t* labels, int B, int K, int64_t HW,
+                       int ignore_index, const float* loss_px, const float* sel, const float* d_loss, void* d_logits,
+                       void* stream);
+
+/* Momentum (EMA) update of the key encoder as one multi-tensor stream.  Replaces the ~600 per-parameter
+ * `param_k.data = param_k.data * m + param_q.data * (1. - m)` of PixPro._momentum_update_key_encoder
+ * (pixcontrast_18/contrast/models/PixPro_swin_v5.py:258-289); bit-exact with the eager expression
+ * (two rounded products, one rounded sum).  k_params / q_params / numels are HOST arrays of n_tensors
+ * device pointers (fp32 tensors, contiguous) and element counts. */
+int stswin_ema_update(void* const* k_params, const void* const* q_params, const int64_t* numels, int n_tensors, float m,
+                      float one_minus_m, void* stream);
+
+/* LARS-scaled SGD step of one parameter group.  Replaces LARS.apply_adaptive_lrs + the wrapped
+ * torch.optim.SGD.step (pixcontrast_18/contrast/lars.py:109-152): per tensor
+ *   g = grad + weight_decay * p (:121-122); if `lars`: g *= trust_coef * |p| / (|g| + eps) when both norms
+ *   are positive (:125-135); grad <- g (the reference rebinds p.grad); buf = g on a tensor's first step
+ *   (first_step[t] != 0) else momentum * buf + (1 - dampening) * g; p -= lr * (nesterov ? g + momentum * buf : buf).
+ * The norms are reduced on the device (no .norm() host reads, :127-133).  params / grads / momentum_bufs /
+ * numels / first_step are HOST arrays over the group's tensors (fp32, contiguous); momentum_bufs may be NULL
+ * when momentum == 0; norms_ws: device [2 * n_tensors] fp64 scratch (only when `lars`). */
+int stswin_lars_sgd_step(void* const* params, void* const* grads, void* const* momentum_bufs, const int64_t* numels,
+                         const uint8_t* first_step, int n_tensors, float lr, float momentum, float dampening,
+                         int nesterov, float weight_decay, int lars, float trust_coef, float eps, double* norms_ws,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif

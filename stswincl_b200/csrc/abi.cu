@@ -5,7 +5,7 @@
 
 extern "C" {
 
-int stswin_abi_version(void) { return 1; }
+int stswin_abi_version(void) { return 2; }
 const char* stswin_last_error(void) { return stswin::last_error(); }
 int stswin_set_device(int device) {
   STSWIN_CUDA(cudaSetDevice(device));
@@ -67,6 +67,31 @@ int stswin_pixloss_bwd(const void* const* keys, const uint8_t* lq, const uint8_t
                        const float* ksum, const float* d_loss, int n_sets, int N, int C, int HW, float* dq32,
                        void* stream) {
   return stswin::pixloss_bwd(keys, lq, lk, coef, ksum, d_loss, n_sets, N, C, HW, dq32, static_cast<cudaStream_t>(stream));
+}
+
+int64_t stswin_ohem_ws_bytes(void) { return stswin::ohem_ws_bytes(); }
+int stswin_ohem_ce_fwd(const void* logits, int logits_is_f32, const int64_t* labels, int B, int K, int64_t HW,
+                       int ignore_index, float thresh, int64_t n_min, float* loss_px, void* ws, float* loss, float* sel,
+                       void* stream) {
+  return stswin::ohem_ce_fwd(logits, logits_is_f32, labels, B, K, HW, ignore_index, thresh, n_min, loss_px, ws, loss, sel,
+                             static_cast<cudaStream_t>(stream));
+}
+int stswin_ohem_ce_bwd(const void* logits, int logits_is_f32, const int64_t* labels, int B, int K, int64_t HW,
+                       int ignore_index, const float* loss_px, const float* sel, const float* d_loss, void* d_logits,
+                       void* stream) {
+  return stswin::ohem_ce_bwd(logits, logits_is_f32, labels, B, K, HW, ignore_index, loss_px, sel, d_loss, d_logits,
+                             static_cast<cudaStream_t>(stream));
+}
+int stswin_ema_update(void* const* k_params, const void* const* q_params, const int64_t* numels, int n_tensors, float m,
+                      float one_minus_m, void* stream) {
+  return stswin::ema_update(k_params, q_params, numels, n_tensors, m, one_minus_m, static_cast<cudaStream_t>(stream));
+}
+int stswin_lars_sgd_step(void* const* params, void* const* grads, void* const* momentum_bufs, const int64_t* numels,
+                         const uint8_t* first_step, int n_tensors, float lr, float momentum, float dampening,
+                         int nesterov, float weight_decay, int lars, float trust_coef, float eps, double* norms_ws,
+                         void* stream) {
+  return stswin::lars_sgd_step(params, grads, momentum_bufs, numels, first_step, n_tensors, lr, momentum, dampening,
+                               nesterov, weight_decay, lars, trust_coef, eps, norms_ws, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

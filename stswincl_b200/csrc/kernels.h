@@ -32,4 +32,16 @@ int pixloss_bwd(const void* const* keys, const uint8_t* lq, const uint8_t* const
                 const float* ksum, const float* d_loss, int n_sets, int N, int C, int HW, float* dq32,
                 cudaStream_t stream);
 
+// training-step kernels around the hot paths (trainaux.cu)
+long ohem_ws_bytes();
+int ohem_ce_fwd(const void* logits, int logits_is_f32, const int64_t* labels, int B, int K, long HW, int ignore_index,
+                float thresh, long n_min, float* loss_px, void* ws, float* loss, float* sel, cudaStream_t stream);
+int ohem_ce_bwd(const void* logits, int logits_is_f32, const int64_t* labels, int B, int K, long HW, int ignore_index,
+                const float* loss_px, const float* sel, const float* d_loss, void* d_logits, cudaStream_t stream);
+int ema_update(void* const* k_params, const void* const* q_params, const int64_t* numels, int n_tensors, float m,
+               float one_minus_m, cudaStream_t stream);
+int lars_sgd_step(void* const* params, void* const* grads, void* const* bufs, const int64_t* numels,
+                  const uint8_t* first_step, int n_tensors, float lr, float momentum, float dampening, int nesterov,
+                  float weight_decay, int lars, float trust_coef, float eps, double* norms_ws, cudaStream_t stream);
+
 }  // namespace stswin
