@@ -160,22 +160,39 @@ __global__ void __launch_bounds__(kThreads) ohem_px_kernel(const T* __restrict__
   }
 }
 
-// walk a histogram from its top bin down to the bin holding the k-th largest key (k is 1-based);
-// returns the bin and leaves the rank inside that bin in k.  Whole block; result is block-uniform.
+// find the bin holding the k-th largest key of a histogram (k is 1-based, counted from the top bin); returns the bin
+// and leaves the rank inside that bin in k.  Whole block (suffix sums by warp shuffles); the result is block-uniform.
 __device__ int pick_bin(const unsigned int* hist, int bins, unsigned long long& k, unsigned int* s_part, int* s_res,
                         unsigned long long* s_k) {
-  const int per = bins / kThreads;
-  unsigned int part = 0;
-  for (int i = 0; i < per; ++i) part += hist[threadIdx.x * per + i];
-  s_part[threadIdx.x] = part;
+  const int per = bins / kThreads;              // 8 or 4 bins per thread
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned int h[8], part = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    h[i] = i < per ? hist[threadIdx.x * per + i] : 0u;
+    part += h[i];
+  }
+  unsigned int incl = part;                     // -> sum over the threads at or above this one
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned int v = __shfl_down_sync(0xffffffffu, incl, o);
+    if (lane + o < 32) incl += v;
+  }
+  if (lane == 0) s_part[warp] = incl;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned long long kk = k;
-    int t = kThreads - 1;
-    while (t > 0 && kk > s_part[t]) { kk -= s_part[t]; --t; }
-    int bin = t * per + per - 1;
-    while (bin > t * per && kk > hist[bin]) { kk -= hist[bin]; --bin; }
-    *s_res = bin;
+  for (int w = warp + 1; w < kThreads / 32; ++w) incl += s_part[w];
+  const unsigned long long above = incl - part;
+  if (above < k && k <= incl) {                 // exactly one thread: its bins hold the k-th key
+    unsigned long long kk = k - above;
+    int res = 0;
+    bool found = false;
+#pragma unroll
+    for (int i = 7; i >= 0; --i) {
+      if (i < per && !found) {
+        if (kk <= h[i] || i == 0) { res = i; found = true; } else kk -= h[i];
+      }
+    }
+    *s_res = threadIdx.x * per + res;
     *s_k = kk;
   }
   __syncthreads();
@@ -191,7 +208,7 @@ template <int PASS>
 __global__ void __launch_bounds__(kThreads) ohem_hist_kernel(const float* __restrict__ loss_px, long M, long n_min, OhemWs* ws) {
   if (ws->cnt_gt > (unsigned long long)n_min) return;
   __shared__ unsigned int s_hist[kBins];
-  __shared__ unsigned int s_part[kThreads];
+  __shared__ unsigned int s_part[kThreads / 32];
   __shared__ int s_res;
   __shared__ unsigned long long s_k;
   unsigned int prefix = 0;
@@ -204,16 +221,32 @@ __global__ void __launch_bounds__(kThreads) ohem_hist_kernel(const float* __rest
   for (int i = threadIdx.x; i < kBins; i += kThreads) s_hist[i] = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  const long warp0 = ((long)blockIdx.x * kThreads + (threadIdx.x & ~31));
-  for (long i0 = warp0; i0 < M; i0 += (long)gridDim.x * kThreads) {
-    const long i = i0 + lane;
-    unsigned int bin = 0xffffffffu;
-    if (i < M) {
-      const unsigned int key = __float_as_uint(loss_px[i]);
-      if (PASS == 0 || (key >> pshift) == prefix) bin = (key >> shift) & mask;
+  auto count = [&](unsigned int key, bool valid) {
+    if (PASS == 0) {
+      // the top digit (sign, exponent, two mantissa bits) is shared by most losses: one shared-memory atomic per
+      // distinct bin of the warp
+      const unsigned int bin = valid ? (key >> shift) & mask : 0xffffffffu;
+      const unsigned int peers = __match_any_sync(0xffffffffu, bin);
+      if (valid && lane == __ffs(peers) - 1) atomicAdd(&s_hist[bin], (unsigned int)__popc(peers));
+    } else if (valid && (key >> pshift) == prefix) {    // few keys survive the prefix filter
+      atomicAdd(&s_hist[(key >> shift) & mask], 1u);
     }
-    const unsigned int peers = __match_any_sync(0xffffffffu, bin);       // one shared-memory atomic per distinct bin
-    if (bin != 0xffffffffu && lane == __ffs(peers) - 1) atomicAdd(&s_hist[bin], (unsigned int)__popc(peers));
+  };
+  const long M4 = M >> 2;                               // loss_px is 16-byte aligned (our own buffer)
+  const long warp0 = (long)blockIdx.x * kThreads + (threadIdx.x & ~31);
+  for (long i0 = warp0; i0 < M4; i0 += (long)gridDim.x * kThreads) {
+    const long i = i0 + lane;
+    const bool valid = i < M4;
+    const float4 v = valid ? __ldg(reinterpret_cast<const float4*>(loss_px) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    count(__float_as_uint(v.x), valid);
+    count(__float_as_uint(v.y), valid);
+    count(__float_as_uint(v.z), valid);
+    count(__float_as_uint(v.w), valid);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < 32) {            // the last M % 4 losses
+    const long i = (M4 << 2) + lane;
+    const bool valid = i < M;
+    count(valid ? __float_as_uint(loss_px[i]) : 0u, valid);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < kBins; i += kThreads)
@@ -232,7 +265,7 @@ __global__ void __launch_bounds__(kThreads) ohem_final_kernel(const float* __res
     }
     return;
   }
-  __shared__ unsigned int s_part[kThreads];
+  __shared__ unsigned int s_part[kThreads / 32];
   __shared__ int s_res;
   __shared__ unsigned long long s_k;
   __shared__ float s_sum[kThreads / 32];
@@ -245,8 +278,16 @@ __global__ void __launch_bounds__(kThreads) ohem_final_kernel(const float* __res
   const float cut = __uint_as_float(key);            // the n_min-th largest loss
   float lsum = 0.f;
   unsigned int lcnt = 0;
-  for (long i = (long)blockIdx.x * kThreads + threadIdx.x; i < M; i += (long)gridDim.x * kThreads) {
-    const float v = loss_px[i];
+  const long M4 = M >> 2;
+  for (long i = (long)blockIdx.x * kThreads + threadIdx.x; i < M4; i += (long)gridDim.x * kThreads) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(loss_px) + i);
+    if (v.x > cut) { lsum += v.x; ++lcnt; }
+    if (v.y > cut) { lsum += v.y; ++lcnt; }
+    if (v.z > cut) { lsum += v.z; ++lcnt; }
+    if (v.w > cut) { lsum += v.w; ++lcnt; }
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (M & 3)) {
+    const float v = loss_px[(M4 << 2) + threadIdx.x];
     if (v > cut) { lsum += v; ++lcnt; }
   }
   lsum = warp_sum(lsum);
@@ -524,7 +565,9 @@ int ohem_ce_fwd(const void* logits, int logits_is_f32, const int64_t* labels, in
     if (vec) ohem_px_kernel<__nv_bfloat16, 4><<<grid, kThreads, 0, stream>>>(static_cast<const __nv_bfloat16*>(logits), labels, B, K, HW, ignore_index, thresh, loss_px, w);
     else ohem_px_kernel<__nv_bfloat16, 1><<<grid, kThreads, 0, stream>>>(static_cast<const __nv_bfloat16*>(logits), labels, B, K, HW, ignore_index, thresh, loss_px, w);
   }
-  const int g2 = stream_grid(M);
+  STSWIN_CHECK_ARG((reinterpret_cast<uintptr_t>(loss_px) & 15) == 0, "ohem_ce_fwd: loss_px must be 16-byte aligned");
+  int g2 = stream_grid(M / 4);
+  if (g2 > 2 * num_sms()) g2 = 2 * num_sms();        // fixed per-block cost (histogram clear / flush, digit picks)
   ohem_hist_kernel<0><<<g2, kThreads, 0, stream>>>(loss_px, M, n_min, w);
   ohem_hist_kernel<1><<<g2, kThreads, 0, stream>>>(loss_px, M, n_min, w);
   ohem_hist_kernel<2><<<g2, kThreads, 0, stream>>>(loss_px, M, n_min, w);

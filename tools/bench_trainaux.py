@@ -18,10 +18,29 @@ PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
 dev = torch.device("cuda", 0)
 
 
-def timeit(fn, n=20, warm=3):
+def timeit(fn, n=20, warm=3, graph=True):
+    """Average device time of fn.  Our paths are replayed from a CUDA graph (the host side of one call -- ctypes
+    pointer tables, allocations -- would otherwise bound these sub-millisecond launches); the eager torch
+    sequences have host reads and are timed as they run in the reference."""
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
+    if graph:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                fn()
+            torch.cuda.current_stream().wait_stream(side)
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                fn()
+            fn = gr.replay
+            fn()
+            torch.cuda.synchronize()
+        except Exception as e:
+            print(f"graph capture failed: {type(e).__name__}: {e}", file=sys.stderr)
+            torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(n):
@@ -65,7 +84,7 @@ for tag, margin in (("threshold_branch", 0.0), ("topk_branch", 12.0)):
         l.mean().backward()
 
     px = B * H * W
-    t_f, t_fb, t_ref = timeit(fwd), timeit(fwdbwd), timeit(ref_fwdbwd, n=5, warm=2)
+    t_f, t_fb, t_ref = timeit(fwd), timeit(fwdbwd), timeit(ref_fwdbwd, n=5, warm=2, graph=False)
     k, v = row(f"ohem_fwd_{tag}", t_f, px * (K * 4 + 8 + 4))
     out[k] = v
     k, v = row(f"ohem_fwd_bwd_{tag}", t_fb, px * (K * 4 + 8 + 4) + px * (K * 4 + 8 + 4) + (px * K * 4 if margin == 0.0 else 0), t_ref)
@@ -85,7 +104,7 @@ def ref_ema():
             b.data = b.data * 0.99 + a.data * (1. - 0.99)
 
 
-k, v = row("ema_update", timeit(lambda: optim.momentum_update(qp, kp, 0.99)), 3 * n_bytes, timeit(ref_ema, n=5, warm=2))
+k, v = row("ema_update", timeit(lambda: optim.momentum_update(qp, kp, 0.99)), 3 * n_bytes, timeit(ref_ema, n=5, warm=2, graph=False))
 v["tensors"] = len(qp)
 out[k] = v
 
@@ -122,7 +141,7 @@ lars_step()
 t = timeit(lars_step)
 for p, gr in zip(qp, grads):
     p.grad = gr
-t_ref = timeit(ref_lars_step, n=5, warm=2)
+t_ref = timeit(ref_lars_step, n=5, warm=2, graph=False)
 decay_bytes = sum(p.numel() for p in qp if p.dim() > 1) * 4
 k, v = row("lars_sgd_step", t, 6 * n_bytes + 2 * decay_bytes, t_ref)     # update: p, g, buf in and out; norms: p, g of the LARS group
 out[k] = v
