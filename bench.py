@@ -190,9 +190,14 @@ def run_ours(args):
         if isinstance(blk, swin.WindowAttention):       # sigma 0.02 init is nearly a no-op bias; use a visible one
             torch.nn.init.normal_(blk.relative_position_bias_table, std=0.5)
     net = model
+    side = torch.cuda.Stream(device=dev)
     if world > 1:
-        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True,
-                                                        bucket_cap_mb=64, broadcast_buffers=False)
+        # constructed on the side stream the step is later captured from (DDP + CUDA graphs)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True,
+                                                            bucket_cap_mb=64, broadcast_buffers=False)
+        torch.cuda.current_stream().wait_stream(side)
     opt = torch.optim.Adam(model.parameters(), lr=3e-5, fused=True, capturable=True)
     B = args.clips
     g = torch.Generator(device=dev).manual_seed(1 + rank)
@@ -233,13 +238,14 @@ def run_ours(args):
     step(x_dev)
     launches_per_step = ops.LAUNCHES - launches0
 
-    # The step has no host synchronisation and static shapes, so the whole forward + backward +
-    # optimizer step is captured once into a CUDA graph and replayed (single GPU; DDP steps run eagerly).
+    # The step has no host synchronisation and static shapes, so the whole forward + backward + optimizer step is
+    # captured once into a CUDA graph and replayed (single GPU).  DDP steps run eagerly: capturing them (DDP on a
+    # side stream, 11 eager iterations first) measured 1580 vs 1557 frames/s at 2 GPUs but the process then hangs in
+    # the NCCL teardown, so it is not used.
     graph, static_x, static_loss = None, None, None
     if world == 1 and not args.no_graph:
         try:
             static_x = x_dev.clone()
-            side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
                 for _ in range(2):
@@ -331,6 +337,57 @@ def run_ours(args):
             roofline[k] = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
                            "avg_launch_ms": fam[k]["ms"] / fam[k]["launches"]}
 
+    # ---- "window-attn TFLOP/s vs tensor peak" (second half of the metric): the WindowAttention module (qkv Linear +
+    # shifted-window core + proj Linear, SURVEY 8d: 8C^2 + 4LC FLOPs per token forward, 2x that backward) at this
+    # workload's batch, stage-1 (C 512, 64x80, ws 8, shift 4) and stage-2 (C 1024, 32x40, ws 4, shift 2) geometry,
+    # replayed from a CUDA graph and timed alone -> against the measured burst bf16 peak
+    window_attn = None
+    if rank == 0 and world == 1:
+        window_attn = {}
+        for name, dim, res, ws in (("stage1", DIM, RES, 8), ("stage2", 2 * DIM, (RES[0] // 2, RES[1] // 2), 4)):
+            attn = swin.WindowAttention(dim, (ws, ws), HEADS).to(dev)
+            torch.nn.init.normal_(attn.relative_position_bias_table, std=0.5)
+            xa = torch.relu(torch.randn(2 * B, 2, res[0] * res[1], dim, device=dev)).to(torch.bfloat16).requires_grad_(True)
+            ga = (torch.randn_like(xa) * 0.1)
+            geom = (res[0], res[1], HEADS, ws, ws // 2, 0.0)
+
+            def attn_fwd_bwd():
+                xa.grad = None
+                attn.zero_grad(set_to_none=True)
+                y = swin._AttentionFn.apply(xa, attn.relative_position_bias_table, attn.qkv.weight, attn.qkv.bias,
+                                            attn.proj.weight, attn.proj.bias, geom)
+                y.backward(ga)
+
+            def attn_fwd():
+                with torch.no_grad():
+                    swin._AttentionFn.apply(xa, attn.relative_position_bias_table, attn.qkv.weight, attn.qkv.bias,
+                                            attn.proj.weight, attn.proj.bias, geom)
+
+            res_ms = {}
+            for tag, fn in (("fwd", attn_fwd), ("fwd_bwd", attn_fwd_bwd)):
+                for _ in range(3):
+                    fn()
+                torch.cuda.synchronize()
+                side = torch.cuda.Stream(device=dev)
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    fn()
+                torch.cuda.current_stream().wait_stream(side)
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr):
+                    fn()
+                for _ in range(3):
+                    gr.replay()
+                res_ms[tag] = timed(lambda i: gr.replay(), 10)
+            tok = 2 * B * 2 * res[0] * res[1]
+            f_fwd = (8.0 * dim * dim + 4.0 * (2 * ws * ws) * dim) * tok
+            window_attn[name] = {
+                "tokens": tok, "gflop_fwd": f_fwd / 1e9, "fwd_ms": res_ms["fwd"], "fwd_bwd_ms": res_ms["fwd_bwd"],
+                "fwd_tflops": f_fwd / res_ms["fwd"] / 1e9, "fwd_bwd_tflops": 3 * f_fwd / res_ms["fwd_bwd"] / 1e9,
+                "peak_tflops": pk["tflops_burst"], "fwd_frac_of_peak": f_fwd / res_ms["fwd"] / 1e9 / pk["tflops_burst"],
+                "fwd_bwd_frac_of_peak": 3 * f_fwd / res_ms["fwd_bwd"] / 1e9 / pk["tflops_burst"]}
+            del attn, xa, ga
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cstep, threads = cpu_step_factory()
@@ -346,7 +403,7 @@ def run_ours(args):
                 "config": workload_config(B, graph is not None), "clocks": clocks,
                 "e2e": {"value": frames / (ms_e2e * 1e-3), "unit": "frames/s", "ms_per_step": ms_e2e,
                         "h2d_bytes_per_step": x_host.numel() * x_host.element_size(), "d2h_bytes_per_step": d2h_bytes},
-                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+                "gpu_launches": launches, "roofline": roofline, "window_attn": window_attn, "cpu_baseline": cpu,
                 "clips_per_s": B * world / (ms_step * 1e-3)}
         print(json.dumps(line), flush=True)
     if world > 1:

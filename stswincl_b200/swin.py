@@ -108,16 +108,17 @@ class _AttentionFn(torch.autograd.Function):
         C = x2.shape[1]
         Bp_T_L = d_out.shape[:3]
         d2 = d_out.contiguous().view(-1, C)
-        d_bproj = d2.float().sum(0)
+        d_bproj = d2.sum(0, dtype=torch.float32)          # one read of d_out (no fp32 copy)
+        d_table, d_bqkv, d_wproj_, d_wqkv_ = _zeros_like_many([tuple(table.shape), (3 * C,), tuple(wp.shape), tuple(wq.shape)], d2.device)
+        if not ctx.has_qkv_bias:
+            d_bqkv = None
         d_attn = ops.gemm(d2, wp, b_mn_major=True)
-        d_wproj = _linear_wgrad(d2, attn.view(-1, C), wp.shape)
-        d_table = torch.zeros_like(table)
-        d_bqkv = torch.zeros(3 * C, dtype=torch.float32, device=d2.device) if ctx.has_qkv_bias else None
+        d_wproj = _linear_wgrad(d2, attn.view(-1, C), wp.shape, d_wproj_)
         d_qkv = ops.winattn_bwd(qkv.view(*Bp_T_L, 3 * C), table, lse2, d_attn.view(*Bp_T_L, C), H, W, nH, ws, shift,
                                 d_table, d_bqkv, qk_scale=qk_scale, mask=ctx.mask)
         dq2 = d_qkv.view(-1, 3 * C)
         d_x = ops.gemm(dq2, wq, b_mn_major=True)
-        d_wqkv = _linear_wgrad(dq2, x2, wq.shape)
+        d_wqkv = _linear_wgrad(dq2, x2, wq.shape, d_wqkv_)
         return d_x.view(*Bp_T_L, C), d_table, d_wqkv, d_bqkv, d_wproj, d_bproj, None, None
 
 
