@@ -47,6 +47,9 @@ def parse():
     ap.add_argument("--clips", type=int, default=8, help="clips per GPU per step (reference recipe: batch 8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="do not capture the step in a CUDA graph")
+    ap.add_argument("--dp", default="flat", choices=["flat", "ddp"],
+                    help="N > 1: 'flat' = forward + backward replayed from a CUDA graph, ONE NCCL all-reduce (average) of the "
+                         "flattened fp32 gradients, optimizer step; 'ddp' = torch DistributedDataParallel, eager steps")
     return ap.parse_args()
 
 
@@ -193,13 +196,19 @@ def run_ours(args):
             torch.nn.init.normal_(blk.relative_position_bias_table, std=0.5)
     net = model
     side = torch.cuda.Stream(device=dev)
-    if world > 1:
-        # constructed on the side stream the step is later captured from (DDP + CUDA graphs)
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True,
-                                                            bucket_cap_mb=64, broadcast_buffers=False)
-        torch.cuda.current_stream().wait_stream(side)
+    flat_dp = world > 1 and args.dp == "flat"
+    params = list(model.parameters())
+    if world > 1 and not flat_dp:
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True,
+                                                        bucket_cap_mb=64, broadcast_buffers=False)
+    flat_grad, grad_views = None, None
+    if flat_dp:
+        for p_ in params:                                  # replicas start identical (DDP's constructor does the same)
+            dist.broadcast(p_.data, src=0)
+        sizes = [(p_.numel() + 3) // 4 * 4 for p_ in params]
+        flat_grad = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+        offs = [sum(sizes[:i]) for i in range(len(sizes))]
+        grad_views = [flat_grad[o:o + p_.numel()].view_as(p_) for o, p_ in zip(offs, params)]
     opt = torch.optim.Adam(model.parameters(), lr=3e-5, fused=True, capturable=True)
     B = args.clips
     g = torch.Generator(device=dev).manual_seed(1 + rank)
@@ -207,12 +216,25 @@ def run_ours(args):
     g1 = (torch.randn(B, T, DIM, RES[0], RES[1], generator=g, device=dev) * 0.1).to(torch.bfloat16)
     g2 = (torch.randn(B, T, 2 * DIM, RES[0] // 2, RES[1] // 2, generator=g, device=dev) * 0.1).to(torch.bfloat16)
 
-    def step(x):
+    def fwd_bwd(x):
         opt.zero_grad(set_to_none=True)
         y1, y2 = net(x)
         loss = torch.sum(y1 * g1, dtype=torch.float32) + torch.sum(y2 * g2, dtype=torch.float32)
         loss.backward()
+        if flat_dp:                                        # gather the gradients into the all-reduce buffer
+            torch._foreach_copy_(grad_views, [p_.grad for p_ in params])
+        return loss
+
+    def reduce_and_update():
+        if flat_dp:                                        # the data-parallel exchange: one all-reduce over NVLink
+            dist.all_reduce(flat_grad, op=dist.ReduceOp.AVG)
+            for p_, v in zip(params, grad_views):
+                p_.grad = v
         opt.step()
+
+    def step(x):
+        loss = fwd_bwd(x)
+        reduce_and_update()
         return loss
 
     def barrier():
@@ -240,12 +262,14 @@ def run_ours(args):
     step(x_dev)
     launches_per_step = ops.LAUNCHES - launches0
 
-    # The step has no host synchronisation and static shapes, so the whole forward + backward + optimizer step is
-    # captured once into a CUDA graph and replayed (single GPU).  DDP steps run eagerly: capturing them (DDP on a
-    # side stream, 11 eager iterations first) measured 1580 vs 1557 frames/s at 2 GPUs but the process then hangs in
-    # the NCCL teardown, so it is not used.
+    # The step has no host synchronisation and static shapes, so it is captured once into a CUDA graph and replayed:
+    # on one GPU the whole forward + backward + optimizer step; on N GPUs (--dp flat) forward + backward + the gather of
+    # the gradients into one flat buffer, followed -- outside the graph -- by one NCCL all-reduce and the optimizer step.
+    # torch DDP steps (--dp ddp) run eagerly: capturing them (DDP on a side stream, 11 eager iterations first) measured
+    # 1580 vs 1557 frames/s at 2 GPUs but the process then hangs in the NCCL teardown.
     graph, static_x, static_loss = None, None, None
-    if world == 1 and not args.no_graph:
+    captured = fwd_bwd if flat_dp else step
+    if (world == 1 or flat_dp) and not args.no_graph:
         try:
             static_x = x_dev.clone()
             side.wait_stream(torch.cuda.current_stream())
@@ -256,13 +280,20 @@ def run_ours(args):
             opt.zero_grad(set_to_none=True)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                static_loss = step(static_x)
+                static_loss = captured(static_x)
             graph.replay()
+            if flat_dp:
+                reduce_and_update()
             torch.cuda.synchronize()
         except Exception as e:                      # capture is an optimisation of the harness, not of the product
             print(f"bench.py: CUDA graph capture failed ({type(e).__name__}: {e}); timing eager steps", file=sys.stderr)
             graph = None
             torch.cuda.synchronize()
+        if flat_dp:          # every rank replays, or none does
+            ok = torch.tensor([1 if graph is not None else 0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok) == 0:
+                graph = None
 
     def run_step(x):
         if graph is None:
@@ -270,6 +301,8 @@ def run_ours(args):
         if x is not static_x:
             static_x.copy_(x, non_blocking=True)
         graph.replay()
+        if flat_dp:
+            reduce_and_update()
         return static_loss
 
     for _ in range(2):
@@ -407,7 +440,10 @@ def run_ours(args):
         line = {"metric": METRIC, "value": frames / (ms_step * 1e-3), "unit": "frames/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": workload_config(B, graph is not None), "clocks": clocks,
+                "config": dict(workload_config(B, graph is not None),
+                               parallelism=("dp%d: %s" % (world, "one flat fp32 gradient all-reduce (NCCL, average) per step" if flat_dp
+                                                          else "torch DDP, bucketed all-reduce overlapped with backward")) if world > 1 else "single GPU"),
+                "clocks": clocks,
                 "e2e": {"value": frames / (ms_e2e * 1e-3), "unit": "frames/s", "ms_per_step": ms_e2e,
                         "h2d_bytes_per_step": x_host.numel() * x_host.element_size(), "d2h_bytes_per_step": d2h_bytes},
                 "gpu_launches": launches, "roofline": roofline, "window_attn": window_attn, "cpu_baseline": cpu,
