@@ -15,7 +15,8 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(_HERE, "libstswin_b200.so")
+# STSWIN_B200_LIB: load another build of the same ABI (A/B timing of a kernel change); never a different implementation
+LIB_PATH = os.environ.get("STSWIN_B200_LIB") or os.path.join(_HERE, "libstswin_b200.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-shared",

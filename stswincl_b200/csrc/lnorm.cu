@@ -84,23 +84,25 @@ ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gam
   };
 #pragma unroll
   for (int s = 0; s < NSTG - 1; ++s) issue(row0 + s * stride, s);
-  // gamma / beta of this lane's columns stay in registers for every row of the warp
-  float gr[NV][8], br[NV][8];
+  // gamma / beta of this lane's columns stay in registers for every row of the warp, as fp32 pairs: the row
+  // arithmetic runs on packed FADD2 / FFMA2 (two columns per issue slot -- these kernels are issue-bound at the
+  // power-capped clock of a training step, not HBM-bound)
+  uint64_t gr[NV][4], br[NV][4];
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int vi = lane + 32 * i;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      gr[i][k] = vi < nvec ? __ldg(gamma + vi * 8 + k) : 0.f;
-      br[i][k] = vi < nvec ? __ldg(beta + vi * 8 + k) : 0.f;
+    for (int k = 0; k < 4; ++k) {
+      gr[i][k] = vi < nvec ? f2_pack(__ldg(gamma + vi * 8 + 2 * k), __ldg(gamma + vi * 8 + 2 * k + 1)) : f2_pack(0.f, 0.f);
+      br[i][k] = vi < nvec ? f2_pack(__ldg(beta + vi * 8 + 2 * k), __ldg(beta + vi * 8 + 2 * k + 1)) : f2_pack(0.f, 0.f);
     }
   }
   int stg = 0;
   for (long row = row0; row < M; row += stride) {
     issue(row + (NSTG - 1) * stride, stg == 0 ? NSTG - 1 : stg - 1);
     cp_async_wait<NSTG - 1>();
-    float v[NV][8];
-    float s = 0.f;
+    uint64_t v[NV][4];
+    uint64_t s2 = f2_pack(0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int vi = lane + 32 * i;
@@ -110,34 +112,41 @@ ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gam
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const float2 f = unpack_bf16(w[k]);
-          v[i][2 * k] = f.x; v[i][2 * k + 1] = f.y;
-          s += f.x + f.y;
+          v[i][k] = f2_pack(f.x, f.y);
+          s2 = f2_add(s2, v[i][k]);
         }
       } else {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) v[i][k] = 0.f;
+        for (int k = 0; k < 4; ++k) v[i][k] = f2_pack(0.f, 0.f);
       }
     }
-    const float mu = warp_sum(s) / Ctot;
-    float ss = 0.f;
+    float s_lo, s_hi;
+    f2_unpack(s2, s_lo, s_hi);
+    const float mu = warp_sum(s_lo + s_hi) / Ctot;
+    const uint64_t nmu2 = f2_pack(-mu, -mu);
+    uint64_t ss2 = f2_pack(0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < NV; ++i)
       if (lane + 32 * i < nvec) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { const float d = v[i][k] - mu; ss += d * d; }
+        for (int k = 0; k < 4; ++k) { const uint64_t d = f2_add(v[i][k], nmu2); ss2 = f2_fma(d, d, ss2); }
       }
-    const float rs = rsqrtf(warp_sum(ss) / Ctot + eps);
+    float ss_lo, ss_hi;
+    f2_unpack(ss2, ss_lo, ss_hi);
+    const float rs = rsqrtf(warp_sum(ss_lo + ss_hi) / Ctot + eps);
     if (lane == 0) { mean[row] = mu; rstd[row] = rs; }
+    const uint64_t rs2 = f2_pack(rs, rs), nm2 = f2_pack(-mu * rs, -mu * rs);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int vi = lane + 32 * i;
       if (vi < nvec) {
-        const float nm = -mu * rs;
         uint32_t w[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          w[k] = pack_bf16(fmaf(fmaf(v[i][2 * k], rs, nm), gr[i][2 * k], br[i][2 * k]),
-                           fmaf(fmaf(v[i][2 * k + 1], rs, nm), gr[i][2 * k + 1], br[i][2 * k + 1]));
+        for (int k = 0; k < 4; ++k) {
+          float y0, y1;
+          f2_unpack(f2_fma(f2_fma(v[i][k], rs2, nm2), gr[i][k], br[i][k]), y0, y1);
+          w[k] = pack_bf16(y0, y1);
+        }
         *reinterpret_cast<uint4*>(y + row * Ctot + vi * 8) = make_uint4(w[0], w[1], w[2], w[3]);   // output rows are always dense
       }
     }
@@ -158,13 +167,14 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = Ctot >> 3;
   uint4* ring = s_ring4 + (size_t)warp * NSTG * NARR * nvec;
-  float a_dg[NV][8], a_db[NV][8], a_cs[COLSUM ? NV : 1][8];
+  // column accumulators and the row arithmetic are fp32 pairs (packed FADD2 / FMUL2 / FFMA2: two columns per issue slot)
+  uint64_t a_dg[NV][4], a_db[NV][4], a_cs[COLSUM ? NV : 1][4];
 #pragma unroll
   for (int i = 0; i < NV; ++i)
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      a_dg[i][k] = 0.f; a_db[i][k] = 0.f;
-      if (COLSUM) a_cs[i][k] = 0.f;
+    for (int k = 0; k < 4; ++k) {
+      a_dg[i][k] = f2_pack(0.f, 0.f); a_db[i][k] = f2_pack(0.f, 0.f);
+      if (COLSUM) a_cs[i][k] = f2_pack(0.f, 0.f);
     }
   constexpr bool has_res = RES;
   const long stride = (long)gridDim.x * LN_WARPS;
@@ -186,12 +196,13 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
   };
 #pragma unroll
   for (int s = 0; s < NSTG - 1; ++s) issue(row0 + s * stride, s);
-  float gmr[NV][8];                      // gamma of this lane's columns
+  uint64_t gmr[NV][4];                   // gamma of this lane's columns
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int vi = lane + 32 * i;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) gmr[i][k] = vi < nvec ? __ldg(gamma + vi * 8 + k) : 0.f;
+    for (int k = 0; k < 4; ++k)
+      gmr[i][k] = vi < nvec ? f2_pack(__ldg(gamma + vi * 8 + 2 * k), __ldg(gamma + vi * 8 + 2 * k + 1)) : f2_pack(0.f, 0.f);
   }
   int stg = 0;
   float n_mu = 0.f, n_rs = 0.f;
@@ -202,32 +213,36 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
     if (row + stride < M) { n_mu = mean[row + stride]; n_rs = rstd[row + stride]; }
     cp_async_wait<NSTG - 1>();
     const uint4* cur = ring + stg * NARR * nvec;
-    float s1 = 0.f, s2 = 0.f;
+    const uint64_t nmu2 = f2_pack(-mu, -mu), rs2 = f2_pack(rs, rs);
+    uint64_t s1p = f2_pack(0.f, 0.f), s2p = f2_pack(0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int vi = lane + 32 * i;
       if (vi < nvec) {
-        const float (&gm)[8] = gmr[i];
         const uint4 cd = cur[vi], cx = cur[nvec + vi];
         const uint32_t wd[4] = {cd.x, cd.y, cd.z, cd.w}, wx[4] = {cx.x, cx.y, cx.z, cx.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const float2 fd = unpack_bf16(wd[k]), fx = unpack_bf16(wx[k]);
-          const float h0 = (fx.x - mu) * rs, h1 = (fx.y - mu) * rs;
-          a_dg[i][2 * k] += fd.x * h0; a_dg[i][2 * k + 1] += fd.y * h1;
-          a_db[i][2 * k] += fd.x;      a_db[i][2 * k + 1] += fd.y;
-          const float q0 = fd.x * gm[2 * k], q1 = fd.y * gm[2 * k + 1];
-          s1 += q0 + q1;
-          s2 += q0 * h0 + q1 * h1;
+          const uint64_t d2 = f2_pack(fd.x, fd.y);
+          const uint64_t h = f2_mul(f2_add(f2_pack(fx.x, fx.y), nmu2), rs2);      // normalised input
+          a_dg[i][k] = f2_fma(d2, h, a_dg[i][k]);
+          a_db[i][k] = f2_add(a_db[i][k], d2);
+          const uint64_t q = f2_mul(d2, gmr[i][k]);
+          s1p = f2_add(s1p, q);
+          s2p = f2_fma(q, h, s2p);
         }
       }
     }
-    const float m1 = warp_sum(s1) / Ctot, m2 = warp_sum(s2) / Ctot;
+    float s1a, s1b, s2a, s2b;
+    f2_unpack(s1p, s1a, s1b);
+    f2_unpack(s2p, s2a, s2b);
+    const float m1 = warp_sum(s1a + s1b) / Ctot, m2 = warp_sum(s2a + s2b) / Ctot;
+    const uint64_t nm1 = f2_pack(-m1, -m1), nm2 = f2_pack(-m2, -m2);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int vi = lane + 32 * i;
       if (vi < nvec) {
-        const float (&gm)[8] = gmr[i];
         const uint4 cd = cur[vi], cx = cur[nvec + vi];
         const uint32_t wd[4] = {cd.x, cd.y, cd.z, cd.w}, wx[4] = {cx.x, cx.y, cx.z, cx.w};
         uint4 cr = make_uint4(0, 0, 0, 0);
@@ -237,16 +252,19 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const float2 fd = unpack_bf16(wd[k]), fx = unpack_bf16(wx[k]);
-          float o0 = rs * (fd.x * gm[2 * k] - m1 - (fx.x - mu) * rs * m2);
-          float o1 = rs * (fd.y * gm[2 * k + 1] - m1 - (fx.y - mu) * rs * m2);
+          const uint64_t h = f2_mul(f2_add(f2_pack(fx.x, fx.y), nmu2), rs2);
+          // rs * (dy * gamma - m1 - h * m2)
+          uint64_t o = f2_mul(rs2, f2_fma(h, nm2, f2_fma(f2_pack(fd.x, fd.y), gmr[i][k], nm1)));
           if (has_res) {
             const float2 fr = unpack_bf16(wr[k]);
-            o0 += fr.x; o1 += fr.y;
+            o = f2_add(o, f2_pack(fr.x, fr.y));
           }
+          float o0, o1;
+          f2_unpack(o, o0, o1);
           wo[k] = pack_bf16(o0, o1);
           if (COLSUM) {                      // sum what the consumer will read (bf16-rounded)
             const float2 fo = unpack_bf16(wo[k]);
-            a_cs[i][2 * k] += fo.x; a_cs[i][2 * k + 1] += fo.y;
+            a_cs[i][k] = f2_add(a_cs[i][k], f2_pack(fo.x, fo.y));
           }
         }
         *reinterpret_cast<uint4*>(row_ptr<PM>(dx, row, vi, Ctot, pg)) = make_uint4(wo[0], wo[1], wo[2], wo[3]);
@@ -256,14 +274,19 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
   }
   cp_async_wait<0>();
   // CTA-level column reduction, one quantity at a time through s_red[LN_WARPS][Ctot] (the ring is idle now)
-  auto flush = [&](float (&acc)[NV][8], float* out) {
+  auto flush = [&](uint64_t (&acc)[NV][4], float* out) {
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int vi = lane + 32 * i;
       if (vi < nvec) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) s_red[warp * Ctot + vi * 8 + k] = acc[i][k];
+        for (int k = 0; k < 4; ++k) {
+          float lo, hi;
+          f2_unpack(acc[i][k], lo, hi);
+          s_red[warp * Ctot + vi * 8 + 2 * k] = lo;
+          s_red[warp * Ctot + vi * 8 + 2 * k + 1] = hi;
+        }
       }
     }
     __syncthreads();
