@@ -201,14 +201,11 @@ def run_ours(args):
     if world > 1 and not flat_dp:
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True,
                                                         bucket_cap_mb=64, broadcast_buffers=False)
-    flat_grad, grad_views = None, None
+    flat = None
     if flat_dp:
-        for p_ in params:                                  # replicas start identical (DDP's constructor does the same)
-            dist.broadcast(p_.data, src=0)
-        sizes = [(p_.numel() + 3) // 4 * 4 for p_ in params]
-        flat_grad = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
-        offs = [sum(sizes[:i]) for i in range(len(sizes))]
-        grad_views = [flat_grad[o:o + p_.numel()].view_as(p_) for o, p_ in zip(offs, params)]
+        from stswincl_b200 import dist as sdist
+        sdist.broadcast_parameters(params)                 # replicas start identical (DDP's constructor does the same)
+        flat = sdist.FlatGradients(params)
     opt = torch.optim.Adam(model.parameters(), lr=3e-5, fused=True, capturable=True)
     B = args.clips
     g = torch.Generator(device=dev).manual_seed(1 + rank)
@@ -222,14 +219,13 @@ def run_ours(args):
         loss = torch.sum(y1 * g1, dtype=torch.float32) + torch.sum(y2 * g2, dtype=torch.float32)
         loss.backward()
         if flat_dp:                                        # gather the gradients into the all-reduce buffer
-            torch._foreach_copy_(grad_views, [p_.grad for p_ in params])
+            flat.gather()
         return loss
 
     def reduce_and_update():
         if flat_dp:                                        # the data-parallel exchange: one all-reduce over NVLink
-            dist.all_reduce(flat_grad, op=dist.ReduceOp.AVG)
-            for p_, v in zip(params, grad_views):
-                p_.grad = v
+            flat.all_reduce()
+            flat.bind()
         opt.step()
 
     def step(x):

@@ -61,6 +61,55 @@ def average_gradients(params: Iterable[torch.nn.Parameter], *, bucket_bytes: int
     return calls
 
 
+class FlatGradients:
+    """One flat fp32 buffer holding the gradients of ``params`` (each view 16-byte aligned), for a single
+    all-reduce per step instead of DDP's buckets -- the data-parallel exchange of ``bench.py --dp flat``:
+
+        loss.backward()            # may be replayed from a CUDA graph together with ``gather()``
+        flat.gather()              # copy every p.grad into the buffer (one multi-tensor copy)
+        flat.all_reduce()          # ONE collective (mean over ranks)
+        flat.bind()                # p.grad = view of the reduced buffer
+        optimizer.step()
+
+    Backend-agnostic (NCCL on GPUs, gloo in the CPU tests)."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter]):
+        self.params = [p for p in params if p.requires_grad]
+        sizes = [(p.numel() + 3) // 4 * 4 for p in self.params]
+        dev = self.params[0].device
+        self.buffer = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+        self.views, off = [], 0
+        for p, n in zip(self.params, sizes):
+            self.views.append(self.buffer[off:off + p.numel()].view_as(p))
+            off += n
+
+    def gather(self) -> None:
+        grads = [p.grad for p in self.params]
+        if any(g is None for g in grads):
+            raise RuntimeError("FlatGradients.gather: a parameter has no gradient")
+        torch._foreach_copy_(self.views, grads)
+
+    def all_reduce(self, group=None) -> None:
+        world = dist.get_world_size(group)
+        if world == 1:
+            return
+        if dist.get_backend(group) == "nccl":
+            dist.all_reduce(self.buffer, op=dist.ReduceOp.AVG, group=group)
+        else:                                   # gloo has no AVG
+            dist.all_reduce(self.buffer, op=dist.ReduceOp.SUM, group=group)
+            self.buffer.div_(world)
+
+    def bind(self) -> None:
+        for p, v in zip(self.params, self.views):
+            p.grad = v
+
+
+def broadcast_parameters(params: Iterable[torch.nn.Parameter], src: int = 0, group=None) -> None:
+    """Replicas start from rank ``src``'s parameters (what DDP's constructor does)."""
+    for p in params:
+        dist.broadcast(p.data, src=src, group=group)
+
+
 def gather_key_sets(tensors: Sequence[torch.Tensor], group=None) -> List[torch.Tensor]:
     """All-gather every tensor of ``tensors`` from all ranks; returns, per input tensor, the list of
     per-rank copies flattened into one list (own rank's copy first).  Building block of the

@@ -33,6 +33,17 @@ def _worker(rank, world, port, ret):
         ((model(data[idx]) - target[idx]) ** 2).mean().backward()
         sdist.average_gradients(model.parameters(), comm_dtype=torch.bfloat16)
         ok = ok and all(torch.allclose(p.grad, g, atol=2e-2, rtol=2e-2) for p, g in zip(model.parameters(), full))
+        # one flat buffer, one collective (bench.py --dp flat)
+        model.zero_grad()
+        ((model(data[idx]) - target[idx]) ** 2).mean().backward()
+        flat = sdist.FlatGradients(model.parameters())
+        flat.gather(); flat.all_reduce(); flat.bind()
+        ok = ok and all(torch.allclose(p.grad, g, atol=1e-6) for p, g in zip(model.parameters(), full))
+        ok = ok and all(p.grad.data_ptr() == v.data_ptr() and v.data_ptr() % 16 == 0 for p, v in zip(flat.params, flat.views))
+        with torch.no_grad():
+            list(model.parameters())[0].add_(float(rank))          # make the replicas differ, then re-synchronise
+        sdist.broadcast_parameters(model.parameters())
+        ok = ok and torch.equal(list(model.parameters())[0], ref[0])
         # gather: own copy first, then the others
         t = torch.full((2, 3), float(rank))
         got = sdist.gather_key_sets([t, t + 10])
