@@ -69,6 +69,7 @@ ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gam
   extern __shared__ uint4 s_ring4[];     // [LN_WARPS][NSTG][Ctot / 8]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = Ctot >> 3;
+  const float inv_c = 1.0f / Ctot;        // exact for the power-of-two widths of the model; a multiply per row instead of a division
   uint4* ring = s_ring4 + (size_t)warp * NSTG * nvec;
   const long stride = (long)gridDim.x * LN_WARPS;
   const long row0 = (long)blockIdx.x * LN_WARPS + warp;
@@ -122,7 +123,7 @@ ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gam
     }
     float s_lo, s_hi;
     f2_unpack(s2, s_lo, s_hi);
-    const float mu = warp_sum(s_lo + s_hi) / Ctot;
+    const float mu = warp_sum(s_lo + s_hi) * inv_c;
     const uint64_t nmu2 = f2_pack(-mu, -mu);
     uint64_t ss2 = f2_pack(0.f, 0.f);
 #pragma unroll
@@ -133,7 +134,7 @@ ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gam
       }
     float ss_lo, ss_hi;
     f2_unpack(ss2, ss_lo, ss_hi);
-    const float rs = rsqrtf(warp_sum(ss_lo + ss_hi) / Ctot + eps);
+    const float rs = rsqrtf(warp_sum(ss_lo + ss_hi) * inv_c + eps);
     if (lane == 0) { mean[row] = mu; rstd[row] = rs; }
     const uint64_t rs2 = f2_pack(rs, rs), nm2 = f2_pack(-mu * rs, -mu * rs);
 #pragma unroll
@@ -166,6 +167,7 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
   float* s_red = reinterpret_cast<float*>(s_ring4);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = Ctot >> 3;
+  const float inv_c = 1.0f / Ctot;        // exact for the power-of-two widths of the model; a multiply per row instead of a division
   uint4* ring = s_ring4 + (size_t)warp * NSTG * NARR * nvec;
   // column accumulators and the row arithmetic are fp32 pairs (packed FADD2 / FMUL2 / FFMA2: two columns per issue slot)
   uint64_t a_dg[NV][4], a_db[NV][4], a_cs[COLSUM ? NV : 1][4];
@@ -237,7 +239,7 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
     float s1a, s1b, s2a, s2b;
     f2_unpack(s1p, s1a, s1b);
     f2_unpack(s2p, s2a, s2b);
-    const float m1 = warp_sum(s1a + s1b) / Ctot, m2 = warp_sum(s2a + s2b) / Ctot;
+    const float m1 = warp_sum(s1a + s1b) * inv_c, m2 = warp_sum(s2a + s2b) * inv_c;
     const uint64_t nm1 = f2_pack(-m1, -m1), nm2 = f2_pack(-m2, -m2);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
