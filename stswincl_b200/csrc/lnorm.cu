@@ -27,20 +27,26 @@ struct PmGeom {        // PatchMerging gather geometry (pm == 0: plain rows)
   int H, W, C;         // source token grid and channel count; output row has 4*C channels
 };
 
-// pointer to the 8-element group `v` (0 .. Ctot/8) of logical row `row`
-template <bool PM, typename T>
-__device__ __forceinline__ T* row_ptr(T* base, long row, int v, int Ctot, const PmGeom& g) {
-  if (!PM) return base + row * Ctot + v * 8;
+// element (row, 8-element group v) lives at base + row_base(row) + group_off(v): the group offset does not depend on
+// the row, so each lane keeps its NV offsets in registers and a row costs two 32-bit divisions, not one per group
+template <bool PM>
+__device__ __forceinline__ long row_base(long row, int Ctot, const PmGeom& g) {
+  if (!PM) return row * Ctot;
   const int H2 = g.H >> 1, W2 = g.W >> 1;
-  const int per_img = H2 * W2;
-  const long bt = row / per_img;
-  const int rem = int(row - bt * per_img);
+  const unsigned per_img = H2 * W2;
+  const unsigned r32 = static_cast<unsigned>(row);      // gathered rows are counted in 32 bits (checked by the launcher)
+  const unsigned bt = r32 / per_img;
+  const int rem = int(r32 - bt * per_img);
   const int h2 = rem / W2, w2 = rem - h2 * W2;
+  return ((long(bt) * g.H + 2 * h2) * g.W + 2 * w2) * g.C;      // the 2x2 neighbourhood's top-left token
+}
+template <bool PM>
+__device__ __forceinline__ int group_off(int v, const PmGeom& g) {
+  if (!PM) return v * 8;
   const int ch = v * 8;
   const int seg = ch / g.C;                 // 0:(dh0,dw0) 1:(dh1,dw0) 2:(dh0,dw1) 3:(dh1,dw1)   (:266-270)
   const int dh = seg & 1, dw = seg >> 1;
-  const long tok = (bt * g.H + (2 * h2 + dh)) * g.W + (2 * w2 + dw);
-  return base + tok * g.C + (ch - seg * g.C);
+  return (dh * g.W + dw) * g.C + (ch - seg * g.C);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -73,12 +79,16 @@ ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gam
   uint4* ring = s_ring4 + (size_t)warp * NSTG * nvec;
   const long stride = (long)gridDim.x * LN_WARPS;
   const long row0 = (long)blockIdx.x * LN_WARPS + warp;
+  int goff[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) goff[i] = group_off<PM>(lane + 32 * i, pg);
   auto issue = [&](long row, int stg) {
     if (row < M) {
+      const __nv_bfloat16* src = x + row_base<PM>(row, Ctot, pg);
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         const int vi = lane + 32 * i;
-        if (vi < nvec) cp_async16(ring + stg * nvec + vi, row_ptr<PM>(x, row, vi, Ctot, pg));
+        if (vi < nvec) cp_async16(ring + stg * nvec + vi, src + goff[i]);
       }
     }
     cp_async_commit();
@@ -181,15 +191,21 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
   constexpr bool has_res = RES;
   const long stride = (long)gridDim.x * LN_WARPS;
   const long row0 = (long)blockIdx.x * LN_WARPS + warp;
+  int goff[PM ? NV : 1];                 // plain rows: the offset is vi * 8
+  if constexpr (PM) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) goff[i] = group_off<PM>(lane + 32 * i, pg);
+  }
   auto issue = [&](long row, int stg) {
     if (row < M) {
       uint4* d = ring + stg * NARR * nvec;
+      const __nv_bfloat16* xsrc = x + row_base<PM>(row, Ctot, pg);
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         const int vi = lane + 32 * i;
         if (vi < nvec) {
           cp_async16(d + vi, dy + row * Ctot + vi * 8);
-          cp_async16(d + nvec + vi, row_ptr<PM>(x, row, vi, Ctot, pg));
+          cp_async16(d + nvec + vi, xsrc + (PM ? goff[PM ? i : 0] : vi * 8));
           if (has_res) cp_async16(d + 2 * nvec + vi, dres + row * Ctot + vi * 8);
         }
       }
@@ -241,6 +257,7 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
     f2_unpack(s2p, s2a, s2b);
     const float m1 = warp_sum(s1a + s1b) * inv_c, m2 = warp_sum(s2a + s2b) * inv_c;
     const uint64_t nm1 = f2_pack(-m1, -m1), nm2 = f2_pack(-m2, -m2);
+    __nv_bfloat16* dx_row = dx + row_base<PM>(row, Ctot, pg);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int vi = lane + 32 * i;
@@ -269,7 +286,7 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
             a_cs[i][k] = f2_add(a_cs[i][k], f2_pack(fo.x, fo.y));
           }
         }
-        *reinterpret_cast<uint4*>(row_ptr<PM>(dx, row, vi, Ctot, pg)) = make_uint4(wo[0], wo[1], wo[2], wo[3]);
+        *reinterpret_cast<uint4*>(dx_row + (PM ? goff[PM ? i : 0] : vi * 8)) = make_uint4(wo[0], wo[1], wo[2], wo[3]);
       }
     }
     if (++stg == NSTG) stg = 0;
@@ -384,6 +401,7 @@ int check_ln_shape(long M, int Ctot, int pm, int H, int W, int C) {
 int layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, long M,
                   int Ctot, float eps, int pm, int H, int W, int C, cudaStream_t stream) {
   STSWIN_CHECK_ARG(x && gamma && beta && y && mean && rstd, "layernorm_fwd: null pointer");
+  STSWIN_CHECK_ARG(!pm || M < (1L << 31), "layernorm_fwd: more than 2^31 gathered rows");
   int rc = check_ln_shape(M, Ctot, pm, H, W, C);
   if (rc != kOk) return rc;
   PmGeom pg{pm, H, W, C};
@@ -419,6 +437,7 @@ int layernorm_bwd(const void* dy, const void* x, const float* mean, const float*
   STSWIN_CHECK_ARG(dy && x && mean && rstd && gamma && dx && dgamma && dbeta, "layernorm_bwd: null pointer");
   int rc = check_ln_shape(M, Ctot, pm, H, W, C);
   if (rc != kOk) return rc;
+  STSWIN_CHECK_ARG(!pm || M < (1L << 31), "layernorm_bwd: more than 2^31 gathered rows");
   STSWIN_CHECK_ARG(!(pm && dres), "layernorm_bwd: residual input is not supported together with the patch-merging scatter");
   PmGeom pg{pm, H, W, C};
   const int nv = (Ctot + 255) / 256;
