@@ -287,24 +287,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           uint32_t out2w[MODE == kBiasGelu ? 32 : 1];     // second output of the GELU mode (gelu'(u))
           // the 64 columns are processed as two halves of 32 (rolled, except in the two-output mode
           // whose second output has to stay in registers) to keep the code I-cache resident
-          auto do_half = [&](int half) {
-            uint32_t v[32];
-            tmem_ld32(t_row + c * 64 + half * 32, v);
-            float bv[32];                                // bias of the 32 columns (same for every row)
-            if (p.bias != nullptr) {
+          // bias of the chunk's 64 columns, requested before the TMEM loads so that its latency overlaps theirs
+          // (the first bias add was the top long-scoreboard stall of the epilogue); N is a multiple of 8, so a
+          // group of four columns is inside the matrix or entirely outside
+          float bias_r[2][32];
+          if (p.bias != nullptr) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const int n = cbase + half * 32 + 4 * j;
-                const float4 b4 = (n + 3 < p.N) ? __ldg(reinterpret_cast<const float4*>(p.bias + n))
-                                                : make_float4(n < p.N ? __ldg(p.bias + n) : 0.f,
-                                                              n + 1 < p.N ? __ldg(p.bias + n + 1) : 0.f,
-                                                              n + 2 < p.N ? __ldg(p.bias + n + 2) : 0.f, 0.f);
-                bv[4 * j] = b4.x; bv[4 * j + 1] = b4.y; bv[4 * j + 2] = b4.z; bv[4 * j + 3] = b4.w;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) bv[j] = 0.f;
+            for (int j = 0; j < 16; ++j) {
+              const int n = cbase + 4 * j;
+              const float4 b4 = n < p.N ? __ldg(reinterpret_cast<const float4*>(p.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+              bias_r[j >> 3][4 * (j & 7)] = b4.x; bias_r[j >> 3][4 * (j & 7) + 1] = b4.y;
+              bias_r[j >> 3][4 * (j & 7) + 2] = b4.z; bias_r[j >> 3][4 * (j & 7) + 3] = b4.w;
             }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { bias_r[0][j] = 0.f; bias_r[1][j] = 0.f; }
+          }
+          auto do_half = [&](int half, uint32_t (&v)[32], bool load_here) {
+            if (load_here) tmem_ld32(t_row + c * 64 + half * 32, v);
+            const float (&bv)[32] = bias_r[half];        // bias of the 32 columns (same for every row)
             uint32_t auxw[has_aux ? 16 : 1];             // this row's aux for the 32 columns of this half
             if constexpr (has_aux) {
 #pragma unroll
@@ -349,11 +350,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                   make_uint4(outw[4 * j], outw[4 * j + 1], outw[4 * j + 2], outw[4 * j + 3]);
           };
           if constexpr (MODE == kBiasGelu) {
-            do_half(0);
-            do_half(1);
+            uint32_t va[32];
+            do_half(0, va, true);
+            do_half(1, va, true);
           } else {
-#pragma unroll 1
-            for (int half = 0; half < 2; ++half) do_half(half);
+            // both TMEM loads of the chunk are issued before the first wait: the MMA warp was measured waiting for
+            // this accumulator (acc_empty) while the epilogue warps sat in tcgen05.wait::ld four times per tile
+            uint32_t va[32], vb[32];
+            tmem_ld32(t_row + c * 64, va);
+            tmem_ld32(t_row + c * 64 + 32, vb);
+            do_half(0, va, false);
+            do_half(1, vb, false);
           }
           store_staged(&tmD, my_buf, cbase);
           if (p.colsum != nullptr) {
