@@ -315,6 +315,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               }
             }
             tmem_ld_wait();
+            // the tile's last TMEM read of this warp has landed in registers: hand the accumulator back now (the MMA
+            // warp waits for it), not after the arithmetic, staging and stores of this chunk
+            if (c == BN / 128 - 1 && half == (MODE == kBiasGelu ? 1 : 0)) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive_cluster(mapa_u32(&acc_empty[acc], 0));   // the leader's MMA warp owns both accumulators
+            }
             uint32_t outw[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -395,10 +402,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           for (int c = 0; c < BN / 128; ++c) do_chunk(c, std::integral_constant<int, 0>{});
         }
       }
-      // all TMEM reads of this accumulator are done -> hand it back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(mapa_u32(&acc_empty[acc], 0));   // the leader's MMA warp owns both accumulators
+      if constexpr (MODE == kF32Reduce) {
+        // all TMEM reads of this accumulator are done -> hand it back to the MMA warp (the bf16 modes did so right
+        // after their last TMEM load)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(mapa_u32(&acc_empty[acc], 0));
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (lane == 0) tma_wait_group<0>();
