@@ -12,6 +12,9 @@ modules themselves, imported in the authoring container by
 ``oracle/make_goldens.py`` (which needs ``/root/reference``) and committed as
 fixtures under ``tests/golden/``.  ``tests/test_oracle_golden.py`` re-checks
 the restatement against those fixtures on every run, with no access to the
-reference tree.
+reference tree.  The training-step kernels (OHEM cross-entropy, LARS, key-encoder
+EMA) have their own restatement ``trainaux_oracle.py``, pinned the same way by
+``make_goldens_trainaux.py`` -> ``tests/golden/trainaux_cases.npz``
+(``tests/test_trainaux_oracle.py``).
 """
 from . import index_oracle, swin_oracle, loss_oracle  # noqa: F401
