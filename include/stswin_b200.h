@@ -134,31 +134,65 @@ int stswin_copy_strided(void* dst, int64_t dst_stride, const void* src, int64_t 
 
 /* ---------------------------------------------------------------------------------------------
  * Pixel-level contrastive loss (K7).  Replaces regression_loss / posMask / negMask of
- * pixcontrast_18/contrast/models/PixPro_swin_v5.py:48-129 and the F.normalize(dim=1) calls
- * feeding it (:330,362,400,432,463,494,526,557).
+ * pixcontrast_18/contrast/models/PixPro_swin_v5.py:48-129, the F.normalize(dim=1) calls feeding it
+ * (:330,362,400,432,463,494,526,557) and the tail of ConsistencyLoss.forward (:584-597: nearest
+ * down-sampling of the six label maps, two symmetric regression_loss calls sharing four key sets).
  *
- * stswin_pix_normalize : x [N,C,HW] (fp32 if x_is_f32 else bf16) -> xn [N,C,HW] bf16 =
- *     x / max(||x||_2 over C, 1e-12) when do_normalize, else a plain cast; inv_norm [N,HW] fp32
- *     (may be NULL); ksum [N,C] fp32 = per-channel sums of xn over pixels (may be NULL).
- * stswin_pixloss_fwd   : q, keys[s] [N,C,HW] bf16 (unit-norm pixel embeddings, channel-major as
- *     in the reference); lq, lk[s] [N,HW] u8 labels.  `keys` / `lk` are HOST arrays of n_sets
- *     device pointers, ordered (k, adj1, adj2, adj3, neg3) like the reference's arguments; any
- *     1 <= n_sets <= 64 is accepted (launched 8 sets at a time) (extra sets extend the positive pool and the negative sum).
- *     row_stats [N,HW,n_sets,4] fp32 workspace; loss: device scalar, overwritten with
- *     -mean log(e^P/(e^P+e^N)+1e-6); coef [N,HW,1+n_sets] fp32 (may be NULL when no gradient
- *     is needed): per-row dloss/dz coefficients for the backward.
- * stswin_pixloss_bwd   : dq32 [N,HW,C] fp32 (overwritten) = d_loss * dloss/dq, pixel-major;
- *     ksum [n_sets,N,C] fp32 are the per-channel key sums from stswin_pix_normalize;
- *     d_loss is a device scalar (the upstream gradient).  Keys receive no gradient (they are
- *     built under no_grad in the reference, :366).
+ * One loss STEP evaluates Q <= 2 "queries" (one regression_loss call each), every query against S <= 64
+ * key sets.  The embedding maps and label maps of a step live in SLOTS of caller-owned workspaces; host
+ * tables say which slot each query / key set uses, so a map shared by both queries is prepared once.
+ * With HW = H*W pixels per map, HWp = HW rounded up to 256, GLp = HWp/32 rounded up to 16:
+ *
+ *   xn         [slots, N, C, HW]   bf16  prepared maps: query maps in pixel order, key maps in LABEL order
+ *   inv_norm   [slots, N, HW]      fp32  1 / max(|x|, 1e-12) per pixel (pixel order)
+ *   ksum       [slots, N, C]       fp32  per-channel sums of a key map over its pixels
+ *   lab_nat    [lslots, N, HWp]    u8    labels in pixel order (255 = padding / out of range)
+ *   lab_sorted [lslots, N, HWp]    u8    labels in sorted (key) order
+ *   glab       [lslots, N, GLp]    u8    label of each group of 32 sorted keys (254 = mixed, 255 = padding)
+ *   perm       [lslots, N, HW]     u16   sorted position of pixel j (stable counting sort by label)
+ *   hist       [lslots, N, 256]    i32   pixels per label
+ *   ctl        [2]                 i32   [0] |= 1 when a label is outside [0, class_num) -- the loss is then
+ *                                        NaN (the reference's F.one_hot raises, :54-55); [1] finalize ticket
+ *
+ * stswin_pixloss_labels : label maps labels[i] ([N,1,Hs,Ws], dtypes[i]: 0 u8, 1 f32, 2 i64, 3 i32, 4 bf16,
+ *     5 f16; HOST arrays of n_labels device pointers / codes) -> slots slot_off.. of the label workspaces:
+ *     F.interpolate(mode='nearest') to H x W (:585-590), .long() (:54), range check, counting sort.
+ *     slot_off == 0 also clears ctl.  1 <= class_num <= 254; H*W a multiple of 8, <= 8192.
+ * stswin_pixloss_prepare: maps[i] ([N,C,HW], dtypes[i]: 0 bf16, 1 f32, 2 f16) -> slots slot_off.. of xn /
+ *     inv_norm / ksum: x / max(|x|_2 over C, 1e-12) when do_normalize (else a plain cast), stored in the
+ *     order of label slot label_slots[i] (key maps) or in pixel order (label_slots[i] = -1, query maps).
+ *     C a multiple of 64, <= 256.
+ * stswin_pixloss_fwd    : qmap/qlab [Q], kmap/klab [Q*S] (HOST int arrays): map slot and label slot of
+ *     every query and of its key sets, ordered (k, adj1, adj2, adj3, neg3, extra sets...) like the
+ *     reference's arguments (extra sets extend the positive pool and the negative sum).
+ *     stats [Q,N,HW,S,2,2] fp32 workspace; loss: device scalar = sum over queries of
+ *     -mean log(e^P/(e^P+e^N)+1e-6); loss_per_query [Q] or NULL; coef [Q,N,HW,1+S] fp32 (NULL when no
+ *     gradient is needed): per-row dloss/dz coefficients for the backward; partial: fp32 scratch of
+ *     Q*ceil(N*HW/256) elements; ticket = &ctl[1].
+ * stswin_pixloss_bwd    : dq_out[q] (HOST array of Q device pointers, [N,C,HW], out_dtype 0 bf16 / 1 f32 /
+ *     2 f16) = d_loss * dloss/d(query map q); with inv_norm != NULL through the Jacobian of the fused
+ *     normalisation.  dq32 [Q,N,HW,C] fp32 scratch; d_loss: device scalar (the upstream gradient).
+ *     Keys receive no gradient (they are built under no_grad in the reference, :366).
  */
-int stswin_pix_normalize(const void* x, int x_is_f32, void* xn, float* inv_norm, float* ksum,
-                         int N, int C, int HW, int do_normalize, void* stream);
-int stswin_pixloss_fwd(const void* q, const void* const* keys, const uint8_t* lq, const uint8_t* const* lk,
-                       int n_sets, int N, int C, int HW, float* row_stats, float* loss, float* coef, void* stream);
-int stswin_pixloss_bwd(const void* const* keys, const uint8_t* lq, const uint8_t* const* lk, const float* coef,
-                       const float* ksum, const float* d_loss, int n_sets, int N, int C, int HW, float* dq32,
-                       void* stream);
+int stswin_pixloss_labels(const void* const* labels, const int* dtypes, int n_labels, int slot_off,
+                          int N, int Hs, int Ws, int H, int W, int class_num,
+                          uint8_t* lab_nat, uint8_t* lab_sorted, uint8_t* glab, uint16_t* perm, int32_t* hist,
+                          int32_t* ctl, void* stream);
+int stswin_pixloss_prepare(const void* const* maps, const int* dtypes, const int* label_slots, int n_maps, int slot_off,
+                           int N, int C, int HW, int do_normalize, const uint16_t* perm,
+                           void* xn, float* inv_norm, float* ksum, void* stream);
+int stswin_pixloss_fwd(const void* xn, int n_slots, int n_label_slots,
+                       const uint8_t* lab_nat, const uint8_t* lab_sorted, const uint8_t* glab, const int32_t* hist,
+                       const int* qmap, const int* qlab, const int* kmap, const int* klab,
+                       int Q, int S, int N, int C, int HW,
+                       float* stats, float* loss, float* loss_per_query, float* coef,
+                       const int32_t* ctl, float* partial, uint32_t* ticket, void* stream);
+int stswin_pixloss_bwd(const void* xn, int n_slots, int n_label_slots,
+                       const uint8_t* lab_nat, const uint8_t* lab_sorted, const uint8_t* glab,
+                       const int* qmap, const int* qlab, const int* kmap, const int* klab,
+                       int Q, int S, int N, int C, int HW,
+                       const float* coef, const float* ksum, const float* d_loss, float* dq32,
+                       const float* inv_norm, void* const* dq_out, int out_dtype, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Training-step kernels either side of the two hot paths.

@@ -86,9 +86,10 @@ SIGNATURES = {
     "stswin_layernorm_bwd": ([_vp, _vp, _fp, _fp, _fp, _vp, _vp, _fp, _fp, _fp, _i64, _i, _i, _i, _i, _i, _vp], ctypes.c_int),
     "stswin_transpose": ([_vp, _i, _vp, _i, _i64, _i, _i, _vp], ctypes.c_int),
     "stswin_copy_strided": ([_vp, _i64, _vp, _i64, _i64, _i, _vp], ctypes.c_int),
-    "stswin_pix_normalize": ([_vp, _i, _vp, _fp, _fp, _i, _i, _i, _i, _vp], ctypes.c_int),
-    "stswin_pixloss_fwd": ([_vp, _vp, _vp, _vp, _i, _i, _i, _i, _fp, _fp, _fp, _vp], ctypes.c_int),
-    "stswin_pixloss_bwd": ([_vp, _vp, _vp, _fp, _fp, _fp, _i, _i, _i, _i, _fp, _vp], ctypes.c_int),
+    "stswin_pixloss_labels": ([_vp, _vp] + [_i] * 8 + [_vp] * 7, ctypes.c_int),
+    "stswin_pixloss_prepare": ([_vp, _vp, _vp] + [_i] * 6 + [_vp] * 5, ctypes.c_int),
+    "stswin_pixloss_fwd": ([_vp, _i, _i] + [_vp] * 8 + [_i] * 5 + [_vp] * 8, ctypes.c_int),
+    "stswin_pixloss_bwd": ([_vp, _i, _i] + [_vp] * 7 + [_i] * 5 + [_vp] * 6 + [_i, _vp], ctypes.c_int),
     "stswin_ohem_ws_bytes": ([], ctypes.c_int64),
     "stswin_ohem_ce_fwd": ([_vp, _i, _vp, _i, _i, _i64, _i, ctypes.c_float, _i64, _fp, _vp, _fp, _fp, _vp], ctypes.c_int),
     "stswin_ohem_ce_bwd": ([_vp, _i, _vp, _i, _i, _i64, _i, _fp, _fp, _fp, _vp, _vp], ctypes.c_int),
@@ -109,6 +110,13 @@ def load():
         if _lib is None:
             if not os.path.exists(LIB_PATH):
                 build()
+            elif _stale() and not os.environ.get("STSWIN_B200_LIB"):
+                # sources newer than the library: rebuild when a compiler is here, refuse otherwise -- never run a
+                # library that does not match csrc/ silently
+                if shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc"):
+                    build()
+                else:
+                    raise StswinError(f"{LIB_PATH} is older than its sources under {CSRC} and nvcc is not available")
             lib = ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_GLOBAL)
             for name, (argtypes, restype) in SIGNATURES.items():
                 fn = getattr(lib, name)

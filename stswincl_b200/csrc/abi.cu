@@ -5,7 +5,7 @@
 
 extern "C" {
 
-int stswin_abi_version(void) { return 2; }
+int stswin_abi_version(void) { return 3; }
 const char* stswin_last_error(void) { return stswin::last_error(); }
 int stswin_set_device(int device) {
   STSWIN_CUDA(cudaSetDevice(device));
@@ -55,18 +55,31 @@ int stswin_copy_strided(void* dst, int64_t dst_stride, const void* src, int64_t 
   return stswin::copy_strided(dst, dst_stride, src, src_stride, bytes, batches, static_cast<cudaStream_t>(stream));
 }
 
-int stswin_pix_normalize(const void* x, int x_is_f32, void* xn, float* inv_norm, float* ksum, int N, int C, int HW,
-                         int do_normalize, void* stream) {
-  return stswin::pix_normalize(x, x_is_f32, xn, inv_norm, ksum, N, C, HW, do_normalize, static_cast<cudaStream_t>(stream));
+int stswin_pixloss_labels(const void* const* labels, const int* dtypes, int n_labels, int slot_off, int N, int Hs, int Ws,
+                          int H, int W, int class_num, uint8_t* lab_nat, uint8_t* lab_sorted, uint8_t* glab, uint16_t* perm,
+                          int32_t* hist, int32_t* err_flag, void* stream) {
+  return stswin::pixloss_labels(labels, dtypes, n_labels, slot_off, N, Hs, Ws, H, W, class_num, lab_nat, lab_sorted, glab,
+                                perm, hist, err_flag, static_cast<cudaStream_t>(stream));
 }
-int stswin_pixloss_fwd(const void* q, const void* const* keys, const uint8_t* lq, const uint8_t* const* lk, int n_sets,
-                       int N, int C, int HW, float* row_stats, float* loss, float* coef, void* stream) {
-  return stswin::pixloss_fwd(q, keys, lq, lk, n_sets, N, C, HW, row_stats, loss, coef, static_cast<cudaStream_t>(stream));
+int stswin_pixloss_prepare(const void* const* maps, const int* dtypes, const int* label_slots, int n_maps, int slot_off,
+                           int N, int C, int HW, int do_normalize, const uint16_t* perm, void* xn, float* inv_norm,
+                           float* ksum, void* stream) {
+  return stswin::pixloss_prepare(maps, dtypes, label_slots, n_maps, slot_off, N, C, HW, do_normalize, perm, xn, inv_norm,
+                                 ksum, static_cast<cudaStream_t>(stream));
 }
-int stswin_pixloss_bwd(const void* const* keys, const uint8_t* lq, const uint8_t* const* lk, const float* coef,
-                       const float* ksum, const float* d_loss, int n_sets, int N, int C, int HW, float* dq32,
-                       void* stream) {
-  return stswin::pixloss_bwd(keys, lq, lk, coef, ksum, d_loss, n_sets, N, C, HW, dq32, static_cast<cudaStream_t>(stream));
+int stswin_pixloss_fwd(const void* xn, int n_slots, int n_label_slots, const uint8_t* lab_nat, const uint8_t* lab_sorted,
+                       const uint8_t* glab, const int32_t* hist, const int* qmap, const int* qlab, const int* kmap,
+                       const int* klab, int Q, int S, int N, int C, int HW, float* stats, float* loss, float* loss_per_query,
+                       float* coef, const int32_t* err_flag, float* partial, uint32_t* ticket, void* stream) {
+  return stswin::pixloss_fwd(xn, n_slots, n_label_slots, lab_nat, lab_sorted, glab, hist, qmap, qlab, kmap, klab, Q, S, N,
+                             C, HW, stats, loss, loss_per_query, coef, err_flag, partial, ticket, static_cast<cudaStream_t>(stream));
+}
+int stswin_pixloss_bwd(const void* xn, int n_slots, int n_label_slots, const uint8_t* lab_nat, const uint8_t* lab_sorted,
+                       const uint8_t* glab, const int* qmap, const int* qlab, const int* kmap, const int* klab, int Q,
+                       int S, int N, int C, int HW, const float* coef, const float* ksum, const float* d_loss, float* dq32,
+                       const float* inv_norm, void* const* dq_out, int out_dtype, void* stream) {
+  return stswin::pixloss_bwd(xn, n_slots, n_label_slots, lab_nat, lab_sorted, glab, qmap, qlab, kmap, klab, Q, S, N, C, HW,
+                             coef, ksum, d_loss, dq32, inv_norm, dq_out, out_dtype, static_cast<cudaStream_t>(stream));
 }
 
 int64_t stswin_ohem_ws_bytes(void) { return stswin::ohem_ws_bytes(); }

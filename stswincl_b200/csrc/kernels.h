@@ -24,13 +24,20 @@ int layernorm_bwd(const void* dy, const void* x, const float* mean, const float*
 int transpose_cvt(const void* in, int in_f32, void* out, int out_f32, long batch, int R, int Cc, cudaStream_t stream);
 int copy_strided(void* dst, long dst_stride, const void* src, long src_stride, long bytes, int batches, cudaStream_t stream);
 
-int pix_normalize(const void* x, int x_is_f32, void* xn, float* inv_norm, float* ksum, int N, int C, int HW,
-                  int do_normalize, cudaStream_t stream);
-int pixloss_fwd(const void* q, const void* const* keys, const uint8_t* lq, const uint8_t* const* lk, int n_sets, int N,
-                int C, int HW, float* row_stats, float* loss, float* coef, cudaStream_t stream);
-int pixloss_bwd(const void* const* keys, const uint8_t* lq, const uint8_t* const* lk, const float* coef,
-                const float* ksum, const float* d_loss, int n_sets, int N, int C, int HW, float* dq32,
-                cudaStream_t stream);
+int pixloss_labels(const void* const* labels, const int* dtypes, int n_labels, int slot_off, int N, int Hs, int Ws, int H,
+                   int W, int class_num, uint8_t* lab_nat, uint8_t* lab_sorted, uint8_t* glab, uint16_t* perm, int* hist,
+                   int* err_flag, cudaStream_t stream);
+int pixloss_prepare(const void* const* maps, const int* dtypes, const int* label_slots, int n_maps, int slot_off, int N,
+                    int C, int HW, int do_normalize, const uint16_t* perm, void* xn, float* inv_norm, float* ksum,
+                    cudaStream_t stream);
+int pixloss_fwd(const void* xn, int n_slots, int n_label_slots, const uint8_t* lab_nat, const uint8_t* lab_sorted,
+                const uint8_t* glab, const int* hist, const int* qmap, const int* qlab, const int* kmap, const int* klab,
+                int Q, int S, int N, int C, int HW, float* stats, float* loss, float* loss_per_query, float* coef, const int* err_flag,
+                float* partial, unsigned int* ticket, cudaStream_t stream);
+int pixloss_bwd(const void* xn, int n_slots, int n_label_slots, const uint8_t* lab_nat, const uint8_t* lab_sorted,
+                const uint8_t* glab, const int* qmap, const int* qlab, const int* kmap, const int* klab, int Q, int S,
+                int N, int C, int HW, const float* coef, const float* ksum, const float* d_loss, float* dq32,
+                const float* inv_norm, void* const* dq_out, int out_dtype, cudaStream_t stream);
 
 // training-step kernels around the hot paths (trainaux.cu)
 long ohem_ws_bytes();

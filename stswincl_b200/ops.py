@@ -16,7 +16,12 @@ EPI_BIAS, EPI_BIAS_RES, EPI_BIAS_GELU, EPI_MUL_AUX, EPI_F32_REDUCE, EPI_BIAS_GEL
 
 # ---------------------------------------------------------------------------------------------
 # launch accounting (bench.py): every C-ABI kernel launch is counted; with an EventProfiler
-# installed each launch is also bracketed by CUDA events on the launching stream.
+# installed each launch is also bracketed by CUDA events on the launching stream.  The counter and
+# the profiler are shared by every thread that calls into the library (autograd workers,
+# nn.DataParallel replica threads): both are only touched under ``_ACCT``.
+import threading
+
+_ACCT = threading.Lock()
 LAUNCHES = 0
 
 
@@ -30,7 +35,9 @@ class EventProfiler:
     def summary(self):
         torch.cuda.synchronize()
         out = {}
-        for fam, work, e0, e1 in self.records:
+        with _ACCT:
+            records = list(self.records)
+        for fam, work, e0, e1 in records:
             d = out.setdefault(fam, {"launches": 0, "ms": 0.0, "work": 0.0})
             d["launches"] += 1
             d["ms"] += e0.elapsed_time(e1)
@@ -43,26 +50,55 @@ _PROFILER: Optional["EventProfiler"] = None
 
 def set_profiler(p: Optional["EventProfiler"]) -> None:
     global _PROFILER
-    _PROFILER = p
+    with _ACCT:
+        _PROFILER = p
+
+
+def count_extra_launches(n: int) -> None:
+    """Kernels a C-ABI call launches beyond its first one (counted for bench.py's ``gpu_launches``)."""
+    global LAUNCHES
+    with _ACCT:
+        LAUNCHES += n
 
 
 class _launch:
+    """Context of one C-ABI call: makes the tensor's device current for the duration of the call -- on the torch side
+    (``torch.cuda.device``, restored on exit, so a call on a tensor of another GPU never changes the caller's current
+    device) and inside the library (``stswin_set_device``: a fresh autograd-worker / DataParallel replica thread has no
+    driver context bound yet, and tensor-map encoding is a driver call) -- counts the launch and, with a profiler
+    installed, brackets it with CUDA events on the launching stream."""
+
     def __init__(self, family: str, work: float, ref: torch.Tensor):
         self.family, self.work, self.ref = family, work, ref
 
     def __enter__(self):
         global LAUNCHES
-        LAUNCHES += 1
-        if _PROFILER is not None:
-            self.e0 = torch.cuda.Event(enable_timing=True)
-            self.e0.record(torch.cuda.current_stream(self.ref.device))
+        dev = self.ref.device
+        self.guard = torch.cuda.device(dev)
+        self.guard.__enter__()
+        try:
+            idx = dev.index if dev.index is not None else torch.cuda.current_device()
+            _lib.check(_lib.load().stswin_set_device(idx), "stswin_set_device")
+            with _ACCT:
+                LAUNCHES += 1
+                self.prof = _PROFILER
+            if self.prof is not None:
+                self.e0 = torch.cuda.Event(enable_timing=True)
+                self.e0.record(torch.cuda.current_stream(dev))
+        except BaseException:
+            self.guard.__exit__(None, None, None)
+            raise
         return self
 
     def __exit__(self, *exc):
-        if _PROFILER is not None and exc[0] is None:
-            e1 = torch.cuda.Event(enable_timing=True)
-            e1.record(torch.cuda.current_stream(self.ref.device))
-            _PROFILER.records.append((self.family, self.work, self.e0, e1))
+        try:
+            if self.prof is not None and exc[0] is None:
+                e1 = torch.cuda.Event(enable_timing=True)
+                e1.record(torch.cuda.current_stream(self.ref.device))
+                with _ACCT:
+                    self.prof.records.append((self.family, self.work, self.e0, e1))
+        finally:
+            self.guard.__exit__(*exc)
         return False
 
 
@@ -71,10 +107,7 @@ def _ptr(t: Optional[torch.Tensor]):
 
 
 def _stream(t: torch.Tensor):
-    """Current stream of the tensor's device; also binds this thread to that device inside the
-    library (autograd worker / DataParallel replica threads start without a current context)."""
-    idx = t.device.index if t.device.index is not None else torch.cuda.current_device()
-    _lib.check(_lib.load().stswin_set_device(idx), "stswin_set_device")
+    """Current stream of the tensor's device (call inside a ``_launch`` block)."""
     return torch.cuda.current_stream(t.device).cuda_stream
 
 

@@ -151,8 +151,107 @@ def test_out_of_range_label_raises_and_cpu_raises():
     from stswincl_b200._lib import StswinError
     labels, emb = mg.loss_case_inputs("l0", 1, 64, 8, 14, 12, None)
     bad = labels[2].clone(); bad[0, 0, 0, 0] = 12.0
-    with pytest.raises(RuntimeError):
-        contrast.regression_loss(*[e[:1].cuda() for e in emb], labels[0][:1].cuda(), labels[1][:1].cuda(), bad[:1].cuda(),
-                                 *[l[:1].cuda() for l in labels[3:]], 12)
+    args = [e[:1].cuda() for e in emb] + [labels[0][:1].cuda(), labels[1][:1].cuda(), bad[:1].cuda()] + [l[:1].cuda() for l in labels[3:]]
+    with pytest.raises(RuntimeError):                 # the reference's F.one_hot behaviour, on request (one host read)
+        contrast.regression_loss(*args, 12, validate_labels=True)
+    # default: checked on the device, no host synchronisation -- the loss is NaN
+    assert torch.isnan(contrast.regression_loss(*args, 12)).item()
     with pytest.raises(StswinError):
         contrast.regression_loss(*[e[:1] for e in emb], *[l[:1] for l in labels], 12)
+    with pytest.raises(StswinError):                  # labels live in one byte
+        contrast.regression_loss(*args, 255)
+
+
+@pytest.mark.parametrize("N,H,W,Hs,Ws,K,coarse,dtype", [
+    (2, 32, 56, 256, 448, 12, (4, 7), torch.float32), (3, 8, 14, 8, 14, 5, (8, 14), torch.uint8),
+    (1, 28, 28, 100, 150, 26, (5, 6), torch.int64), (2, 24, 40, 24, 40, 254, (24, 40), torch.float32)])
+def test_label_tables_exact(N, H, W, Hs, Ws, K, coarse, dtype):
+    """Device label pass (nearest down-sampling, .long(), stable counting sort, group labels, histograms) against
+    numpy -- integer work, exact."""
+    from oracle import index_oracle as ix, loss_oracle as lo
+    from stswincl_b200 import contrast
+    maps = lo.make_label_maps(111, 3, N, Hs, Ws, K, coarse=coarse)
+    nat, srt, glab, perm, hist, ctl = [t.cpu().numpy() for t in contrast.label_tables([m.to(dtype).cuda() for m in maps], H, W, K)]
+    HW, HWp = H * W, (H * W + 255) // 256 * 256
+    assert ctl[0] == 0
+    for li, m in enumerate(maps):
+        ref = ix.downsample_labels(m.numpy(), H, W).reshape(N, HW).astype(np.int64)
+        for n in range(N):
+            assert np.array_equal(nat[li, n, :HW], ref[n]) and (nat[li, n, HW:] == 255).all()
+            order = np.argsort(ref[n], kind="stable")
+            assert np.array_equal(srt[li, n, :HW], ref[n][order]) and (srt[li, n, HW:] == 255).all()
+            inv = np.empty(HW, dtype=np.int64); inv[order] = np.arange(HW)
+            assert np.array_equal(perm[li, n].astype(np.int64) & 0xffff, inv)
+            assert np.array_equal(hist[li, n], np.bincount(ref[n], minlength=256))
+            groups = srt[li, n].reshape(HWp // 32, 32)
+            want = np.where((groups == groups[:, :1]).all(1), groups[:, 0], 254)
+            assert np.array_equal(glab[li, n, :HWp // 32], want)
+
+
+@pytest.mark.parametrize("N,C,H,W,K,coarse", [(2, 256, 32, 56, 12, (4, 7)), (1, 64, 28, 28, 26, (28, 28)), (3, 128, 8, 16, 9, (2, 2))])
+def test_symmetric_tail_fused_normalize_vs_oracle(N, C, H, W, K, coarse):
+    """ConsistencyLoss tail (:584-597) as ONE fused step with F.normalize inside, against the oracle: full-resolution
+    label maps, raw (un-normalised) embeddings, gradients to both query maps.  coarse = (H, W) gives per-pixel random
+    labels: nearly every 32-key group is mixed (the per-element path of both kernels)."""
+    from oracle import loss_oracle as lo
+    from stswincl_b200 import contrast
+    full = lo.make_label_maps(121, 6, N, 8 * H, 8 * W, K, coarse=coarse)
+    ds = [torch.nn.functional.interpolate(m, size=[H, W], mode="nearest") for m in full]
+    gen = torch.Generator().manual_seed(122)
+    raw = [e * (0.5 + 2.0 * torch.rand(N, 1, H, W, generator=gen)) for e in lo.make_embeddings(123, ds + ds[:2], C, K)]
+    pred = [raw[6].clone().requires_grad_(True), raw[7].clone().requires_grad_(True)]
+    nrm = lo.l2_normalize
+    bf = lambda t: nrm(t).to(torch.bfloat16).float()
+    ref = lo.consistency_tail(nrm(pred[0]), nrm(pred[1]), bf(raw[0]), bf(raw[1]), [bf(r) for r in raw[2:6]], full[0], full[1], full[2:], K)
+    (2.0 * ref).backward()
+    c = lambda t: t.cuda()
+    p1, p2 = c(raw[6]).requires_grad_(True), c(raw[7]).requires_grad_(True)
+    loss = contrast.consistency_loss_tail(p1, p2, *[c(r) for r in raw[:6]], *[c(m) for m in full], K, normalize=True)
+    (2.0 * loss).backward()
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(ref)) < 3e-3 * abs(float(ref))
+    assert rel_err(p1.grad.cpu(), pred[0].grad) < TOL
+    assert rel_err(p2.grad.cpu(), pred[1].grad) < TOL
+
+
+def test_tail_is_cuda_graph_capturable_and_deterministic():
+    """No host synchronisation anywhere in the step: capture forward + backward once, replay on new data."""
+    from oracle import loss_oracle as lo
+    from stswincl_b200 import contrast
+    N, C, H, W, K = 2, 128, 16, 28, 12
+    def data(seed):
+        labels = lo.make_label_maps(seed, 6, N, H, W, K)
+        emb = lo.make_embeddings(seed + 1, labels + labels[:2], C, K)
+        return [e.cuda() for e in emb], [l.cuda() for l in labels]
+    emb, labels = data(131)
+    static_e = [e.clone() for e in emb]
+    static_l = [l.clone() for l in labels]
+    q1, q2 = static_e[6].requires_grad_(True), static_e[7].requires_grad_(True)
+    def step():
+        q1.grad = None; q2.grad = None
+        loss = contrast.consistency_loss_tail(q1, q2, *static_e[:6], *static_l, K)
+        loss.backward()
+        return loss
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        step()
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        out = step()
+    for seed in (131, 141):
+        emb, labels = data(seed)
+        with torch.no_grad():
+            for d, src in zip(static_e, emb): d.copy_(src)
+            for d, src in zip(static_l, labels): d.copy_(src)
+        g.replay()
+        got, g1 = float(out), q1.grad.clone()
+        g.replay()
+        assert float(out) == got                                   # bit-reproducible loss (the gradient sums use fp32 atomics)
+        assert rel_err(q1.grad, g1) < 1e-5
+        e1, e2 = emb[6].clone().requires_grad_(True), emb[7].clone().requires_grad_(True)
+        ref = contrast.consistency_loss_tail(e1, e2, *emb[:6], *labels, K)
+        ref.backward()
+        assert float(ref) == got
+        assert rel_err(g1, e1.grad) < 1e-5
