@@ -218,6 +218,7 @@ class _PixStepFn(torch.autograd.Function):
         ctx.plan = (qmap, qlab, kmap, klab, Q, S, N, C, HW, flops)
         ctx.q_meta = [(q.shape, q.dtype) for q in queries]
         ctx.mark_non_differentiable(loss_q, ctl)
+        ctx.set_materialize_grads(False)              # no zero-filled gradients for the two auxiliary outputs
         return loss, loss_q, ctl
 
     @staticmethod

@@ -304,29 +304,6 @@ __device__ __forceinline__ void bulk_load_1d(void* smem, const void* gptr, uint3
                "l"(reinterpret_cast<uint64_t>(gptr)), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
-// cluster-scope release / acquire on an mbarrier that orders GENERIC shared-memory writes of one CTA before the
-// tcgen05.mma the pair's leader issues on them (operands generated by threads, not by TMA)
-__device__ __forceinline__ void mbar_arrive_release_cluster(uint32_t bar_cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_acquire_cluster(uint64_t* bar, uint32_t parity) {
-  uint32_t spins = 0;
-  for (;;) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred P;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, P;\n\t"
-        "}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    if (ok) break;
-    if (++spins > STSWIN_SPIN_LIMIT) __trap();
-  }
-}
-
 // ----------------------------------------------------------------------------- clusters
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;

@@ -592,19 +592,23 @@ __global__ void __launch_bounds__(256) pixloss_finalize_kernel(const PixTable ta
     s_last = (done == gridDim.x * gridDim.y - 1);
   }
   __syncthreads();
-  if (s_last && threadIdx.x == 0) {
+  if (s_last && threadIdx.x < 32) {
     __threadfence();
     const bool bad = *p.err != 0;
     float total = 0.f;
     for (int qq = 0; qq < p.Q; ++qq) {
-      float t = 0.f;
-      for (unsigned int b = 0; b < gridDim.x; ++b) t += __ldcg(p.partial + qq * gridDim.x + b);
+      float t = 0.f;                                      // lane-strided partial sums, then a fixed shuffle tree
+      for (unsigned int b = threadIdx.x; b < gridDim.x; b += 32) t += __ldcg(p.partial + qq * gridDim.x + b);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
       t = bad ? __int_as_float(0x7fc00000) : t / (float)rows;     // out-of-range label: NaN (the reference raises)
-      if (p.loss_q != nullptr) p.loss_q[qq] = t;
+      if (threadIdx.x == 0 && p.loss_q != nullptr) p.loss_q[qq] = t;
       total += t;
     }
-    p.loss[0] = total;
-    *p.ticket = 0u;
+    if (threadIdx.x == 0) {
+      p.loss[0] = total;
+      *p.ticket = 0u;
+    }
   }
 }
 
@@ -707,7 +711,7 @@ pixloss_bwd_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
         mbar_wait(&acc_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         for (int kb = 0; kb < p.nkb; ++kb) {
-          mbar_wait_acquire_cluster(&gen_full[gb], gphase);
+          mbar_wait(&gen_full[gb], gphase);
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t aa = smem_u32(s_gen + gb * 16384), ba = smem_u32(s_b + stage * 16384);
@@ -772,7 +776,7 @@ pixloss_bwd_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
         }
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive_release_cluster(mapa_u32(&gen_full[gb], 0));
+        if (lane == 0) mbar_arrive_cluster(mapa_u32(&gen_full[gb], 0));
         if (++gb == PB_GEN) { gb = 0; gphase ^= 1; }
       }
       __syncwarp();
