@@ -1,23 +1,37 @@
 #!/usr/bin/env python
 """Headline benchmark: one training step of the STswinCL Swin head (the window-attention hot
-path, BASELINE.json north_star) on synthetic EndoVis18-shaped clips.
+path, BASELINE.json north_star) on synthetic EndoVis18-shaped clips, plus the pixel contrastive
+loss step (the second hot path) timed beside it.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                  [--config seg|cadis|finetune_sgd|pretrain]
 
-A step = forward + backward + optimizer step of ``SwinTransformerLayerv5`` (dim 512, 64x80
-tokens, 4 heads, 12 blocks + PatchMerging -- seg18/net/Ours/swin_512.py:280-327) over one batch
-of ``--clips`` clips x 4 frames of OS-8 features [clips, 4, 512, 64, 80] (configs[1] of
-BASELINE.json: batch 8, bf16, 1 B200).  frames/s counts input frames (clips x 4 per step).
+Default (``--config seg`` = configs[1] of BASELINE.json: batch 8, bf16, 1 B200): a step = forward +
+backward + optimizer step of ``SwinTransformerLayerv5`` (dim 512, 64x80 tokens, 4 heads, 12 blocks +
+PatchMerging -- seg18/net/Ours/swin_512.py:280-327) over one batch of ``--clips`` clips x 4 frames of
+OS-8 features [clips, 4, 512, 64, 80].  frames/s counts input frames (clips x 4 per step).
+The other configs are the remaining BASELINE.json configs at the same boundary:
+
+  cadis         configs[4]: the same head on CaDIS-shaped features (64x120 tokens), 4 clips per GPU
+  finetune_sgd  configs[2]: the fine-tune recipe of seg18/train_CL_ft_mswin_sgd_minput.py:147-165 (SGD momentum 0.9,
+                weight decay 1e-4, batch 4 per GPU) on the head
+  pretrain      configs[3]: the pre-training step of pixcontrast_18/main_pretrain_swinv5.py:150-185 on the head:
+                2 query passes (forward + backward) + key-encoder EMA + 6 no-grad key passes at 32x56 tokens, the fused
+                symmetric pixel contrastive loss (keys all-gathered across ranks when N > 1), LARS-SGD step
 
 Prints ONE JSON line (rank 0).  ``value`` has the inputs resident in HBM; ``e2e`` feeds the same
 module from pinned HOST buffers (H2D copy every step, loss read back every step).  ``roofline``
 is measured with CUDA events around every launch of the dominant kernel family during extra,
-separately timed steps; ``cpu_baseline`` is the CPU oracle (a port of the reference path, see
-oracle/) timed on this box's host cores on a bounded sample (N=1, rank 0 only).
+separately timed steps; ``pixloss`` is the symmetric two-call loss step of ConsistencyLoss.forward
+(PixPro_swin_v5.py:584-597) at the reference batch, replayed from CUDA graphs; ``cpu_baseline`` is the CPU
+oracle (a port of the reference path, see oracle/) timed on this box's host cores on a bounded sample (N=1,
+rank 0 only).
 
-``--impl reference`` times the reference's CPU path (the oracle port: the reference is pure
-Python/PyTorch with no compiled artefact to build; /root/reference does not exist on the GPU
-box) with all host threads and prints the same line with "impl": "reference".
+``--impl reference`` times the reference's CPU path with all host threads and prints the same line with
+"impl": "reference": the UNMODIFIED reference module when a copy of the reference tree is present
+(``baseline/_ref`` or $STSWIN_REFERENCE_ROOT; kind "reference"), otherwise the oracle port (kind "port":
+the reference is pure Python/PyTorch with no build or install step, and /root/reference does not exist
+on the GPU box).
 """
 from __future__ import annotations
 
@@ -28,14 +42,29 @@ import statistics
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "STswin-T train frames/s at 1/2/4/8 B200; window-attn TFLOP/s vs tensor peak"
-DIM, RES, HEADS, T = 512, (64, 80), 4, 4
+DIM, HEADS, T = 512, 4, 4
+CONFIGS = {
+    # name: (token grid, default clips per GPU, optimizer, description)
+    "seg": ((64, 80), 8, "adam",
+            "configs[1]: Swin head train step (SwinTransformerLayerv5 dim 512, 64x80 tokens, 4 heads; fwd+bwd+Adam) on "
+            "EndoVis18-shaped OS-8 features, bf16"),
+    "cadis": ((64, 120), 4, "adam",
+              "configs[4]: Swin head train step (SwinTransformerLayerv5 dim 512, 64x120 tokens, 4 heads; fwd+bwd+Adam) on "
+              "CaDIS-shaped (512x960 crop) OS-8 features, bf16"),
+    "finetune_sgd": ((64, 80), 4, "sgd",
+                     "configs[2]: multi-frame fine-tune recipe (train_CL_ft_mswin_sgd_minput.py:147-165: SGD momentum 0.9, "
+                     "weight decay 1e-4, batch 4 per GPU) on the Swin head, 64x80 tokens, bf16"),
+    "pretrain": ((32, 56), 4, "lars",
+                 "configs[3]: contrastive pre-training step on the Swin head at 32x56 tokens (main_pretrain_swinv5.py:150-185): "
+                 "2 query passes fwd+bwd, key-encoder EMA, 6 no-grad key passes, fused symmetric pixel contrastive loss "
+                 "(256 ch, 12 classes; shared key sets all-gathered across ranks when N > 1), LARS-SGD step; bf16"),
+}
 
 
 def parse():
@@ -44,13 +73,21 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--clips", type=int, default=8, help="clips per GPU per step (reference recipe: batch 8)")
+    ap.add_argument("--config", default="seg", choices=sorted(CONFIGS))
+    ap.add_argument("--clips", type=int, default=0, help="clips per GPU per step (default: the config's recipe)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pixloss", action="store_true", help="skip the pixel contrastive loss object")
     ap.add_argument("--no-graph", action="store_true", help="do not capture the step in a CUDA graph")
     ap.add_argument("--dp", default="flat", choices=["flat", "ddp"],
-                    help="N > 1: 'flat' = forward + backward replayed from a CUDA graph, ONE NCCL all-reduce (average) of the "
-                         "flattened fp32 gradients, optimizer step; 'ddp' = torch DistributedDataParallel, eager steps")
-    return ap.parse_args()
+                    help="N > 1: 'flat' = forward + backward replayed from CUDA graph segments whose gradient buckets are "
+                         "all-reduced (NCCL, average) on a side stream while the next segment runs, then the optimizer "
+                         "step; 'ddp' = torch DistributedDataParallel, eager steps")
+    ap.add_argument("--wire", default="bf16", choices=["fp32", "bf16"], help="--dp flat: dtype of the gradients on the wire")
+    ap.add_argument("--segments", type=int, default=4, help="--dp flat: graph segments of the backward (1 = one all-reduce)")
+    args = ap.parse_args()
+    if args.clips <= 0:
+        args.clips = CONFIGS[args.config][1]
+    return args
 
 
 def peaks():
@@ -67,7 +104,7 @@ class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index: int):
+    def __init__(self, index):
         self.index, self.proc, self.path = index, None, None
 
     def __enter__(self):
@@ -114,40 +151,79 @@ class ClockSampler:
         return out
 
 
+def workload_config(name, clips, graph=None, extra=None):
+    res = CONFIGS[name][0]
+    opt = {"adam": "multi-tensor Adam (stswin kernel; writes the bf16 shadow of the weights) on the 96.6M Swin-head parameters",
+           "sgd": "torch.optim.SGD(momentum 0.9, weight_decay 1e-4), foreach",
+           "lars": "stswincl_b200.optim.LARS(torch.optim.SGD(add_weight_decay(...), momentum 0.9)) -- fused LARS-SGD kernels"}
+    cfg = {"cuda_graph": graph, "workload": CONFIGS[name][3], "clips_per_gpu": clips, "frames_per_clip": T,
+           "feature_shape": [clips, T, DIM, res[0], res[1]], "optimizer": opt[CONFIGS[name][2]],
+           "l2": "inputs larger than L2 (%d MB of features per step, GBs of activations touched)"
+                 % (clips * T * DIM * res[0] * res[1] * 2 * (6 if name == "pretrain" else 1) // 2 ** 20)}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
 # ----------------------------------------------------------------------------------------------
-# CPU path (oracle port of the reference) -- cpu_baseline leg and --impl reference
+# CPU path -- cpu_baseline leg and --impl reference
 # ----------------------------------------------------------------------------------------------
-def cpu_step_factory():
+def _reference_root():
+    for cand in (os.environ.get("STSWIN_REFERENCE_ROOT"), os.path.join(ROOT, "baseline", "_ref")):
+        if cand and os.path.isfile(os.path.join(cand, "seg18", "net", "Ours", "swin_512.py")):
+            return cand
+    return None
+
+
+def cpu_step_factory(res):
+    """One clip (4 frames) of the config's workload, fp32, forward + backward on the host cores.
+    Returns (step, threads, kind, sample text)."""
     import torch
-    from oracle import swin_oracle as so          # checker / CPU baseline only (never on the product path)
     torch.set_num_threads(os.cpu_count() or 1)
-    params = so.make_layer_params(DIM, RES, HEADS, seed=0)
+    from oracle import swin_oracle as so          # checker / CPU baseline only (never on the product path)
+    x = so.make_features(1, 1, T, DIM, res[0], res[1])
+    g1 = so.make_features(2, 1, T, DIM, res[0], res[1]) - 0.4
+    g2 = so.make_features(3, 1, T, 2 * DIM, res[0] // 2, res[1] // 2) - 0.4
+    ref_root = _reference_root()
+    shape = "[1,4,%d,%d,%d]" % (DIM, res[0], res[1])
+    if ref_root is not None:
+        os.environ["STSWIN_REFERENCE_ROOT"] = ref_root
+        from oracle import ref_shims                  # arranges sys.path so the reference's own file imports unmodified
+        torch.manual_seed(0)
+        model = ref_shims.import_swin().SwinTransformerLayerv5(dim=DIM, input_resolution=res, num_heads=HEADS)
+
+        def step():
+            model.zero_grad(set_to_none=True)
+            y1, y2 = model(x)
+            loss = (y1 * g1).sum() + (y2 * g2).sum()
+            loss.backward()
+            return float(loss)
+
+        return step, torch.get_num_threads(), "reference", ("1 clip (4 frames) of the same workload %s, fp32, forward+backward, "
+                                                             "the unmodified reference module (%s)" % (shape, ref_root))
+    params = so.make_layer_params(DIM, res, HEADS, seed=0)
     leaf = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and not k.endswith("attn_mask") else v)
             for k, v in params.items()}
-    x = so.make_features(1, 1, T, DIM, RES[0], RES[1])
-    g1 = so.make_features(2, 1, T, DIM, RES[0], RES[1]) - 0.4
-    g2 = so.make_features(3, 1, T, 2 * DIM, RES[0] // 2, RES[1] // 2) - 0.4
 
     def step():
         for v in leaf.values():
             if v.is_floating_point() and v.requires_grad:
                 v.grad = None
-        y1, y2 = so.swin_layer_v5(x, leaf, DIM, RES, HEADS)
+        y1, y2 = so.swin_layer_v5(x, leaf, DIM, res, HEADS)
         loss = (y1 * g1).sum() + (y2 * g2).sum()
         loss.backward()
         return float(loss)
 
-    return step, torch.get_num_threads()
-
-
-SAMPLE = "1 clip (4 frames) of the same workload [1,4,512,64,80], fp32, forward+backward, oracle port of the reference"
+    return step, torch.get_num_threads(), "port", ("1 clip (4 frames) of the same workload %s, fp32, forward+backward, oracle "
+                                                   "port of the reference (no copy of the reference tree on this box)" % shape)
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    step, threads = cpu_step_factory()
+    res = CONFIGS[args.config][0]
+    step, threads, kind, sample = cpu_step_factory(res)
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
@@ -158,18 +234,82 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args.clips),
-            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port", "sample": SAMPLE},
+            # this arm steps ONE clip per step on the host cores (a bounded sample of the workload), normalised to frames/s
+            "config": workload_config(args.config, 1, extra={"optimizer": "none (forward + backward only)",
+                                                             "arm": "CPU, %s, %d threads" % (kind, threads)}),
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-def workload_config(clips, graph=None):
-    return {"cuda_graph": graph, "workload": "configs[1]: Swin head train step (SwinTransformerLayerv5 dim 512, 64x80 tokens, 4 heads; "
-                        "fwd+bwd+Adam) on EndoVis18-shaped OS-8 features, bf16",
-            "clips_per_gpu": clips, "frames_per_clip": T, "feature_shape": [clips, T, DIM, RES[0], RES[1]],
-            "optimizer": "torch.optim.Adam(fused=True) on the 96.6M Swin-head parameters",
-            "l2": "inputs larger than L2 (168 MB of features per step, >10 GB of activations touched)"}
+# ----------------------------------------------------------------------------------------------
+# pixel contrastive loss (HP-2): the symmetric two-call step of ConsistencyLoss.forward
+# ----------------------------------------------------------------------------------------------
+def bench_pixloss(dev, pk, timed, n=4, sets_in_rotation=3):
+    """N = 4 per GPU (main_pretrain_swinv5.py recipe), C 256, 32x56 = 1792 pixels, 5 key sets per call, 12 classes,
+    six full-resolution 256x448 label maps, fp32 projector outputs with F.normalize fused in: forward + backward of both
+    symmetric calls as one step, replayed from CUDA graphs.  `sets_in_rotation` independent input sets (each its own
+    captured graph) are replayed round-robin so the inputs of a step are not L2-resident from the previous one."""
+    import torch
+    from stswincl_b200 import contrast, ops
+    K, C, H, W = 12, 256, 32, 56
+    graphs = []
+    gen = torch.Generator(device=dev).manual_seed(7)
+    for _ in range(sets_in_rotation):
+        labels = [torch.randint(0, K, (n, 1, 4, 7), generator=gen, device=dev).float()
+                  .repeat_interleave(64, 2).repeat_interleave(64, 3).contiguous() for _ in range(6)]
+        emb = [torch.randn(n, C, H, W, generator=gen, device=dev) for _ in range(8)]
+        q1, q2 = emb[6].requires_grad_(True), emb[7].requires_grad_(True)
+
+        def step(q1=q1, q2=q2, emb=emb, labels=labels):
+            q1.grad = None; q2.grad = None
+            loss = contrast.consistency_loss_tail(q1, q2, *emb[:6], *labels, K, normalize=True)
+            loss.backward()
+            return loss
+
+        for _ in range(2):
+            step()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            step()
+        torch.cuda.current_stream().wait_stream(side)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            step()
+        graphs.append((g, step))
+    for g, _ in graphs:
+        g.replay()
+    ms = timed(lambda i: graphs[i % len(graphs)][0].replay(), 30)
+    l0 = ops.LAUNCHES
+    graphs[0][1]()
+    launches = ops.LAUNCHES - l0
+    prof = ops.EventProfiler()
+    for g, step in graphs[:2]:
+        g.replay()
+        ops.set_profiler(prof)
+        step()
+        ops.set_profiler(None)
+    fam = prof.summary()
+    dense = 2.0 * 2 * 5 * 2 * (H * W) ** 2 * C * n            # fwd + bwd, 2 queries x 5 key sets
+    in_bytes = 8 * n * C * H * W * 4
+    out = {"workload": "ConsistencyLoss.forward tail (PixPro_swin_v5.py:584-597): 2 symmetric regression_loss calls x 5 key sets, "
+                       "N=%d per GPU, C=256, 32x56 pixels, 12 classes, 6 label maps 256x448, fp32 inputs with F.normalize fused, "
+                       "forward + backward, CUDA-graph replay" % n,
+           "ms_per_step": ms, "dense_gflop": dense / 1e9, "tflops": dense / ms / 1e9, "peak_tflops": pk["tflops_burst"],
+           "frac_of_peak": dense / ms / 1e9 / pk["tflops_burst"], "bound": "tensor (dense form)",
+           "launches_per_step": launches, "host_syncs_per_step": 0, "graph": True,
+           "l2": "%d input sets in rotation (%d MB of inputs, > L2)" % (sets_in_rotation, sets_in_rotation * in_bytes // 2 ** 20),
+           "kernels": {}}
+    for k, v in fam.items():
+        d = {"ms": v["ms"] / v["launches"]}
+        if k in ("pixloss_fwd", "pixloss_bwd"):
+            d.update(tflops=v["work"] / v["ms"] / 1e9, frac_of_peak=v["work"] / v["ms"] / 1e9 / pk["tflops_burst"],
+                     note="includes the finalize / dq-finish kernel launched by the same C-ABI call")
+        else:
+            d.update(gbs=v["work"] / v["ms"] / 1e6, frac_of_hbm=v["work"] / v["ms"] / 1e6 / pk["hbm_gbs"])
+        out["kernels"][k] = d
+    return out
 
 
 # ----------------------------------------------------------------------------------------------
@@ -187,13 +327,21 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    from stswincl_b200 import ops, swin
+    from stswincl_b200 import contrast, ops, optim as soptim, swin
 
+    RES, _, opt_kind, _ = CONFIGS[args.config]
+    pretrain = args.config == "pretrain"
     torch.manual_seed(0)
     model = swin.SwinTransformerLayerv5(dim=DIM, input_resolution=RES, num_heads=HEADS).to(dev)
     for blk in model.modules():
         if isinstance(blk, swin.WindowAttention):       # sigma 0.02 init is nearly a no-op bias; use a visible one
             torch.nn.init.normal_(blk.relative_position_bias_table, std=0.5)
+    key_model = None
+    if pretrain:
+        key_model = swin.SwinTransformerLayerv5(dim=DIM, input_resolution=RES, num_heads=HEADS).to(dev)
+        key_model.load_state_dict(model.state_dict())
+        for p in key_model.parameters():
+            p.requires_grad_(False)
     net = model
     side = torch.cuda.Stream(device=dev)
     flat_dp = world > 1 and args.dp == "flat"
@@ -201,37 +349,45 @@ def run_ours(args):
     if world > 1 and not flat_dp:
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True,
                                                         bucket_cap_mb=64, broadcast_buffers=False)
-    flat = None
-    if flat_dp:
-        from stswincl_b200 import dist as sdist
+    from stswincl_b200 import dist as sdist
+    if world > 1:
         sdist.broadcast_parameters(params)                 # replicas start identical (DDP's constructor does the same)
-        flat = sdist.FlatGradients(params)
-    opt = torch.optim.Adam(model.parameters(), lr=3e-5, fused=True, capturable=True)
+    if opt_kind == "adam":
+        opt = soptim.FusedAdam(model.parameters(), lr=3e-5)
+    elif opt_kind == "sgd":
+        opt = torch.optim.SGD(model.parameters(), lr=1e-3, momentum=0.9, weight_decay=1e-4, foreach=True)
+    else:
+        opt = soptim.LARS(torch.optim.SGD(soptim.add_weight_decay(model, 1e-5), lr=sdist.scaled_lr(1.0, args.clips, world),
+                                          momentum=0.9))
     B = args.clips
     g = torch.Generator(device=dev).manual_seed(1 + rank)
-    x_dev = torch.relu(torch.randn(B, T, DIM, RES[0], RES[1], generator=g, device=dev)).to(torch.bfloat16)
-    g1 = (torch.randn(B, T, DIM, RES[0], RES[1], generator=g, device=dev) * 0.1).to(torch.bfloat16)
-    g2 = (torch.randn(B, T, 2 * DIM, RES[0] // 2, RES[1] // 2, generator=g, device=dev) * 0.1).to(torch.bfloat16)
+    n_seq = 6 if pretrain else 1
+    x_dev = torch.relu(torch.randn(n_seq * B, T, DIM, RES[0], RES[1], generator=g, device=dev)).to(torch.bfloat16)
+    if pretrain:
+        K = 12
+        masks = [torch.randint(0, K, (B, 1, 4, 7), generator=g, device=dev).float()
+                 .repeat_interleave(8 * RES[0] // 4, 2).repeat_interleave(8 * RES[1] // 7, 3).contiguous() for _ in range(6)]
+    else:
+        g1 = (torch.randn(B, T, DIM, RES[0], RES[1], generator=g, device=dev) * 0.1).to(torch.bfloat16)
+        g2 = (torch.randn(B, T, 2 * DIM, RES[0] // 2, RES[1] // 2, generator=g, device=dev) * 0.1).to(torch.bfloat16)
 
-    def fwd_bwd(x):
-        opt.zero_grad(set_to_none=True)
-        y1, y2 = net(x)
-        loss = torch.sum(y1 * g1, dtype=torch.float32) + torch.sum(y2 * g2, dtype=torch.float32)
-        loss.backward()
-        if flat_dp:                                        # gather the gradients into the all-reduce buffer
-            flat.gather()
-        return loss
+    def embed(y1):
+        # stand-in for the projection head (ResNet / ASPP / projector are the caller's side of the boundary): the first 256
+        # channels of the last frame's stage-1 output are the pixel embedding, un-normalised (F.normalize is fused in the loss)
+        return y1[:, -1, :256]
 
-    def reduce_and_update():
-        if flat_dp:                                        # the data-parallel exchange: one all-reduce over NVLink
-            flat.all_reduce()
-            flat.bind()
-        opt.step()
-
-    def step(x):
-        loss = fwd_bwd(x)
-        reduce_and_update()
-        return loss
+    def forward_loss(x):
+        if not pretrain:
+            y1, y2 = net(x)
+            return torch.sum(y1 * g1, dtype=torch.float32) + torch.sum(y2 * g2, dtype=torch.float32)
+        # PixPro.forward (PixPro_swin_v5.py:291-561) on the Swin head: two query passes, EMA, six no-grad key passes
+        y1, _ = net(x[:2 * B])
+        pred_1, pred_2 = embed(y1[:B]), embed(y1[B:])
+        with torch.no_grad():
+            soptim.momentum_update(list(model.parameters()), list(key_model.parameters()), 0.99)
+            k1, _ = key_model(x)
+            keys = [embed(k1[i * B:(i + 1) * B]) for i in range(6)]
+        return contrast.consistency_loss_tail(pred_1, pred_2, *keys, *masks, K, normalize=True, cross_rank_negatives=world > 1)
 
     def barrier():
         if world > 1:
@@ -251,21 +407,53 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms) / n
 
-    # ---- device-resident throughput
+    # ------------------------------------------------------------------------------------------
+    # the step.  1 GPU: forward + backward + optimizer, captured whole.  N GPUs (--dp flat): the backward is cut into
+    # `--segments` autograd segments, each captured as its own CUDA graph; after a segment's replay its gradient bucket
+    # (bf16 on the wire by default) is all-reduced on a side stream while the next segment runs, so only the last
+    # bucket's collective is exposed (sdist.SegmentedStep).
+    # ------------------------------------------------------------------------------------------
+    use_graph = not args.no_graph and not (pretrain and world > 1)      # NCCL all-gather inside the loss: eager
+    stepper = None
+    if flat_dp and not pretrain:
+        stepper = sdist.SegmentedStep(model, opt, lambda y: torch.sum(y[0] * g1, dtype=torch.float32) + torch.sum(y[1] * g2, dtype=torch.float32),
+                                      segments=max(1, args.segments), wire_dtype=torch.bfloat16 if args.wire == "bf16" else torch.float32,
+                                      use_graph=use_graph)
+    flat = sdist.FlatGradients(params) if (flat_dp and stepper is None) else None
+
+    def fwd_bwd(x):
+        opt.zero_grad(set_to_none=True)
+        loss = forward_loss(x)
+        loss.backward()
+        if flat is not None:
+            flat.gather()
+        return loss
+
+    def reduce_and_update():
+        if flat is not None:
+            flat.all_reduce()
+            flat.bind()
+        opt.step()
+
+    def step(x):
+        if stepper is not None:
+            return stepper.step(x)
+        loss = fwd_bwd(x)
+        reduce_and_update()
+        return loss
+
     for _ in range(args.warmup):
         step(x_dev)
     launches0 = ops.LAUNCHES
     step(x_dev)
     launches_per_step = ops.LAUNCHES - launches0
 
-    # The step has no host synchronisation and static shapes, so it is captured once into a CUDA graph and replayed:
-    # on one GPU the whole forward + backward + optimizer step; on N GPUs (--dp flat) forward + backward + the gather of
-    # the gradients into one flat buffer, followed -- outside the graph -- by one NCCL all-reduce and the optimizer step.
-    # torch DDP steps (--dp ddp) run eagerly: capturing them (DDP on a side stream, 11 eager iterations first) measured
-    # 1580 vs 1557 frames/s at 2 GPUs but the process then hangs in the NCCL teardown.
     graph, static_x, static_loss = None, None, None
-    captured = fwd_bwd if flat_dp else step
-    if (world == 1 or flat_dp) and not args.no_graph:
+    if stepper is not None:
+        graph = stepper if stepper.captured else None
+        static_x = x_dev
+    elif use_graph and (world == 1 or flat is not None):
+        captured = fwd_bwd if flat is not None else step
         try:
             static_x = x_dev.clone()
             side.wait_stream(torch.cuda.current_stream())
@@ -278,38 +466,42 @@ def run_ours(args):
             with torch.cuda.graph(graph):
                 static_loss = captured(static_x)
             graph.replay()
-            if flat_dp:
+            if flat is not None:
                 reduce_and_update()
             torch.cuda.synchronize()
         except Exception as e:                      # capture is an optimisation of the harness, not of the product
             print(f"bench.py: CUDA graph capture failed ({type(e).__name__}: {e}); timing eager steps", file=sys.stderr)
             graph = None
             torch.cuda.synchronize()
-        if flat_dp:          # every rank replays, or none does
+        if flat is not None:          # every rank replays, or none does
             ok = torch.tensor([1 if graph is not None else 0], device=dev)
             dist.all_reduce(ok, op=dist.ReduceOp.MIN)
             if int(ok) == 0:
                 graph = None
 
     def run_step(x):
+        if stepper is not None:
+            return stepper.step(x)
         if graph is None:
             return step(x)
         if x is not static_x:
             static_x.copy_(x, non_blocking=True)
         graph.replay()
-        if flat_dp:
+        if flat is not None:
             reduce_and_update()
         return static_loss
+
+    def cur_x():
+        return static_x if (graph is not None and stepper is None) else x_dev
 
     for _ in range(2):
         run_step(x_dev)
     # nvidia-smi is started by rank 0 only and well before the timed steps: its start-up (NVML initialisation over
-    # all GPUs of the box) stalls kernel launches of every process for ~0.1-0.2 s -- measured at 4 GPUs, where one
-    # sampler per rank starting inside the timed region cost the eager DDP steps 58 instead of 41 ms
+    # all GPUs of the box) stalls kernel launches of every process for ~0.1-0.2 s
     with ClockSampler(local if rank == 0 else None) as clk:
         for _ in range(12):
-            run_step(static_x if graph is not None else x_dev)
-        ms_step = timed(lambda i: run_step(static_x if graph is not None else x_dev), args.steps)
+            run_step(cur_x())
+        ms_step = timed(lambda i: run_step(cur_x()), args.steps)
     launches = launches_per_step * args.steps
     clocks = clk.summary()
 
@@ -344,25 +536,19 @@ def run_ours(args):
         e2e_step(i)
     ms_e2e = timed(e2e_step, args.steps)
 
-    # ---- roofline of the dominant kernel family: CUDA events around every launch (separate steps)
+    # ---- roofline of the dominant kernel family: CUDA events around every launch (separate, eager steps).  A replay of
+    # the captured step is queued in front of each, so the host stays ahead of the GPU and every event pair brackets its
+    # kernel back to back with its neighbours on a GPU as warm as in the timed region.
     pk = peaks()
-    # The profiled steps run eagerly.  A replay of the captured step (one launch for the host, a whole step of real
-    # work for the GPU) is queued in front of each, so the host stays ahead of the GPU and every event pair brackets
-    # its kernel back to back with its neighbours on a GPU as warm as in the timed region -- without the head start
-    # the short kernels' times include the host's launch gaps.
     prof = ops.EventProfiler()
     for _ in range(2):
-        if graph is not None:
-            graph.replay()
-        else:
-            step(x_dev)
+        run_step(cur_x())
         ops.set_profiler(prof)
         step(x_dev)
         ops.set_profiler(None)
     fam = prof.summary()
     total_ms = sum(v["ms"] for v in fam.values()) or 1.0
     shares = {k: round(v["ms"] / total_ms, 4) for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])}
-    dom = max(("gemm", "gemm_wgrad"), key=lambda k: fam.get(k, {"ms": 0})["ms"])
     gsum = {"ms": fam["gemm"]["ms"] + fam["gemm_wgrad"]["ms"], "work": fam["gemm"]["work"] + fam["gemm_wgrad"]["work"],
             "launches": fam["gemm"]["launches"] + fam["gemm_wgrad"]["launches"]}
     achieved = gsum["work"] / (gsum["ms"] * 1e-3) / 1e12
@@ -376,7 +562,7 @@ def run_ours(args):
                 "launches_timed": gsum["launches"], "avg_launch_ms": gsum["ms"] / gsum["launches"],
                 "share_of_step": round(gsum["ms"] / total_ms, 4), "family_time_shares": shares}
     # secondary, HBM-bound: the window-attention core kernels and the row-wise / layout kernels
-    for k in ("winattn_fwd", "winattn_bwd", "layernorm_fwd", "layernorm_bwd", "transpose", "copy"):
+    for k in ("winattn_fwd", "winattn_bwd", "layernorm_fwd", "layernorm_bwd", "transpose", "copy", "adam", "ema_update", "lars_sgd_step"):
         if k in fam:
             gbs = fam[k]["work"] / (fam[k]["ms"] * 1e-3) / 1e9
             roofline[k] = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
@@ -384,10 +570,10 @@ def run_ours(args):
 
     # ---- "window-attn TFLOP/s vs tensor peak" (second half of the metric): the WindowAttention module (qkv Linear +
     # shifted-window core + proj Linear, SURVEY 8d: 8C^2 + 4LC FLOPs per token forward, 2x that backward) at this
-    # workload's batch, stage-1 (C 512, 64x80, ws 8, shift 4) and stage-2 (C 1024, 32x40, ws 4, shift 2) geometry,
+    # workload's batch, stage-1 (C 512, ws 8, shift 4) and stage-2 (C 1024, ws 4, shift 2) geometry,
     # replayed from a CUDA graph and timed alone -> against the measured burst bf16 peak
     window_attn = None
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and not pretrain:
         window_attn = {}
         for name, dim, res, ws in (("stage1", DIM, RES, 8), ("stage2", 2 * DIM, (RES[0] // 2, RES[1] // 2), 4)):
             attn = swin.WindowAttention(dim, (ws, ws), HEADS).to(dev)
@@ -413,11 +599,11 @@ def run_ours(args):
                 for _ in range(3):
                     fn()
                 torch.cuda.synchronize()
-                side = torch.cuda.Stream(device=dev)
-                side.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(side):
+                side2 = torch.cuda.Stream(device=dev)
+                side2.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side2):
                     fn()
-                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.current_stream().wait_stream(side2)
                 gr = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(gr):
                     fn()
@@ -433,26 +619,36 @@ def run_ours(args):
                 "fwd_bwd_frac_of_peak": 3 * f_fwd / res_ms["fwd_bwd"] / 1e9 / pk["tflops_burst"]}
             del attn, xa, ga
 
+    pixloss = None
+    if rank == 0 and world == 1 and not args.no_pixloss:
+        pixloss = bench_pixloss(dev, pk, timed)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cstep, threads = cpu_step_factory()
+        cstep, threads, kind, sample = cpu_step_factory(RES)
         cstep()                                           # warm-up (page-in, thread pool)
         t0 = time.perf_counter(); cstep(); dt = time.perf_counter() - t0
-        cpu = {"value": T / dt, "unit": "frames/s", "cores": threads, "kind": "port", "sample": SAMPLE, "seconds": dt}
+        cpu = {"value": T / dt, "unit": "frames/s", "cores": threads, "kind": kind, "sample": sample, "seconds": dt}
 
     if rank == 0:
-        frames = B * T * world
+        frames = n_seq * B * T * world
+        if world == 1:
+            par = "single GPU"
+        elif stepper is not None:
+            par = "dp%d: %s" % (world, stepper.describe())
+        elif flat is not None:
+            par = "dp%d: one flat fp32 gradient all-reduce (NCCL, average) per step" % world
+        else:
+            par = "dp%d: torch DDP, bucketed all-reduce overlapped with backward" % world
         line = {"metric": METRIC, "value": frames / (ms_step * 1e-3), "unit": "frames/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": dict(workload_config(B, graph is not None),
-                               parallelism=("dp%d: %s" % (world, "one flat fp32 gradient all-reduce (NCCL, average) per step" if flat_dp
-                                                          else "torch DDP, bucketed all-reduce overlapped with backward")) if world > 1 else "single GPU"),
+                "config": dict(workload_config(args.config, B, graph is not None), parallelism=par),
                 "clocks": clocks,
                 "e2e": {"value": frames / (ms_e2e * 1e-3), "unit": "frames/s", "ms_per_step": ms_e2e,
                         "h2d_bytes_per_step": x_host.numel() * x_host.element_size(), "d2h_bytes_per_step": d2h_bytes},
-                "gpu_launches": launches, "roofline": roofline, "window_attn": window_attn, "cpu_baseline": cpu,
-                "clips_per_s": B * world / (ms_step * 1e-3)}
+                "gpu_launches": launches, "roofline": roofline, "window_attn": window_attn, "pixloss": pixloss,
+                "cpu_baseline": cpu, "clips_per_s": n_seq * B * world / (ms_step * 1e-3)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -126,6 +126,10 @@ int stswin_layernorm_bwd(const void* dy, const void* x, const float* mean, const
  * (swin_512.py:314,319,326). */
 int stswin_transpose(const void* in, int in_is_f32, void* out, int out_is_f32, int64_t batch, int R, int Cc, void* stream);
 
+/* out[c] += sum_r x[r, c] for a dense bf16 matrix x [R, C] (C a multiple of 8): the bias gradient of nn.Linear
+ * (proj.bias when WindowAttention runs stand-alone, swin_512.py:139; Mlp.fc2.bias, :22).  out is fp32 [C]. */
+int stswin_colsum(const void* x, float* out, int64_t R, int C, void* stream);
+
 /* Batched strided copy: dst[b*dst_stride + i] = src[b*src_stride + i] for i < bytes, b < batches (all in bytes;
  * pointers, strides and `bytes` multiples of 16).  Moves the frame slices of the middle Swin layer
  * (x[:, 1:3] in, cat([x[:, :1], y, x[:, 3:]]) out, swin_512.py:302-307) at copy bandwidth. */
@@ -239,6 +243,24 @@ int stswin_lars_sgd_step(void* const* params, void* const* grads, void* const* m
                          const uint8_t* first_step, int n_tensors, float lr, float momentum, float dampening,
                          int nesterov, float weight_decay, int lars, float trust_coef, float eps, double* norms_ws,
                          void* stream);
+
+/* Adam step over a list of tensors (the optimiser of seg18/train_swin.py: torch.optim.Adam, no amsgrad), emitting the
+ * bf16 copy of the updated weights that the Swin kernels consume (replaces the optimiser's own pass plus one cast
+ * kernel per weight tensor and step).  Per element, with t = *step after the increment this call performs:
+ *   g = grad_scale * grad + weight_decay * p;  m = m + (1 - beta1) (g - m);  v = beta2 v + (1 - beta2) g^2;
+ *   p -= lr / (1 - beta1^t) * m / (sqrt(v) / sqrt(1 - beta2^t) + eps);  shadow = bf16(p)
+ * params / exp_avg / exp_avg_sq: fp32; grads: fp32, or bf16 when grads_are_bf16 (gradients that arrive from a bf16
+ * all-reduce); shadows: bf16 or NULL (whole array or per tensor).  All tables are HOST arrays of n_tensors device
+ * pointers; step is a device float (the step count, kept on the device so that the call is graph-capturable). */
+int stswin_adam_step(void* const* params, const void* const* grads, void* const* exp_avg, void* const* exp_avg_sq,
+                     void* const* shadows, const int64_t* numels, int n_tensors, int grads_are_bf16, float lr, float beta1,
+                     float beta2, float eps, float weight_decay, float grad_scale, float* step, void* stream);
+
+/* dst[t] = cast(src[t]) over a list of fp32 tensors (HOST arrays of n_tensors device pointers / element counts):
+ * gathers the gradients a backward segment produced into the flat bucket of the data-parallel all-reduce (SURVEY.md
+ * section 8e, C1), rounding to bf16 when dst_is_bf16 (bytes on the wire halved) -- one launch per 48 tensors. */
+int stswin_gather_cast(void* const* dst, const void* const* src, const int64_t* numels, int n_tensors, int dst_is_bf16,
+                       void* stream);
 
 #ifdef __cplusplus
 }

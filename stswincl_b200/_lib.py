@@ -85,6 +85,7 @@ SIGNATURES = {
     "stswin_layernorm_fwd": ([_vp, _fp, _fp, _vp, _fp, _fp, _i64, _i, ctypes.c_float, _i, _i, _i, _i, _vp], ctypes.c_int),
     "stswin_layernorm_bwd": ([_vp, _vp, _fp, _fp, _fp, _vp, _vp, _fp, _fp, _fp, _i64, _i, _i, _i, _i, _i, _vp], ctypes.c_int),
     "stswin_transpose": ([_vp, _i, _vp, _i, _i64, _i, _i, _vp], ctypes.c_int),
+    "stswin_colsum": ([_vp, _vp, _i64, _i, _vp], ctypes.c_int),
     "stswin_copy_strided": ([_vp, _i64, _vp, _i64, _i64, _i, _vp], ctypes.c_int),
     "stswin_pixloss_labels": ([_vp, _vp] + [_i] * 8 + [_vp] * 7, ctypes.c_int),
     "stswin_pixloss_prepare": ([_vp, _vp, _vp] + [_i] * 6 + [_vp] * 5, ctypes.c_int),
@@ -96,6 +97,8 @@ SIGNATURES = {
     "stswin_ema_update": ([_vp, _vp, _vp, _i, ctypes.c_float, ctypes.c_float, _vp], ctypes.c_int),
     "stswin_lars_sgd_step": ([_vp, _vp, _vp, _vp, _vp, _i] + [ctypes.c_float] * 3 + [_i, ctypes.c_float, _i,
                              ctypes.c_float, ctypes.c_float, _vp, _vp], ctypes.c_int),
+    "stswin_adam_step": ([_vp] * 6 + [_i, _i] + [ctypes.c_float] * 6 + [_vp, _vp], ctypes.c_int),
+    "stswin_gather_cast": ([_vp, _vp, _vp, _i, _i, _vp], ctypes.c_int),
     "stswin_gemm_bf16": ([_vp, _i, _i64, _vp, _i, _i64, _vp, _i64, _vp, _vp, _i64, _fp, _fp, _i, _i, _i, _i, _i, _vp], ctypes.c_int),
 }
 

@@ -50,6 +50,9 @@ int stswin_transpose(const void* in, int in_is_f32, void* out, int out_is_f32, i
                      void* stream) {
   return stswin::transpose_cvt(in, in_is_f32, out, out_is_f32, batch, R, Cc, static_cast<cudaStream_t>(stream));
 }
+int stswin_colsum(const void* x, float* out, int64_t R, int C, void* stream) {
+  return stswin::colsum_bf16(x, out, R, C, static_cast<cudaStream_t>(stream));
+}
 int stswin_copy_strided(void* dst, int64_t dst_stride, const void* src, int64_t src_stride, int64_t bytes, int batches,
                         void* stream) {
   return stswin::copy_strided(dst, dst_stride, src, src_stride, bytes, batches, static_cast<cudaStream_t>(stream));
@@ -105,6 +108,18 @@ int stswin_lars_sgd_step(void* const* params, void* const* grads, void* const* m
                          void* stream) {
   return stswin::lars_sgd_step(params, grads, momentum_bufs, numels, first_step, n_tensors, lr, momentum, dampening,
                                nesterov, weight_decay, lars, trust_coef, eps, norms_ws, static_cast<cudaStream_t>(stream));
+}
+
+int stswin_adam_step(void* const* params, const void* const* grads, void* const* exp_avg, void* const* exp_avg_sq,
+                     void* const* shadows, const int64_t* numels, int n_tensors, int grads_are_bf16, float lr, float beta1,
+                     float beta2, float eps, float weight_decay, float grad_scale, float* step, void* stream) {
+  return stswin::adam_step(params, grads, exp_avg, exp_avg_sq, shadows, numels, n_tensors, grads_are_bf16, lr, beta1, beta2,
+                           eps, weight_decay, grad_scale, step, static_cast<cudaStream_t>(stream));
+}
+
+int stswin_gather_cast(void* const* dst, const void* const* src, const int64_t* numels, int n_tensors, int dst_is_bf16,
+                       void* stream) {
+  return stswin::gather_cast(dst, src, numels, n_tensors, dst_is_bf16, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -22,6 +22,7 @@ int layernorm_bwd(const void* dy, const void* x, const float* mean, const float*
                   const void* dres, void* dx, float* dgamma, float* dbeta, float* dx_colsum, long M, int Ctot, int pm,
                   int H, int W, int C, cudaStream_t stream);
 int transpose_cvt(const void* in, int in_f32, void* out, int out_f32, long batch, int R, int Cc, cudaStream_t stream);
+int colsum_bf16(const void* x, float* out, long R, int C, cudaStream_t stream);
 int copy_strided(void* dst, long dst_stride, const void* src, long src_stride, long bytes, int batches, cudaStream_t stream);
 
 int pixloss_labels(const void* const* labels, const int* dtypes, int n_labels, int slot_off, int N, int Hs, int Ws, int H,
@@ -50,5 +51,11 @@ int ema_update(void* const* k_params, const void* const* q_params, const int64_t
 int lars_sgd_step(void* const* params, void* const* grads, void* const* bufs, const int64_t* numels,
                   const uint8_t* first_step, int n_tensors, float lr, float momentum, float dampening, int nesterov,
                   float weight_decay, int lars, float trust_coef, float eps, double* norms_ws, cudaStream_t stream);
+
+int adam_step(void* const* params, const void* const* grads, void* const* exp_avg, void* const* exp_avg_sq,
+              void* const* shadows, const int64_t* numels, int n_tensors, int grads_are_bf16, float lr, float beta1,
+              float beta2, float eps, float weight_decay, float grad_scale, float* step, cudaStream_t stream);
+int gather_cast(void* const* dst, const void* const* src, const int64_t* numels, int n_tensors, int dst_is_bf16,
+                cudaStream_t stream);
 
 }  // namespace stswin

@@ -478,6 +478,36 @@ int layernorm_bwd(const void* dy, const void* x, const float* mean, const float*
 }
 
 // see include/stswin_b200.h : stswin_copy_strided
+// column sums of a bf16 matrix [R, C] (C a multiple of 8): a CTA owns a slab of rows, a thread one 16-byte column
+// group; fp32 partial sums leave through one atomic per column and CTA
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, long R,
+                                                           int C, int rows_per_cta) {
+  const int groups = C >> 3;                              // 16-byte groups per row
+  const int lanes_r = 256 / groups > 0 ? 256 / groups : 1; // rows walked in parallel by the CTA
+  __shared__ float s_acc[256][9];
+  const int g = threadIdx.x % groups, rsub = threadIdx.x / groups;
+  const long r0 = (long)blockIdx.x * rows_per_cta, r1 = r0 + rows_per_cta < R ? r0 + rows_per_cta : R;
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+#pragma unroll 4
+  for (long r = r0 + rsub; r < r1 && rsub < lanes_r; r += lanes_r) {
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(x + r * C + g * 8));
+    const float2 a = unpack_bf16(q.x), b = unpack_bf16(q.y), c = unpack_bf16(q.z), d = unpack_bf16(q.w);
+    acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y; acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s_acc[threadIdx.x][k] = acc[k];
+  __syncthreads();
+  if (rsub == 0) {                                         // one atomic per column and CTA
+    for (int rs = 1; rs < lanes_r; ++rs)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += s_acc[rs * groups + g][k];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) atomicAdd(out + g * 8 + k, acc[k]);
+  }
+}
+
 int copy_strided(void* dst, long dst_stride, const void* src, long src_stride, long bytes, int batches, cudaStream_t stream) {
   STSWIN_CHECK_ARG(dst && src && bytes > 0 && batches > 0, "copy_strided: bad argument");
   STSWIN_CHECK_ARG(batches <= 65535, "copy_strided: %d batches exceed gridDim.y", batches);
@@ -516,6 +546,19 @@ int transpose_cvt(const void* in, int in_f32, void* out, int out_f32, long batch
     transpose_kernel<__nv_bfloat16, float><<<grid, block, 0, stream>>>(static_cast<const __nv_bfloat16*>(in), static_cast<float*>(out), R, Cc);
   else
     transpose_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, block, 0, stream>>>(static_cast<const __nv_bfloat16*>(in), static_cast<__nv_bfloat16*>(out), R, Cc);
+  STSWIN_CUDA(cudaGetLastError());
+  return kOk;
+}
+
+int colsum_bf16(const void* x, float* out, long R, int C, cudaStream_t stream) {
+  STSWIN_CHECK_ARG(x && out && R > 0 && C > 0, "colsum: bad argument");
+  STSWIN_CHECK_ARG(C % 8 == 0 && C <= 2048, "colsum: C=%d must be a multiple of 8, <= 2048", C);
+  STSWIN_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0, "colsum: x must be 16-byte aligned");
+  int ctas = 4 * num_sms();
+  long rows_per_cta = (R + ctas - 1) / ctas;
+  if (rows_per_cta < 32) rows_per_cta = 32;
+  ctas = (int)((R + rows_per_cta - 1) / rows_per_cta);
+  colsum_bf16_kernel<<<ctas, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), out, R, C, (int)rows_per_cta);
   STSWIN_CUDA(cudaGetLastError());
   return kOk;
 }

@@ -225,6 +225,9 @@ __device__ __forceinline__ void prepare_body(const PrepArgs& p, const TI* __rest
   const int j0 = blockIdx.x * 64 + lane * 2;
   const bool ok = j0 < p.HW;                     // HW is even: both pixels or none
   const int slot = p.slot_off + z;
+  const int ls = p.lslot[z];
+  uint32_t pr = 0;                               // sorted positions of the two pixels (requested before the tile)
+  if (ls >= 0 && ok) pr = *reinterpret_cast<const uint32_t*>(p.perm + ((size_t)ls * p.N + n) * p.HW + j0);
   float2 v[CPW];
   float ss0 = 0.f, ss1 = 0.f;
 #pragma unroll
@@ -247,10 +250,8 @@ __device__ __forceinline__ void prepare_body(const PrepArgs& p, const TI* __rest
     if (warp == 0 && ok && p.inv_norm != nullptr)
       *reinterpret_cast<float2*>(p.inv_norm + ((size_t)slot * p.N + n) * p.HW + j0) = make_float2(inv0, inv1);
   }
-  const int ls = p.lslot[z];
   int d0 = j0, d1 = j0 + 1;
   if (ls >= 0 && ok) {
-    const uint32_t pr = *reinterpret_cast<const uint32_t*>(p.perm + ((size_t)ls * p.N + n) * p.HW + j0);
     d0 = pr & 0xffffu;
     d1 = pr >> 16;
   }
@@ -280,7 +281,7 @@ __device__ __forceinline__ void prepare_body(const PrepArgs& p, const TI* __rest
 }
 
 template <int CPW>
-__global__ void __launch_bounds__(256) pix_prepare_kernel(const PrepArgs p) {
+__global__ void __launch_bounds__(256, 3) pix_prepare_kernel(const PrepArgs p) {
   __shared__ float s_ss[8][64];
   const int z = blockIdx.z, n = blockIdx.y;
   const size_t off = (size_t)n * p.C * p.HW;

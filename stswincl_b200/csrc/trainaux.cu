@@ -2,12 +2,14 @@
 //   * OHEM cross-entropy        -- OhemCELoss2D, seg18/utils/losses.py:16-40
 //   * key-encoder momentum (EMA) update -- PixPro._momentum_update_key_encoder, PixPro_swin_v5.py:258-289
 //   * LARS-scaled SGD step      -- contrast/lars.py:109-152 (+ torch.optim.SGD it wraps)
+//   * Adam step + bf16 weight shadow -- torch.optim.Adam of seg18/train_swin.py
 // All three are HBM-bound element streams: 16-byte accesses, grids sized from the SM count or the
 // element count, no host synchronisation (every data-dependent decision is taken on the device).
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "common.cuh"
 #include "host_util.h"
 #include "kernels.h"
 
@@ -524,6 +526,121 @@ __global__ void __launch_bounds__(kThreads) lars_sgd_kernel(const __grid_constan
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Adam (torch.optim.Adam semantics, no amsgrad) as a multi-tensor stream that also emits the bf16 shadow of the
+// weights the Swin kernels consume: one pass instead of the optimizer's own pass plus one cast kernel per weight
+// and step.  The step count lives on the device (CUDA-graph capturable).
+constexpr int AD_MAX = 32;
+struct AdamArgs {
+  float* p[AD_MAX];
+  const void* g[AD_MAX];
+  float* m[AD_MAX];
+  float* v[AD_MAX];
+  __nv_bfloat16* shadow[AD_MAX];     // may be null per tensor
+  long numel[AD_MAX];
+  int block_start[AD_MAX + 1];
+  int n;
+  int grad_bf16;
+  float lr, beta1, beta2, eps, wd, grad_scale;
+  const float* step;                 // device scalar: the step being taken (>= 1)
+};
+
+__global__ void adam_tick_kernel(float* step) { *step += 1.0f; }
+
+__global__ void __launch_bounds__(kThreads) adam_kernel(const __grid_constant__ AdamArgs t) {
+  int lo = 0, hi = t.n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (t.block_start[mid] <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const int ti = lo;
+  float* __restrict__ p = t.p[ti];
+  float* __restrict__ m = t.m[ti];
+  float* __restrict__ v = t.v[ti];
+  __nv_bfloat16* __restrict__ sh = t.shadow[ti];
+  const long n = t.numel[ti];
+  const long base = (long)(blockIdx.x - t.block_start[ti]) * MT_CHUNK;
+  const long end = base + MT_CHUNK < n ? base + MT_CHUNK : n;
+  const float stepf = __ldg(t.step);
+  const float bc1 = 1.0f - powf(t.beta1, stepf), bc2 = 1.0f - powf(t.beta2, stepf);
+  const float step_size = t.lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
+  auto one = [&](float pv, float gv, float& mv, float& vv) -> float {
+    gv *= t.grad_scale;
+    if (t.wd != 0.f) gv = fmaf(t.wd, pv, gv);
+    mv = fmaf(gv - mv, 1.0f - t.beta1, mv);                    // lerp(m, g, 1 - beta1)
+    vv = fmaf(vv, t.beta2, (1.0f - t.beta2) * gv * gv);
+    const float denom = sqrtf(vv) * inv_sqrt_bc2 + t.eps;
+    return pv - step_size * (mv / denom);
+  };
+  const bool al = ((((uintptr_t)p | (uintptr_t)m | (uintptr_t)v | (uintptr_t)t.g[ti]) & 15) == 0) &&
+                  ((((uintptr_t)sh) & 7) == 0);
+  long i = base + threadIdx.x * 4;
+  if (al) {
+    const long end4 = base + ((end - base) & ~3L);
+#pragma unroll 2
+    for (; i < end4; i += kThreads * 4) {
+      float4 pv = *reinterpret_cast<const float4*>(p + i);
+      float4 mv = *reinterpret_cast<const float4*>(m + i);
+      float4 vv = *reinterpret_cast<const float4*>(v + i);
+      float4 gv;
+      if (t.grad_bf16) {
+        const uint2 raw = __ldg(reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(t.g[ti]) + i));
+        const float2 a = unpack_bf16(raw.x), b = unpack_bf16(raw.y);
+        gv = make_float4(a.x, a.y, b.x, b.y);
+      } else {
+        gv = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(t.g[ti]) + i));
+      }
+      pv.x = one(pv.x, gv.x, mv.x, vv.x);
+      pv.y = one(pv.y, gv.y, mv.y, vv.y);
+      pv.z = one(pv.z, gv.z, mv.z, vv.z);
+      pv.w = one(pv.w, gv.w, mv.w, vv.w);
+      *reinterpret_cast<float4*>(p + i) = pv;
+      *reinterpret_cast<float4*>(m + i) = mv;
+      *reinterpret_cast<float4*>(v + i) = vv;
+      if (sh != nullptr) *reinterpret_cast<uint2*>(sh + i) = make_uint2(pack_bf16(pv.x, pv.y), pack_bf16(pv.z, pv.w));
+    }
+    i = end4 + threadIdx.x;
+  } else {
+    i = base + threadIdx.x;
+  }
+  for (; i < end; i += kThreads) {
+    const float gv = t.grad_bf16 ? __bfloat162float(static_cast<const __nv_bfloat16*>(t.g[ti])[i])
+                                 : static_cast<const float*>(t.g[ti])[i];
+    float mv = m[i], vv = v[i];
+    const float pv = one(p[i], gv, mv, vv);
+    p[i] = pv; m[i] = mv; v[i] = vv;
+    if (sh != nullptr) sh[i] = __float2bfloat16_rn(pv);
+  }
+}
+
+// dst[t] = cast(src[t]) for a list of fp32 tensors: gathers the gradients of a backward segment into the flat
+// bucket a data-parallel all-reduce sends (bf16 on the wire, or fp32)
+__global__ void __launch_bounds__(kThreads) mt_gather_kernel(const __grid_constant__ MtArgs t, int to_bf16) {
+  const int ti = mt_find(t, blockIdx.x);
+  const float* __restrict__ src = static_cast<const float*>(t.b[ti]);
+  const long n = t.numel[ti];
+  const long base = (long)(blockIdx.x - t.block_start[ti]) * MT_CHUNK;
+  const long end = base + MT_CHUNK < n ? base + MT_CHUNK : n;
+  long i = base + threadIdx.x * 4;
+  const bool al = ((((uintptr_t)src) & 15) == 0) && ((((uintptr_t)t.a[ti]) & (to_bf16 ? 7 : 15)) == 0);
+  if (al) {
+    const long end4 = base + ((end - base) & ~3L);
+#pragma unroll 4
+    for (; i < end4; i += kThreads * 4) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(src + i));
+      if (to_bf16) *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(t.a[ti]) + i) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+      else *reinterpret_cast<float4*>(static_cast<float*>(t.a[ti]) + i) = v;
+    }
+    i = end4 + threadIdx.x;
+  } else {
+    i = base + threadIdx.x;
+  }
+  for (; i < end; i += kThreads) {
+    if (to_bf16) static_cast<__nv_bfloat16*>(t.a[ti])[i] = __float2bfloat16_rn(src[i]);
+    else static_cast<float*>(t.a[ti])[i] = src[i];
+  }
+}
+
 // fill MtArgs for tensors [t0, t0 + cnt); returns the number of blocks
 int mt_fill(MtArgs& m, void* const* a, void* const* b, void* const* c, const int64_t* numels, const uint8_t* flags, int t0,
             int cnt) {
@@ -627,6 +744,54 @@ int lars_sgd_step(void* const* params, void* const* grads, void* const* bufs, co
     if (blocks == 0) continue;
     if (lars) lars_norm_kernel<<<blocks, kThreads, 0, stream>>>(args, weight_decay, norms_ws + 2 * t0);
     lars_sgd_kernel<<<blocks, kThreads, 0, stream>>>(args, a, norms_ws ? norms_ws + 2 * t0 : nullptr);
+  }
+  STSWIN_CUDA(cudaGetLastError());
+  return kOk;
+}
+
+int adam_step(void* const* params, const void* const* grads, void* const* exp_avg, void* const* exp_avg_sq,
+              void* const* shadows, const int64_t* numels, int n_tensors, int grads_are_bf16, float lr, float beta1,
+              float beta2, float eps, float weight_decay, float grad_scale, float* step, cudaStream_t stream) {
+  STSWIN_CHECK_ARG(n_tensors >= 0 && (n_tensors == 0 || (params && grads && exp_avg && exp_avg_sq && numels)), "adam_step: null table");
+  STSWIN_CHECK_ARG(step != nullptr, "adam_step: null step counter");
+  STSWIN_CHECK_ARG(beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps >= 0.f, "adam_step: bad hyper-parameters");
+  if (n_tensors == 0) return kOk;
+  adam_tick_kernel<<<1, 1, 0, stream>>>(step);
+  for (int t0 = 0; t0 < n_tensors; t0 += AD_MAX) {
+    AdamArgs a;
+    const int cnt = n_tensors - t0 < AD_MAX ? n_tensors - t0 : AD_MAX;
+    int blocks = 0;
+    a.n = cnt;
+    for (int i = 0; i < cnt; ++i) {
+      STSWIN_CHECK_ARG(params[t0 + i] && grads[t0 + i] && exp_avg[t0 + i] && exp_avg_sq[t0 + i], "adam_step: null tensor %d", t0 + i);
+      a.p[i] = static_cast<float*>(params[t0 + i]);
+      a.g[i] = grads[t0 + i];
+      a.m[i] = static_cast<float*>(exp_avg[t0 + i]);
+      a.v[i] = static_cast<float*>(exp_avg_sq[t0 + i]);
+      a.shadow[i] = shadows ? static_cast<__nv_bfloat16*>(shadows[t0 + i]) : nullptr;
+      a.numel[i] = numels[t0 + i];
+      a.block_start[i] = blocks;
+      blocks += (int)((numels[t0 + i] + MT_CHUNK - 1) / MT_CHUNK);
+    }
+    a.block_start[cnt] = blocks;
+    a.grad_bf16 = grads_are_bf16; a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.wd = weight_decay;
+    a.grad_scale = grad_scale; a.step = step;
+    if (blocks == 0) continue;
+    adam_kernel<<<blocks, kThreads, 0, stream>>>(a);
+  }
+  STSWIN_CUDA(cudaGetLastError());
+  return kOk;
+}
+
+int gather_cast(void* const* dst, const void* const* src, const int64_t* numels, int n_tensors, int dst_is_bf16,
+                cudaStream_t stream) {
+  STSWIN_CHECK_ARG(n_tensors >= 0 && (n_tensors == 0 || (dst && src && numels)), "gather_cast: null table");
+  for (int t0 = 0; t0 < n_tensors; t0 += MT_MAX) {
+    MtArgs args;
+    const int cnt = n_tensors - t0 < MT_MAX ? n_tensors - t0 : MT_MAX;
+    const int blocks = mt_fill(args, dst, const_cast<void* const*>(src), nullptr, numels, nullptr, t0, cnt);
+    if (blocks == 0) continue;
+    mt_gather_kernel<<<blocks, kThreads, 0, stream>>>(args, dst_is_bf16);
   }
   STSWIN_CUDA(cudaGetLastError());
   return kOk;

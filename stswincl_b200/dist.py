@@ -104,6 +104,195 @@ class FlatGradients:
             p.grad = v
 
 
+class SegmentedStep:
+    """Data-parallel training step whose gradient exchange overlaps the backward.
+
+    ``model.stages(x)`` gives the forward as a chain of stages (``SwinTransformerLayerv5.stages``).  The autograd graph
+    is cut at the stage boundaries, so the backward runs stage by stage, last stage first; as soon as a stage's
+    backward is done its gradients are copied (and rounded to ``wire_dtype``) into that stage's flat bucket and the
+    bucket is all-reduced (average) on a side stream while the earlier stages' backward still runs.  Only the first
+    stage's bucket -- the smallest one for the Swin head -- is exposed.  The forward and every backward segment are
+    captured as CUDA graphs sharing one memory pool and replayed in order (``use_graph``); the collectives and the
+    optimizer step are issued between / after the replays.
+
+    The optimizer step reads the reduced gradients straight from the buckets when the optimizer accepts
+    ``step(grads=...)`` (``optim.FusedAdam``: fp32 or bf16 gradients); otherwise they are copied back into
+    ``p.grad`` first.  Backend-agnostic (NCCL on GPUs, gloo in the CPU tests; there ``use_graph=False``)."""
+
+    def __init__(self, model, optimizer, loss_fn, *, segments: int = 4, wire_dtype: torch.dtype = torch.bfloat16,
+                 use_graph: bool = True, group=None, example_input: Optional[torch.Tensor] = None):
+        self.model, self.opt, self.loss_fn, self.group = model, optimizer, loss_fn, group
+        self.wire_dtype = wire_dtype
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.nccl = self.world > 1 and dist.get_backend(group) == "nccl"
+        self.segments = max(1, segments)
+        self.use_graph = use_graph
+        self.captured = False
+        self._built = False
+        self._static_x = None
+        if example_input is not None:
+            self._build(example_input)
+
+    # ---- construction
+    def _build(self, x):
+        stages = self.model.stages(x)
+        K = min(self.segments, len(stages))
+        # merge neighbouring stages, keeping the LAST stages separate (their backward runs first, their buckets are the
+        # large ones for the Swin head) -- e.g. 4 stages in 2 segments: [0,1,2] + [3]
+        groups = [[] for _ in range(K)]
+        n = len(stages)
+        for i in range(n):
+            groups[max(0, K - (n - i))].append(i)
+        self._stage_fns = [[stages[i][0] for i in g] for g in groups]
+        self._stage_params = [[p for i in g for p in stages[i][1] if p.requires_grad] for g in groups]
+        dev = x.device
+        self._buckets, self._views = [], []
+        for ps in self._stage_params:
+            sizes = [(p.numel() + 7) // 8 * 8 for p in ps]
+            buf = torch.zeros(sum(sizes), dtype=self.wire_dtype, device=dev)
+            views, off = [], 0
+            for p, sz in zip(ps, sizes):
+                views.append(buf[off:off + p.numel()].view_as(p))
+                off += sz
+            self._buckets.append(buf)
+            self._views.append(views)
+        self._view_of = {id(p): v for ps, vs in zip(self._stage_params, self._views) for p, v in zip(ps, vs)}
+        self._direct = hasattr(self.opt, "step") and "grads" in getattr(self.opt.step, "__code__", type("c", (), {"co_varnames": ()})).co_varnames
+        self._opt_grads = [self._view_of[id(p)] for g in self.opt.param_groups for p in g["params"] if p.requires_grad]
+        self._cuda = dev.type == "cuda"
+        if self._cuda:
+            self._comm = torch.cuda.Stream(device=dev)
+            self._events = [torch.cuda.Event() for _ in self._buckets]
+        self._built = True
+
+    def describe(self) -> str:
+        sizes = ", ".join("%.0f MB" % (b.numel() * b.element_size() / 2 ** 20) for b in reversed(self._buckets))
+        return ("backward in %d %s, one %s gradient bucket per segment (%s) all-reduced (average) on a side stream while the "
+                "next segment's backward runs" % (len(self._buckets), "CUDA-graph segments" if self.captured else "eager segments",
+                                                  str(self.wire_dtype).replace("torch.", ""), sizes))
+
+    # ---- one step, segment by segment
+    def _forward(self, x):
+        self._ins, self._outs = [], []
+        state = (x,)
+        for k, fns in enumerate(self._stage_fns):
+            ins = tuple(s if k == 0 else s.detach().requires_grad_(True) for s in state)
+            state = ins
+            for fn in fns:
+                state = fn(*state)
+            self._ins.append(ins)
+            self._outs.append(state)
+        self._loss = self.loss_fn(state)
+        return self._loss
+
+    def _backward_segment(self, k):
+        if k == len(self._stage_fns) - 1:
+            self._loss.backward()
+        else:
+            pairs = [(o, i.grad) for o, i in zip(self._outs[k], self._ins[k + 1]) if i.grad is not None]
+            torch.autograd.backward([o for o, _ in pairs], [g for _, g in pairs])
+        ps = self._stage_params[k]
+        if ps:
+            grads = [p.grad for p in ps]
+            if self._cuda and all(g.dtype == torch.float32 and g.is_contiguous() for g in grads) and \
+                    self.wire_dtype in (torch.float32, torch.bfloat16):
+                from . import ops
+                ops.gather_cast(self._views[k], grads)           # one multi-tensor launch per 48 tensors
+            else:
+                torch._foreach_copy_(self._views[k], grads)
+
+    def _reduce(self, k):
+        if self.world == 1 or self._buckets[k].numel() == 0:
+            return
+        buf = self._buckets[k]
+        if self._cuda:
+            self._events[k].record(torch.cuda.current_stream(buf.device))
+            with torch.cuda.stream(self._comm):
+                self._comm.wait_event(self._events[k])
+                self._all_reduce(buf)
+        else:
+            self._all_reduce(buf)
+
+    def _all_reduce(self, buf):
+        if self.nccl:
+            dist.all_reduce(buf, op=dist.ReduceOp.AVG, group=self.group)
+        else:
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
+            buf.div_(self.world)
+
+    def _update(self):
+        if self._cuda and self.world > 1:
+            torch.cuda.current_stream().wait_stream(self._comm)
+        if self._direct:
+            self.opt.step(grads=self._opt_grads)
+        else:
+            ps = [p for st in self._stage_params for p in st]
+            torch._foreach_copy_([p.grad for p in ps], [self._view_of[id(p)] for p in ps])
+            self.opt.step()
+
+    def _eager(self, x):
+        self.opt.zero_grad(set_to_none=True)
+        loss = self._forward(x)
+        for k in reversed(range(len(self._stage_fns))):
+            self._backward_segment(k)
+            self._reduce(k)
+        self._update()
+        return loss
+
+    def _capture(self, x):
+        dev = x.device
+        self._static_x = x.clone()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self._eager(self._static_x)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.opt.zero_grad(set_to_none=True)
+        self._g_fwd = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._g_fwd):
+            self._forward(self._static_x)
+        pool = self._g_fwd.pool()
+        self._g_bwd = {}
+        for k in reversed(range(len(self._stage_fns))):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=pool):
+                self._backward_segment(k)
+            self._g_bwd[k] = g
+        self.captured = True
+
+    def step(self, x):
+        """One training step on ``x``; returns the (device) loss."""
+        if not self._built:
+            self._build(x)
+        if not (self.use_graph and self._cuda):
+            return self._eager(x)
+        if not self.captured:
+            try:
+                self._capture(x)
+            except Exception as e:                 # capture is an optimisation; every rank must agree (checked below)
+                import sys
+                print(f"SegmentedStep: CUDA graph capture failed ({type(e).__name__}: {e}); running eager segments", file=sys.stderr)
+                self.use_graph = False
+                torch.cuda.synchronize()
+            if self.world > 1:
+                ok = torch.tensor([1 if self.captured else 0], device=x.device)
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+                if int(ok) == 0:
+                    self.captured, self.use_graph = False, False
+            if not self.captured:
+                return self._eager(x)
+        if x is not self._static_x:
+            self._static_x.copy_(x, non_blocking=True)
+        self._g_fwd.replay()
+        for k in reversed(range(len(self._stage_fns))):
+            self._g_bwd[k].replay()
+            self._reduce(k)
+        self._update()
+        return self._loss
+
+
 def broadcast_parameters(params: Iterable[torch.nn.Parameter], src: int = 0, group=None) -> None:
     """Replicas start from rank ``src``'s parameters (what DDP's constructor does)."""
     for p in params:

@@ -292,3 +292,32 @@ def copy_frames(dst: torch.Tensor, src: torch.Tensor) -> None:
         st = _lib.load().stswin_copy_strided(dst.data_ptr(), ds, src.data_ptr(), ss, inner, b, _stream(dst))
     _lib.check(st, "stswin_copy_strided")
 
+
+
+def colsum(x: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """out[c] += sum_r x[r, c] for bf16 x [R, C] (bias gradient of a Linear whose output gradient is x);
+    ``out`` fp32 [C], accumulated into (stswin_colsum)."""
+    _req(x, torch.bfloat16, "x"); _req(out, torch.float32, "out")
+    assert x.dim() == 2 and x.is_contiguous() and out.numel() == x.shape[1] and out.is_contiguous()
+    with _launch("colsum", float(x.numel() * 2), x):
+        st = _lib.load().stswin_colsum(x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1], _stream(x))
+    _lib.check(st, "stswin_colsum")
+    return out
+
+
+def gather_cast(dst, src) -> None:
+    """dst[i].copy_(src[i]) for lists of contiguous CUDA tensors, src fp32, dst fp32 or bf16 (all the same), as
+    multi-tensor launches (stswin_gather_cast): the gradient gather of ``dist.SegmentedStep``."""
+    import ctypes
+    assert len(dst) == len(src) and len(dst) > 0
+    to_bf16 = dst[0].dtype == torch.bfloat16
+    for d, s in zip(dst, src):
+        _req(s, torch.float32, "src"); _req(d, torch.bfloat16 if to_bf16 else torch.float32, "dst")
+        assert d.numel() == s.numel() and d.is_contiguous() and s.is_contiguous()
+    n = len(dst)
+    with _launch("gather_cast", float(sum(s.numel() for s in src) * (4 + dst[0].element_size())), dst[0]):
+        st = _lib.load().stswin_gather_cast((ctypes.c_void_p * n)(*[d.data_ptr() for d in dst]),
+                                            (ctypes.c_void_p * n)(*[s.data_ptr() for s in src]),
+                                            (ctypes.c_int64 * n)(*[s.numel() for s in src]), n, int(to_bf16), _stream(dst[0]))
+    _lib.check(st, "stswin_gather_cast")
+    count_extra_launches((n + 47) // 48 - 1)

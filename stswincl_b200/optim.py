@@ -23,22 +23,18 @@ from torch.optim.optimizer import Optimizer
 from . import _lib, ops
 from ._lib import StswinError
 
-__all__ = ["LARS", "add_weight_decay", "momentum_update"]
+__all__ = ["LARS", "FusedAdam", "add_weight_decay", "momentum_update", "bf16_weight"]
 
 
 def add_weight_decay(model, weight_decay=1e-5, skip_list=()):
-    """Split parameters into a no-decay group (1-D tensors: biases, norms; flagged ``ignore`` for LARS) and a
-    decay group (``lars.py:7-32``)."""
-    decay, no_decay = [], []
+    """The two parameter groups of ``lars.py:7-32``: vectors (biases, norm scales) and anything named in ``skip_list``
+    get no weight decay and are exempt from LARS scaling (``ignore``); every other trainable tensor decays."""
+    groups = {True: [], False: []}
     for name, param in model.named_parameters():
-        if not param.requires_grad:
-            continue
-        if len(param.shape) == 1 or name in skip_list:
-            no_decay.append(param)
-        else:
-            decay.append(param)
-    return [{'params': no_decay, 'weight_decay': 0, 'ignore': True},
-            {'params': decay, 'weight_decay': weight_decay, 'ignore': False}]
+        if param.requires_grad:
+            groups[param.dim() == 1 or name in skip_list].append(param)
+    return [dict(params=groups[True], weight_decay=0, ignore=True),
+            dict(params=groups[False], weight_decay=weight_decay, ignore=False)]
 
 
 def _check_f32(tensors: Iterable[torch.Tensor], what: str) -> None:
@@ -165,4 +161,92 @@ class LARS(Optimizer):
                                               float(group['weight_decay']), int(lars), float(self.trust_coef), float(self.eps),
                                               norms.data_ptr() if norms is not None else None, ops._stream(params[0]))
             _lib.check(st, "stswin_lars_sgd_step")
+        return loss
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# bf16 shadow of the weights
+# ---------------------------------------------------------------------------------------------------------------
+def bf16_weight(w: torch.Tensor) -> torch.Tensor:
+    """The bf16 copy of a weight the GEMM kernels consume.  ``FusedAdam`` keeps a shadow copy per parameter that its
+    update kernel rewrites every step, so the forward needs no cast kernel; the shadow is valid as long as nobody else
+    wrote the parameter (tracked by the tensor's version counter -- the kernel does not bump it).  Without a valid
+    shadow this is ``w.to(bfloat16)``."""
+    sh = getattr(w, "_stswin_shadow", None)
+    if sh is not None:
+        if sh[1] == w._version and sh[0].device == w.device:
+            return sh[0]
+        with torch.no_grad():                       # someone else updated the parameter: refresh
+            sh[0].copy_(w)
+        w._stswin_shadow = (sh[0], w._version)
+        return sh[0]
+    return w.to(torch.bfloat16)
+
+
+class FusedAdam(Optimizer):
+    """``torch.optim.Adam`` semantics (the optimiser of ``seg18/train_swin.py``; no amsgrad / maximize) as multi-tensor
+    launches of ``stswin_adam_step``: 32 tensors per launch, step count on the device (CUDA-graph capturable), and the
+    bf16 shadow of every >= 2-D weight written in the same pass (``bf16_weight``).  State keys ``exp_avg`` /
+    ``exp_avg_sq`` as in torch; the step count is one device scalar per group (``group['step_t']``).
+
+    ``step(grads=...)`` takes the gradients from a list (fp32 or bf16, one per parameter with a gradient) instead of
+    ``p.grad`` -- the bf16 bucket views of a data-parallel all-reduce (``dist.SegmentedStep``)."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, shadow: bool = True):
+        if lr < 0 or eps < 0 or not (0 <= betas[0] < 1) or not (0 <= betas[1] < 1) or weight_decay < 0:
+            raise ValueError("FusedAdam: invalid hyper-parameter")
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self.shadow = shadow
+
+    def _state(self, p):
+        st = self.state[p]
+        if not st:
+            st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+            st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+            if self.shadow and p.dim() >= 2:
+                p._stswin_shadow = (p.detach().to(torch.bfloat16), p._version)
+        return st
+
+    @torch.no_grad()
+    def step(self, closure=None, grads=None, grad_scale: float = 1.0):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        lib = _lib.load()
+        gi = 0
+        for group in self.param_groups:
+            if grads is None:
+                params = [p for p in group["params"] if p.grad is not None]
+                gl = [p.grad for p in params]
+            else:
+                params = [p for p in group["params"] if p.requires_grad]
+                gl = list(grads[gi:gi + len(params)])
+                gi += len(params)
+            if not params:
+                continue
+            _check_f32(params, "FusedAdam.step")
+            gdt = gl[0].dtype
+            if gdt not in (torch.float32, torch.bfloat16) or any(g.dtype != gdt or not g.is_contiguous() or not g.is_cuda for g in gl):
+                raise StswinError("FusedAdam.step: gradients must be contiguous CUDA tensors, all fp32 or all bf16")
+            states = [self._state(p) for p in params]
+            if "step_t" not in group:
+                group["step_t"] = torch.zeros((), dtype=torch.float32, device=params[0].device)
+            shadows = []
+            for p in params:
+                sh = getattr(p, "_stswin_shadow", None)
+                if sh is not None and sh[1] != p._version:       # stale shadow: the kernel rewrites it anyway
+                    p._stswin_shadow = sh = (sh[0], p._version)
+                shadows.append(sh[0].data_ptr() if sh is not None else None)
+            n_bytes = sum(p.numel() for p in params) * (28 + gl[0].element_size() - 4 + 2)
+            b1, b2 = group["betas"]
+            with ops._launch("adam", float(n_bytes), params[0]):
+                st = lib.stswin_adam_step(_ptrs(params), _ptrs(gl), _ptrs([s["exp_avg"] for s in states]),
+                                          _ptrs([s["exp_avg_sq"] for s in states]),
+                                          (ctypes.c_void_p * len(shadows))(*shadows), _numels(params), len(params),
+                                          int(gdt == torch.bfloat16), float(group["lr"]), float(b1), float(b2), float(group["eps"]),
+                                          float(group["weight_decay"]), float(grad_scale), group["step_t"].data_ptr(),
+                                          ops._stream(params[0]))
+            _lib.check(st, "stswin_adam_step")
+            ops.count_extra_launches((len(params) + 31) // 32)
         return loss

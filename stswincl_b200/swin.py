@@ -28,6 +28,7 @@ import torch.nn as nn
 
 from . import ops
 from ._lib import StswinError
+from .optim import bf16_weight as _w16
 
 _BF16 = torch.bfloat16
 
@@ -91,7 +92,7 @@ class _AttentionFn(torch.autograd.Function):
         H, W, nH, ws, shift, qk_scale = geom
         Bp, T, L, C = x.shape
         x2 = x.reshape(-1, C)
-        wq, wp = w_qkv.to(_BF16), w_proj.to(_BF16)
+        wq, wp = _w16(w_qkv), _w16(w_proj)
         qkv = ops.gemm(x2, wq, bias=b_qkv)
         attn, lse2 = ops.winattn_fwd(qkv.view(Bp, T, L, 3 * C), table, H, W, nH, ws, shift, qk_scale=qk_scale, mask=mask)
         out = ops.gemm(attn.view(-1, C), wp, bias=b_proj)
@@ -108,8 +109,8 @@ class _AttentionFn(torch.autograd.Function):
         C = x2.shape[1]
         Bp_T_L = d_out.shape[:3]
         d2 = d_out.contiguous().view(-1, C)
-        d_bproj = d2.sum(0, dtype=torch.float32)          # one read of d_out (no fp32 copy)
-        d_table, d_bqkv, d_wproj_, d_wqkv_ = _zeros_like_many([tuple(table.shape), (3 * C,), tuple(wp.shape), tuple(wq.shape)], d2.device)
+        d_table, d_bqkv, d_bproj, d_wproj_, d_wqkv_ = _zeros_like_many([tuple(table.shape), (3 * C,), (C,), tuple(wp.shape), tuple(wq.shape)], d2.device)
+        ops.colsum(d2, d_bproj)                           # proj bias gradient: one read of d_out
         if not ctx.has_qkv_bias:
             d_bqkv = None
         d_attn = ops.gemm(d2, wp, b_mn_major=True)
@@ -136,7 +137,7 @@ class _BlockFn(torch.autograd.Function):
         geom = geom[:7]
         Bp, T, L, C = x.shape
         x2 = x.reshape(-1, C)
-        wq, wp, w1, w2 = w_qkv.to(_BF16), w_proj.to(_BF16), w_fc1.to(_BF16), w_fc2.to(_BF16)
+        wq, wp, w1, w2 = _w16(w_qkv), _w16(w_proj), _w16(w_fc1), _w16(w_fc2)
         qkv = ops.gemm(x2, wq, bias=b_qkv)
         attn, lse2 = ops.winattn_fwd(qkv.view(Bp, T, L, 3 * C), table, H, W, nH, ws, shift, qk_scale=qk_scale)
         y = ops.gemm(attn.view(-1, C), wp, bias=b_proj, aux=x2, mode=ops.EPI_BIAS_RES)
@@ -201,7 +202,7 @@ class _PatchMergeFn(torch.autograd.Function):
         H, W, eps = geom
         B, T, L, C = x.shape
         xn, mean, rstd = ops.layernorm_fwd(x.reshape(B * T, L, C), gamma, beta, eps, patch_merge_hw=(H, W))
-        wr = w_red.to(_BF16)
+        wr = _w16(w_red)
         out = ops.gemm(xn, wr)
         ctx.save_for_backward(x, xn, mean, rstd, gamma, wr)
         ctx.geom = geom
@@ -234,55 +235,81 @@ class _TransposeFn(torch.autograd.Function):
         return ops.transpose(g.contiguous(), ctx.in_dtype), None
 
 
-class _SplitMidFn(torch.autograd.Function):
-    """x [B, 4, L, C] -> (frames 1..2 as a contiguous [B, 2, L, C] copy, x itself).
+class _FnCtx:
+    """Minimal stand-in for an autograd context, used to run ``_BlockFn`` inside another Function."""
 
-    Together with ``_PutMidFn`` this is ``x[:, 1:3]`` -> blocks -> ``cat([x[:, :1], y, x[:, 3:]])``
-    (swin_512.py:302-307, middle layer) without the cat kernel and without any zero-fill / add in the
-    backward: ``_PutMidFn.backward`` allocates the gradient of x and fills frames 0 and 3, this
-    backward fills frames 1..2 of that same buffer."""
+    def __init__(self, n_inputs: int):
+        self.needs_input_grad = (True,) * n_inputs
+        self.saved_tensors = ()
+
+    def save_for_backward(self, *tensors):
+        self.saved_tensors = tensors
+
+
+class _MidLayerFn(torch.autograd.Function):
+    """The middle layer of a stage (swin_512.py:302-307): ``cat([x[:, :1], blk1(blk0(x[:, 1:3])), x[:, 3:]])`` as ONE
+    autograd node.  Forward: frames 1..2 are copied out, run through the two blocks, and the output is assembled from
+    the block result and frames 0 / 3 of x (no ``cat``).  Backward: the incoming gradient is only read; the gradient of
+    x is a fresh buffer filled from three sources (frames 0 / 3 of d_out, the blocks' input gradient for frames 1..2),
+    so there is no zero-fill and no gradient accumulation for the pass-through frames."""
+
+    N_BLOCK_ARGS = 13
 
     @staticmethod
-    def forward(ctx, x):
-        ctx.shape, ctx.dtype = x.shape, x.dtype
+    def forward(ctx, x, geom0, geom1, *params):
+        n = _MidLayerFn.N_BLOCK_ARGS
         B, _, L, C = x.shape
         xm = torch.empty((B, 2, L, C), dtype=x.dtype, device=x.device)
         ops.copy_frames(xm, x[:, 1:3])
-        return xm, x.view_as(x)
-
-    @staticmethod
-    def backward(ctx, d_xm, d_pass):
-        if d_pass is None:
-            d_pass = torch.zeros(ctx.shape, dtype=ctx.dtype, device=d_xm.device)
-        if d_xm is not None:
-            ops.copy_frames(d_pass[:, 1:3], d_xm.contiguous())
-        else:
-            d_pass[:, 1:3].zero_()
-        return d_pass
-
-
-class _PutMidFn(torch.autograd.Function):
-    """(x_pass [B, 4, L, C], y [B, 2, L, C]) -> x_pass with frames 1..2 replaced by y."""
-
-    @staticmethod
-    def forward(ctx, x_pass, y):
-        out = torch.empty_like(x_pass)
-        ops.copy_frames(out[:, 0], x_pass[:, 0])
-        ops.copy_frames(out[:, 3], x_pass[:, 3])
-        ops.copy_frames(out[:, 1:3], y.contiguous())
+        c0, c1 = _FnCtx(n + 2), _FnCtx(n + 2)
+        y = _BlockFn.forward(c1, _BlockFn.forward(c0, xm, *params[:n], geom0), *params[n:], geom1)
+        out = torch.empty_like(x)
+        ops.copy_frames(out[:, 0], x[:, 0])
+        ops.copy_frames(out[:, 3], x[:, 3])
+        ops.copy_frames(out[:, 1:3], y)
+        ctx.blocks = (c0, c1)
         return out
 
     @staticmethod
     def backward(ctx, d_out):
-        # frames 1..2 of d_pass are left for _SplitMidFn.backward to fill (a fresh buffer, never aliased)
+        c0, c1 = ctx.blocks
         d_out = d_out.contiguous()
-        d_pass = torch.empty_like(d_out)
-        ops.copy_frames(d_pass[:, 0], d_out[:, 0])
-        ops.copy_frames(d_pass[:, 3], d_out[:, 3])
         B, _, L, C = d_out.shape
         d_y = torch.empty((B, 2, L, C), dtype=d_out.dtype, device=d_out.device)
         ops.copy_frames(d_y, d_out[:, 1:3])
-        return d_pass, d_y
+        g1 = _BlockFn.backward(c1, d_y)
+        g0 = _BlockFn.backward(c0, g1[0])
+        d_x = torch.empty_like(d_out)
+        ops.copy_frames(d_x[:, 0], d_out[:, 0])
+        ops.copy_frames(d_x[:, 3], d_out[:, 3])
+        ops.copy_frames(d_x[:, 1:3], g0[0].contiguous())
+        return (d_x, None, None, *g0[1:-1], *g1[1:-1])
+
+
+class _MlpFn(torch.autograd.Function):
+    """Stand-alone Mlp.forward (swin_512.py:17-23) on bf16 rows [..., C_in]."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2):
+        x2 = x.reshape(-1, x.shape[-1])
+        w1b, w2b = _w16(w1), _w16(w2)
+        dgelu = torch.empty((x2.shape[0], w1b.shape[0]), dtype=_BF16, device=x.device)
+        h = ops.gemm(x2, w1b, bias=b1, mode=ops.EPI_BIAS_GELU, out2=dgelu)
+        y = ops.gemm(h, w2b, bias=b2)
+        ctx.save_for_backward(x2, h, dgelu, w1b, w2b)
+        return y.view(*x.shape[:-1], w2b.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, h, dgelu, w1b, w2b = ctx.saved_tensors
+        d2 = dy.contiguous().view(-1, w2b.shape[0])
+        d_b2, d_b1, d_w2_, d_w1_ = _zeros_like_many([(w2b.shape[0],), (w1b.shape[0],), tuple(w2b.shape), tuple(w1b.shape)], d2.device)
+        ops.colsum(d2, d_b2)
+        du = ops.gemm(d2, w2b, b_mn_major=True, mode=ops.EPI_MUL_AUX, aux=dgelu, colsum=d_b1)
+        d_w2 = _linear_wgrad(d2, h, w2b.shape, d_w2_)
+        dx = ops.gemm(du, w1b, b_mn_major=True)
+        d_w1 = _linear_wgrad(du, x2, w1b.shape, d_w1_)
+        return dx.view(*dy.shape[:-1], w1b.shape[1]), d_w1, d_b1, d_w2, d_b2
 
 
 def _as_tokens_bf16(x: torch.Tensor) -> torch.Tensor:
@@ -307,6 +334,13 @@ class Mlp(nn.Module):
         self.act = act_layer()
         self.fc2 = nn.Linear(hidden_features, out_features)
         self.drop = nn.Dropout(drop)
+
+    def forward(self, x):
+        """fc1 -> GELU (erf) -> fc2 on the last dim (swin_512.py:17-23), stand-alone: two GEMMs with the bias / GELU
+        epilogues fused.  Inside ``SwinTransformerBlock`` the same GEMMs run with the residual fused as well."""
+        in_dtype = x.dtype
+        y = _MlpFn.apply(_as_tokens_bf16(x).contiguous(), self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias)
+        return y if in_dtype == _BF16 else y.to(in_dtype)
 
 
 class WindowAttention(nn.Module):
@@ -396,15 +430,18 @@ class SwinTransformerBlock(nn.Module):
         H, W = self.input_resolution
         return (H, W, self.num_heads, self.window_size, self.shift_size, self.attn._qk_scale_arg(), self.norm1.eps)
 
+    def _block_params(self):
+        a, m = self.attn, self.mlp
+        return (a.relative_position_bias_table, a.qkv.weight, a.qkv.bias, a.proj.weight, a.proj.bias,
+                self.norm1.weight, self.norm1.bias, self.norm2.weight, self.norm2.bias,
+                m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias)
+
     def forward_tokens(self, x: torch.Tensor) -> torch.Tensor:
         """bf16 in, bf16 out; no dtype round trip (used by the layer container)."""
-        a, m = self.attn, self.mlp
         # grad mode is decided here: inside autograd.Function.forward it always reads "disabled", and
         # ctx.needs_input_grad ignores torch.no_grad()
         infer = not torch.is_grad_enabled()
-        return _BlockFn.apply(x, a.relative_position_bias_table, a.qkv.weight, a.qkv.bias, a.proj.weight, a.proj.bias,
-                              self.norm1.weight, self.norm1.bias, self.norm2.weight, self.norm2.bias,
-                              m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias, self._geom() + (infer,))
+        return _BlockFn.apply(x, *self._block_params(), self._geom() + (infer,))
 
     def forward(self, x_v):
         H, W = self.input_resolution
@@ -473,25 +510,67 @@ class SwinTransformerLayerv5(nn.Module):
         if both_pairs:
             y = blk1.forward_tokens(blk0.forward_tokens(x.view(B * 2, 2, L, C)))
             return y.view(B, 4, L, C)
-        xm, x_pass = _SplitMidFn.apply(x)
-        return _PutMidFn.apply(x_pass, blk1.forward_tokens(blk0.forward_tokens(xm)))
+        if not torch.is_grad_enabled():
+            xm = torch.empty((B, 2, L, C), dtype=x.dtype, device=x.device)
+            ops.copy_frames(xm, x[:, 1:3])
+            out = torch.empty_like(x)
+            ops.copy_frames(out[:, 0], x[:, 0])
+            ops.copy_frames(out[:, 3], x[:, 3])
+            ops.copy_frames(out[:, 1:3], blk1.forward_tokens(blk0.forward_tokens(xm)))
+            return out
+        return _MidLayerFn.apply(x, blk0._geom() + (False,), blk1._geom() + (False,), *blk0._block_params(), *blk1._block_params())
 
-    def forward(self, x_v):
+    def _check_input(self, x_v):
         B, T, C, H, W = x_v.shape
         assert T == 4, "input feature has wrong size"
         assert (H, W) == self.input_resolution and C == self.dim, "input feature has wrong size"
         if not x_v.is_cuda:
             raise StswinError("stswincl_b200 modules need CUDA tensors (no CPU path)")
-        out_dtype = x_v.dtype if x_v.dtype in (torch.float32, _BF16) else torch.float32
+        # outputs keep the input dtype like the reference's (:326); under autocast its last op, LayerNorm, returns fp32
+        keep = x_v.dtype if not torch.is_autocast_enabled() else torch.float32
+        out_dtype = keep if keep in (torch.float32, _BF16) else torch.float32
+        return keep, out_dtype
+
+    def _to_tokens(self, x_v):
+        B, T, C, H, W = x_v.shape
         x_in = x_v if x_v.dtype in (torch.float32, _BF16) else x_v.float()
-        t = _TransposeFn.apply(x_in.reshape(B * T, C, H * W), _BF16).view(B, T, H * W, C)
-        t = self._run_layer(t, 0, True)
-        t = self._run_layer(t, 1, False)
-        t = self._run_layer(t, 2, True)
-        out1 = _TransposeFn.apply(t.reshape(B * T, H * W, C), out_dtype).view(B, T, C, H, W)
-        t = self.downsample.forward_tokens(t.contiguous())
-        t = self._run_layer(t, 3, True)
-        t = self._run_layer(t, 4, False)
-        t = self._run_layer(t, 5, True)
-        out2 = _TransposeFn.apply(t.reshape(B * T, (H // 2) * (W // 2), 2 * C), out_dtype).view(B, T, 2 * C, H // 2, W // 2)
-        return out1, out2
+        return _TransposeFn.apply(x_in.reshape(B * T, C, H * W), _BF16).view(B, T, H * W, C)
+
+    def _from_tokens(self, t, stage: int, out_dtype, keep):
+        B, T = t.shape[:2]
+        H, W = self.input_resolution
+        C = self.dim
+        if stage == 2:
+            H, W, C = H // 2, W // 2, 2 * C
+        out = _TransposeFn.apply(t.reshape(B * T, H * W, C), out_dtype).view(B, T, C, H, W)
+        return out if keep == out_dtype else out.to(keep)       # fp16 / fp64 callers: cast at the boundary
+
+    def stages(self, like: torch.Tensor):
+        """The forward as a chain of four stages, each ``(fn, parameters)`` with ``fn`` mapping a tuple of tensors to
+        the next tuple; composing them on ``(x,)`` gives ``forward(x)``.  ``dist.SegmentedStep`` cuts the autograd
+        graph at the stage boundaries, so that the gradients of a stage are complete -- and can travel -- while the
+        backward of the stages before it still runs.  ``like``: an input tensor (fixes the output dtype)."""
+        keep, out_dtype = self._check_input(like)
+        L = self.layers
+
+        def s0(x):
+            return (self._run_layer(self._to_tokens(x), 0, True),)
+
+        def s1(t):
+            return (self._run_layer(self._run_layer(t, 1, False), 2, True),)
+
+        def s2(t):
+            return (self._from_tokens(t, 1, out_dtype, keep), self._run_layer(self.downsample.forward_tokens(t.contiguous()), 3, True))
+
+        def s3(out1, u):
+            return (out1, self._from_tokens(self._run_layer(self._run_layer(u, 4, False), 5, True), 2, out_dtype, keep))
+
+        return [(s0, list(L[0].parameters())), (s1, list(L[1].parameters()) + list(L[2].parameters())),
+                (s2, list(self.downsample.parameters()) + list(L[3].parameters())),
+                (s3, list(L[4].parameters()) + list(L[5].parameters()))]
+
+    def forward(self, x_v):
+        state = (x_v,)
+        for fn, _ in self.stages(x_v):
+            state = fn(*state)
+        return state

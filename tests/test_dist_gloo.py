@@ -63,6 +63,64 @@ def test_two_rank_gradient_average_matches_full_batch():
     assert dict(ret) == {0: True, 1: True}
 
 
+class _Staged(torch.nn.Module):
+    """Toy model with the ``stages(x)`` contract of SwinTransformerLayerv5 (a chain of (fn, parameters))."""
+
+    def __init__(self):
+        super().__init__()
+        self.a, self.b, self.c = torch.nn.Linear(6, 8), torch.nn.Linear(8, 8), torch.nn.Linear(8, 3)
+
+    def stages(self, like):
+        return [(lambda x: (torch.tanh(self.a(x)),), list(self.a.parameters())),
+                (lambda h: (h, torch.tanh(self.b(h))), list(self.b.parameters())),
+                (lambda h, g: (self.c(h + g),), list(self.c.parameters()))]
+
+    def forward(self, x):
+        state = (x,)
+        for fn, _ in self.stages(x):
+            state = fn(*state)
+        return state
+
+
+def _seg_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        data = torch.randn(8, 6, generator=torch.Generator().manual_seed(1))
+        target = torch.randn(8, 3, generator=torch.Generator().manual_seed(2))
+        ok = True
+        for segments in (1, 2, 3):
+            torch.manual_seed(0)
+            full, mine = _Staged(), _Staged()
+            mine.load_state_dict(full.state_dict())
+            o_full = torch.optim.SGD(full.parameters(), lr=0.1, momentum=0.9)
+            o_mine = torch.optim.SGD(mine.parameters(), lr=0.1, momentum=0.9)
+            idx = sdist.shard_indices(8, rank, world)
+            stepper = sdist.SegmentedStep(mine, o_mine, lambda y: ((y[0] - target[idx]) ** 2).mean(), segments=segments,
+                                          wire_dtype=torch.float32, use_graph=False)
+            for _ in range(3):
+                o_full.zero_grad()
+                ((full(data)[0] - target) ** 2).mean().backward()
+                o_full.step()
+                stepper.step(data[idx])
+            ok = ok and all(torch.allclose(p, q, atol=1e-6) for p, q in zip(full.parameters(), mine.parameters()))
+            ok = ok and len(stepper._buckets) == segments
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_segmented_step_two_ranks_equal_the_full_batch_step():
+    """dist.SegmentedStep (backward cut at stage boundaries, one bucket all-reduce per segment): two ranks on half the
+    batch each reproduce the single-process step on the whole batch, for 1 / 2 / 3 segments."""
+    world = 2
+    port = 29800 + os.getpid() % 200
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_seg_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert dict(ret) == {0: True, 1: True}
+
+
 def test_shard_indices_cover_and_pad():
     for n, world in [(8, 2), (7, 2), (5, 4), (3, 8)]:
         shards = [sdist.shard_indices(n, r, world) for r in range(world)]

@@ -235,3 +235,40 @@ def test_cpu_tensor_raises():
     m = swin.SwinTransformerBlock(128, (16, 24), 2)
     with pytest.raises(StswinError):
         m(torch.zeros(1, 2, 384, 128))
+
+
+def test_standalone_mlp_forward_backward():
+    """Mlp.forward (swin_512.py:17-23) called on its own, against fp32 torch."""
+    from stswincl_b200 import swin
+    torch.manual_seed(3)
+    m = swin.Mlp(128, 512).cuda()
+    x = torch.randn(2, 50, 128).cuda()
+    xr = x.clone().requires_grad_(True)
+    ref = torch.nn.functional.linear(torch.nn.functional.gelu(torch.nn.functional.linear(xr.to(torch.bfloat16).float(), m.fc1.weight, m.fc1.bias)),
+                                     m.fc2.weight, m.fc2.bias)
+    w = torch.randn_like(ref)
+    (ref * w).sum().backward()
+    ref_grads = [p.grad.clone() for p in m.parameters()]
+    m.zero_grad()
+    xg = x.clone().requires_grad_(True)
+    y = m(xg)
+    assert y.dtype == torch.float32 and y.shape == ref.shape
+    (y * w).sum().backward()
+    assert rel_err(y, ref) < 2e-2 and rel_err(xg.grad, xr.grad) < 2e-2
+    for p, g in zip(m.parameters(), ref_grads):
+        assert rel_err(p.grad, g) < 2e-2
+
+
+def test_layer_dtype_contract_fp16_and_autocast():
+    """The reference's layer returns its input dtype (:326); under amp.autocast its last op (LayerNorm) returns fp32."""
+    from stswincl_b200 import swin
+    torch.manual_seed(4)
+    layer = swin.SwinTransformerLayerv5(dim=128, input_resolution=(16, 24), num_heads=2).cuda()
+    x = torch.relu(torch.randn(1, 4, 128, 16, 24)).cuda()
+    with torch.no_grad():
+        a1, a2 = layer(x)
+        h1, h2 = layer(x.half())
+        with torch.autocast("cuda", dtype=torch.float16):
+            c1, c2 = layer(x.half())
+    assert a1.dtype == torch.float32 and h1.dtype == torch.float16 and h2.dtype == torch.float16 and c1.dtype == torch.float32
+    assert rel_err(h1.float(), a1) < 2e-2 and rel_err(c2, a2) < 2e-2

@@ -194,3 +194,54 @@ def test_ema_large_and_unaligned_bit_exact():
     torch.cuda.synchronize()
     for a, b in zip(k, want):
         assert torch.equal(a, b)
+
+
+def test_fused_adam_matches_torch_adam_and_keeps_the_bf16_shadow():
+    """stswin_adam_step against torch.optim.Adam (the optimiser of seg18/train_swin.py) run on the CPU in fp32: three
+    steps, weight decay, odd sizes (unaligned tails), fp32 and bf16 gradients; the bf16 shadow equals bf16(param)."""
+    from stswincl_b200 import optim as so
+    gen = torch.Generator().manual_seed(5)
+    shapes = [(33, 17), (128,), (7,), (64, 96), (1, 5, 3)]
+    for wd, gdtype in ((0.0, torch.float32), (1e-2, torch.float32), (0.0, torch.bfloat16)):
+        ref = [torch.nn.Parameter(torch.randn(s, generator=gen)) for s in shapes]
+        ours = [torch.nn.Parameter(p.detach().clone().cuda()) for p in ref]
+        o_ref = torch.optim.Adam(ref, lr=1e-2, betas=(0.9, 0.99), eps=1e-8, weight_decay=wd)
+        o_our = so.FusedAdam(ours, lr=1e-2, betas=(0.9, 0.99), eps=1e-8, weight_decay=wd)
+        for step in range(3):
+            grads = [torch.randn(s, generator=gen) * (0.1 + step) for s in shapes]
+            if gdtype == torch.bfloat16:
+                grads = [g.to(torch.bfloat16).float() for g in grads]
+            for p, g in zip(ref, grads):
+                p.grad = g.clone()
+            o_ref.step()
+            if gdtype == torch.bfloat16:
+                o_our.step(grads=[g.to(torch.bfloat16).cuda() for g in grads])
+            else:
+                for p, g in zip(ours, grads):
+                    p.grad = g.cuda()
+                o_our.step()
+        torch.cuda.synchronize()
+        for p, q in zip(ref, ours):
+            assert rel_err(q.detach().cpu(), p.detach()) < 1e-5
+            assert rel_err(o_our.state[q]["exp_avg_sq"].cpu(), o_ref.state[p]["exp_avg_sq"]) < 1e-5
+            if q.dim() >= 2:
+                assert torch.equal(so.bf16_weight(q), q.detach().to(torch.bfloat16))       # written by the update kernel
+                assert so.bf16_weight(q).data_ptr() == q._stswin_shadow[0].data_ptr()
+        with torch.no_grad():                                # someone else writes the parameter: the shadow is refreshed
+            ours[0].mul_(2.0)
+        assert torch.equal(so.bf16_weight(ours[0]), ours[0].detach().to(torch.bfloat16))
+
+
+def test_colsum_and_gather_cast():
+    from stswincl_b200 import ops
+    gen = torch.Generator().manual_seed(9)
+    for R, C in ((1000, 512), (37, 64), (5000, 1024), (3, 2048)):
+        x = torch.randn(R, C, generator=gen).to(torch.bfloat16)
+        out = torch.full((C,), 0.5, dtype=torch.float32).cuda()
+        ops.colsum(x.cuda(), out)
+        assert rel_err(out.cpu(), x.double().sum(0) + 0.5) < 1e-5
+    src = [torch.randn(n, generator=gen).cuda() for n in (5, 4096, 100003, 8)] * 15     # 60 tensors: two launches
+    for dt in (torch.bfloat16, torch.float32):
+        dst = [torch.empty(s.numel(), dtype=dt, device="cuda") for s in src]
+        ops.gather_cast(dst, src)
+        assert all(torch.equal(d, s.to(dt)) for d, s in zip(dst, src))
