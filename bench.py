@@ -371,22 +371,24 @@ def run_ours(args):
         g1 = (torch.randn(B, T, DIM, RES[0], RES[1], generator=g, device=dev) * 0.1).to(torch.bfloat16)
         g2 = (torch.randn(B, T, 2 * DIM, RES[0] // 2, RES[1] // 2, generator=g, device=dev) * 0.1).to(torch.bfloat16)
 
-    def embed(y1):
-        # stand-in for the projection head (ResNet / ASPP / projector are the caller's side of the boundary): the first 256
-        # channels of the last frame's stage-1 output are the pixel embedding, un-normalised (F.normalize is fused in the loss)
-        return y1[:, -1, :256]
+    def embed(y1, y2):
+        # stand-in for the projection head (ResNet / ASPP / projector are the caller's side of the boundary, PixPro_swin_v5.py:
+        # 311-330): 256 channels of the last frame's stage-1 output plus the nearest-upsampled stage-2 output are the pixel
+        # embedding, un-normalised (F.normalize is fused in the loss)
+        up = torch.nn.functional.interpolate(y2[:, -1, :256], size=y1.shape[-2:], mode="nearest")
+        return y1[:, -1, :256] + up
 
     def forward_loss(x):
         if not pretrain:
             y1, y2 = net(x)
             return torch.sum(y1 * g1, dtype=torch.float32) + torch.sum(y2 * g2, dtype=torch.float32)
         # PixPro.forward (PixPro_swin_v5.py:291-561) on the Swin head: two query passes, EMA, six no-grad key passes
-        y1, _ = net(x[:2 * B])
-        pred_1, pred_2 = embed(y1[:B]), embed(y1[B:])
+        y1, y2 = net(x[:2 * B])
+        pred_1, pred_2 = embed(y1[:B], y2[:B]), embed(y1[B:], y2[B:])
         with torch.no_grad():
             soptim.momentum_update(list(model.parameters()), list(key_model.parameters()), 0.99)
-            k1, _ = key_model(x)
-            keys = [embed(k1[i * B:(i + 1) * B]) for i in range(6)]
+            k1, k2 = key_model(x)
+            keys = [embed(k1[i * B:(i + 1) * B], k2[i * B:(i + 1) * B]) for i in range(6)]
         return contrast.consistency_loss_tail(pred_1, pred_2, *keys, *masks, K, normalize=True, cross_rank_negatives=world > 1)
 
     def barrier():
@@ -544,7 +546,7 @@ def run_ours(args):
     for _ in range(2):
         run_step(cur_x())
         ops.set_profiler(prof)
-        step(x_dev)
+        (stepper.eager if stepper is not None else step)(x_dev)
         ops.set_profiler(None)
     fam = prof.summary()
     total_ms = sum(v["ms"] for v in fam.values()) or 1.0

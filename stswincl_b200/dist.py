@@ -230,6 +230,12 @@ class SegmentedStep:
             torch._foreach_copy_([p.grad for p in ps], [self._view_of[id(p)] for p in ps])
             self.opt.step()
 
+    def eager(self, x):
+        """The same step without graph replays (every kernel launched by the host: profiling, debugging)."""
+        if not self._built:
+            self._build(x)
+        return self._eager(x)
+
     def _eager(self, x):
         self.opt.zero_grad(set_to_none=True)
         loss = self._forward(x)
