@@ -233,6 +233,18 @@ def gen_loss(px) -> None:
     np.savez_compressed(os.path.join(OUT, "loss_cases.npz"), **out)
 
 
+def gen_state_dict_contract(sw) -> None:
+    """Key names / shapes of the reference layer's state_dict (tests/test_state_dict_contract.py)."""
+    import json
+    small = sw.SwinTransformerLayerv5(dim=128, input_resolution=(16, 24), num_heads=2)
+    default = sw.SwinTransformerLayerv5()
+    out = {"layer_128_16x24_h2": {k: list(v.shape) for k, v in small.state_dict().items()},
+           "layer_default": {k: list(v.shape) for k, v in default.state_dict().items()},
+           "layer_default_param_count": sum(p.numel() for p in default.parameters())}
+    with open(os.path.join(OUT, "state_dict_contract.json"), "w") as f:
+        json.dump(out, f)
+
+
 def main() -> None:
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
@@ -243,6 +255,7 @@ def main() -> None:
     gen_block(sw)
     gen_layer(sw)
     gen_loss(px)
+    gen_state_dict_contract(sw)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -1,0 +1,81 @@
+"""Golden fixture of the FULL reference model with the Swin head inside (``tests/golden/tswinplus.npz``).
+
+TEST INFRASTRUCTURE; needs ``/root/reference`` (authoring container only).  Imports the UNMODIFIED reference
+``TswinPlus`` (seg18/net/Ours/base18.py:52-108; shims of SURVEY.md 8c: ``timm`` stand-in, the hard-coded
+``resnet18-5c106cde.pth`` load returns a torchvision resnet18 state_dict), fills it from
+``tswin_oracle.synth_state_dict`` and records, on CPU in fp32:
+
+  * the state_dict key list + shapes (the restated caller model must load strictly),
+  * eval-mode logits of one synthetic 4-frame 512x640 clip, sub-sampled [::8, ::8], their arg-max map at full
+    resolution (u8) and the top-2 margin map (fp16) -- the fp32 bar is an exact arg-max match,
+  * a 3-step training trajectory (train mode, image-pool BN in eval, Adam 1e-4, cross-entropy):
+    the three loss values.
+
+    python -m oracle.make_goldens_tswin
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+from . import ref_shims, tswin_oracle as to
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "tswinplus.npz")
+CLASSES, SEED = 12, 5
+
+
+def reference_model():
+    ref_shims.import_swin()
+    import torchvision
+    real_load = torch.load
+    torch.load = lambda *a, **k: torchvision.models.resnet18().state_dict()      # resnet.py:100 hard-codes a checkpoint path
+    try:
+        import importlib
+        base18 = importlib.import_module("net.Ours.base18")
+        model = base18.TswinPlus(CLASSES)
+    finally:
+        torch.load = real_load
+    return model
+
+
+def main():
+    torch.set_num_threads(os.cpu_count() or 1)
+    model = reference_model()
+    sd = to.synth_state_dict(model.state_dict(), SEED)
+    model.load_state_dict(sd, strict=True)
+    # the restatement loads the same dictionary strictly and agrees with the reference to fp32 rounding
+    from stswincl_b200 import swin as _  # noqa: F401  (import check only; the CPU check below uses the reference's head)
+    clip = to.make_clip(SEED + 1)
+    model.eval()
+    with torch.no_grad():
+        logits = model(clip)
+    top2 = logits.topk(2, dim=1).values
+    out = {"keys": np.array(json.dumps({k: list(v.shape) for k, v in sd.items()})),
+           "logits_sub": logits[0, :, ::8, ::8].numpy().astype(np.float32),
+           "argmax": logits.argmax(1)[0].numpy().astype(np.uint8),
+           "margin": (top2[:, 0] - top2[:, 1])[0].numpy().astype(np.float16),
+           "logit_absmax": np.float32(logits.abs().max())}
+    # 3-step trajectory
+    model.load_state_dict(sd, strict=True)
+    model.train()
+    model.aspp.bn_conv_1x1_2.eval()
+    target = to.make_targets(SEED + 2, 1, 512, 640, CLASSES)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    losses = []
+    for _ in range(3):
+        opt.zero_grad()
+        loss = torch.nn.functional.cross_entropy(model(clip), target)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    out["losses"] = np.array(losses, dtype=np.float64)
+    np.savez_compressed(OUT, **out)
+    print("wrote", OUT, {k: (v.shape, str(v.dtype)) for k, v in out.items()}, "losses", losses, file=sys.stderr)
+
+
+if __name__ == "__main__":
+    main()

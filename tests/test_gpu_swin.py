@@ -272,3 +272,122 @@ def test_layer_dtype_contract_fp16_and_autocast():
             c1, c2 = layer(x.half())
     assert a1.dtype == torch.float32 and h1.dtype == torch.float16 and h2.dtype == torch.float16 and c1.dtype == torch.float32
     assert rel_err(h1.float(), a1) < 2e-2 and rel_err(c2, a2) < 2e-2
+
+
+REAL_GEOMETRIES = [("S1_unshifted", 512, (64, 80), 4, 8, 0), ("S1_shifted", 512, (64, 80), 4, 8, 4),
+                   ("S2_unshifted", 1024, (32, 40), 4, 4, 0), ("S2_shifted", 1024, (32, 40), 4, 4, 2)]
+BLOCK_GRADS = ["attn.relative_position_bias_table", "attn.qkv.weight", "attn.qkv.bias", "attn.proj.weight", "attn.proj.bias",
+               "norm1.weight", "norm1.bias", "norm2.weight", "norm2.bias", "mlp.fc1.weight", "mlp.fc1.bias",
+               "mlp.fc2.weight", "mlp.fc2.bias"]
+
+
+@pytest.mark.parametrize("case", REAL_GEOMETRIES, ids=lambda c: c[0])
+def test_real_geometry_block_forward_backward_vs_oracle(case):
+    """SwinTransformerBlock forward AND backward at the shipped geometries (stage 1: C 512, 64x80 tokens, ws 8,
+    shift 0 / 4; stage 2: C 1024, 32x40, ws 4, shift 0 / 2; 4 heads, B = 2 frame pairs) against the CPU oracle
+    (swin_512.py:196-237): output, input gradient and all 13 parameter gradients at the bf16 bar, 2e-2."""
+    from oracle import swin_oracle as so
+    from stswincl_b200 import swin
+    tag, dim, res, heads, ws, shift = case
+    L = res[0] * res[1]
+    params = so.make_block_params(dim, res, heads, ws, shift, seed=91)
+    m = _load(swin.SwinTransformerBlock(dim, res, heads, window_size=ws, shift_size=shift), params)
+    x = so.make_features(92, 2, 2, L, dim)
+    w = so.make_features(93, 2, 2, L, dim) - 0.4
+    leaf = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and k != "attn_mask" else v) for k, v in params.items()}
+    xr = x.to(torch.bfloat16).float().requires_grad_(True)
+    ref = so.swin_block(xr, leaf, res, heads, ws, shift)
+    (ref * w).sum().backward()
+    xg = x.cuda().requires_grad_(True)
+    y = m(xg)
+    (y * w.cuda()).sum().backward()
+    torch.cuda.synchronize()
+    assert rel_err(y.cpu(), ref) < TOL
+    assert rel_err(xg.grad.cpu(), xr.grad) < TOL
+    sd = dict(m.named_parameters())
+    for n in BLOCK_GRADS:
+        assert rel_err(sd[n].grad.cpu(), leaf[n].grad) < TOL, n
+
+
+def test_full_size_layer_forward_backward_vs_oracle():
+    """The whole SwinTransformerLayerv5 at the bench geometry (dim 512, 64x80 tokens, 4 heads, 12 blocks + PatchMerging;
+    swin_512.py:280-327), one clip, forward and backward against the CPU oracle.  Outputs at 2e-2; the gradients have
+    passed 12 blocks of bf16 storage: 4e-2 (input gradient, first / last blocks' parameters)."""
+    from oracle import swin_oracle as so
+    from stswincl_b200 import swin
+    dim, res, heads = 512, (64, 80), 4
+    params = so.make_layer_params(dim, res, heads, seed=95)
+    m = _load(swin.SwinTransformerLayerv5(dim=dim, input_resolution=res, num_heads=heads), params)
+    x = so.make_features(96, 1, 4, dim, res[0], res[1])
+    w1 = so.make_features(97, 1, 4, dim, res[0], res[1]) - 0.4
+    w2 = so.make_features(98, 1, 4, 2 * dim, res[0] // 2, res[1] // 2) - 0.4
+    names = ["layers.0.0.attn.relative_position_bias_table", "layers.0.0.attn.qkv.weight", "layers.0.1.mlp.fc1.bias",
+             "layers.2.1.norm1.weight", "layers.3.0.attn.qkv.bias", "layers.5.1.mlp.fc2.weight", "layers.5.1.norm1.bias",
+             "downsample.norm.weight", "downsample.reduction.weight"]
+    leaf = {k: (v.clone().requires_grad_(True) if k in names else v) for k, v in params.items()}
+    xr = x.to(torch.bfloat16).float().requires_grad_(True)
+    r1, r2 = so.swin_layer_v5(xr, leaf, dim, res, heads)
+    ((r1 * w1).sum() + (r2 * w2).sum()).backward()
+    xg = x.cuda().requires_grad_(True)
+    y1, y2 = m(xg)
+    ((y1 * w1.cuda()).sum() + (y2 * w2.cuda()).sum()).backward()
+    torch.cuda.synchronize()
+    assert rel_err(y1.cpu(), r1) < TOL and rel_err(y2.cpu(), r2) < TOL
+    assert rel_err(xg.grad.cpu(), xr.grad) < 2 * TOL
+    sd = dict(m.named_parameters())
+    for n in names:
+        assert rel_err(sd[n].grad.cpu(), leaf[n].grad) < 2 * TOL, n
+
+
+def _swapped_model():
+    """The reference's full segmentation model with ``model.swin`` replaced by the product: the caller
+    side (ResNet-18 OS8, ASPP, projections, classifier -- plain torch on the GPU) is the restatement pinned against the
+    reference by tests/test_oracle_golden.py; weights are the synthetic state_dict of the golden."""
+    import json
+    from oracle import tswin_oracle as to
+    from stswincl_b200 import swin
+    g = np.load(os.path.join(GOLDEN, "tswinplus.npz"))
+    model = to.TswinPlus(12, swin.SwinTransformerLayerv5())
+    assert {k: list(v.shape) for k, v in model.state_dict().items()} == json.loads(str(g["keys"]))
+    model.load_state_dict(to.synth_state_dict(model.state_dict(), 5), strict=True)
+    return model.cuda(), g, to
+
+
+def test_full_model_with_swapped_head_logits_and_argmax():
+    """TswinPlus (seg18/net/Ours/base18.py:52-108, head call at :94) with the head swapped, eval mode, one 4-frame
+    512x640 clip: logits within 2e-2 of the reference's fp32 run, arg-max labels equal wherever the reference's top-2
+    margin exceeds the bf16 noise floor."""
+    model, g, to = _swapped_model()
+    model.eval()
+    with torch.no_grad(), torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+        torch.backends.cuda.matmul.allow_tf32 = False
+        logits = model(to.make_clip(6).cuda())
+    scale = float(g["logit_absmax"])
+    err = float(np.abs(logits[0, :, ::8, ::8].float().cpu().numpy() - g["logits_sub"]).max()) / scale
+    assert err < TOL, err
+    am = logits.argmax(1)[0].cpu().numpy()
+    margin = g["margin"].astype(np.float32)
+    decided = margin > 2 * TOL * scale
+    assert np.array_equal(am[decided], g["argmax"][decided])
+    assert (am == g["argmax"]).mean() > 0.97
+
+
+def test_full_model_three_step_loss_trajectory():
+    """Three Adam steps (lr 1e-4, cross-entropy, train mode with the image-pool BatchNorm in eval) of the
+    swapped model follow the reference's loss trajectory within 2e-2."""
+    model, g, to = _swapped_model()
+    model.train()
+    model.aspp.bn_conv_1x1_2.eval()
+    clip = to.make_clip(6).cuda()
+    target = to.make_targets(7, 1, 512, 640, 12).cuda()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    losses = []
+    with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+        for _ in range(3):
+            opt.zero_grad()
+            loss = torch.nn.functional.cross_entropy(model(clip), target)
+            loss.backward()
+            opt.step()
+            losses.append(float(loss))
+    ref = g["losses"]
+    assert all(abs(a - b) < TOL * abs(b) for a, b in zip(losses, ref)), (losses, list(ref))

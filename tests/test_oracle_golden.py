@@ -153,3 +153,25 @@ def test_out_of_range_label_raises():
     bad = labels[2].clone(); bad[0, 0, 0, 0] = 12.0
     with pytest.raises(RuntimeError):
         lo.regression_loss(emb[0][:1], [e[:1] for e in emb[1:]], labels[0][:1], [labels[1][:1], bad[:1], *[l[:1] for l in labels[3:]]], 12)
+
+
+def test_restated_caller_model_matches_the_reference_full_model():
+    """oracle/tswin_oracle.py (TswinPlus / ResNet18_OS8 / ASPP restated around a pluggable Swin head) against
+    tests/golden/tswinplus.npz, written from the UNMODIFIED reference model by oracle/make_goldens_tswin.py: the state_dict
+    key list is identical (strict load of the synthetic weights) and the eval-mode logits of the 512x640 clip agree
+    to fp32 rounding, with the functional head oracle plugged in for seg18/net/Ours/swin_512.py."""
+    import json
+    from oracle import tswin_oracle as to
+    g = np.load(os.path.join(GOLDEN, "tswinplus.npz"))
+    keys = json.loads(str(g["keys"]))
+    model = to.TswinPlus(12, to.OracleSwin(to.swin_shapes_from_keys(keys)))
+    ours = {k: list(v.shape) for k, v in model.state_dict().items()}
+    assert ours == keys
+    model.load_state_dict(to.synth_state_dict(model.state_dict(), 5), strict=True)
+    model.eval()
+    with torch.no_grad():
+        logits = model(to.make_clip(6))
+    assert float(np.abs(logits[0, :, ::8, ::8].numpy() - g["logits_sub"]).max()) < 1e-3 * float(g["logit_absmax"])
+    am = logits.argmax(1)[0].numpy()
+    decided = g["margin"].astype(np.float32) > 1e-3 * float(g["logit_absmax"])
+    assert np.array_equal(am[decided], g["argmax"][decided]) and decided.mean() > 0.99
