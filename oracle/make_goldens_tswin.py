@@ -8,8 +8,11 @@ TEST INFRASTRUCTURE; needs ``/root/reference`` (authoring container only).  Impo
   * the state_dict key list + shapes (the restated caller model must load strictly),
   * eval-mode logits of one synthetic 4-frame 512x640 clip, sub-sampled [::8, ::8], their arg-max map at full
     resolution (u8) and the top-2 margin map (fp16) -- the fp32 bar is an exact arg-max match,
-  * a 3-step training trajectory (train mode, image-pool BN in eval, Adam 1e-4, cross-entropy):
-    the three loss values.
+  * a 3-step training trajectory (train mode, image-pool BN in eval, SGD lr 2e-4 momentum 0.9,
+    cross-entropy): the three loss values.  (Adam 1e-4, the recipe's optimiser, moves this synthetic model so far per
+    step that the trajectory is chaotic: rounding only the head's OUTPUTS to bf16 in the fp32 reference changes the third
+    loss by 2.6 %; with this SGD setting the same perturbation moves it by 1.6e-4 while the loss still falls from 2.94
+    to 2.53, so the trajectory is a meaningful 2e-2 check.)
 
     python -m oracle.make_goldens_tswin
 """
@@ -64,7 +67,7 @@ def main():
     model.train()
     model.aspp.bn_conv_1x1_2.eval()
     target = to.make_targets(SEED + 2, 1, 512, 640, CLASSES)
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    opt = torch.optim.SGD(model.parameters(), lr=2e-4, momentum=0.9)
     losses = []
     for _ in range(3):
         opt.zero_grad()

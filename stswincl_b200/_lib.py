@@ -99,6 +99,13 @@ SIGNATURES = {
                              ctypes.c_float, ctypes.c_float, _vp, _vp], ctypes.c_int),
     "stswin_adam_step": ([_vp] * 6 + [_i, _i] + [ctypes.c_float] * 6 + [_vp, _vp], ctypes.c_int),
     "stswin_gather_cast": ([_vp, _vp, _vp, _i, _i, _vp], ctypes.c_int),
+    "stswin_f32_split": ([_vp, _vp, _i64, _i, _i, _i, _i, _vp], ctypes.c_int),
+    "stswin_f32_rowop": ([_vp, _vp, _vp, _vp, _i64, _i, _i, _vp], ctypes.c_int),
+    "stswin_f32_colsum": ([_vp, _vp, _i64, _i, _vp], ctypes.c_int),
+    "stswin_f32_layernorm_fwd": ([_vp] * 6 + [_i64, _i, ctypes.c_float, _i, _i, _i, _i, _vp], ctypes.c_int),
+    "stswin_f32_layernorm_bwd": ([_vp] * 9 + [_i64, _i, _i, _i, _i, _i, _vp], ctypes.c_int),
+    "stswin_winattn_f32_fwd": ([_vp] * 4 + [_i] * 8 + [ctypes.c_float, _vp, _i, _vp], ctypes.c_int),
+    "stswin_winattn_f32_bwd": ([_vp] * 8 + [_i] * 8 + [ctypes.c_float, _vp, _i, _vp], ctypes.c_int),
     "stswin_gemm_bf16": ([_vp, _i, _i64, _vp, _i, _i64, _vp, _i64, _vp, _vp, _i64, _fp, _fp, _i, _i, _i, _i, _i, _vp], ctypes.c_int),
 }
 

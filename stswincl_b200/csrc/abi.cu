@@ -122,4 +122,35 @@ int stswin_gather_cast(void* const* dst, const void* const* src, const int64_t* 
   return stswin::gather_cast(dst, src, numels, n_tensors, dst_is_bf16, static_cast<cudaStream_t>(stream));
 }
 
+int stswin_f32_split(const float* x, void* out, int64_t R, int C, int layout, int pattern, int op, void* stream) {
+  return stswin::f32_split(x, out, R, C, layout, pattern, op, static_cast<cudaStream_t>(stream));
+}
+int stswin_f32_rowop(float* out, const float* bias, const float* res, const float* aux, int64_t R, int C, int mode, void* stream) {
+  return stswin::f32_rowop(out, bias, res, aux, R, C, mode, static_cast<cudaStream_t>(stream));
+}
+int stswin_f32_colsum(const float* x, float* out, int64_t R, int C, void* stream) {
+  return stswin::f32_colsum(x, out, R, C, static_cast<cudaStream_t>(stream));
+}
+int stswin_f32_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd,
+                             int64_t M, int row_len, float eps, int pm, int H, int W, int C, void* stream) {
+  return stswin::f32_layernorm_fwd(x, gamma, beta, y, mean, rstd, M, row_len, eps, pm, H, W, C, static_cast<cudaStream_t>(stream));
+}
+int stswin_f32_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
+                             const float* dres, float* dx, float* dgamma, float* dbeta, int64_t M, int row_len, int pm, int H,
+                             int W, int C, void* stream) {
+  return stswin::f32_layernorm_bwd(dy, x, mean, rstd, gamma, dres, dx, dgamma, dbeta, M, row_len, pm, H, W, C,
+                                   static_cast<cudaStream_t>(stream));
+}
+int stswin_winattn_f32_fwd(const float* qkv, const float* bias_table, float* out, float* lse, int B, int T, int H, int W, int C,
+                           int nH, int ws, int shift, float qk_scale, const float* mask, int mask_windows, void* stream) {
+  return stswin::winattn_f32_fwd(qkv, bias_table, out, lse, B, T, H, W, C, nH, ws, shift, qk_scale, mask, mask_windows,
+                                 static_cast<cudaStream_t>(stream));
+}
+int stswin_winattn_f32_bwd(const float* qkv, const float* bias_table, const float* out, const float* lse, const float* d_out,
+                           float* d_qkv, float* d_bias_table, float* delta_ws, int B, int T, int H, int W, int C, int nH, int ws,
+                           int shift, float qk_scale, const float* mask, int mask_windows, void* stream) {
+  return stswin::winattn_f32_bwd(qkv, bias_table, out, lse, d_out, d_qkv, d_bias_table, delta_ws, B, T, H, W, C, nH, ws, shift,
+                                 qk_scale, mask, mask_windows, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

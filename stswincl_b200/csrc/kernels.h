@@ -58,4 +58,19 @@ int adam_step(void* const* params, const void* const* grads, void* const* exp_av
 int gather_cast(void* const* dst, const void* const* src, const int64_t* numels, int n_tensors, int dst_is_bf16,
                 cudaStream_t stream);
 
+// fp32-accurate mode (f32path.cu)
+int f32_split(const float* x, void* out, long R, int C, int layout, int pattern, int op, cudaStream_t stream);
+int f32_rowop(float* out, const float* bias, const float* res, const float* aux, long R, int C, int mode, cudaStream_t stream);
+int f32_colsum(const float* x, float* out, long R, int C, cudaStream_t stream);
+int f32_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd, long M,
+                      int row_len, float eps, int pm, int H, int W, int C, cudaStream_t stream);
+int f32_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
+                      const float* dres, float* dx, float* dgamma, float* dbeta, long M, int row_len, int pm, int H, int W,
+                      int C, cudaStream_t stream);
+int winattn_f32_fwd(const float* qkv, const float* bias_table, float* out, float* lse, int B, int T, int H, int W, int C, int nH,
+                    int ws, int shift, float qk_scale, const float* mask, int mask_windows, cudaStream_t stream);
+int winattn_f32_bwd(const float* qkv, const float* bias_table, const float* out, const float* lse, const float* d_out,
+                    float* d_qkv, float* d_bias_table, float* delta_ws, int B, int T, int H, int W, int C, int nH, int ws,
+                    int shift, float qk_scale, const float* mask, int mask_windows, cudaStream_t stream);
+
 }  // namespace stswin

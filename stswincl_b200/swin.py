@@ -262,7 +262,9 @@ class _MidLayerFn(torch.autograd.Function):
         xm = torch.empty((B, 2, L, C), dtype=x.dtype, device=x.device)
         ops.copy_frames(xm, x[:, 1:3])
         c0, c1 = _FnCtx(n + 2), _FnCtx(n + 2)
-        y = _BlockFn.forward(c1, _BlockFn.forward(c0, xm, *params[:n], geom0), *params[n:], geom1)
+        blk = _BlockFn32 if x.dtype == torch.float32 else _BlockFn
+        ctx.blk = blk
+        y = blk.forward(c1, blk.forward(c0, xm, *params[:n], geom0), *params[n:], geom1)
         out = torch.empty_like(x)
         ops.copy_frames(out[:, 0], x[:, 0])
         ops.copy_frames(out[:, 3], x[:, 3])
@@ -277,8 +279,8 @@ class _MidLayerFn(torch.autograd.Function):
         B, _, L, C = d_out.shape
         d_y = torch.empty((B, 2, L, C), dtype=d_out.dtype, device=d_out.device)
         ops.copy_frames(d_y, d_out[:, 1:3])
-        g1 = _BlockFn.backward(c1, d_y)
-        g0 = _BlockFn.backward(c0, g1[0])
+        g1 = ctx.blk.backward(c1, d_y)
+        g0 = ctx.blk.backward(c0, g1[0])
         d_x = torch.empty_like(d_out)
         ops.copy_frames(d_x[:, 0], d_out[:, 0])
         ops.copy_frames(d_x[:, 3], d_out[:, 3])
@@ -312,6 +314,182 @@ class _MlpFn(torch.autograd.Function):
         return dx.view(*dy.shape[:-1], w1b.shape[1]), d_w1, d_b1, d_w2, d_b2
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# fp32-accurate mode (ops32): the reference's no-AMP run at <= 1e-3
+# ---------------------------------------------------------------------------------------------------------------
+_PRECISION = "bf16"
+
+
+def set_precision(mode: str) -> str:
+    """Arithmetic of the drop-in modules: ``"bf16"`` (default: bf16 storage, fp32 accumulation -- the counterpart of the
+    reference under ``amp.autocast``), ``"fp32"`` (activations stay fp32, dense layers as split-bf16 tcgen05 GEMMs, the
+    attention core as fp32 SIMT kernels: <= 1e-3 against the reference's fp32 run) or ``"auto"`` (fp32 for fp32 inputs
+    outside autocast, bf16 otherwise).  A module's own ``precision`` attribute, when set, wins.  Returns the old mode."""
+    global _PRECISION
+    if mode not in ("bf16", "fp32", "auto"):
+        raise ValueError("precision must be 'bf16', 'fp32' or 'auto'")
+    old, _PRECISION = _PRECISION, mode
+    return old
+
+
+def _use_fp32(module, x: torch.Tensor) -> bool:
+    mode = getattr(module, "precision", None) or _PRECISION
+    if mode == "auto":
+        return x.dtype == torch.float32 and not torch.is_autocast_enabled()
+    return mode == "fp32"
+
+
+def _zeros_f32(shape, dev):
+    return torch.zeros(shape, dtype=torch.float32, device=dev)
+
+
+class _AttentionFn32(torch.autograd.Function):
+    """``_AttentionFn`` in the fp32-accurate mode: x [Bp, T, H*W, C] fp32."""
+
+    @staticmethod
+    def forward(ctx, x, table, w_qkv, b_qkv, w_proj, b_proj, geom, mask=None):
+        from . import ops32 as o32
+        H, W, nH, ws, shift, qk_scale = geom
+        Bp, T, L, C = x.shape
+        x2 = x.reshape(-1, C)
+        qkv = o32.linear(x2, w_qkv, b_qkv)
+        attn, lse = o32.winattn_fwd(qkv.view(Bp, T, L, 3 * C), table, H, W, nH, ws, shift, qk_scale, mask)
+        out = o32.linear(attn.view(-1, C), w_proj, b_proj)
+        ctx.save_for_backward(x2, qkv, attn, lse, table, w_qkv, w_proj)
+        ctx.geom, ctx.mask, ctx.has_qkv_bias = geom, mask, b_qkv is not None
+        return out.view(Bp, T, L, C)
+
+    @staticmethod
+    def backward(ctx, d_out):
+        from . import ops32 as o32
+        x2, qkv, attn, lse, table, w_qkv, w_proj = ctx.saved_tensors
+        H, W, nH, ws, shift, qk_scale = ctx.geom
+        C = x2.shape[1]
+        shp = d_out.shape[:3]
+        d2 = d_out.contiguous().view(-1, C)
+        dev = d2.device
+        d_bproj = o32.colsum(d2, _zeros_f32((C,), dev))
+        d_attn = o32.linear_dgrad(d2, w_proj)
+        d_wproj = o32.linear_wgrad(d2, attn.view(-1, C))
+        d_table = _zeros_f32(tuple(table.shape), dev)
+        d_qkv = o32.winattn_bwd(qkv.view(*shp, 3 * C), table, attn, lse, d_attn.view(*shp, C), H, W, nH, ws, shift, d_table,
+                                qk_scale, ctx.mask)
+        dq2 = d_qkv.view(-1, 3 * C)
+        d_bqkv = o32.colsum(dq2, _zeros_f32((3 * C,), dev)) if ctx.has_qkv_bias else None
+        d_x = o32.linear_dgrad(dq2, w_qkv)
+        d_wqkv = o32.linear_wgrad(dq2, x2)
+        return d_x.view(*shp, C), d_table, d_wqkv, d_bqkv, d_wproj, d_bproj, None, None
+
+
+class _BlockFn32(torch.autograd.Function):
+    """``_BlockFn`` (one post-norm SwinTransformerBlock, swin_512.py:196-237) in the fp32-accurate mode."""
+
+    @staticmethod
+    def forward(ctx, x, table, w_qkv, b_qkv, w_proj, b_proj, g1, be1, g2, be2, w_fc1, b_fc1, w_fc2, b_fc2, geom):
+        from . import ops32 as o32
+        H, W, nH, ws, shift, qk_scale, eps, infer = geom
+        Bp, T, L, C = x.shape
+        x2 = x.reshape(-1, C)
+        qkv = o32.linear(x2, w_qkv, b_qkv)
+        attn, lse = o32.winattn_fwd(qkv.view(Bp, T, L, 3 * C), table, H, W, nH, ws, shift, qk_scale)
+        y = o32.linear(attn.view(-1, C), w_proj, b_proj, res=x2)
+        yn, mean2, rstd2 = o32.layernorm_fwd(y, g2, be2, eps)
+        u = o32.linear(yn, w_fc1, b_fc1)
+        z = o32.linear(u, w_fc2, b_fc2, res=y, gelu_input=True)
+        out, mean1, rstd1 = o32.layernorm_fwd(z, g1, be1, eps)
+        if not infer:
+            ctx.save_for_backward(x2, qkv, attn, lse, y, yn, mean2, rstd2, u, z, mean1, rstd1, table, w_qkv, w_proj, w_fc1, w_fc2, g1, g2)
+            ctx.geom, ctx.has_qkv_bias = geom[:7], b_qkv is not None
+        return out.view(Bp, T, L, C)
+
+    @staticmethod
+    def backward(ctx, d_out):
+        from . import ops32 as o32
+        (x2, qkv, attn, lse, y, yn, mean2, rstd2, u, z, mean1, rstd1, table, w_qkv, w_proj, w_fc1, w_fc2, g1, g2) = ctx.saved_tensors
+        H, W, nH, ws, shift, qk_scale, eps = ctx.geom
+        C = x2.shape[1]
+        shp = d_out.shape[:3]
+        dev = x2.device
+        d2 = d_out.contiguous().view(-1, C)
+        d_g1, d_be1, d_g2, d_be2 = (_zeros_f32((C,), dev) for _ in range(4))
+        dz = o32.layernorm_bwd(d2, z, mean1, rstd1, g1, d_g1, d_be1)
+        d_bfc2 = o32.colsum(dz, _zeros_f32((C,), dev))
+        dh = o32.linear_dgrad(dz, w_fc2)
+        d_wfc2 = o32.linear_wgrad(dz, u, gelu_input=True)
+        du = o32.mul_gelu_grad(dh, u)
+        d_bfc1 = o32.colsum(du, _zeros_f32((w_fc1.shape[0],), dev))
+        dyn = o32.linear_dgrad(du, w_fc1)
+        d_wfc1 = o32.linear_wgrad(du, yn)
+        dy = o32.layernorm_bwd(dyn, y, mean2, rstd2, g2, d_g2, d_be2, dres=dz)
+        d_bproj = o32.colsum(dy, _zeros_f32((C,), dev))
+        d_attn = o32.linear_dgrad(dy, w_proj)
+        d_wproj = o32.linear_wgrad(dy, attn.view(-1, C))
+        d_table = _zeros_f32(tuple(table.shape), dev)
+        d_qkv = o32.winattn_bwd(qkv.view(*shp, 3 * C), table, attn, lse, d_attn.view(*shp, C), H, W, nH, ws, shift, d_table, qk_scale)
+        dq2 = d_qkv.view(-1, 3 * C)
+        d_bqkv = o32.colsum(dq2, _zeros_f32((3 * C,), dev)) if ctx.has_qkv_bias else None
+        d_x = o32.linear_dgrad(dq2, w_qkv, res=dy)
+        d_wqkv = o32.linear_wgrad(dq2, x2)
+        return (d_x.view(*shp, C), d_table, d_wqkv, d_bqkv, d_wproj, d_bproj, d_g1, d_be1, d_g2, d_be2,
+                d_wfc1, d_bfc1, d_wfc2, d_bfc2, None)
+
+
+class _PatchMergeFn32(torch.autograd.Function):
+    """``_PatchMergeFn`` in the fp32-accurate mode."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, w_red, geom):
+        from . import ops32 as o32
+        H, W, eps = geom
+        B, T, L, C = x.shape
+        xn, mean, rstd = o32.layernorm_fwd(x.reshape(B * T, L, C), gamma, beta, eps, patch_merge_hw=(H, W))
+        out = o32.linear(xn, w_red)
+        ctx.save_for_backward(x, xn, mean, rstd, gamma, w_red)
+        ctx.geom = geom
+        return out.view(B, T, L // 4, w_red.shape[0])
+
+    @staticmethod
+    def backward(ctx, d_out):
+        from . import ops32 as o32
+        x, xn, mean, rstd, gamma, w_red = ctx.saved_tensors
+        H, W, eps = ctx.geom
+        B, T, L, C = x.shape
+        d2 = d_out.contiguous().view(-1, w_red.shape[0])
+        dxn = o32.linear_dgrad(d2, w_red)
+        d_w = o32.linear_wgrad(d2, xn)
+        d_gamma, d_beta = _zeros_f32((4 * C,), x.device), _zeros_f32((4 * C,), x.device)
+        dx = o32.layernorm_bwd(dxn, x.reshape(B * T, L, C), mean, rstd, gamma, d_gamma, d_beta, patch_merge_hw=(H, W))
+        return dx.view(B, T, L, C), d_gamma, d_beta, d_w, None
+
+
+class _MlpFn32(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2):
+        from . import ops32 as o32
+        x2 = x.reshape(-1, x.shape[-1])
+        u = o32.linear(x2, w1, b1)
+        y = o32.linear(u, w2, b2, gelu_input=True)
+        ctx.save_for_backward(x2, u, w1, w2)
+        return y.view(*x.shape[:-1], w2.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        from . import ops32 as o32
+        x2, u, w1, w2 = ctx.saved_tensors
+        d2 = dy.contiguous().view(-1, w2.shape[0])
+        d_b2 = o32.colsum(d2, _zeros_f32((w2.shape[0],), d2.device))
+        du = o32.mul_gelu_grad(o32.linear_dgrad(d2, w2), u)
+        d_w2 = o32.linear_wgrad(d2, u, gelu_input=True)
+        d_b1 = o32.colsum(du, _zeros_f32((w1.shape[0],), d2.device))
+        return o32.linear_dgrad(du, w1).view(*dy.shape[:-1], w1.shape[1]), o32.linear_wgrad(du, x2), d_b1, d_w2, d_b2
+
+
+def _as_f32(x: torch.Tensor) -> torch.Tensor:
+    if not x.is_cuda:
+        raise StswinError("stswincl_b200 modules need CUDA tensors (no CPU path)")
+    return x if x.dtype == torch.float32 else x.float()
+
+
 def _as_tokens_bf16(x: torch.Tensor) -> torch.Tensor:
     if not x.is_cuda:
         raise StswinError("stswincl_b200 modules need CUDA tensors (no CPU path)")
@@ -339,6 +517,9 @@ class Mlp(nn.Module):
         """fc1 -> GELU (erf) -> fc2 on the last dim (swin_512.py:17-23), stand-alone: two GEMMs with the bias / GELU
         epilogues fused.  Inside ``SwinTransformerBlock`` the same GEMMs run with the residual fused as well."""
         in_dtype = x.dtype
+        if _use_fp32(self, x):
+            y = _MlpFn32.apply(_as_f32(x).contiguous(), self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias)
+            return y if in_dtype == torch.float32 else y.to(in_dtype)
         y = _MlpFn.apply(_as_tokens_bf16(x).contiguous(), self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias)
         return y if in_dtype == _BF16 else y.to(in_dtype)
 
@@ -385,8 +566,11 @@ class WindowAttention(nn.Module):
         assert N == ws * ws and C == self.dim, "input feature has wrong size"
         in_dtype = x_v.dtype
         geom = (ws, ws, self.num_heads, ws, 0, self._qk_scale_arg())
-        out = _AttentionFn.apply(_as_tokens_bf16(x_v).contiguous(), self.relative_position_bias_table,
-                                 self.qkv.weight, self.qkv.bias, self.proj.weight, self.proj.bias, geom, mask)
+        args = (self.relative_position_bias_table, self.qkv.weight, self.qkv.bias, self.proj.weight, self.proj.bias, geom, mask)
+        if _use_fp32(self, x_v):
+            out = _AttentionFn32.apply(_as_f32(x_v).contiguous(), *args)
+            return out if in_dtype == torch.float32 else out.to(in_dtype)
+        out = _AttentionFn.apply(_as_tokens_bf16(x_v).contiguous(), *args)
         return out if in_dtype == _BF16 else out.to(in_dtype)
 
 
@@ -441,15 +625,17 @@ class SwinTransformerBlock(nn.Module):
         # grad mode is decided here: inside autograd.Function.forward it always reads "disabled", and
         # ctx.needs_input_grad ignores torch.no_grad()
         infer = not torch.is_grad_enabled()
-        return _BlockFn.apply(x, *self._block_params(), self._geom() + (infer,))
+        fn = _BlockFn32 if x.dtype == torch.float32 else _BlockFn          # fp32 tokens: the fp32-accurate mode
+        return fn.apply(x, *self._block_params(), self._geom() + (infer,))
 
     def forward(self, x_v):
         H, W = self.input_resolution
         B, T, L, C = x_v.shape
         assert L == H * W, "input feature has wrong size"
         in_dtype = x_v.dtype
-        out = self.forward_tokens(_as_tokens_bf16(x_v).contiguous())
-        return out if in_dtype == _BF16 else out.to(in_dtype)
+        tokens = _as_f32(x_v) if _use_fp32(self, x_v) else _as_tokens_bf16(x_v)
+        out = self.forward_tokens(tokens.contiguous())
+        return out if in_dtype == out.dtype else out.to(in_dtype)
 
 
 class PatchMerging(nn.Module):
@@ -464,7 +650,8 @@ class PatchMerging(nn.Module):
 
     def forward_tokens(self, x: torch.Tensor) -> torch.Tensor:
         H, W = self.input_resolution
-        return _PatchMergeFn.apply(x, self.norm.weight, self.norm.bias, self.reduction.weight, (H, W, self.norm.eps))
+        fn = _PatchMergeFn32 if x.dtype == torch.float32 else _PatchMergeFn
+        return fn.apply(x, self.norm.weight, self.norm.bias, self.reduction.weight, (H, W, self.norm.eps))
 
     def forward(self, x):
         H, W = self.input_resolution
@@ -472,8 +659,9 @@ class PatchMerging(nn.Module):
         assert L == H * W, "input feature has wrong size"
         assert H % 2 == 0 and W % 2 == 0, f"x size ({H}*{W}) are not even."
         in_dtype = x.dtype
-        out = self.forward_tokens(_as_tokens_bf16(x).contiguous())
-        return out if in_dtype == _BF16 else out.to(in_dtype)
+        tokens = _as_f32(x) if _use_fp32(self, x) else _as_tokens_bf16(x)
+        out = self.forward_tokens(tokens.contiguous())
+        return out if in_dtype == out.dtype else out.to(in_dtype)
 
 
 class SwinTransformerLayerv5(nn.Module):
@@ -534,7 +722,8 @@ class SwinTransformerLayerv5(nn.Module):
     def _to_tokens(self, x_v):
         B, T, C, H, W = x_v.shape
         x_in = x_v if x_v.dtype in (torch.float32, _BF16) else x_v.float()
-        return _TransposeFn.apply(x_in.reshape(B * T, C, H * W), _BF16).view(B, T, H * W, C)
+        tok_dtype = torch.float32 if _use_fp32(self, x_v) else _BF16        # fp32 tokens select the fp32-accurate blocks
+        return _TransposeFn.apply(x_in.reshape(B * T, C, H * W), tok_dtype).view(B, T, H * W, C)
 
     def _from_tokens(self, t, stage: int, out_dtype, keep):
         B, T = t.shape[:2]

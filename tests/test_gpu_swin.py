@@ -293,7 +293,10 @@ def test_real_geometry_block_forward_backward_vs_oracle(case):
     params = so.make_block_params(dim, res, heads, ws, shift, seed=91)
     m = _load(swin.SwinTransformerBlock(dim, res, heads, window_size=ws, shift_size=shift), params)
     x = so.make_features(92, 2, 2, L, dim)
-    w = so.make_features(93, 2, 2, L, dim) - 0.4
+    # the upstream gradient is made bf16-representable: half of relu(N) - 0.4 is the single value -0.4, whose bf16
+    # rounding error (+1e-3 relative, the same sign for every element) would otherwise add up over the 20480 rows into
+    # a 1.6e-2 bias of the norm1 gradients that no kernel could avoid
+    w = (so.make_features(93, 2, 2, L, dim) - 0.4).to(torch.bfloat16).float()
     leaf = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and k != "attn_mask" else v) for k, v in params.items()}
     xr = x.to(torch.bfloat16).float().requires_grad_(True)
     ref = so.swin_block(xr, leaf, res, heads, ws, shift)
@@ -319,8 +322,8 @@ def test_full_size_layer_forward_backward_vs_oracle():
     params = so.make_layer_params(dim, res, heads, seed=95)
     m = _load(swin.SwinTransformerLayerv5(dim=dim, input_resolution=res, num_heads=heads), params)
     x = so.make_features(96, 1, 4, dim, res[0], res[1])
-    w1 = so.make_features(97, 1, 4, dim, res[0], res[1]) - 0.4
-    w2 = so.make_features(98, 1, 4, 2 * dim, res[0] // 2, res[1] // 2) - 0.4
+    w1 = (so.make_features(97, 1, 4, dim, res[0], res[1]) - 0.4).to(torch.bfloat16).float()       # bf16-representable upstream gradients
+    w2 = (so.make_features(98, 1, 4, 2 * dim, res[0] // 2, res[1] // 2) - 0.4).to(torch.bfloat16).float()
     names = ["layers.0.0.attn.relative_position_bias_table", "layers.0.0.attn.qkv.weight", "layers.0.1.mlp.fc1.bias",
              "layers.2.1.norm1.weight", "layers.3.0.attn.qkv.bias", "layers.5.1.mlp.fc2.weight", "layers.5.1.norm1.bias",
              "downsample.norm.weight", "downsample.reduction.weight"]
@@ -373,14 +376,15 @@ def test_full_model_with_swapped_head_logits_and_argmax():
 
 
 def test_full_model_three_step_loss_trajectory():
-    """Three Adam steps (lr 1e-4, cross-entropy, train mode with the image-pool BatchNorm in eval) of the
-    swapped model follow the reference's loss trajectory within 2e-2."""
+    """Three SGD steps (lr 2e-4, momentum 0.9, cross-entropy, train mode with the image-pool BatchNorm in eval)
+    of the swapped model follow the reference's loss trajectory within 2e-2 (see oracle/make_goldens_tswin.py for why
+    not Adam 1e-4: that trajectory is chaotic on this synthetic model)."""
     model, g, to = _swapped_model()
     model.train()
     model.aspp.bn_conv_1x1_2.eval()
     clip = to.make_clip(6).cuda()
     target = to.make_targets(7, 1, 512, 640, 12).cuda()
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    opt = torch.optim.SGD(model.parameters(), lr=2e-4, momentum=0.9)
     losses = []
     with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
         for _ in range(3):
