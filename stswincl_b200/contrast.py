@@ -146,7 +146,7 @@ class _PixStepFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, plan, *queries):
-        (slots, qmap, qlab, kmap, klab, S, class_num, normalize, gather) = plan
+        (slots, qmap, qlab, kmap, klab, S, class_num, normalize, gather, fp32) = plan
         lib = _lib.load()
         q0 = queries[0]
         dev = q0.device
@@ -168,6 +168,10 @@ class _PixStepFn(torch.autograd.Function):
         if gather is not None:
             world, n_shared = gather[1], gather[2]
         n_slots = n_local + world * n_shared if world > 1 else n_local
+        if fp32:                                   # second bf16 term of every map behind the first ones
+            if world > 1:
+                raise StswinError("precision='fp32' and cross_rank_negatives cannot be combined")
+            n_slots = 2 * n_local
         nl_slots = nl_local + world * n_shared if world > 1 else nl_local
         HWp, GLp = (HW + 255) // 256 * 256, ((HW + 255) // 256 * 8 + 15) // 16 * 16
         xn = torch.empty((n_slots, N, C, HW), dtype=_BF16, device=dev)
@@ -179,7 +183,8 @@ class _PixStepFn(torch.autograd.Function):
         perm = torch.empty((nl_local, N, HW), dtype=torch.int16, device=dev)
         hist = torch.empty((nl_slots, N, 256), dtype=torch.int32, device=dev)
         ctl = torch.empty(2, dtype=torch.int32, device=dev)               # [0] bad-label flag, [1] finalize ticket
-        stats = torch.empty((Q, N, HW, S, 2, 2), dtype=torch.float32, device=dev)
+        n_terms = 3 if fp32 else 1
+        stats = torch.empty((n_terms, Q, N, HW, S, 2, 2), dtype=torch.float32, device=dev)
         loss = torch.empty((), dtype=torch.float32, device=dev)
         loss_q = torch.empty(Q, dtype=torch.float32, device=dev)
         need_grad = any(ctx.needs_input_grad[1:])
@@ -194,7 +199,7 @@ class _PixStepFn(torch.autograd.Function):
         in_bytes = float(sum(m.numel() * m.element_size() for m in maps) + 2 * n_local * N * C * HW)
         with ops._launch("pix_prepare", in_bytes, q0):
             st = lib.stswin_pixloss_prepare(_parr([m.data_ptr() for m in maps]), _iarr([_MAP_DTYPES[m.dtype] for m in maps]),
-                                            _iarr(slots.map_label), n_local, 0, N, C, HW, int(normalize), perm.data_ptr(),
+                                            _iarr(slots.map_label), n_local, 0, N, C, HW, int(normalize), n_local if fp32 else 0, perm.data_ptr(),
                                             xn.data_ptr(), ops._ptr(inv_norm), ksum.data_ptr(), stream)
         _lib.check(st, "stswin_pixloss_prepare")
         if world > 1:
@@ -207,15 +212,21 @@ class _PixStepFn(torch.autograd.Function):
                                       (glab, ls, nl_local), (hist, ls, nl_local)):
                 tdist.all_gather_into_tensor(buf[n_loc:].view(world, -1), buf[first:first + n_shared].reshape(-1), group=group)
         flops = 2.0 * Q * S * N * HW * HW * C
-        with ops._launch("pixloss_fwd", flops, q0):
+        if fp32:          # (q_hi, k_hi), (q_hi, k_lo), (q_lo, k_hi); backward: k_hi, k_lo
+            lo = lambda idx: [i + n_local for i in idx]
+            qmap_f, kmap_f = qmap + qmap + lo(qmap), kmap + lo(kmap) + kmap
+            kmap_b, qmap_lo = kmap + lo(kmap), _iarr(lo(qmap))
+        else:
+            qmap_f, kmap_f, kmap_b, qmap_lo = qmap, kmap, kmap, None
+        with ops._launch("pixloss_fwd", flops * n_terms, q0):
             st = lib.stswin_pixloss_fwd(xn.data_ptr(), n_slots, nl_slots, lab_nat.data_ptr(), lab_sorted.data_ptr(), glab.data_ptr(),
-                                        hist.data_ptr(), _iarr(qmap), _iarr(qlab), _iarr(kmap), _iarr(klab), Q, S, N, C, HW,
+                                        hist.data_ptr(), _iarr(qmap_f), _iarr(qlab), _iarr(kmap_f), _iarr(klab), n_terms, Q, S, N, C, HW,
                                         stats.data_ptr(), loss.data_ptr(), loss_q.data_ptr(), ops._ptr(coef), ctl.data_ptr(), partial.data_ptr(),
                                         ctl.data_ptr() + 4, stream)
         _lib.check(st, "stswin_pixloss_fwd")
-        ops.count_extra_launches(1)                       # finalize kernel inside stswin_pixloss_fwd
+        ops.count_extra_launches(n_terms)                 # further terms + finalize kernel inside stswin_pixloss_fwd
         ctx.ws = (xn, lab_nat, lab_sorted, glab, coef, ksum, inv_norm, n_slots, nl_slots)
-        ctx.plan = (qmap, qlab, kmap, klab, Q, S, N, C, HW, flops)
+        ctx.plan = (qmap, qmap_lo, qlab, kmap_b, klab, 2 if fp32 else 1, Q, S, N, C, HW, flops)
         ctx.q_meta = [(q.shape, q.dtype) for q in queries]
         ctx.mark_non_differentiable(loss_q, ctl)
         ctx.set_materialize_grads(False)              # no zero-filled gradients for the two auxiliary outputs
@@ -224,19 +235,20 @@ class _PixStepFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_loss, _d_per_query, _d_flag):
         xn, lab_nat, lab_sorted, glab, coef, ksum, inv_norm, n_slots, nl_slots = ctx.ws
-        qmap, qlab, kmap, klab, Q, S, N, C, HW, flops = ctx.plan
+        qmap, qmap_lo, qlab, kmap, klab, n_terms, Q, S, N, C, HW, flops = ctx.plan
         dev = xn.device
         out_dtype = ctx.q_meta[0][1] if ctx.q_meta[0][1] in _MAP_DTYPES else torch.float32
         outs = [torch.empty((N, C, HW), dtype=out_dtype, device=dev) for _ in range(Q)]
         dq32 = torch.empty((Q, N, HW, C), dtype=torch.float32, device=dev)
         g = d_loss.detach().to(torch.float32).contiguous()
-        with ops._launch("pixloss_bwd", flops, xn):
+        with ops._launch("pixloss_bwd", flops * n_terms, xn):
             st = _lib.load().stswin_pixloss_bwd(xn.data_ptr(), n_slots, nl_slots, lab_nat.data_ptr(), lab_sorted.data_ptr(),
-                                                glab.data_ptr(), _iarr(qmap), _iarr(qlab), _iarr(kmap), _iarr(klab), Q, S, N, C, HW,
+                                                glab.data_ptr(), _iarr(qmap), qmap_lo, _iarr(qlab), _iarr(kmap), _iarr(klab), n_terms,
+                                                Q, S, N, C, HW,
                                                 coef.data_ptr(), ksum.data_ptr(), g.data_ptr(), dq32.data_ptr(), ops._ptr(inv_norm),
                                                 _parr([o.data_ptr() for o in outs]), _MAP_DTYPES[out_dtype], ops._stream(xn))
         _lib.check(st, "stswin_pixloss_bwd")
-        ops.count_extra_launches(1)                       # dq finish kernel inside stswin_pixloss_bwd
+        ops.count_extra_launches(n_terms)                 # further term + dq finish kernel inside stswin_pixloss_bwd
         grads = []
         for o, (shape, dtype) in zip(outs, ctx.q_meta):
             o = o.view(shape)
@@ -246,7 +258,7 @@ class _PixStepFn(torch.autograd.Function):
 
 def _loss_step(queries: Sequence[Tuple[torch.Tensor, torch.Tensor]],
                key_sets: Sequence[Sequence[Tuple[torch.Tensor, torch.Tensor]]], class_num: int, *, normalize: bool,
-               validate_labels, gather=None):
+               validate_labels, gather=None, precision: str = "bf16"):
     """queries: [(q map, its label map)]; key_sets[q]: [(key map, its label map)] -- the same number for every query.
     Returns (total loss, per-query losses, int32 control words: [0] != 0 when a label was out of range)."""
     if not 1 <= class_num <= MAX_CLASSES:
@@ -286,7 +298,10 @@ def _loss_step(queries: Sequence[Tuple[torch.Tensor, torch.Tensor]],
         S = S + (world - 1) * n_sh
         kmap, klab = kmap2, klab2
         gather = (group, world, n_sh, ms[0], ls[0])
-    plan = (slots, qmap, qlab, kmap, klab, S, class_num, bool(normalize), gather)
+    if precision not in ("bf16", "fp32", "auto"):
+        raise ValueError("precision must be 'bf16', 'fp32' or 'auto'")
+    fp32 = precision == "fp32" or (precision == "auto" and queries[0][0].dtype == torch.float32 and not torch.is_autocast_enabled())
+    plan = (slots, qmap, qlab, kmap, klab, S, class_num, bool(normalize), gather, fp32)
     total, per_query, flag = _PixStepFn.apply(plan, *[q for q, _ in queries])
     if validate_labels is True or validate_labels == "host":
         if int(flag[0]) != 0:                             # F.one_hot raises for labels outside [0, class_num) (:54-55)
@@ -296,7 +311,7 @@ def _loss_step(queries: Sequence[Tuple[torch.Tensor, torch.Tensor]],
 
 def pixel_contrast_loss(q: torch.Tensor, keys: Sequence[torch.Tensor], label_q: torch.Tensor,
                         labels_k: Sequence[torch.Tensor], class_num: int, *, normalize: bool = False,
-                        validate_labels="device") -> torch.Tensor:
+                        validate_labels="device", precision: str = "bf16") -> torch.Tensor:
     """General form: any 1..64 key sets (e.g. key sets all-gathered from other ranks).  ``normalize=True``
     fuses ``F.normalize(dim=1)`` of q and of every key into the loss (otherwise the inputs are taken as already
     unit-norm, like the reference's ``regression_loss``).
@@ -308,21 +323,22 @@ def pixel_contrast_loss(q: torch.Tensor, keys: Sequence[torch.Tensor], label_q: 
         raise StswinError("stswincl_b200.contrast needs CUDA tensors (no CPU path)")
     assert len(keys) == len(labels_k) and 1 <= len(keys) <= 64
     total, _, _ = _loss_step([(q, label_q)], [list(zip(keys, labels_k))], class_num, normalize=normalize,
-                             validate_labels=validate_labels)
+                             validate_labels=validate_labels, precision=precision)
     return total
 
 
 def regression_loss(q, k, adj1, adj2, adj3, neg3, label_patch1, label_patch2, label_adj1, label_adj2, label_adj3,
-                    label_neg3, class_num, validate_labels="device"):
-    """Same signature and value as PixPro_swin_v5.py:71-129 (inputs already L2-normalised)."""
+                    label_neg3, class_num, validate_labels="device", precision: str = "bf16"):
+    """Same signature and value as PixPro_swin_v5.py:71-129 (inputs already L2-normalised).  ``precision="fp32"``: the
+    similarities as three bf16 product terms (hi*hi + hi*lo + lo*hi), loss and gradient <= 1e-3 against the fp32 run."""
     return pixel_contrast_loss(q, [k, adj1, adj2, adj3, neg3], label_patch1,
                                [label_patch2, label_adj1, label_adj2, label_adj3, label_neg3], class_num,
-                               validate_labels=validate_labels)
+                               validate_labels=validate_labels, precision=precision)
 
 
 def consistency_loss_tail(pred_1, pred_2, proj_1_ng, proj_2_ng, proj_adj1_ng, proj_adj2_ng, proj_adj3_ng, proj_neg3_ng,
                           mask_1, mask_2, mask_3, mask_4, mask_5, mask_6, class_num, *, normalize: bool = False,
-                          cross_rank_negatives: bool = False, group=None, validate_labels="device"):
+                          cross_rank_negatives: bool = False, group=None, validate_labels="device", precision: str = "bf16"):
     """``ConsistencyLoss.forward`` after ``self.pixpro(...)`` (:584-597): nearest label down-sampling to the embedding
     resolution, then the symmetric sum of two ``regression_loss`` calls -- here ONE fused step: both calls share the
     label pass, the normalise / cast pass, one similarity launch and one backward launch; the four shared key sets are
@@ -340,7 +356,7 @@ def consistency_loss_tail(pred_1, pred_2, proj_1_ng, proj_2_ng, proj_adj1_ng, pr
             gather = (group, tdist.get_world_size(group), shared)
     total, _, _ = _loss_step([(pred_1, mask_1), (pred_2, mask_2)],
                              [[(proj_2_ng, mask_2), *shared], [(proj_1_ng, mask_1), *shared]], class_num,
-                             normalize=normalize, validate_labels=validate_labels, gather=gather)
+                             normalize=normalize, validate_labels=validate_labels, gather=gather, precision=precision)
     return total
 
 

@@ -65,23 +65,24 @@ int stswin_pixloss_labels(const void* const* labels, const int* dtypes, int n_la
                                 perm, hist, err_flag, static_cast<cudaStream_t>(stream));
 }
 int stswin_pixloss_prepare(const void* const* maps, const int* dtypes, const int* label_slots, int n_maps, int slot_off,
-                           int N, int C, int HW, int do_normalize, const uint16_t* perm, void* xn, float* inv_norm,
-                           float* ksum, void* stream) {
-  return stswin::pixloss_prepare(maps, dtypes, label_slots, n_maps, slot_off, N, C, HW, do_normalize, perm, xn, inv_norm,
-                                 ksum, static_cast<cudaStream_t>(stream));
+                           int N, int C, int HW, int do_normalize, int lo_slot_off, const uint16_t* perm, void* xn,
+                           float* inv_norm, float* ksum, void* stream) {
+  return stswin::pixloss_prepare(maps, dtypes, label_slots, n_maps, slot_off, N, C, HW, do_normalize, lo_slot_off, perm, xn,
+                                 inv_norm, ksum, static_cast<cudaStream_t>(stream));
 }
 int stswin_pixloss_fwd(const void* xn, int n_slots, int n_label_slots, const uint8_t* lab_nat, const uint8_t* lab_sorted,
                        const uint8_t* glab, const int32_t* hist, const int* qmap, const int* qlab, const int* kmap,
-                       const int* klab, int Q, int S, int N, int C, int HW, float* stats, float* loss, float* loss_per_query,
+                       const int* klab, int n_terms, int Q, int S, int N, int C, int HW, float* stats, float* loss,
+                       float* loss_per_query,
                        float* coef, const int32_t* err_flag, float* partial, uint32_t* ticket, void* stream) {
-  return stswin::pixloss_fwd(xn, n_slots, n_label_slots, lab_nat, lab_sorted, glab, hist, qmap, qlab, kmap, klab, Q, S, N,
+  return stswin::pixloss_fwd(xn, n_slots, n_label_slots, lab_nat, lab_sorted, glab, hist, qmap, qlab, kmap, klab, n_terms, Q, S, N,
                              C, HW, stats, loss, loss_per_query, coef, err_flag, partial, ticket, static_cast<cudaStream_t>(stream));
 }
 int stswin_pixloss_bwd(const void* xn, int n_slots, int n_label_slots, const uint8_t* lab_nat, const uint8_t* lab_sorted,
-                       const uint8_t* glab, const int* qmap, const int* qlab, const int* kmap, const int* klab, int Q,
-                       int S, int N, int C, int HW, const float* coef, const float* ksum, const float* d_loss, float* dq32,
+                       const uint8_t* glab, const int* qmap, const int* qmap_lo, const int* qlab, const int* kmap,
+                       const int* klab, int n_terms, int Q, int S, int N, int C, int HW, const float* coef, const float* ksum, const float* d_loss, float* dq32,
                        const float* inv_norm, void* const* dq_out, int out_dtype, void* stream) {
-  return stswin::pixloss_bwd(xn, n_slots, n_label_slots, lab_nat, lab_sorted, glab, qmap, qlab, kmap, klab, Q, S, N, C, HW,
+  return stswin::pixloss_bwd(xn, n_slots, n_label_slots, lab_nat, lab_sorted, glab, qmap, qmap_lo, qlab, kmap, klab, n_terms, Q, S, N, C, HW,
                              coef, ksum, d_loss, dq32, inv_norm, dq_out, out_dtype, static_cast<cudaStream_t>(stream));
 }
 

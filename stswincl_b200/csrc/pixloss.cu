@@ -200,6 +200,7 @@ struct PrepArgs {
   uint8_t dtype[PX_MAX_PTRS];     // 0 bf16, 1 f32, 2 f16
   int8_t lslot[PX_MAX_PTRS];      // label slot whose sort orders this map's pixels; -1 = pixel order (query maps)
   int n_maps, slot_off, N, C, HW, do_normalize;
+  int lo_off;                     // > 0: also store the second bf16 term (x - bf16(x)) in slot (slot + lo_off) -- fp32 mode
   const uint16_t* perm;           // [label slots, N, HW]
   __nv_bfloat16* xn;              // [slots, N, C, HW]
   float* inv_norm;                // [slots, N, HW] (pixel order) or null
@@ -262,7 +263,8 @@ __device__ __forceinline__ void prepare_body(const PrepArgs& p, const TI* __rest
 #pragma unroll
   for (int u = 0; u < CPW; ++u) {
     const int c = warp + 8 * u;
-    const __nv_bfloat162 b = __floats2bfloat162_rn(v[u].x * inv0, v[u].y * inv1);
+    const float x0 = v[u].x * inv0, x1 = v[u].y * inv1;
+    const __nv_bfloat162 b = __floats2bfloat162_rn(x0, x1);
     if (ok) {
       if (ls < 0) {
         *reinterpret_cast<__nv_bfloat162*>(ob + (size_t)c * p.HW + j0) = b;
@@ -272,6 +274,17 @@ __device__ __forceinline__ void prepare_body(const PrepArgs& p, const TI* __rest
       }
       const float2 f = __bfloat1622float2(b);       // sum what the tensor core will read (bf16-rounded)
       cs[u] = f.x + f.y;
+      if (p.lo_off > 0) {                           // fp32 mode: second term, and the channel sum of the fp32 values
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(x0 - f.x, x1 - f.y);
+        __nv_bfloat16* ol = ob + (size_t)p.lo_off * p.N * p.C * p.HW;
+        if (ls < 0) {
+          *reinterpret_cast<__nv_bfloat162*>(ol + (size_t)c * p.HW + j0) = lo;
+        } else {
+          ol[(size_t)c * p.HW + d0] = lo.x;
+          ol[(size_t)c * p.HW + d1] = lo.y;
+        }
+        cs[u] = x0 + x1;
+      }
     }
   }
   if (ls >= 0) {                                    // key maps only: the backward's  b_s * sum_j k_j  term
@@ -531,7 +544,8 @@ pixloss_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const PixTable tab,
 // finalize: per-row loss and backward coefficients, one thread per query pixel; the mean is a two-level sum in
 // a fixed order (block partials, summed by the last block to finish), so the loss is bit-reproducible.
 struct PixFinArgs {
-  int N, HW, HWp, Q, S;
+  int N, HW, HWp, Q, S, n_terms;
+  long term_stride;         // floats between the stats of consecutive terms
   const float* stats;       // [Q, N, HW, S, 2, 2]
   const uint8_t* lab_nat;
   const int* hist;          // [label slots, N, 256]
@@ -556,8 +570,12 @@ __global__ void __launch_bounds__(256) pixloss_finalize_kernel(const PixTable ta
     const float* st = p.stats + ((size_t)q * rows + r) * p.S * 4;
     float psum = 0.f, pcnt = 0.f, nterm = 0.f;
     for (int s = 0; s < p.S; ++s) {
-      const float4 v = *reinterpret_cast<const float4*>(st + s * 4);      // (same, total) of the two column halves
-      const float same = v.x + v.z, total = v.y + v.w;
+      float same = 0.f, total = 0.f;
+      for (int t = 0; t < p.n_terms; ++t) {                                // fp32 mode: hi*hi + hi*lo + lo*hi
+        const float4 v = *reinterpret_cast<const float4*>(st + t * p.term_stride + s * 4);   // (same, total) x 2 column halves
+        same += v.x + v.z;
+        total += v.y + v.w;
+      }
       const float cnt = (float)p.hist[((size_t)tab.klab[q][s] * p.N + n) * 256 + lrow];
       psum += same;
       pcnt += cnt;
@@ -626,6 +644,7 @@ struct PixBwdArgs {
   const float* coef;     // [Q, N, HW, 1 + S]
   const float* ksum;     // [slots, N, C]
   const float* d_loss;   // device scalar (upstream gradient)
+  int add_ksum;          // 0 for the second (lo) key term of the fp32 mode: the b_s * colsum(K_s) part is added once
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PX_THREADS, 1)
@@ -805,6 +824,7 @@ pixloss_bwd_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
       }
       const float* ks = p.ksum + ((size_t)tab.kmap[q][s] * p.N + n) * p.C;
       const float cm = ca - cb_;
+      if (!p.add_ksum) cb_ = 0.f;
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
       const int nc32 = p.C / 32;
@@ -856,6 +876,7 @@ pixloss_bwd_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
 struct FinishArgs {
   void* out[PX_MAX_Q];
   int16_t qmap[PX_MAX_Q];
+  int16_t qmap_lo[PX_MAX_Q];         // second bf16 term of the query map (fp32 mode), or -1
   int N, C, HW, out_dtype, chain;      // out_dtype: 0 bf16, 1 f32, 2 f16
   const float* dq32;
   const __nv_bfloat16* xn;
@@ -887,6 +908,8 @@ __global__ void __launch_bounds__(256) pix_dq_finish_kernel(const FinishArgs p) 
     for (int u = 0; u < CPW; ++u) {
       const int c = warp + 8 * u;
       xq[u] = ok ? __bfloat162float(xb[(size_t)c * p.HW + i]) : 0.f;
+      if (ok && p.qmap_lo[q] >= 0)
+        xq[u] += __bfloat162float(p.xn[(((size_t)p.qmap_lo[q] * p.N + n) * p.C + c) * p.HW + i]);
       part = fmaf(xq[u], s_fin[lane * ld + c], part);
     }
     s_dot[warp * 32 + lane] = part;
@@ -972,8 +995,9 @@ int pixloss_labels(const void* const* labels, const int* dtypes, int n_labels, i
 
 // see include/stswin_b200.h : stswin_pixloss_prepare
 int pixloss_prepare(const void* const* maps, const int* dtypes, const int* label_slots, int n_maps, int slot_off, int N,
-                    int C, int HW, int do_normalize, const uint16_t* perm, void* xn, float* inv_norm, float* ksum,
-                    cudaStream_t stream) {
+                    int C, int HW, int do_normalize, int lo_slot_off, const uint16_t* perm, void* xn, float* inv_norm,
+                    float* ksum, cudaStream_t stream) {
+  STSWIN_CHECK_ARG(lo_slot_off == 0 || lo_slot_off >= n_maps, "pixloss_prepare: lo_slot_off must be 0 or >= n_maps");
   STSWIN_CHECK_ARG(maps && dtypes && label_slots && xn && ksum && perm, "pixloss_prepare: null pointer");
   STSWIN_CHECK_ARG(n_maps >= 1 && N > 0, "pixloss_prepare: bad shape");
   STSWIN_CHECK_ARG(!do_normalize || inv_norm != nullptr, "pixloss_prepare: normalisation needs inv_norm");
@@ -993,6 +1017,7 @@ int pixloss_prepare(const void* const* maps, const int* dtypes, const int* label
       a.lslot[i] = (int8_t)label_slots[src];
     }
     a.n_maps = nm; a.slot_off = slot_off + off; a.N = N; a.C = C; a.HW = HW; a.do_normalize = do_normalize;
+    a.lo_off = lo_slot_off;
     a.perm = perm; a.xn = static_cast<__nv_bfloat16*>(xn); a.inv_norm = inv_norm; a.ksum = ksum;
     const dim3 grid((HW + 63) / 64, N, nm);
     switch (C / 64) {
@@ -1009,29 +1034,35 @@ int pixloss_prepare(const void* const* maps, const int* dtypes, const int* label
 // see include/stswin_b200.h : stswin_pixloss_fwd
 int pixloss_fwd(const void* xn, int n_slots, int n_label_slots, const uint8_t* lab_nat, const uint8_t* lab_sorted,
                 const uint8_t* glab, const int* hist, const int* qmap, const int* qlab, const int* kmap, const int* klab,
-                int Q, int S, int N, int C, int HW, float* stats, float* loss, float* loss_per_query, float* coef, const int* err_flag,
-                float* partial, unsigned int* ticket, cudaStream_t stream) {
+                int n_terms, int Q, int S, int N, int C, int HW, float* stats, float* loss, float* loss_per_query, float* coef,
+                const int* err_flag, float* partial, unsigned int* ticket, cudaStream_t stream) {
   STSWIN_CHECK_ARG(xn && lab_nat && lab_sorted && glab && hist && qmap && qlab && kmap && klab && stats && loss &&
                        err_flag && partial && ticket, "pixloss_fwd: null pointer");
+  STSWIN_CHECK_ARG(n_terms >= 1 && n_terms <= 3, "pixloss_fwd: n_terms=%d out of range [1,3]", n_terms);
   int rc = check_pix_shape(Q, S, N, C, HW);
   if (rc != kOk) return rc;
-  PixTable tab;
-  if ((rc = fill_table(&tab, qmap, qlab, kmap, klab, Q, S, n_slots, n_label_slots)) != kOk) return rc;
   CUtensorMap tm;
   if ((rc = map_tmap(&tm, xn, n_slots * N, C, HW, 64)) != kOk) return rc;
   PixFwdArgs a;
   a.N = N; a.C = C; a.HW = HW; a.HWp = px_hwp(HW); a.GLp = px_glp(HW); a.Q = Q; a.S = S; a.nkb = C / 64;
   a.num_mbp = a.HWp / 256; a.num_tiles = a.HWp / 256;
-  a.lab_nat = lab_nat; a.lab_sorted = lab_sorted; a.glab = glab; a.stats = stats;
+  a.lab_nat = lab_nat; a.lab_sorted = lab_sorted; a.glab = glab;
   const int smem = 1024 + 4 * PF_AKB + PF_STAGES * PF_BSTAGE + 2 * (a.HWp + a.GLp) + 256;
   STSWIN_CUDA(cudaFuncSetAttribute(pixloss_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int items = Q * N * a.num_mbp * S;
   const int max_clusters = num_sms() / 2;
   const int grid = 2 * (items < max_clusters ? items : max_clusters);
-  pixloss_fwd_kernel<<<grid, PX_THREADS, smem, stream>>>(tm, tab, a);
-  STSWIN_CUDA(cudaGetLastError());
+  const long term_stride = (long)Q * N * HW * S * 4;
+  PixTable tab;
+  for (int t = 0; t < n_terms; ++t) {      // fp32 mode: one launch per product term (the row sums are linear in the similarities)
+    if ((rc = fill_table(&tab, qmap + t * Q, qlab, kmap + t * Q * S, klab, Q, S, n_slots, n_label_slots)) != kOk) return rc;
+    a.stats = stats + t * term_stride;
+    pixloss_fwd_kernel<<<grid, PX_THREADS, smem, stream>>>(tm, tab, a);
+    STSWIN_CUDA(cudaGetLastError());
+  }
   PixFinArgs f;
-  f.N = N; f.HW = HW; f.HWp = a.HWp; f.Q = Q; f.S = S; f.stats = stats; f.lab_nat = lab_nat; f.hist = hist; f.err = err_flag;
+  f.N = N; f.HW = HW; f.HWp = a.HWp; f.Q = Q; f.S = S; f.n_terms = n_terms; f.term_stride = term_stride;
+  f.stats = stats; f.lab_nat = lab_nat; f.hist = hist; f.err = err_flag;
   f.loss = loss; f.loss_q = loss_per_query; f.coef = coef; f.partial = partial; f.ticket = ticket;
   const long rows = (long)N * HW;
   pixloss_finalize_kernel<<<dim3((unsigned)((rows + 255) / 256), Q), 256, 0, stream>>>(tab, f);
@@ -1041,16 +1072,16 @@ int pixloss_fwd(const void* xn, int n_slots, int n_label_slots, const uint8_t* l
 
 // see include/stswin_b200.h : stswin_pixloss_bwd
 int pixloss_bwd(const void* xn, int n_slots, int n_label_slots, const uint8_t* lab_nat, const uint8_t* lab_sorted,
-                const uint8_t* glab, const int* qmap, const int* qlab, const int* kmap, const int* klab, int Q, int S,
-                int N, int C, int HW, const float* coef, const float* ksum, const float* d_loss, float* dq32,
-                const float* inv_norm, void* const* dq_out, int out_dtype, cudaStream_t stream) {
+                const uint8_t* glab, const int* qmap, const int* qmap_lo, const int* qlab, const int* kmap, const int* klab,
+                int n_terms, int Q, int S, int N, int C, int HW, const float* coef, const float* ksum, const float* d_loss,
+                float* dq32, const float* inv_norm, void* const* dq_out, int out_dtype, cudaStream_t stream) {
   STSWIN_CHECK_ARG(xn && lab_nat && lab_sorted && glab && qmap && qlab && kmap && klab && coef && ksum && d_loss && dq32 &&
                        dq_out, "pixloss_bwd: null pointer");
   STSWIN_CHECK_ARG(out_dtype >= 0 && out_dtype <= 2, "pixloss_bwd: bad output dtype %d", out_dtype);
+  STSWIN_CHECK_ARG(n_terms >= 1 && n_terms <= 2, "pixloss_bwd: n_terms=%d out of range [1,2]", n_terms);
   int rc = check_pix_shape(Q, S, N, C, HW);
   if (rc != kOk) return rc;
   PixTable tab;
-  if ((rc = fill_table(&tab, qmap, qlab, kmap, klab, Q, S, n_slots, n_label_slots)) != kOk) return rc;
   CUtensorMap tk, tdq;
   if ((rc = map_tmap(&tk, xn, n_slots * N, C, HW, (uint32_t)(C / 2))) != kOk) return rc;
   {
@@ -1069,12 +1100,17 @@ int pixloss_bwd(const void* xn, int n_slots, int n_label_slots, const uint8_t* l
   const int items = Q * N * a.num_mbp * S;
   const int max_clusters = num_sms() / 2;
   const int grid = 2 * (items < max_clusters ? items : max_clusters);
-  pixloss_bwd_kernel<<<grid, PX_THREADS, smem, stream>>>(tk, tdq, tab, a);
-  STSWIN_CUDA(cudaGetLastError());
+  for (int t = n_terms - 1; t >= 0; --t) {   // fp32 mode: keys = hi + lo, two launches reducing into the same dq (t = 0 last: its table feeds the finish kernel)
+    if ((rc = fill_table(&tab, qmap, qlab, kmap + t * Q * S, klab, Q, S, n_slots, n_label_slots)) != kOk) return rc;
+    a.add_ksum = (t == 0);
+    pixloss_bwd_kernel<<<grid, PX_THREADS, smem, stream>>>(tk, tdq, tab, a);
+    STSWIN_CUDA(cudaGetLastError());
+  }
   FinishArgs f;
   for (int q = 0; q < PX_MAX_Q; ++q) {
     f.out[q] = dq_out[q < Q ? q : 0];
     f.qmap[q] = tab.qmap[q < Q ? q : 0];
+    f.qmap_lo[q] = (int16_t)(qmap_lo != nullptr ? qmap_lo[q < Q ? q : 0] : -1);
     STSWIN_CHECK_ARG(f.out[q] != nullptr, "pixloss_bwd: null gradient output %d", q);
   }
   f.N = N; f.C = C; f.HW = HW; f.out_dtype = out_dtype; f.chain = inv_norm != nullptr; f.dq32 = dq32;

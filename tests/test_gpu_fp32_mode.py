@@ -188,3 +188,46 @@ def test_full_model_fp32_mode_exact_argmax():
     assert err < TOL, err
     am = logits.argmax(1)[0].cpu().numpy()
     assert np.array_equal(am, g["argmax"]), int((am != g["argmax"]).sum())
+
+
+@pytest.mark.parametrize("idx", range(5))
+def test_regression_loss_fp32_vs_reference_golden(idx):
+    """regression_loss (PixPro_swin_v5.py:71-129) with precision='fp32' against the goldens written from the reference's
+    fp32 run: loss value and dq at 1e-3 (incl. the absent-class and single-class key-set cases)."""
+    from oracle import make_goldens as mg
+    from stswincl_b200 import contrast
+    case = mg.LOSS_CASES[idx]
+    tag, N, C, H, W, K, special = case
+    g = _g("loss_cases.npz")
+    labels, emb = mg.loss_case_inputs(*case)
+    q = emb[0].cuda().requires_grad_(True)
+    loss = contrast.regression_loss(q, *[e.cuda() for e in emb[1:]], *[l.cuda() for l in labels], K, precision="fp32")
+    loss.backward()
+    torch.cuda.synchronize()
+    ref = float(g[f"{tag}_loss"])
+    assert abs(float(loss) - ref) < TOL * abs(ref)
+    assert rel_err(q.grad.cpu(), g[f"{tag}_dq"]) < TOL
+
+
+@pytest.mark.parametrize("N,C,H,W,K,coarse", [(2, 256, 32, 56, 12, (4, 7)), (1, 64, 28, 28, 26, (28, 28))])
+def test_symmetric_tail_fp32_fused_normalize_vs_oracle(N, C, H, W, K, coarse):
+    """The fused symmetric step (ConsistencyLoss tail with F.normalize inside) in fp32 mode against the un-rounded fp32
+    oracle: loss and both query gradients at 1e-3."""
+    from oracle import loss_oracle as lo
+    from stswincl_b200 import contrast
+    full = lo.make_label_maps(121, 6, N, 8 * H, 8 * W, K, coarse=coarse)
+    ds = [torch.nn.functional.interpolate(m, size=[H, W], mode="nearest") for m in full]
+    gen = torch.Generator().manual_seed(122)
+    raw = [e * (0.5 + 2.0 * torch.rand(N, 1, H, W, generator=gen)) for e in lo.make_embeddings(123, ds + ds[:2], C, K)]
+    pred = [raw[6].clone().requires_grad_(True), raw[7].clone().requires_grad_(True)]
+    nrm = lo.l2_normalize
+    ref = lo.consistency_tail(nrm(pred[0]), nrm(pred[1]), nrm(raw[0]), nrm(raw[1]), [nrm(r) for r in raw[2:6]], full[0], full[1], full[2:], K)
+    ref.backward()
+    c = lambda t: t.cuda()
+    p1, p2 = c(raw[6]).requires_grad_(True), c(raw[7]).requires_grad_(True)
+    loss = contrast.consistency_loss_tail(p1, p2, *[c(r) for r in raw[:6]], *[c(m) for m in full], K, normalize=True, precision="fp32")
+    loss.backward()
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(ref)) < TOL * abs(float(ref))
+    assert rel_err(p1.grad.cpu(), pred[0].grad) < TOL
+    assert rel_err(p2.grad.cpu(), pred[1].grad) < TOL
