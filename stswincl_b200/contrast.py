@@ -379,9 +379,10 @@ class ConsistencyLoss(nn.Module):
         super().__init__()
         self.pixpro_pos_ratio = getattr(args, "pixpro_pos_ratio", None)
         if pixpro is None:
-            from .pixpro import PixPro
-            pixpro = PixPro(args)
+            raise ValueError("ConsistencyLoss needs the built `pixpro` module (the reference class, or stswincl_b200.pixpro.PixPro "
+                             "around the caller's encoders): ResNet / ASPP / projection heads are not part of this library")
         self.pixpro = pixpro
+        self.fuse_normalize = bool(getattr(pixpro, "fuse_normalize", False))
         if args.data == 'endo18':
             self.class_num = 12
         elif args.data == 'cata':
@@ -396,4 +397,5 @@ class ConsistencyLoss(nn.Module):
          proj_neg3_ng) = self.pixpro(im_1, im_2, im_3, im_4, im_5, im_6)
         return consistency_loss_tail(pred_1, pred_2, proj_1_ng, proj_2_ng, proj_adj1_ng, proj_adj2_ng, proj_adj3_ng,
                                      proj_neg3_ng, mask_1, mask_2, mask_3, mask_4, mask_5, mask_6, self.class_num,
-                                     cross_rank_negatives=self.cross_rank_negatives, validate_labels=self.validate_labels)
+                                     normalize=self.fuse_normalize, cross_rank_negatives=self.cross_rank_negatives,
+                                     validate_labels=self.validate_labels)

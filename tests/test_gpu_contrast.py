@@ -255,3 +255,67 @@ def test_tail_is_cuda_graph_capturable_and_deterministic():
         ref.backward()
         assert float(ref) == got
         assert rel_err(g1, e1.grad) < 1e-5
+
+
+class _StubSegmentor(torch.nn.Module):
+    """Tiny stand-in for the caller's segmentor (TswinPlusv5: resnet -> swin -> aspp + three projections)."""
+
+    def __init__(self, head):
+        super().__init__()
+        self.resnet = torch.nn.Conv2d(3, 128, 8, stride=8)
+        self.swin = head
+        self.aspp = torch.nn.Conv2d(256, 24, 1)
+        self.project1, self.project2, self.project3 = torch.nn.Conv2d(128, 8, 1), torch.nn.Conv2d(128, 8, 1), torch.nn.Conv2d(256, 8, 1)
+
+
+def test_pixpro_wrapper_and_consistency_loss_module():
+    """stswincl_b200.pixpro.PixPro around caller-built encoders + contrast.ConsistencyLoss(args, pixpro)
+    (PixPro_swin_v5.py:138-597): head swap with strict weight load, reference state_dict key names, no-grad key passes,
+    cosine-scheduled multi-tensor EMA, and the fused loss equal to the oracle on the returned embeddings."""
+    import math
+    import types
+    from oracle import loss_oracle as lo, tswin_oracle as to
+    from stswincl_b200 import contrast, pixpro, swin
+    torch.manual_seed(0)
+    shapes = {k: (tuple(v.shape), isinstance(v, torch.nn.Parameter), v.dtype) for k, v in
+              list(swin.SwinTransformerLayerv5(128, (16, 24), 2).named_parameters()) + list(swin.SwinTransformerLayerv5(128, (16, 24), 2).named_buffers())}
+    def make_segmentor():      # the caller hands over a segmentor whose head is NOT ours (here: the CPU oracle module)
+        head = to.OracleSwin(shapes, dim=128, input_resolution=(16, 24), num_heads=2)
+        ref = swin.SwinTransformerLayerv5(128, (16, 24), 2)
+        head.load_state_dict(ref.state_dict(), strict=True)
+        return _StubSegmentor(head).cuda()
+    args = types.SimpleNamespace(pixpro_momentum=0.9, pixpro_transform_layer=1, num_instances=64, batch_size=2, epochs=4,
+                                 start_epoch=1, data="endo18", pixpro_pos_ratio=0.7)
+    pp = pixpro.PixPro(args, make_segmentor, lambda: torch.nn.Conv2d(48, 64, 1).cuda(), fuse_normalize=True).cuda()
+    assert isinstance(pp.encoder_2, swin.SwinTransformerLayerv5) and isinstance(pp.encoder_k_2, swin.SwinTransformerLayerv5)
+    keys = set(pp.state_dict().keys())
+    assert {"encoder_2.layers.0.0.attn.qkv.weight", "encoder_k_2.downsample.reduction.weight", "value_transform.weight",
+            "encoder_1.weight", "proj_k_3.bias", "projector_k.weight"} <= keys
+    assert all(not p.requires_grad for p in pp.encoder_k_2.parameters()) and all(p.requires_grad for p in pp.encoder_2.parameters())
+    with torch.no_grad():                                   # make the query encoder differ from the key encoder
+        for p in pp.encoder_2.parameters():
+            p.add_(0.01 * torch.randn_like(p))
+    before = [p.clone() for p in pp.encoder_k_2.parameters()]
+    model = contrast.ConsistencyLoss(args, pp)
+    assert model.class_num == 12
+    gen = torch.Generator().manual_seed(1)
+    ims = [torch.rand(2, 4, 3, 128, 192, generator=gen).cuda() for _ in range(6)]
+    masks = [m.cuda() for m in lo.make_label_maps(2, 6, 2, 128, 192, 12, coarse=(2, 3))]
+    loss = model(*ims, *masks)
+    loss.backward()
+    torch.cuda.synchronize()
+    m = 1. - (1. - 0.9) * (math.cos(math.pi * 0 / pp.K) + 1) / 2.
+    assert pp.k == 1
+    for b, kp, qp in zip(before, pp.encoder_k_2.parameters(), pp.encoder_2.parameters()):
+        assert torch.equal(kp, b * m + qp.detach() * (1. - m))                      # bit-exact EMA
+    assert pp.encoder_2.layers[0][0].attn.qkv.weight.grad is not None and pp.encoder_k_2.layers[0][0].attn.qkv.weight.grad is None
+    with torch.no_grad():
+        outs = pp(*ims)
+    assert len(outs) == 8 and outs[0].shape == (2, 64, 16, 24)
+    pp.k -= 1                                               # the second call advanced the schedule; the loss check below only needs embeddings
+    nrm = lo.l2_normalize
+    emb = [nrm(o.float().cpu()) for o in outs]
+    ref = lo.consistency_tail(emb[0], emb[1], emb[2], emb[3], emb[4:8], masks[0].cpu(), masks[1].cpu(), [m_.cpu() for m_ in masks[2:]], 12)
+    with torch.no_grad():
+        again = contrast.consistency_loss_tail(*outs, *masks, 12, normalize=True)
+    assert abs(float(again) - float(ref)) < 5e-3 * abs(float(ref))

@@ -113,3 +113,33 @@ def test_cross_rank_key_all_gather_matches_the_concatenated_oracle():
     ret = mgr.dict()
     mp.spawn(_c3_worker, args=(2, 29900 + os.getpid() % 200, ret), nprocs=2, join=True)
     assert all(v[0] for v in dict(ret).values()) and len(ret) == 2, dict(ret)
+
+
+def test_data_parallel_two_replica_threads():
+    """nn.DataParallel (seg18/train_swin.py:131-135): two replica threads call the kernels concurrently on two devices;
+    output and parameter gradients equal the single-device run; the caller's current device is left alone."""
+    _need_two()
+    from oracle import swin_oracle as so
+    from stswincl_b200 import swin
+    dim, res, heads, ws, shift = 128, (16, 24), 2, 8, 4
+    params = so.make_block_params(dim, res, heads, ws, shift, seed=21)
+    x = so.make_features(22, 4, 2, res[0] * res[1], dim)
+    w = (so.make_features(23, 4, 2, res[0] * res[1], dim) - 0.4).to(torch.bfloat16).float()
+    single = swin.SwinTransformerBlock(dim, res, heads, window_size=ws, shift_size=shift)
+    single.load_state_dict(params, strict=True)
+    single = single.cuda(0)
+    y0 = single(x.cuda(0))
+    (y0 * w.cuda(0)).sum().backward()
+    want = {n: p.grad.clone() for n, p in single.named_parameters()}
+    multi = swin.SwinTransformerBlock(dim, res, heads, window_size=ws, shift_size=shift)
+    multi.load_state_dict(params, strict=True)
+    dp = torch.nn.DataParallel(multi.cuda(0), device_ids=[0, 1])
+    for _ in range(3):                                   # repeated: a race would not show on every run
+        multi.zero_grad()
+        y = dp(x.cuda(0))
+        (y * w.cuda(0)).sum().backward()
+        torch.cuda.synchronize()
+        assert torch.cuda.current_device() == 0
+        assert rel_err(y, y0) < 1e-3
+        for n, p in multi.named_parameters():
+            assert rel_err(p.grad, want[n]) < 5e-3, n
