@@ -111,6 +111,19 @@ def _stream(t: torch.Tensor):
     return torch.cuda.current_stream(t.device).cuda_stream
 
 
+def _al16(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    """A 16-byte aligned, contiguous version of a small parameter tensor (bias, LayerNorm scale, bias table).  Replica
+    parameters of nn.DataParallel are views into one coalesced broadcast buffer and can start at any 4-byte offset; the
+    kernels read these vectors with 16-byte loads."""
+    if t is None:
+        return None
+    if t.data_ptr() % 16 != 0 or not t.is_contiguous():
+        t = t.contiguous()
+        if t.data_ptr() % 16 != 0:
+            t = t.clone()
+    return t
+
+
 def _req(t: torch.Tensor, dtype, name: str) -> None:
     if not t.is_cuda:
         raise StswinError(f"{name} must be a CUDA tensor (stswincl_b200 has no CPU path)")
@@ -143,7 +156,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn_major: bool = False, b_mn_maj
     if aux is not None:
         _req(aux, torch.bfloat16, "aux"); assert aux.shape == (M, N) and aux.stride(1) == 1
     if bias is not None:
-        _req(bias, torch.float32, "bias"); assert bias.numel() == N and bias.is_contiguous()
+        bias = _al16(bias)
+        _req(bias, torch.float32, "bias"); assert bias.numel() == N
     if colsum is not None:
         _req(colsum, torch.float32, "colsum"); assert colsum.numel() == N and colsum.is_contiguous()
     lib = _lib.load()
@@ -175,9 +189,10 @@ def winattn_fwd(qkv: torch.Tensor, bias_table: torch.Tensor, H: int, W: int, num
                 out: Optional[torch.Tensor] = None, qk_scale: float = 0.0, mask: Optional[torch.Tensor] = None):
     """qkv [B, T, H*W, 3C] bf16 (natural token order) -> (out [B, T, H*W, C] bf16, lse2 fp32).
     stswin_winattn_fwd: gather (roll+partition) / QK^T / bias+mask / softmax / PV / scatter."""
+    bias_table = _al16(bias_table)
     _req(qkv, torch.bfloat16, "qkv"); _req(bias_table, torch.float32, "bias_table")
     B, T, L, C3 = qkv.shape
-    assert L == H * W and C3 % 3 == 0 and qkv.is_contiguous() and bias_table.is_contiguous()
+    assert L == H * W and C3 % 3 == 0 and qkv.is_contiguous()
     C = C3 // 3
     assert bias_table.shape == ((2 * ws - 1) ** 2, num_heads)
     if out is None:
@@ -197,6 +212,7 @@ def winattn_bwd(qkv: torch.Tensor, bias_table: torch.Tensor, lse2: torch.Tensor,
                 qk_scale: float = 0.0, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Gradient of winattn_fwd: returns d_qkv [B,T,H*W,3C] bf16; accumulates into d_table (fp32
     [(2ws-1)^2, nH]) and, if given, into d_qkv_colsum (fp32 [3C])."""
+    bias_table = _al16(bias_table)
     _req(qkv, torch.bfloat16, "qkv"); _req(d_out, torch.bfloat16, "d_out")
     _req(d_table, torch.float32, "d_table"); _req(lse2, torch.float32, "lse2")
     B, T, L, C3 = qkv.shape
@@ -221,6 +237,7 @@ def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps:
     """LayerNorm over the last dim of x [M, C] (bf16) -> (y bf16, mean fp32 [M], rstd fp32 [M]).
     With ``patch_merge_hw=(H, W)``: x is [BT, H*W, C]; rows are the 2x2-gathered 4C vectors of
     PatchMerging (swin_512.py:266-274) and y is [BT*H*W/4, 4C]."""
+    gamma, beta = _al16(gamma), _al16(beta)
     _req(x, torch.bfloat16, "x"); _req(gamma, torch.float32, "gamma"); _req(beta, torch.float32, "beta")
     assert x.is_contiguous()
     if patch_merge_hw is None:
@@ -245,6 +262,7 @@ def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, mean: torch.Tensor, rstd: t
                   dgamma: torch.Tensor, dbeta: torch.Tensor, *, dres: Optional[torch.Tensor] = None,
                   dx_colsum: Optional[torch.Tensor] = None, patch_merge_hw=None) -> torch.Tensor:
     """Returns dx (layout of x); accumulates dgamma / dbeta (fp32) and optionally the column sums of dx."""
+    gamma = _al16(gamma)
     _req(dy, torch.bfloat16, "dy"); _req(x, torch.bfloat16, "x")
     assert dy.is_contiguous() and x.is_contiguous()
     if patch_merge_hw is None:

@@ -7,7 +7,7 @@ from typing import Optional
 import torch
 
 from . import _lib, ops
-from .ops import _launch, _ptr, _req, _stream
+from .ops import _al16, _launch, _ptr, _req, _stream
 
 _F32 = torch.float32
 SPLIT_A, SPLIT_B = 0, 1          # operand patterns (hi, hi, lo) / (hi, lo, hi)
@@ -16,8 +16,9 @@ COLS, ROWS = 0, 1                # reduction over columns ([R, 3C]) / over rows 
 
 def split(x: torch.Tensor, layout: int, pattern: int, gelu: bool = False) -> torch.Tensor:
     """fp32 [R, C] -> the three bf16 terms of ``stswin_f32_split`` ([R, 3C] or [3R, C])."""
+    x = _al16(x)
     _req(x, _F32, "x")
-    assert x.dim() == 2 and x.is_contiguous()
+    assert x.dim() == 2
     R, C = x.shape
     out = torch.empty((R, 3 * C) if layout == COLS else (3 * R, C), dtype=torch.bfloat16, device=x.device)
     with _launch("f32_split", float(x.numel() * 10), x):
@@ -29,6 +30,7 @@ def split(x: torch.Tensor, layout: int, pattern: int, gelu: bool = False) -> tor
 def rows_init(shape, device, bias: Optional[torch.Tensor] = None, res: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[r, c] = bias[c] + res[r, c] -- what a ``D += acc`` GEMM starts from."""
     out = torch.empty(shape, dtype=_F32, device=device)
+    bias = _al16(bias)
     if bias is None and res is None:
         return out.zero_()
     with _launch("f32_rowop", float(out.numel() * (8 if res is not None else 4)), out):
@@ -86,6 +88,7 @@ def linear_wgrad(dy: torch.Tensor, x: torch.Tensor, gelu_input: bool = False) ->
 
 
 def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, patch_merge_hw=None):
+    gamma, beta = gamma.contiguous(), beta.contiguous()
     _req(x, _F32, "x")
     assert x.is_contiguous()
     if patch_merge_hw is None:
@@ -127,10 +130,11 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, dres=None, patch_merg
 
 def winattn_fwd(qkv, table, H, W, nH, ws, shift, qk_scale=0.0, mask=None):
     """fp32 qkv [B, T, H*W, 3C] -> (out [B, T, H*W, C] fp32, lse)."""
+    table = table.contiguous()
     _req(qkv, _F32, "qkv"); _req(table, _F32, "bias_table")
     B, T, L, C3 = qkv.shape
     C = C3 // 3
-    assert L == H * W and qkv.is_contiguous() and table.is_contiguous()
+    assert L == H * W and qkv.is_contiguous()
     out = torch.empty((B, T, L, C), dtype=_F32, device=qkv.device)
     lse = torch.empty(B * T * L * nH, dtype=_F32, device=qkv.device)
     with _launch("winattn_f32_fwd", 16.0 * C * B * T * L, qkv):
