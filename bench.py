@@ -625,6 +625,27 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_pixloss:
         pixloss = bench_pixloss(dev, pk, timed)
 
+    # ---- the fp32-accurate mode (north_star: <= 1e-3 against the reference's fp32 run): the same head step, fp32 features,
+    # 2 clips, forward + backward, eager (stated throughput of the accuracy mode, not a headline)
+    fp32_mode = None
+    if rank == 0 and world == 1 and not pretrain and not args.no_pixloss:
+        m32 = swin.SwinTransformerLayerv5(dim=DIM, input_resolution=RES, num_heads=HEADS).to(dev)
+        m32.precision = "fp32"
+        x32 = torch.relu(torch.randn(2, T, DIM, RES[0], RES[1], device=dev))
+        w32a, w32b = torch.randn_like(x32) * 0.1, torch.randn(2, T, 2 * DIM, RES[0] // 2, RES[1] // 2, device=dev) * 0.1
+
+        def step32(i):
+            m32.zero_grad(set_to_none=True)
+            a, b = m32(x32)
+            ((a * w32a).sum() + (b * w32b).sum()).backward()
+
+        step32(0)
+        ms32 = timed(step32, 3)
+        fp32_mode = {"workload": "SwinTransformerLayerv5 forward + backward, 2 clips x 4 frames, fp32 features, precision='fp32' "
+                                 "(split-bf16 tcgen05 GEMMs over K' = 3K, fp32 SIMT window attention, fp32 LayerNorm), eager",
+                     "ms_per_step": ms32, "frames_per_s": 2 * T / (ms32 * 1e-3), "parity_bar": "1e-3 (tests/test_gpu_fp32_mode.py)"}
+        del m32, x32, w32a, w32b
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cstep, threads, kind, sample = cpu_step_factory(RES)
@@ -649,7 +670,7 @@ def run_ours(args):
                 "clocks": clocks,
                 "e2e": {"value": frames / (ms_e2e * 1e-3), "unit": "frames/s", "ms_per_step": ms_e2e,
                         "h2d_bytes_per_step": x_host.numel() * x_host.element_size(), "d2h_bytes_per_step": d2h_bytes},
-                "gpu_launches": launches, "roofline": roofline, "window_attn": window_attn, "pixloss": pixloss,
+                "gpu_launches": launches, "roofline": roofline, "window_attn": window_attn, "pixloss": pixloss, "fp32_mode": fp32_mode,
                 "cpu_baseline": cpu, "clips_per_s": n_seq * B * world / (ms_step * 1e-3)}
         print(json.dumps(line), flush=True)
     if world > 1:
