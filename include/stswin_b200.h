@@ -178,6 +178,12 @@ int stswin_copy_strided(void* dst, int64_t dst_stride, const void* src, int64_t 
  *     normalisation.  dq32 [Q,N,HW,C] fp32 scratch; d_loss: device scalar (the upstream gradient).
  *     Keys receive no gradient (they are built under no_grad in the reference, :366).
  *
+ * Launch chaining: the kernels of a step are launched with programmatic dependent launch (each one's prologue -- barrier
+ * initialisation, TMEM allocation, descriptor prefetch -- overlaps its predecessor's tail; STSWIN_PDL=0 disables it), and
+ * buffer clears ride on neighbouring kernels instead of memset nodes: stswin_pixloss_labels (slot_off == 0) clears
+ * ksum_to_clear[0 .. ksum_elems) -- stswin_pixloss_prepare ACCUMULATES into ksum and expects it cleared --, and
+ * stswin_pixloss_fwd clears dq32_to_clear ([Q,N,HW,C] fp32, may be NULL) for a backward called with dq32_is_clear = 1.
+ *
  * fp32-accurate mode (loss value and gradient <= 1e-3 against the reference's fp32 run): stswin_pixloss_prepare with
  * lo_slot_off > 0 also stores the second bf16 term x - bf16(x) of every map in slot (slot + lo_slot_off) and sums the
  * channels in fp32; the row sums are linear in the similarities, so stswin_pixloss_fwd takes n_terms = 3 tables
@@ -188,7 +194,7 @@ int stswin_copy_strided(void* dst, int64_t dst_stride, const void* src, int64_t 
 int stswin_pixloss_labels(const void* const* labels, const int* dtypes, int n_labels, int slot_off,
                           int N, int Hs, int Ws, int H, int W, int class_num,
                           uint8_t* lab_nat, uint8_t* lab_sorted, uint8_t* glab, uint16_t* perm, int32_t* hist,
-                          int32_t* ctl, void* stream);
+                          int32_t* ctl, float* ksum_to_clear, int64_t ksum_elems, void* stream);
 int stswin_pixloss_prepare(const void* const* maps, const int* dtypes, const int* label_slots, int n_maps, int slot_off,
                            int N, int C, int HW, int do_normalize, int lo_slot_off, const uint16_t* perm,
                            void* xn, float* inv_norm, float* ksum, void* stream);
@@ -197,12 +203,12 @@ int stswin_pixloss_fwd(const void* xn, int n_slots, int n_label_slots,
                        const int* qmap, const int* qlab, const int* kmap, const int* klab,
                        int n_terms, int Q, int S, int N, int C, int HW,
                        float* stats, float* loss, float* loss_per_query, float* coef,
-                       const int32_t* ctl, float* partial, uint32_t* ticket, void* stream);
+                       const int32_t* ctl, float* partial, uint32_t* ticket, float* dq32_to_clear, void* stream);
 int stswin_pixloss_bwd(const void* xn, int n_slots, int n_label_slots,
                        const uint8_t* lab_nat, const uint8_t* lab_sorted, const uint8_t* glab,
                        const int* qmap, const int* qmap_lo, const int* qlab, const int* kmap, const int* klab,
                        int n_terms, int Q, int S, int N, int C, int HW,
-                       const float* coef, const float* ksum, const float* d_loss, float* dq32,
+                       const float* coef, const float* ksum, const float* d_loss, float* dq32, int dq32_is_clear,
                        const float* inv_norm, void* const* dq_out, int out_dtype, void* stream);
 
 /* ---------------------------------------------------------------------------------------------

@@ -134,7 +134,7 @@ def label_tables(labels: Sequence[torch.Tensor], H: int, W: int, class_num: int)
     with ops._launch("pix_labels", float(sum(l.numel() for l in labels)), labels[0]):
         st = _lib.load().stswin_pixloss_labels(_parr([l.data_ptr() for l in labels]), _iarr([_LABEL_DTYPES[l.dtype] for l in labels]),
                                                L, 0, N, Hs, Ws, H, W, class_num, lab_nat.data_ptr(), lab_sorted.data_ptr(),
-                                               glab.data_ptr(), perm.data_ptr(), hist.data_ptr(), ctl.data_ptr(),
+                                               glab.data_ptr(), perm.data_ptr(), hist.data_ptr(), ctl.data_ptr(), None, 0,
                                                ops._stream(labels[0]))
     _lib.check(st, "stswin_pixloss_labels")
     return lab_nat, lab_sorted, glab, perm, hist, ctl
@@ -190,11 +190,12 @@ class _PixStepFn(torch.autograd.Function):
         need_grad = any(ctx.needs_input_grad[1:])
         coef = torch.empty((Q, N, HW, S + 1), dtype=torch.float32, device=dev) if need_grad else None
         partial = torch.empty(Q * ((N * HW + 255) // 256), dtype=torch.float32, device=dev)
+        dq32 = torch.empty((Q, N, HW, C), dtype=torch.float32, device=dev) if need_grad else None   # cleared by the forward
         stream = ops._stream(q0)
         with ops._launch("pix_labels", float(sum(l.numel() for l in labels)), q0):
             st = lib.stswin_pixloss_labels(_parr([l.data_ptr() for l in labels]), _iarr([_LABEL_DTYPES[l.dtype] for l in labels]),
                                            nl_local, 0, N, Hs, Ws, H, W, class_num, lab_nat.data_ptr(), lab_sorted.data_ptr(),
-                                           glab.data_ptr(), perm.data_ptr(), hist.data_ptr(), ctl.data_ptr(), stream)
+                                           glab.data_ptr(), perm.data_ptr(), hist.data_ptr(), ctl.data_ptr(), ksum.data_ptr(), n_local * N * C, stream)
         _lib.check(st, "stswin_pixloss_labels")
         in_bytes = float(sum(m.numel() * m.element_size() for m in maps) + 2 * n_local * N * C * HW)
         with ops._launch("pix_prepare", in_bytes, q0):
@@ -222,10 +223,10 @@ class _PixStepFn(torch.autograd.Function):
             st = lib.stswin_pixloss_fwd(xn.data_ptr(), n_slots, nl_slots, lab_nat.data_ptr(), lab_sorted.data_ptr(), glab.data_ptr(),
                                         hist.data_ptr(), _iarr(qmap_f), _iarr(qlab), _iarr(kmap_f), _iarr(klab), n_terms, Q, S, N, C, HW,
                                         stats.data_ptr(), loss.data_ptr(), loss_q.data_ptr(), ops._ptr(coef), ctl.data_ptr(), partial.data_ptr(),
-                                        ctl.data_ptr() + 4, stream)
+                                        ctl.data_ptr() + 4, ops._ptr(dq32), stream)
         _lib.check(st, "stswin_pixloss_fwd")
         ops.count_extra_launches(n_terms)                 # further terms + finalize kernel inside stswin_pixloss_fwd
-        ctx.ws = (xn, lab_nat, lab_sorted, glab, coef, ksum, inv_norm, n_slots, nl_slots)
+        ctx.ws = (xn, lab_nat, lab_sorted, glab, coef, ksum, inv_norm, n_slots, nl_slots, dq32)
         ctx.plan = (qmap, qmap_lo, qlab, kmap_b, klab, 2 if fp32 else 1, Q, S, N, C, HW, flops)
         ctx.q_meta = [(q.shape, q.dtype) for q in queries]
         ctx.mark_non_differentiable(loss_q, ctl)
@@ -234,18 +235,19 @@ class _PixStepFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, d_loss, _d_per_query, _d_flag):
-        xn, lab_nat, lab_sorted, glab, coef, ksum, inv_norm, n_slots, nl_slots = ctx.ws
+        xn, lab_nat, lab_sorted, glab, coef, ksum, inv_norm, n_slots, nl_slots, dq32 = ctx.ws
         qmap, qmap_lo, qlab, kmap, klab, n_terms, Q, S, N, C, HW, flops = ctx.plan
         dev = xn.device
         out_dtype = ctx.q_meta[0][1] if ctx.q_meta[0][1] in _MAP_DTYPES else torch.float32
         outs = [torch.empty((N, C, HW), dtype=out_dtype, device=dev) for _ in range(Q)]
-        dq32 = torch.empty((Q, N, HW, C), dtype=torch.float32, device=dev)
+        clear = 1 if not getattr(ctx, "dq32_used", False) else 0       # a second backward through the same graph clears again
+        ctx.dq32_used = True
         g = d_loss.detach().to(torch.float32).contiguous()
         with ops._launch("pixloss_bwd", flops * n_terms, xn):
             st = _lib.load().stswin_pixloss_bwd(xn.data_ptr(), n_slots, nl_slots, lab_nat.data_ptr(), lab_sorted.data_ptr(),
                                                 glab.data_ptr(), _iarr(qmap), qmap_lo, _iarr(qlab), _iarr(kmap), _iarr(klab), n_terms,
                                                 Q, S, N, C, HW,
-                                                coef.data_ptr(), ksum.data_ptr(), g.data_ptr(), dq32.data_ptr(), ops._ptr(inv_norm),
+                                                coef.data_ptr(), ksum.data_ptr(), g.data_ptr(), dq32.data_ptr(), clear, ops._ptr(inv_norm),
                                                 _parr([o.data_ptr() for o in outs]), _MAP_DTYPES[out_dtype], ops._stream(xn))
         _lib.check(st, "stswin_pixloss_bwd")
         ops.count_extra_launches(n_terms)                 # further term + dq finish kernel inside stswin_pixloss_bwd

@@ -60,9 +60,9 @@ int stswin_copy_strided(void* dst, int64_t dst_stride, const void* src, int64_t 
 
 int stswin_pixloss_labels(const void* const* labels, const int* dtypes, int n_labels, int slot_off, int N, int Hs, int Ws,
                           int H, int W, int class_num, uint8_t* lab_nat, uint8_t* lab_sorted, uint8_t* glab, uint16_t* perm,
-                          int32_t* hist, int32_t* err_flag, void* stream) {
+                          int32_t* hist, int32_t* err_flag, float* ksum_to_clear, int64_t ksum_elems, void* stream) {
   return stswin::pixloss_labels(labels, dtypes, n_labels, slot_off, N, Hs, Ws, H, W, class_num, lab_nat, lab_sorted, glab,
-                                perm, hist, err_flag, static_cast<cudaStream_t>(stream));
+                                perm, hist, err_flag, ksum_to_clear, ksum_elems, static_cast<cudaStream_t>(stream));
 }
 int stswin_pixloss_prepare(const void* const* maps, const int* dtypes, const int* label_slots, int n_maps, int slot_off,
                            int N, int C, int HW, int do_normalize, int lo_slot_off, const uint16_t* perm, void* xn,
@@ -74,16 +74,16 @@ int stswin_pixloss_fwd(const void* xn, int n_slots, int n_label_slots, const uin
                        const uint8_t* glab, const int32_t* hist, const int* qmap, const int* qlab, const int* kmap,
                        const int* klab, int n_terms, int Q, int S, int N, int C, int HW, float* stats, float* loss,
                        float* loss_per_query,
-                       float* coef, const int32_t* err_flag, float* partial, uint32_t* ticket, void* stream) {
+                       float* coef, const int32_t* err_flag, float* partial, uint32_t* ticket, float* dq32_to_clear, void* stream) {
   return stswin::pixloss_fwd(xn, n_slots, n_label_slots, lab_nat, lab_sorted, glab, hist, qmap, qlab, kmap, klab, n_terms, Q, S, N,
-                             C, HW, stats, loss, loss_per_query, coef, err_flag, partial, ticket, static_cast<cudaStream_t>(stream));
+                             C, HW, stats, loss, loss_per_query, coef, err_flag, partial, ticket, dq32_to_clear, static_cast<cudaStream_t>(stream));
 }
 int stswin_pixloss_bwd(const void* xn, int n_slots, int n_label_slots, const uint8_t* lab_nat, const uint8_t* lab_sorted,
                        const uint8_t* glab, const int* qmap, const int* qmap_lo, const int* qlab, const int* kmap,
                        const int* klab, int n_terms, int Q, int S, int N, int C, int HW, const float* coef, const float* ksum, const float* d_loss, float* dq32,
-                       const float* inv_norm, void* const* dq_out, int out_dtype, void* stream) {
+                       int dq32_is_clear, const float* inv_norm, void* const* dq_out, int out_dtype, void* stream) {
   return stswin::pixloss_bwd(xn, n_slots, n_label_slots, lab_nat, lab_sorted, glab, qmap, qmap_lo, qlab, kmap, klab, n_terms, Q, S, N, C, HW,
-                             coef, ksum, d_loss, dq32, inv_norm, dq_out, out_dtype, static_cast<cudaStream_t>(stream));
+                             coef, ksum, d_loss, dq32, dq32_is_clear, inv_norm, dq_out, out_dtype, static_cast<cudaStream_t>(stream));
 }
 
 int64_t stswin_ohem_ws_bytes(void) { return stswin::ohem_ws_bytes(); }

@@ -304,6 +304,14 @@ __device__ __forceinline__ void bulk_load_1d(void* smem, const void* gptr, uint3
                "l"(reinterpret_cast<uint64_t>(gptr)), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// ----------------------------------------------------------------------------- programmatic dependent launch
+// A kernel launched with the programmatic-stream-serialization attribute (host_util.h: launch_pdl) may start while its
+// predecessor on the stream is still running: everything before pdl_wait() (barrier initialisation, TMEM allocation,
+// descriptor prefetch) overlaps the predecessor's tail; pdl_wait() returns once the predecessor has completed and its
+// memory is visible.  pdl_launch_dependents() lets the NEXT kernel begin its own prologue early.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ----------------------------------------------------------------------------- clusters
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;

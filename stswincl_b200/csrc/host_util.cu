@@ -2,6 +2,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 
 namespace stswin {
@@ -16,6 +17,14 @@ int set_error(int code, const char* fmt, ...) {
   return code;
 }
 const char* last_error() { return g_err; }
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = std::getenv("STSWIN_PDL");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  return on;
+}
 
 int num_sms() {
   static int cached[64] = {0};

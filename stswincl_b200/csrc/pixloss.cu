@@ -66,6 +66,8 @@ struct LabelArgs {
   uint16_t* perm;        // [slots, N, HW]   sorted position of pixel j
   int* hist;             // [slots, N, 256]  pixels per label
   int* err;              // |= 1 when a label is outside [0, class_num)
+  float* zero;           // optional buffer cleared by this launch (the channel sums the prepare kernel accumulates into)
+  long n_zero;
 };
 
 constexpr int LB_WARPS = 8;
@@ -79,6 +81,11 @@ __global__ void __launch_bounds__(32 * LB_WARPS) pix_labels_kernel(const LabelAr
   uint8_t* s_nat = s_dyn;
   uint8_t* s_srt = s_dyn + HWp;
   const size_t row = (size_t)(p.slot_off + z) * p.N + n;
+  pdl_launch_dependents();                  // the prepare kernel may start its prologue; it waits for this grid before reading
+  if (p.zero != nullptr) {
+    const long nb = (long)gridDim.x * gridDim.y, b = (long)blockIdx.y * gridDim.x + blockIdx.x;
+    for (long i = b * (32 * LB_WARPS) + tid; i < p.n_zero; i += nb * (32 * LB_WARPS)) p.zero[i] = 0.f;
+  }
   for (int c = tid; c < LB_WARPS * 256; c += 32 * LB_WARPS) (&s_cnt[0][0])[c] = 0;
   if (tid == 0) s_bad = 0;
   __syncthreads();
@@ -298,6 +305,8 @@ __global__ void __launch_bounds__(256, 3) pix_prepare_kernel(const PrepArgs p) {
   __shared__ float s_ss[8][64];
   const int z = blockIdx.z, n = blockIdx.y;
   const size_t off = (size_t)n * p.C * p.HW;
+  pdl_wait();                               // the label pass (sort permutation, cleared channel sums) is complete
+  pdl_launch_dependents();
   switch (p.dtype[z]) {
     case 1: prepare_body<CPW, float>(p, static_cast<const float*>(p.x[z]) + off, z, n, s_ss); break;
     case 2: prepare_body<CPW, __half>(p, static_cast<const __half*>(p.x[z]) + off, z, n, s_ss); break;
@@ -381,6 +390,8 @@ pixloss_fwd_kernel(const __grid_constant__ CUtensorMap tm_x, const PixTable tab,
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                               // everything above overlapped the prepare kernel's tail
+  pdl_launch_dependents();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -555,6 +566,8 @@ struct PixFinArgs {
   float* coef;              // [Q, N, HW, 1 + S] or null
   float* partial;           // [Q * blocks_per_q]
   unsigned int* ticket;     // zero before the first call; left zero
+  float4* zero;             // optional: the backward's fp32 gradient accumulator, cleared here (saves a memset node)
+  long n_zero4;
 };
 
 __global__ void __launch_bounds__(256) pixloss_finalize_kernel(const PixTable tab, const PixFinArgs p) {
@@ -563,6 +576,11 @@ __global__ void __launch_bounds__(256) pixloss_finalize_kernel(const PixTable ta
   const int q = blockIdx.y;
   const long rows = (long)p.N * p.HW;
   const long r = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p.zero != nullptr) {
+    const long nt = (long)gridDim.x * gridDim.y * blockDim.x, t0 = ((long)blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+    for (long i = t0; i < p.n_zero4; i += nt) p.zero[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  pdl_wait();                               // the similarity kernel's row sums are complete
   float li = 0.f;
   if (r < rows) {
     const int n = (int)(r / p.HW), i = (int)(r - (long)n * p.HW);
@@ -695,6 +713,7 @@ pixloss_bwd_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_consta
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -886,6 +905,7 @@ struct FinishArgs {
 template <int CPW>
 __global__ void __launch_bounds__(256) pix_dq_finish_kernel(const FinishArgs p) {
   extern __shared__ float s_fin[];           // [32][C + 1] gradient tile, then [8][32] partial dots
+  pdl_wait();                                // the add-reductions of the backward kernel are complete
   const int q = blockIdx.z, n = blockIdx.y, i0 = blockIdx.x * 32;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ld = p.C + 1;
@@ -969,7 +989,7 @@ int map_tmap(CUtensorMap* tm, const void* base, int rows3, int C, int HW, uint32
 // see include/stswin_b200.h : stswin_pixloss_labels
 int pixloss_labels(const void* const* labels, const int* dtypes, int n_labels, int slot_off, int N, int Hs, int Ws, int H,
                    int W, int class_num, uint8_t* lab_nat, uint8_t* lab_sorted, uint8_t* glab, uint16_t* perm, int* hist,
-                   int* err_flag, cudaStream_t stream) {
+                   int* err_flag, float* ksum_to_clear, long ksum_elems, cudaStream_t stream) {
   STSWIN_CHECK_ARG(labels && dtypes && lab_nat && lab_sorted && glab && perm && hist && err_flag, "pixloss_labels: null pointer");
   STSWIN_CHECK_ARG(n_labels >= 1 && N > 0 && H > 0 && W > 0 && Hs > 0 && Ws > 0, "pixloss_labels: bad shape");
   STSWIN_CHECK_ARG(class_num >= 1 && class_num <= 254, "pixloss_labels: class_num=%d out of range [1,254]", class_num);
@@ -987,6 +1007,7 @@ int pixloss_labels(const void* const* labels, const int* dtypes, int n_labels, i
     }
     a.n_labels = nl; a.slot_off = slot_off + off; a.N = N; a.Hs = Hs; a.Ws = Ws; a.H = H; a.W = W; a.class_num = class_num;
     a.lab_nat = lab_nat; a.lab_sorted = lab_sorted; a.glab = glab; a.perm = perm; a.hist = hist; a.err = err_flag;
+    a.zero = (off == 0 && slot_off == 0) ? ksum_to_clear : nullptr; a.n_zero = ksum_elems;
     pix_labels_kernel<<<dim3(N, nl), 32 * LB_WARPS, 2 * px_hwp(HW), stream>>>(a);
     STSWIN_CUDA(cudaGetLastError());
   }
@@ -1003,7 +1024,6 @@ int pixloss_prepare(const void* const* maps, const int* dtypes, const int* label
   STSWIN_CHECK_ARG(!do_normalize || inv_norm != nullptr, "pixloss_prepare: normalisation needs inv_norm");
   if (C % 64 != 0 || C > 256) return set_error(kErrUnsupported, "pixloss: C=%d unsupported (multiple of 64, <= 256)", C);
   if (HW % 8 != 0 || HW > 8192) return set_error(kErrUnsupported, "pixloss: H*W=%d unsupported (multiple of 8, <= 8192)", HW);
-  STSWIN_CUDA(cudaMemsetAsync(ksum + (size_t)slot_off * N * C, 0, sizeof(float) * (size_t)n_maps * N * C, stream));
   for (int off = 0; off < n_maps; off += PX_MAX_PTRS) {
     const int nm = n_maps - off < PX_MAX_PTRS ? n_maps - off : PX_MAX_PTRS;
     PrepArgs a;
@@ -1021,10 +1041,10 @@ int pixloss_prepare(const void* const* maps, const int* dtypes, const int* label
     a.perm = perm; a.xn = static_cast<__nv_bfloat16*>(xn); a.inv_norm = inv_norm; a.ksum = ksum;
     const dim3 grid((HW + 63) / 64, N, nm);
     switch (C / 64) {
-      case 1: pix_prepare_kernel<8><<<grid, 256, 0, stream>>>(a); break;
-      case 2: pix_prepare_kernel<16><<<grid, 256, 0, stream>>>(a); break;
-      case 3: pix_prepare_kernel<24><<<grid, 256, 0, stream>>>(a); break;
-      default: pix_prepare_kernel<32><<<grid, 256, 0, stream>>>(a); break;
+      case 1: STSWIN_CUDA(launch_pdl(pix_prepare_kernel<8>, grid, dim3(256), 0, stream, a)); break;
+      case 2: STSWIN_CUDA(launch_pdl(pix_prepare_kernel<16>, grid, dim3(256), 0, stream, a)); break;
+      case 3: STSWIN_CUDA(launch_pdl(pix_prepare_kernel<24>, grid, dim3(256), 0, stream, a)); break;
+      default: STSWIN_CUDA(launch_pdl(pix_prepare_kernel<32>, grid, dim3(256), 0, stream, a)); break;
     }
     STSWIN_CUDA(cudaGetLastError());
   }
@@ -1035,7 +1055,7 @@ int pixloss_prepare(const void* const* maps, const int* dtypes, const int* label
 int pixloss_fwd(const void* xn, int n_slots, int n_label_slots, const uint8_t* lab_nat, const uint8_t* lab_sorted,
                 const uint8_t* glab, const int* hist, const int* qmap, const int* qlab, const int* kmap, const int* klab,
                 int n_terms, int Q, int S, int N, int C, int HW, float* stats, float* loss, float* loss_per_query, float* coef,
-                const int* err_flag, float* partial, unsigned int* ticket, cudaStream_t stream) {
+                const int* err_flag, float* partial, unsigned int* ticket, float* dq32_to_clear, cudaStream_t stream) {
   STSWIN_CHECK_ARG(xn && lab_nat && lab_sorted && glab && hist && qmap && qlab && kmap && klab && stats && loss &&
                        err_flag && partial && ticket, "pixloss_fwd: null pointer");
   STSWIN_CHECK_ARG(n_terms >= 1 && n_terms <= 3, "pixloss_fwd: n_terms=%d out of range [1,3]", n_terms);
@@ -1057,16 +1077,16 @@ int pixloss_fwd(const void* xn, int n_slots, int n_label_slots, const uint8_t* l
   for (int t = 0; t < n_terms; ++t) {      // fp32 mode: one launch per product term (the row sums are linear in the similarities)
     if ((rc = fill_table(&tab, qmap + t * Q, qlab, kmap + t * Q * S, klab, Q, S, n_slots, n_label_slots)) != kOk) return rc;
     a.stats = stats + t * term_stride;
-    pixloss_fwd_kernel<<<grid, PX_THREADS, smem, stream>>>(tm, tab, a);
-    STSWIN_CUDA(cudaGetLastError());
+    STSWIN_CUDA(launch_pdl(pixloss_fwd_kernel, dim3(grid), dim3(PX_THREADS), smem, stream, tm, tab, a));
   }
   PixFinArgs f;
   f.N = N; f.HW = HW; f.HWp = a.HWp; f.Q = Q; f.S = S; f.n_terms = n_terms; f.term_stride = term_stride;
   f.stats = stats; f.lab_nat = lab_nat; f.hist = hist; f.err = err_flag;
   f.loss = loss; f.loss_q = loss_per_query; f.coef = coef; f.partial = partial; f.ticket = ticket;
   const long rows = (long)N * HW;
-  pixloss_finalize_kernel<<<dim3((unsigned)((rows + 255) / 256), Q), 256, 0, stream>>>(tab, f);
-  STSWIN_CUDA(cudaGetLastError());
+  f.zero = reinterpret_cast<float4*>(dq32_to_clear);
+  f.n_zero4 = (long)Q * N * HW * C / 4;
+  STSWIN_CUDA(launch_pdl(pixloss_finalize_kernel, dim3((unsigned)((rows + 255) / 256), Q), dim3(256), 0, stream, tab, f));
   return kOk;
 }
 
@@ -1074,7 +1094,7 @@ int pixloss_fwd(const void* xn, int n_slots, int n_label_slots, const uint8_t* l
 int pixloss_bwd(const void* xn, int n_slots, int n_label_slots, const uint8_t* lab_nat, const uint8_t* lab_sorted,
                 const uint8_t* glab, const int* qmap, const int* qmap_lo, const int* qlab, const int* kmap, const int* klab,
                 int n_terms, int Q, int S, int N, int C, int HW, const float* coef, const float* ksum, const float* d_loss,
-                float* dq32, const float* inv_norm, void* const* dq_out, int out_dtype, cudaStream_t stream) {
+                float* dq32, int dq32_is_clear, const float* inv_norm, void* const* dq_out, int out_dtype, cudaStream_t stream) {
   STSWIN_CHECK_ARG(xn && lab_nat && lab_sorted && glab && qmap && qlab && kmap && klab && coef && ksum && d_loss && dq32 &&
                        dq_out, "pixloss_bwd: null pointer");
   STSWIN_CHECK_ARG(out_dtype >= 0 && out_dtype <= 2, "pixloss_bwd: bad output dtype %d", out_dtype);
@@ -1090,7 +1110,7 @@ int pixloss_bwd(const void* xn, int n_slots, int n_label_slots, const uint8_t* l
     uint32_t box[3] = {32, 32, 1};
     if ((rc = make_tmap(&tdq, TmapDtype::F32, 3, dq32, dims, str, box, true)) != kOk) return rc;
   }
-  STSWIN_CUDA(cudaMemsetAsync(dq32, 0, sizeof(float) * (size_t)Q * N * HW * C, stream));
+  if (!dq32_is_clear) STSWIN_CUDA(cudaMemsetAsync(dq32, 0, sizeof(float) * (size_t)Q * N * HW * C, stream));
   PixBwdArgs a;
   a.N = N; a.C = C; a.HW = HW; a.HWp = px_hwp(HW); a.GLp = px_glp(HW); a.Q = Q; a.S = S;
   a.num_mbp = a.HWp / 256; a.nkb = a.HWp / 64;
@@ -1118,10 +1138,10 @@ int pixloss_bwd(const void* xn, int n_slots, int n_label_slots, const uint8_t* l
   const dim3 fgrid((HW + 31) / 32, N, Q);
   const int fsmem = (32 * (C + 1) + 8 * 32) * (int)sizeof(float);
   switch (C / 64) {
-    case 1: pix_dq_finish_kernel<8><<<fgrid, 256, fsmem, stream>>>(f); break;
-    case 2: pix_dq_finish_kernel<16><<<fgrid, 256, fsmem, stream>>>(f); break;
-    case 3: pix_dq_finish_kernel<24><<<fgrid, 256, fsmem, stream>>>(f); break;
-    default: pix_dq_finish_kernel<32><<<fgrid, 256, fsmem, stream>>>(f); break;
+    case 1: STSWIN_CUDA(launch_pdl(pix_dq_finish_kernel<8>, fgrid, dim3(256), (size_t)fsmem, stream, f)); break;
+    case 2: STSWIN_CUDA(launch_pdl(pix_dq_finish_kernel<16>, fgrid, dim3(256), (size_t)fsmem, stream, f)); break;
+    case 3: STSWIN_CUDA(launch_pdl(pix_dq_finish_kernel<24>, fgrid, dim3(256), (size_t)fsmem, stream, f)); break;
+    default: STSWIN_CUDA(launch_pdl(pix_dq_finish_kernel<32>, fgrid, dim3(256), (size_t)fsmem, stream, f)); break;
   }
   STSWIN_CUDA(cudaGetLastError());
   return kOk;
