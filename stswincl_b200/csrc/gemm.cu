@@ -117,6 +117,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   cluster_sync_all();                       // the peer's barriers exist before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // programmatic dependent launch: barrier initialisation, TMEM allocation and the cluster handshake above overlapped the
+  // previous kernel's tail; from here on its output is read / buffers it may still read are written
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -432,8 +436,7 @@ int launch_mode(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
   const int items = ((num_m + 1) / 2) * num_n * args.k_splits;        // work items of a CTA pair
   const int max_clusters = num_sms() / 2;
   const int grid = 2 * (items < max_clusters ? items : max_clusters);
-  kern<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, tmD, tmD2, args);
-  STSWIN_CUDA(cudaGetLastError());
+  STSWIN_CUDA(launch_pdl(kern, dim3(grid), dim3(NUM_THREADS), (size_t)SMEM_BYTES, stream, tmA, tmB, tmD, tmD2, args));
   return kOk;
 }
 

@@ -73,6 +73,8 @@ ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gam
               __nv_bfloat16* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd, long M, int Ctot,
               float eps, PmGeom pg) {
   extern __shared__ uint4 s_ring4[];     // [LN_WARPS][NSTG][Ctot / 8]
+  pdl_wait();                            // programmatic dependent launch: the launch itself overlapped the previous kernel
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nvec = Ctot >> 3;
   const float inv_c = 1.0f / Ctot;        // exact for the power-of-two widths of the model; a multiply per row instead of a division
@@ -172,6 +174,8 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
               const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
               const __nv_bfloat16* __restrict__ dres, __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma,
               float* __restrict__ dbeta, float* __restrict__ dx_colsum, long M, int Ctot, PmGeom pg) {
+  pdl_wait();                            // programmatic dependent launch: the launch itself overlapped the previous kernel
+  pdl_launch_dependents();
   extern __shared__ uint4 s_ring4[];     // [LN_WARPS][NSTG][NARR][Ctot / 8]; reused as [LN_WARPS][Ctot] floats at the end
   constexpr int NARR = RES ? 3 : 2;      // dy, x (, residual gradient)
   float* s_red = reinterpret_cast<float*>(s_ring4);
@@ -416,7 +420,8 @@ int layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y,
     const int per_sm = smem <= 56 * 1024 ? 4 : (smem <= 112 * 1024 ? 2 : 1);                                    \
     const int grid = (int)(want < (long)num_sms() * per_sm ? want : (long)num_sms() * per_sm);                  \
     STSWIN_CUDA(cudaFuncSetAttribute(ln_fwd_kernel<NV_, NSTG_, PM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-    ln_fwd_kernel<NV_, NSTG_, PM_><<<grid, LN_THREADS, smem, stream>>>(xb, gamma, beta, yb, mean, rstd, M, Ctot, eps, pg); \
+    STSWIN_CUDA(launch_pdl(ln_fwd_kernel<NV_, NSTG_, PM_>, dim3(grid), dim3(LN_THREADS), (size_t)smem, stream, xb, gamma, beta, yb, \
+                           mean, rstd, M, Ctot, eps, pg));                                                       \
   } while (0)
   if (pm) {                      // PatchMerging rows: 4*C channels
     if (nv <= 4) STSWIN_LN_FWD(4, 4, true);
@@ -453,8 +458,8 @@ int layernorm_bwd(const void* dy, const void* x, const float* mean, const float*
     const int per_sm = (smem <= 112 * 1024 && NV_ <= 2) ? 2 : 1;                                                \
     const int grid = (int)(want < (long)num_sms() * per_sm ? want : (long)num_sms() * per_sm);                  \
     STSWIN_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<NV_, CS_, NSTG_, PM_, RES_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-    ln_bwd_kernel<NV_, CS_, NSTG_, PM_, RES_><<<grid, LN_THREADS, smem, stream>>>(dyb, xb, mean, rstd, gamma, rb, dxb, dgamma, dbeta, \
-                                                                       dx_colsum, M, Ctot, pg);                 \
+    STSWIN_CUDA(launch_pdl(ln_bwd_kernel<NV_, CS_, NSTG_, PM_, RES_>, dim3(grid), dim3(LN_THREADS), (size_t)smem, stream, dyb, xb, \
+                           mean, rstd, gamma, rb, dxb, dgamma, dbeta, dx_colsum, M, Ctot, pg));                  \
   } while (0)
   // stages: with / without the residual-gradient row (3 / 2 arrays per stage)
 #define STSWIN_LN_BWD(NV_, NS_RES_, NS_NORES_, PM_)                                     \

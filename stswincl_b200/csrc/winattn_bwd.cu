@@ -127,6 +127,8 @@ winattn_bwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant
   for (int i = threadIdx.x; i < ((NRH + NRL) * SLOT_BYTES + 2 * PD_BYTES) / 16; i += NUM_THREADS)
     reinterpret_cast<uint4*>(s_ringh)[i] = make_uint4(0, 0, 0, 0);
   for (int i = threadIdx.x; i < 2 * (TAB_MAX + 1); i += NUM_THREADS) s_bacc[i] = 0.f;
+  pdl_wait();                // programmatic dependent launch: everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();
   for (int i = threadIdx.x; i < SH * nbias; i += NUM_THREADS) {
     const int sub = i / nbias, k = i - sub * nbias;
     s_tab[sub * (TAB_MAX + 1) + k] = __ldg(bias_table + k * gm.nH + hg * SH + sub) * 1.4426950408889634f;
@@ -695,8 +697,8 @@ int winattn_bwd(const void* qkv, const float* bias_table, const float* lse2, con
 #define STSWIN_LAUNCH_BWD(LL, WW, OO, SS, GG)                                                                  \
   {                                                                                                            \
     if ((rc = set_smem_bwd(winattn_bwd_kernel<LL, WW, OO, SS, GG>, SMEM_BYTES)) != kOk) return rc;             \
-    winattn_bwd_kernel<LL, WW, OO, SS, GG><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(                         \
-        tq, td, static_cast<__nv_bfloat16*>(d_qkv), bias_table, lse2, d_table, d_qkv_colsum, gm);              \
+    STSWIN_CUDA(launch_pdl(winattn_bwd_kernel<LL, WW, OO, SS, GG>, dim3(grid), dim3(NUM_THREADS), (size_t)SMEM_BYTES, stream, \
+                           tq, td, static_cast<__nv_bfloat16*>(d_qkv), bias_table, lse2, d_table, d_qkv_colsum, gm)); \
   }
 #define STSWIN_LAUNCH_BWD_S(LL, WW, OO, GG)                 \
   {                                                         \

@@ -106,6 +106,8 @@ winattn_fwd_kernel(const __grid_constant__ WinMaps tm_qkv, __nv_bfloat16* __rest
   for (int i = threadIdx.x; i < (NSLOT * SLOT_BYTES + P_BYTES) / 16; i += NUM_THREADS)
     reinterpret_cast<uint4*>(s_ring)[i] = make_uint4(0, 0, 0, 0);
   // bias table(s) of this CTA's head group, pre-scaled by log2(e)
+  pdl_wait();                // programmatic dependent launch: everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();
   {
     const int nbias = (2 * gm.ws - 1) * (2 * gm.ws - 1);
     for (int i = threadIdx.x; i < SH * nbias; i += NUM_THREADS) {
@@ -568,7 +570,8 @@ int winattn_fwd(const void* qkv, const float* bias_table, void* out, float* lse2
 #define STSWIN_LAUNCH_FWD(LL, WW, QQ, GG)                                                                      \
   {                                                                                                            \
     if ((rc = set_smem(winattn_fwd_kernel<LL, WW, QQ, GG>, SMEM_BYTES)) != kOk) return rc;                     \
-    winattn_fwd_kernel<LL, WW, QQ, GG><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tq, static_cast<__nv_bfloat16*>(out), bias_table, lse2, gm); \
+    STSWIN_CUDA(launch_pdl(winattn_fwd_kernel<LL, WW, QQ, GG>, dim3(grid), dim3(NUM_THREADS), (size_t)SMEM_BYTES, stream, tq,  \
+                           static_cast<__nv_bfloat16*>(out), bias_table, lse2, gm));                             \
   }
   // fast softmax: the shipped geometries (ws 8 or 4, 1 or 2 frames per window, shift 0 or ws/2, no dense mask)
   const bool fast = !gm.general && mask == nullptr && (shift == 0 || 2 * shift == ws) &&
