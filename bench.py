@@ -256,8 +256,9 @@ def bench_pixloss(dev, pk, timed, n=4, sets_in_rotation=3):
     graphs = []
     gen = torch.Generator(device=dev).manual_seed(7)
     for _ in range(sets_in_rotation):
-        labels = [torch.randint(0, K, (n, 1, 4, 7), generator=gen, device=dev).float()
-                  .repeat_interleave(64, 2).repeat_interleave(64, 3).contiguous() for _ in range(6)]
+        # label maps built by nearest-upsampling a random [n, 1, 8, 14] integer map (coherent blobs)
+        labels = [torch.randint(0, K, (n, 1, 8, 14), generator=gen, device=dev).float()
+                  .repeat_interleave(32, 2).repeat_interleave(32, 3).contiguous() for _ in range(6)]
         emb = [torch.randn(n, C, H, W, generator=gen, device=dev) for _ in range(8)]
         q1, q2 = emb[6].requires_grad_(True), emb[7].requires_grad_(True)
 
@@ -294,7 +295,7 @@ def bench_pixloss(dev, pk, timed, n=4, sets_in_rotation=3):
     dense = 2.0 * 2 * 5 * 2 * (H * W) ** 2 * C * n            # fwd + bwd, 2 queries x 5 key sets
     in_bytes = 8 * n * C * H * W * 4
     out = {"workload": "ConsistencyLoss.forward tail (PixPro_swin_v5.py:584-597): 2 symmetric regression_loss calls x 5 key sets, "
-                       "N=%d per GPU, C=256, 32x56 pixels, 12 classes, 6 label maps 256x448, fp32 inputs with F.normalize fused, "
+                       "N=%d per GPU, C=256, 32x56 pixels, 12 classes, 6 label maps 256x448 (random 8x14 blobs, SURVEY 8d), fp32 inputs with F.normalize fused, "
                        "forward + backward, CUDA-graph replay" % n,
            "ms_per_step": ms, "dense_gflop": dense / 1e9, "tflops": dense / ms / 1e9, "peak_tflops": pk["tflops_burst"],
            "frac_of_peak": dense / ms / 1e9 / pk["tflops_burst"], "bound": "tensor (dense form)",
@@ -365,8 +366,8 @@ def run_ours(args):
     x_dev = torch.relu(torch.randn(n_seq * B, T, DIM, RES[0], RES[1], generator=g, device=dev)).to(torch.bfloat16)
     if pretrain:
         K = 12
-        masks = [torch.randint(0, K, (B, 1, 4, 7), generator=g, device=dev).float()
-                 .repeat_interleave(8 * RES[0] // 4, 2).repeat_interleave(8 * RES[1] // 7, 3).contiguous() for _ in range(6)]
+        masks = [torch.randint(0, K, (B, 1, 8, 14), generator=g, device=dev).float()
+                 .repeat_interleave(8 * RES[0] // 8, 2).repeat_interleave(8 * RES[1] // 14, 3).contiguous() for _ in range(6)]
     else:
         g1 = (torch.randn(B, T, DIM, RES[0], RES[1], generator=g, device=dev) * 0.1).to(torch.bfloat16)
         g2 = (torch.randn(B, T, 2 * DIM, RES[0] // 2, RES[1] // 2, generator=g, device=dev) * 0.1).to(torch.bfloat16)

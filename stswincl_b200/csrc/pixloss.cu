@@ -263,6 +263,7 @@ __device__ __forceinline__ void prepare_body(const PrepArgs& p, const TI* __rest
     d0 = pr & 0xffffu;
     d1 = pr >> 16;
   }
+  const bool pair_store = ls < 0 || (d1 == d0 + 1 && (d0 & 1) == 0);
   __nv_bfloat16* ob = p.xn + ((size_t)slot * p.N + n) * p.C * p.HW;
   float cs[32];
 #pragma unroll
@@ -273,8 +274,8 @@ __device__ __forceinline__ void prepare_body(const PrepArgs& p, const TI* __rest
     const float x0 = v[u].x * inv0, x1 = v[u].y * inv1;
     const __nv_bfloat162 b = __floats2bfloat162_rn(x0, x1);
     if (ok) {
-      if (ls < 0) {
-        *reinterpret_cast<__nv_bfloat162*>(ob + (size_t)c * p.HW + j0) = b;
+      if (pair_store) {       // pixel order, or the two pixels stay neighbours in label order (same label run, even position)
+        *reinterpret_cast<__nv_bfloat162*>(ob + (size_t)c * p.HW + d0) = b;
       } else {
         ob[(size_t)c * p.HW + d0] = b.x;
         ob[(size_t)c * p.HW + d1] = b.y;
@@ -284,8 +285,8 @@ __device__ __forceinline__ void prepare_body(const PrepArgs& p, const TI* __rest
       if (p.lo_off > 0) {                           // fp32 mode: second term, and the channel sum of the fp32 values
         const __nv_bfloat162 lo = __floats2bfloat162_rn(x0 - f.x, x1 - f.y);
         __nv_bfloat16* ol = ob + (size_t)p.lo_off * p.N * p.C * p.HW;
-        if (ls < 0) {
-          *reinterpret_cast<__nv_bfloat162*>(ol + (size_t)c * p.HW + j0) = lo;
+        if (pair_store) {
+          *reinterpret_cast<__nv_bfloat162*>(ol + (size_t)c * p.HW + d0) = lo;
         } else {
           ol[(size_t)c * p.HW + d0] = lo.x;
           ol[(size_t)c * p.HW + d1] = lo.y;

@@ -22,6 +22,7 @@ EPI_BIAS, EPI_BIAS_RES, EPI_BIAS_GELU, EPI_MUL_AUX, EPI_F32_REDUCE, EPI_BIAS_GEL
 import threading
 
 _ACCT = threading.Lock()
+_TLS = threading.local()          # per thread: devices whose context this thread has bound inside the library
 LAUNCHES = 0
 
 
@@ -74,11 +75,19 @@ class _launch:
     def __enter__(self):
         global LAUNCHES
         dev = self.ref.device
-        self.guard = torch.cuda.device(dev)
-        self.guard.__enter__()
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        # the common case -- the tensor lives on the thread's current device -- needs no guard
+        self.guard = None
+        if idx != torch.cuda.current_device():
+            self.guard = torch.cuda.device(idx)
+            self.guard.__enter__()
         try:
-            idx = dev.index if dev.index is not None else torch.cuda.current_device()
-            _lib.check(_lib.load().stswin_set_device(idx), "stswin_set_device")
+            bound = getattr(_TLS, "bound", None)
+            if bound is None:
+                bound = _TLS.bound = set()
+            if idx not in bound or self.guard is not None:      # first call of this thread on this device, or a switch
+                _lib.check(_lib.load().stswin_set_device(idx), "stswin_set_device")
+                bound.add(idx)
             with _ACCT:
                 LAUNCHES += 1
                 self.prof = _PROFILER
@@ -86,7 +95,8 @@ class _launch:
                 self.e0 = torch.cuda.Event(enable_timing=True)
                 self.e0.record(torch.cuda.current_stream(dev))
         except BaseException:
-            self.guard.__exit__(None, None, None)
+            if self.guard is not None:
+                self.guard.__exit__(None, None, None)
             raise
         return self
 
@@ -98,7 +108,8 @@ class _launch:
                 with _ACCT:
                     self.prof.records.append((self.family, self.work, self.e0, e1))
         finally:
-            self.guard.__exit__(*exc)
+            if self.guard is not None:
+                self.guard.__exit__(*exc)      # restores the caller's device (torch issues the cudaSetDevice)
         return False
 
 

@@ -12,7 +12,7 @@ Ns = [int(a) for a in sys.argv[1:]] or [4, 16, 32]
 for N in Ns:
     for normalize in (False, True):
         gen = torch.Generator(device=dev).manual_seed(N)
-        labels = [torch.randint(0, K, (N, 1, 4, 7), generator=gen, device=dev).float().repeat_interleave(64, 2).repeat_interleave(64, 3) for _ in range(6)]
+        labels = [torch.randint(0, K, (N, 1, 8, 14), generator=gen, device=dev).float().repeat_interleave(32, 2).repeat_interleave(32, 3) for _ in range(6)]
         emb = [torch.randn(N, C, H, W, generator=gen, device=dev) for _ in range(8)]
         if not normalize:
             emb = [torch.nn.functional.normalize(e, dim=1) for e in emb]
