@@ -13,7 +13,7 @@
 //                  of a similarity tile almost always carries ONE label and the label compare of the
 //                  epilogue is per group, not per element
 //   pix_prepare    F.normalize(dim=1) (:330,362,...) + bf16 cast + scatter into label order + per-channel
-//                  key sums, every embedding map of the step in one launch
+//                  key sums, every embedding map of the step in one launch (16-byte loads, 8-byte stores of label runs)
 //   pixloss_fwd    similarity tiles q^T k on tcgen05, CTA pairs (cta_group::2): a pair keeps 256 query
 //                  pixels resident and streams 256-key tiles (each CTA loads half of the keys), 256 x 256
 //                  accumulators double-buffered in TMEM; the epilogue sums each 32-key group with packed
@@ -227,82 +227,116 @@ __device__ __forceinline__ float2 ld_pair<__half>(const __half* p) {
   return __half22float2(*reinterpret_cast<const __half2*>(p));
 }
 
+template <typename TI>
+__device__ __forceinline__ float4 ld_quad(const TI* p);
+template <>
+__device__ __forceinline__ float4 ld_quad<float>(const float* p) { return *reinterpret_cast<const float4*>(p); }
+template <>
+__device__ __forceinline__ float4 ld_quad<__nv_bfloat16>(const __nv_bfloat16* p) {
+  const uint2 r = *reinterpret_cast<const uint2*>(p);
+  const float2 a = unpack_bf16(r.x), b = unpack_bf16(r.y);
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+template <>
+__device__ __forceinline__ float4 ld_quad<__half>(const __half* p) {
+  const uint2 r = *reinterpret_cast<const uint2*>(p);
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+
+// A lane owns FOUR adjacent pixels (lane & 15) of CPW / 2 channels (warp, lane >> 4, stride 16): 16-byte loads, and in
+// label order the four pixels usually stay one aligned run (labels are spatially coherent and the sort is stable), so a
+// channel's four values leave as one 8-byte store; otherwise as two pairs or four singles.
 template <int CPW, typename TI>
 __device__ __forceinline__ void prepare_body(const PrepArgs& p, const TI* __restrict__ xb, int z, int n, float (*s_ss)[64]) {
+  constexpr int NU = CPW / 2;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int j0 = blockIdx.x * 64 + lane * 2;
-  const bool ok = j0 < p.HW;                     // HW is even: both pixels or none
+  const int pq = lane & 15, cs = lane >> 4;
+  const int j0 = blockIdx.x * 64 + pq * 4;
+  const bool ok = j0 < p.HW;                     // HW is a multiple of 8: all four pixels or none
   const int slot = p.slot_off + z;
   const int ls = p.lslot[z];
-  uint32_t pr = 0;                               // sorted positions of the two pixels (requested before the tile)
-  if (ls >= 0 && ok) pr = *reinterpret_cast<const uint32_t*>(p.perm + ((size_t)ls * p.N + n) * p.HW + j0);
-  float2 v[CPW];
-  float ss0 = 0.f, ss1 = 0.f;
+  uint2 pr = make_uint2(0u, 0u);                 // sorted positions of the four pixels (requested before the tile)
+  if (ls >= 0 && ok) pr = *reinterpret_cast<const uint2*>(p.perm + ((size_t)ls * p.N + n) * p.HW + j0);
+  float4 v[NU];
+  float4 ss = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-  for (int u = 0; u < CPW; ++u) {
-    const int c = warp + 8 * u;
-    v[u] = ok ? ld_pair<TI>(xb + (size_t)c * p.HW + j0) : make_float2(0.f, 0.f);
-    ss0 = fmaf(v[u].x, v[u].x, ss0);
-    ss1 = fmaf(v[u].y, v[u].y, ss1);
+  for (int u = 0; u < NU; ++u) {
+    const int c = warp * 2 + cs + 16 * u;
+    v[u] = ok ? ld_quad<TI>(xb + (size_t)c * p.HW + j0) : make_float4(0.f, 0.f, 0.f, 0.f);
+    ss.x = fmaf(v[u].x, v[u].x, ss.x); ss.y = fmaf(v[u].y, v[u].y, ss.y);
+    ss.z = fmaf(v[u].z, v[u].z, ss.z); ss.w = fmaf(v[u].w, v[u].w, ss.w);
   }
-  float inv0 = 1.f, inv1 = 1.f;
+  float4 inv = make_float4(1.f, 1.f, 1.f, 1.f);
   if (p.do_normalize) {
-    s_ss[warp][lane * 2] = ss0;
-    s_ss[warp][lane * 2 + 1] = ss1;
+    ss.x += __shfl_xor_sync(0xffffffffu, ss.x, 16); ss.y += __shfl_xor_sync(0xffffffffu, ss.y, 16);
+    ss.z += __shfl_xor_sync(0xffffffffu, ss.z, 16); ss.w += __shfl_xor_sync(0xffffffffu, ss.w, 16);
+    if (cs == 0) *reinterpret_cast<float4*>(&s_ss[warp][pq * 4]) = ss;
     __syncthreads();
-    float t0 = 0.f, t1 = 0.f;
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int w = 0; w < 8; ++w) { t0 += s_ss[w][lane * 2]; t1 += s_ss[w][lane * 2 + 1]; }
-    inv0 = 1.0f / fmaxf(sqrtf(t0), kEpsNorm);
-    inv1 = 1.0f / fmaxf(sqrtf(t1), kEpsNorm);
-    if (warp == 0 && ok && p.inv_norm != nullptr)
-      *reinterpret_cast<float2*>(p.inv_norm + ((size_t)slot * p.N + n) * p.HW + j0) = make_float2(inv0, inv1);
+    for (int w = 0; w < 8; ++w) {
+      const float4 a = *reinterpret_cast<const float4*>(&s_ss[w][pq * 4]);
+      t.x += a.x; t.y += a.y; t.z += a.z; t.w += a.w;
+    }
+    inv = make_float4(1.0f / fmaxf(sqrtf(t.x), kEpsNorm), 1.0f / fmaxf(sqrtf(t.y), kEpsNorm),
+                      1.0f / fmaxf(sqrtf(t.z), kEpsNorm), 1.0f / fmaxf(sqrtf(t.w), kEpsNorm));
+    if (warp == 0 && cs == 0 && ok && p.inv_norm != nullptr)
+      *reinterpret_cast<float4*>(p.inv_norm + ((size_t)slot * p.N + n) * p.HW + j0) = inv;
   }
-  int d0 = j0, d1 = j0 + 1;
+  int d0 = j0, d1 = j0 + 1, d2 = j0 + 2, d3 = j0 + 3;
   if (ls >= 0 && ok) {
-    d0 = pr & 0xffffu;
-    d1 = pr >> 16;
+    d0 = pr.x & 0xffffu; d1 = pr.x >> 16; d2 = pr.y & 0xffffu; d3 = pr.y >> 16;
   }
-  const bool pair_store = ls < 0 || (d1 == d0 + 1 && (d0 & 1) == 0);
+  const bool pair_a = ls < 0 || (d1 == d0 + 1 && (d0 & 1) == 0);
+  const bool pair_b = ls < 0 || (d3 == d2 + 1 && (d2 & 1) == 0);
+  const bool quad = ls < 0 || (pair_a && pair_b && d2 == d0 + 2 && (d0 & 3) == 0);
   __nv_bfloat16* ob = p.xn + ((size_t)slot * p.N + n) * p.C * p.HW;
-  float cs[32];
+  auto store4 = [&](__nv_bfloat16* row, __nv_bfloat162 a, __nv_bfloat162 b) {
+    if (quad) {
+      *reinterpret_cast<uint2*>(row + d0) = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+    } else {
+      if (pair_a) *reinterpret_cast<__nv_bfloat162*>(row + d0) = a; else { row[d0] = a.x; row[d1] = a.y; }
+      if (pair_b) *reinterpret_cast<__nv_bfloat162*>(row + d2) = b; else { row[d2] = b.x; row[d3] = b.y; }
+    }
+  };
+  float cs_sum[16];
 #pragma unroll
-  for (int u = 0; u < 32; ++u) cs[u] = 0.f;
+  for (int u = 0; u < 16; ++u) cs_sum[u] = 0.f;
 #pragma unroll
-  for (int u = 0; u < CPW; ++u) {
-    const int c = warp + 8 * u;
-    const float x0 = v[u].x * inv0, x1 = v[u].y * inv1;
-    const __nv_bfloat162 b = __floats2bfloat162_rn(x0, x1);
+  for (int u = 0; u < NU; ++u) {
+    const int c = warp * 2 + cs + 16 * u;
+    const float x0 = v[u].x * inv.x, x1 = v[u].y * inv.y, x2 = v[u].z * inv.z, x3 = v[u].w * inv.w;
+    const __nv_bfloat162 a = __floats2bfloat162_rn(x0, x1), b = __floats2bfloat162_rn(x2, x3);
     if (ok) {
-      if (pair_store) {       // pixel order, or the two pixels stay neighbours in label order (same label run, even position)
-        *reinterpret_cast<__nv_bfloat162*>(ob + (size_t)c * p.HW + d0) = b;
-      } else {
-        ob[(size_t)c * p.HW + d0] = b.x;
-        ob[(size_t)c * p.HW + d1] = b.y;
-      }
-      const float2 f = __bfloat1622float2(b);       // sum what the tensor core will read (bf16-rounded)
-      cs[u] = f.x + f.y;
+      store4(ob + (size_t)c * p.HW, a, b);
+      const float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);   // sum what the tensor core will read (bf16-rounded)
+      cs_sum[u] = (fa.x + fa.y) + (fb.x + fb.y);
       if (p.lo_off > 0) {                           // fp32 mode: second term, and the channel sum of the fp32 values
-        const __nv_bfloat162 lo = __floats2bfloat162_rn(x0 - f.x, x1 - f.y);
-        __nv_bfloat16* ol = ob + (size_t)p.lo_off * p.N * p.C * p.HW;
-        if (pair_store) {
-          *reinterpret_cast<__nv_bfloat162*>(ol + (size_t)c * p.HW + d0) = lo;
-        } else {
-          ol[(size_t)c * p.HW + d0] = lo.x;
-          ol[(size_t)c * p.HW + d1] = lo.y;
-        }
-        cs[u] = x0 + x1;
+        store4(ob + (size_t)p.lo_off * p.N * p.C * p.HW + (size_t)c * p.HW, __floats2bfloat162_rn(x0 - fa.x, x1 - fa.y),
+               __floats2bfloat162_rn(x2 - fb.x, x3 - fb.y));
+        cs_sum[u] = (x0 + x1) + (x2 + x3);
       }
     }
   }
   if (ls >= 0) {                                    // key maps only: the backward's  b_s * sum_j k_j  term
-    warp_colsum<32>(cs, lane);                      // lane l now holds the sum over the warp's pixels of value l
-    if (lane < CPW) atomicAdd(p.ksum + ((size_t)slot * p.N + n) * p.C + warp + 8 * lane, cs[0]);
+    // butterfly over the 16 pixel-quad lanes: afterwards lane pq holds the 64-pixel sum of value pq
+#pragma unroll
+    for (int nn = 8, off = 8; off >= 1; nn >>= 1, off >>= 1) {
+      const bool hi = (lane & off) != 0;
+#pragma unroll
+      for (int k = 0; k < nn; ++k) {
+        const float send = hi ? cs_sum[k] : cs_sum[k + nn];
+        const float recv = __shfl_xor_sync(0xffffffffu, send, off);
+        cs_sum[k] = (hi ? cs_sum[k + nn] : cs_sum[k]) + recv;
+      }
+    }
+    if (pq < NU) atomicAdd(p.ksum + ((size_t)slot * p.N + n) * p.C + warp * 2 + cs + 16 * pq, cs_sum[0]);
   }
 }
 
 template <int CPW>
-__global__ void __launch_bounds__(256, 3) pix_prepare_kernel(const PrepArgs p) {
+__global__ void __launch_bounds__(256, 2) pix_prepare_kernel(const PrepArgs p) {
   __shared__ float s_ss[8][64];
   const int z = blockIdx.z, n = blockIdx.y;
   const size_t off = (size_t)n * p.C * p.HW;
