@@ -940,38 +940,47 @@ struct FinishArgs {
 template <int CPW>
 __global__ void __launch_bounds__(256) pix_dq_finish_kernel(const FinishArgs p) {
   extern __shared__ float s_fin[];           // [32][C + 1] gradient tile, then [8][32] partial dots
-  pdl_wait();                                // the add-reductions of the backward kernel are complete
   const int q = blockIdx.z, n = blockIdx.y, i0 = blockIdx.x * 32;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ld = p.C + 1;
   float* s_dot = s_fin + 32 * ld;
+  const int i = i0 + lane;
+  const bool ok = i < p.HW;
+  // the normalised query values of this thread's pixel (written by the forward's prepare kernel, long complete): requested
+  // before the wait, so their latency overlaps the backward kernel's tail and the tile load below
+  float xq[CPW];
+  float inv = 1.f;
+  if (p.chain) {
+    const __nv_bfloat16* xb = p.xn + ((size_t)p.qmap[q] * p.N + n) * p.C * p.HW;
+    __nv_bfloat16 raw[CPW], raw_lo[CPW];
+#pragma unroll
+    for (int u = 0; u < CPW; ++u) raw[u] = ok ? xb[(size_t)(warp + 8 * u) * p.HW + i] : __float2bfloat16_rn(0.f);
+    if (p.qmap_lo[q] >= 0) {
+      const __nv_bfloat16* xl = p.xn + ((size_t)p.qmap_lo[q] * p.N + n) * p.C * p.HW;
+#pragma unroll
+      for (int u = 0; u < CPW; ++u) raw_lo[u] = ok ? xl[(size_t)(warp + 8 * u) * p.HW + i] : __float2bfloat16_rn(0.f);
+    }
+    if (ok) inv = p.inv_norm[((size_t)p.qmap[q] * p.N + n) * p.HW + i];
+#pragma unroll
+    for (int u = 0; u < CPW; ++u) xq[u] = __bfloat162float(raw[u]) + (p.qmap_lo[q] >= 0 ? __bfloat162float(raw_lo[u]) : 0.f);
+  }
+  pdl_wait();                                // the add-reductions of the backward kernel are complete
   const float* src = p.dq32 + (((size_t)q * p.N + n) * p.HW + i0) * p.C;
 #pragma unroll
   for (int rr = 0; rr < 4; ++rr) {
     const int r = warp * 4 + rr;
-    for (int c = lane; c < p.C; c += 32) s_fin[r * ld + c] = (i0 + r < p.HW) ? src[(size_t)r * p.C + c] : 0.f;
+    for (int c = lane; c < p.C; c += 32) s_fin[r * ld + c] = (i0 + r < p.HW) ? __ldcg(src + (size_t)r * p.C + c) : 0.f;
   }
   __syncthreads();
-  const int i = i0 + lane;
-  const bool ok = i < p.HW;
-  float xq[CPW];
-  float inv = 1.f, dot = 0.f;
+  float dot = 0.f;
   if (p.chain) {
-    const __nv_bfloat16* xb = p.xn + ((size_t)p.qmap[q] * p.N + n) * p.C * p.HW;
     float part = 0.f;
 #pragma unroll
-    for (int u = 0; u < CPW; ++u) {
-      const int c = warp + 8 * u;
-      xq[u] = ok ? __bfloat162float(xb[(size_t)c * p.HW + i]) : 0.f;
-      if (ok && p.qmap_lo[q] >= 0)
-        xq[u] += __bfloat162float(p.xn[(((size_t)p.qmap_lo[q] * p.N + n) * p.C + c) * p.HW + i]);
-      part = fmaf(xq[u], s_fin[lane * ld + c], part);
-    }
+    for (int u = 0; u < CPW; ++u) part = fmaf(xq[u], s_fin[lane * ld + warp + 8 * u], part);
     s_dot[warp * 32 + lane] = part;
     __syncthreads();
 #pragma unroll
     for (int w = 0; w < 8; ++w) dot += s_dot[w * 32 + lane];
-    if (ok) inv = p.inv_norm[((size_t)p.qmap[q] * p.N + n) * p.HW + i];
   }
   if (!ok) return;
 #pragma unroll
