@@ -172,7 +172,7 @@ int stswin_copy_strided(void* dst, int64_t dst_stride, const void* src, int64_t 
  *     stats [Q,N,HW,S,2,2] fp32 workspace; loss: device scalar = sum over queries of
  *     -mean log(e^P/(e^P+e^N)+1e-6); loss_per_query [Q] or NULL; coef [Q,N,HW,1+S] fp32 (NULL when no
  *     gradient is needed): per-row dloss/dz coefficients for the backward; partial: fp32 scratch of
- *     Q*ceil(N*HW/256) elements; ticket = &ctl[1].
+ *     Q*ceil(N*HW/64) elements; ticket = &ctl[1].
  * stswin_pixloss_bwd    : dq_out[q] (HOST array of Q device pointers, [N,C,HW], out_dtype 0 bf16 / 1 f32 /
  *     2 f16) = d_loss * dloss/d(query map q); with inv_norm != NULL through the Jacobian of the fused
  *     normalisation.  dq32 [Q,N,HW,C] fp32 scratch; d_loss: device scalar (the upstream gradient).
@@ -182,7 +182,8 @@ int stswin_copy_strided(void* dst, int64_t dst_stride, const void* src, int64_t 
  * initialisation, TMEM allocation, descriptor prefetch -- overlaps its predecessor's tail; STSWIN_PDL=0 disables it), and
  * buffer clears ride on neighbouring kernels instead of memset nodes: stswin_pixloss_labels (slot_off == 0) clears
  * ksum_to_clear[0 .. ksum_elems) -- stswin_pixloss_prepare ACCUMULATES into ksum and expects it cleared --, and
- * stswin_pixloss_fwd clears dq32_to_clear ([Q,N,HW,C] fp32, may be NULL) for a backward called with dq32_is_clear = 1.
+ * stswin_pixloss_prepare clears f32_to_clear[0 .. f32_elems) (may be NULL; the [Q,N,HW,C] fp32 accumulator of a backward
+ * that is then called with dq32_is_clear = 1).
  *
  * fp32-accurate mode (loss value and gradient <= 1e-3 against the reference's fp32 run): stswin_pixloss_prepare with
  * lo_slot_off > 0 also stores the second bf16 term x - bf16(x) of every map in slot (slot + lo_slot_off) and sums the
@@ -197,13 +198,13 @@ int stswin_pixloss_labels(const void* const* labels, const int* dtypes, int n_la
                           int32_t* ctl, float* ksum_to_clear, int64_t ksum_elems, void* stream);
 int stswin_pixloss_prepare(const void* const* maps, const int* dtypes, const int* label_slots, int n_maps, int slot_off,
                            int N, int C, int HW, int do_normalize, int lo_slot_off, const uint16_t* perm,
-                           void* xn, float* inv_norm, float* ksum, void* stream);
+                           void* xn, float* inv_norm, float* ksum, float* f32_to_clear, int64_t f32_elems, void* stream);
 int stswin_pixloss_fwd(const void* xn, int n_slots, int n_label_slots,
                        const uint8_t* lab_nat, const uint8_t* lab_sorted, const uint8_t* glab, const int32_t* hist,
                        const int* qmap, const int* qlab, const int* kmap, const int* klab,
                        int n_terms, int Q, int S, int N, int C, int HW,
                        float* stats, float* loss, float* loss_per_query, float* coef,
-                       const int32_t* ctl, float* partial, uint32_t* ticket, float* dq32_to_clear, void* stream);
+                       const int32_t* ctl, float* partial, uint32_t* ticket, void* stream);
 int stswin_pixloss_bwd(const void* xn, int n_slots, int n_label_slots,
                        const uint8_t* lab_nat, const uint8_t* lab_sorted, const uint8_t* glab,
                        const int* qmap, const int* qmap_lo, const int* qlab, const int* kmap, const int* klab,

@@ -88,8 +88,8 @@ SIGNATURES = {
     "stswin_colsum": ([_vp, _vp, _i64, _i, _vp], ctypes.c_int),
     "stswin_copy_strided": ([_vp, _i64, _vp, _i64, _i64, _i, _vp], ctypes.c_int),
     "stswin_pixloss_labels": ([_vp, _vp] + [_i] * 8 + [_vp] * 7 + [_i64, _vp], ctypes.c_int),
-    "stswin_pixloss_prepare": ([_vp, _vp, _vp] + [_i] * 7 + [_vp] * 5, ctypes.c_int),
-    "stswin_pixloss_fwd": ([_vp, _i, _i] + [_vp] * 8 + [_i] * 6 + [_vp] * 9, ctypes.c_int),
+    "stswin_pixloss_prepare": ([_vp, _vp, _vp] + [_i] * 7 + [_vp] * 5 + [_i64, _vp], ctypes.c_int),
+    "stswin_pixloss_fwd": ([_vp, _i, _i] + [_vp] * 8 + [_i] * 6 + [_vp] * 8, ctypes.c_int),
     "stswin_pixloss_bwd": ([_vp, _i, _i] + [_vp] * 8 + [_i] * 6 + [_vp] * 4 + [_i] + [_vp] * 2 + [_i, _vp], ctypes.c_int),
     "stswin_ohem_ws_bytes": ([], ctypes.c_int64),
     "stswin_ohem_ce_fwd": ([_vp, _i, _vp, _i, _i, _i64, _i, ctypes.c_float, _i64, _fp, _vp, _fp, _fp, _vp], ctypes.c_int),

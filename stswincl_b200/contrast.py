@@ -189,7 +189,7 @@ class _PixStepFn(torch.autograd.Function):
         loss_q = torch.empty(Q, dtype=torch.float32, device=dev)
         need_grad = any(ctx.needs_input_grad[1:])
         coef = torch.empty((Q, N, HW, S + 1), dtype=torch.float32, device=dev) if need_grad else None
-        partial = torch.empty(Q * ((N * HW + 255) // 256), dtype=torch.float32, device=dev)
+        partial = torch.empty(Q * ((N * HW + 63) // 64), dtype=torch.float32, device=dev)
         dq32 = torch.empty((Q, N, HW, C), dtype=torch.float32, device=dev) if need_grad else None   # cleared by the forward
         stream = ops._stream(q0)
         with ops._launch("pix_labels", float(sum(l.numel() for l in labels)), q0):
@@ -201,7 +201,7 @@ class _PixStepFn(torch.autograd.Function):
         with ops._launch("pix_prepare", in_bytes, q0):
             st = lib.stswin_pixloss_prepare(_parr([m.data_ptr() for m in maps]), _iarr([_MAP_DTYPES[m.dtype] for m in maps]),
                                             _iarr(slots.map_label), n_local, 0, N, C, HW, int(normalize), n_local if fp32 else 0, perm.data_ptr(),
-                                            xn.data_ptr(), ops._ptr(inv_norm), ksum.data_ptr(), stream)
+                                            xn.data_ptr(), ops._ptr(inv_norm), ksum.data_ptr(), ops._ptr(dq32), dq32.numel() if dq32 is not None else 0, stream)
         _lib.check(st, "stswin_pixloss_prepare")
         if world > 1:
             # C3 (an extension of the reference): the prepared shared key sets of every rank -- embeddings in
@@ -223,7 +223,7 @@ class _PixStepFn(torch.autograd.Function):
             st = lib.stswin_pixloss_fwd(xn.data_ptr(), n_slots, nl_slots, lab_nat.data_ptr(), lab_sorted.data_ptr(), glab.data_ptr(),
                                         hist.data_ptr(), _iarr(qmap_f), _iarr(qlab), _iarr(kmap_f), _iarr(klab), n_terms, Q, S, N, C, HW,
                                         stats.data_ptr(), loss.data_ptr(), loss_q.data_ptr(), ops._ptr(coef), ctl.data_ptr(), partial.data_ptr(),
-                                        ctl.data_ptr() + 4, ops._ptr(dq32), stream)
+                                        ctl.data_ptr() + 4, stream)
         _lib.check(st, "stswin_pixloss_fwd")
         ops.count_extra_launches(n_terms)                 # further terms + finalize kernel inside stswin_pixloss_fwd
         ctx.ws = (xn, lab_nat, lab_sorted, glab, coef, ksum, inv_norm, n_slots, nl_slots, dq32)

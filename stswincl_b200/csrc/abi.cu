@@ -66,17 +66,17 @@ int stswin_pixloss_labels(const void* const* labels, const int* dtypes, int n_la
 }
 int stswin_pixloss_prepare(const void* const* maps, const int* dtypes, const int* label_slots, int n_maps, int slot_off,
                            int N, int C, int HW, int do_normalize, int lo_slot_off, const uint16_t* perm, void* xn,
-                           float* inv_norm, float* ksum, void* stream) {
+                           float* inv_norm, float* ksum, float* f32_to_clear, int64_t f32_elems, void* stream) {
   return stswin::pixloss_prepare(maps, dtypes, label_slots, n_maps, slot_off, N, C, HW, do_normalize, lo_slot_off, perm, xn,
-                                 inv_norm, ksum, static_cast<cudaStream_t>(stream));
+                                 inv_norm, ksum, f32_to_clear, f32_elems, static_cast<cudaStream_t>(stream));
 }
 int stswin_pixloss_fwd(const void* xn, int n_slots, int n_label_slots, const uint8_t* lab_nat, const uint8_t* lab_sorted,
                        const uint8_t* glab, const int32_t* hist, const int* qmap, const int* qlab, const int* kmap,
                        const int* klab, int n_terms, int Q, int S, int N, int C, int HW, float* stats, float* loss,
                        float* loss_per_query,
-                       float* coef, const int32_t* err_flag, float* partial, uint32_t* ticket, float* dq32_to_clear, void* stream) {
+                       float* coef, const int32_t* err_flag, float* partial, uint32_t* ticket, void* stream) {
   return stswin::pixloss_fwd(xn, n_slots, n_label_slots, lab_nat, lab_sorted, glab, hist, qmap, qlab, kmap, klab, n_terms, Q, S, N,
-                             C, HW, stats, loss, loss_per_query, coef, err_flag, partial, ticket, dq32_to_clear, static_cast<cudaStream_t>(stream));
+                             C, HW, stats, loss, loss_per_query, coef, err_flag, partial, ticket, static_cast<cudaStream_t>(stream));
 }
 int stswin_pixloss_bwd(const void* xn, int n_slots, int n_label_slots, const uint8_t* lab_nat, const uint8_t* lab_sorted,
                        const uint8_t* glab, const int* qmap, const int* qmap_lo, const int* qlab, const int* kmap,

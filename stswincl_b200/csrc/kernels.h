@@ -30,11 +30,11 @@ int pixloss_labels(const void* const* labels, const int* dtypes, int n_labels, i
                    int* err_flag, float* ksum_to_clear, long ksum_elems, cudaStream_t stream);
 int pixloss_prepare(const void* const* maps, const int* dtypes, const int* label_slots, int n_maps, int slot_off, int N,
                     int C, int HW, int do_normalize, int lo_slot_off, const uint16_t* perm, void* xn, float* inv_norm,
-                    float* ksum, cudaStream_t stream);
+                    float* ksum, float* f32_to_clear, long f32_elems, cudaStream_t stream);
 int pixloss_fwd(const void* xn, int n_slots, int n_label_slots, const uint8_t* lab_nat, const uint8_t* lab_sorted,
                 const uint8_t* glab, const int* hist, const int* qmap, const int* qlab, const int* kmap, const int* klab,
                 int n_terms, int Q, int S, int N, int C, int HW, float* stats, float* loss, float* loss_per_query, float* coef, const int* err_flag,
-                float* partial, unsigned int* ticket, float* dq32_to_clear, cudaStream_t stream);
+                float* partial, unsigned int* ticket, cudaStream_t stream);
 int pixloss_bwd(const void* xn, int n_slots, int n_label_slots, const uint8_t* lab_nat, const uint8_t* lab_sorted,
                 const uint8_t* glab, const int* qmap, const int* qmap_lo, const int* qlab, const int* kmap, const int* klab,
                 int n_terms, int Q, int S, int N, int C, int HW, const float* coef, const float* ksum, const float* d_loss, float* dq32,

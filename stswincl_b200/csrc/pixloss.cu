@@ -212,6 +212,8 @@ struct PrepArgs {
   __nv_bfloat16* xn;              // [slots, N, C, HW]
   float* inv_norm;                // [slots, N, HW] (pixel order) or null
   float* ksum;                    // [slots, N, C], zero-filled
+  float4* zero;                   // optional: the backward's fp32 gradient accumulator, cleared here (no memset node)
+  long n_zero4;
 };
 
 template <typename TI>
@@ -340,6 +342,10 @@ __global__ void __launch_bounds__(256, 2) pix_prepare_kernel(const PrepArgs p) {
   __shared__ float s_ss[8][64];
   const int z = blockIdx.z, n = blockIdx.y;
   const size_t off = (size_t)n * p.C * p.HW;
+  if (p.zero != nullptr) {                  // a fresh buffer nobody reads yet: cleared while the label pass still runs
+    const long nb = (long)gridDim.x * gridDim.y * gridDim.z, b = ((long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    for (long i = b * 256 + threadIdx.x; i < p.n_zero4; i += nb * 256) p.zero[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   pdl_wait();                               // the label pass (sort permutation, cleared channel sums) is complete
   pdl_launch_dependents();
   switch (p.dtype[z]) {
@@ -601,20 +607,15 @@ struct PixFinArgs {
   float* coef;              // [Q, N, HW, 1 + S] or null
   float* partial;           // [Q * blocks_per_q]
   unsigned int* ticket;     // zero before the first call; left zero
-  float4* zero;             // optional: the backward's fp32 gradient accumulator, cleared here (saves a memset node)
-  long n_zero4;
 };
 
-__global__ void __launch_bounds__(256) pixloss_finalize_kernel(const PixTable tab, const PixFinArgs p) {
+constexpr int FIN_THREADS = 64;      // small CTAs: the kernel is latency-bound and also clears the backward's accumulator
+__global__ void __launch_bounds__(FIN_THREADS) pixloss_finalize_kernel(const PixTable tab, const PixFinArgs p) {
   __shared__ float s_part[8];
   __shared__ bool s_last;
   const int q = blockIdx.y;
   const long rows = (long)p.N * p.HW;
   const long r = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p.zero != nullptr) {
-    const long nt = (long)gridDim.x * gridDim.y * blockDim.x, t0 = ((long)blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
-    for (long i = t0; i < p.n_zero4; i += nt) p.zero[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
   pdl_wait();                               // the similarity kernel's row sums are complete
   float li = 0.f;
   if (r < rows) {
@@ -657,7 +658,7 @@ __global__ void __launch_bounds__(256) pixloss_finalize_kernel(const PixTable ta
   __syncthreads();
   if (threadIdx.x == 0) {
     float t = 0.f;
-    for (int w = 0; w < 8; ++w) t += s_part[w];
+    for (int w = 0; w < FIN_THREADS / 32; ++w) t += s_part[w];
     p.partial[q * gridDim.x + blockIdx.x] = t;
     __threadfence();
     const unsigned int done = atomicAdd(p.ticket, 1u);
@@ -1061,7 +1062,9 @@ int pixloss_labels(const void* const* labels, const int* dtypes, int n_labels, i
 // see include/stswin_b200.h : stswin_pixloss_prepare
 int pixloss_prepare(const void* const* maps, const int* dtypes, const int* label_slots, int n_maps, int slot_off, int N,
                     int C, int HW, int do_normalize, int lo_slot_off, const uint16_t* perm, void* xn, float* inv_norm,
-                    float* ksum, cudaStream_t stream) {
+                    float* ksum, float* f32_to_clear, long f32_elems, cudaStream_t stream) {
+  STSWIN_CHECK_ARG(f32_to_clear == nullptr || (f32_elems % 4 == 0 && (reinterpret_cast<uintptr_t>(f32_to_clear) & 15) == 0),
+                   "pixloss_prepare: the buffer to clear must be 16-byte aligned with a multiple of 4 elements");
   STSWIN_CHECK_ARG(lo_slot_off == 0 || lo_slot_off >= n_maps, "pixloss_prepare: lo_slot_off must be 0 or >= n_maps");
   STSWIN_CHECK_ARG(maps && dtypes && label_slots && xn && ksum && perm, "pixloss_prepare: null pointer");
   STSWIN_CHECK_ARG(n_maps >= 1 && N > 0, "pixloss_prepare: bad shape");
@@ -1082,6 +1085,7 @@ int pixloss_prepare(const void* const* maps, const int* dtypes, const int* label
     }
     a.n_maps = nm; a.slot_off = slot_off + off; a.N = N; a.C = C; a.HW = HW; a.do_normalize = do_normalize;
     a.lo_off = lo_slot_off;
+    a.zero = off == 0 ? reinterpret_cast<float4*>(f32_to_clear) : nullptr; a.n_zero4 = f32_elems / 4;
     a.perm = perm; a.xn = static_cast<__nv_bfloat16*>(xn); a.inv_norm = inv_norm; a.ksum = ksum;
     const dim3 grid((HW + 63) / 64, N, nm);
     switch (C / 64) {
@@ -1099,7 +1103,7 @@ int pixloss_prepare(const void* const* maps, const int* dtypes, const int* label
 int pixloss_fwd(const void* xn, int n_slots, int n_label_slots, const uint8_t* lab_nat, const uint8_t* lab_sorted,
                 const uint8_t* glab, const int* hist, const int* qmap, const int* qlab, const int* kmap, const int* klab,
                 int n_terms, int Q, int S, int N, int C, int HW, float* stats, float* loss, float* loss_per_query, float* coef,
-                const int* err_flag, float* partial, unsigned int* ticket, float* dq32_to_clear, cudaStream_t stream) {
+                const int* err_flag, float* partial, unsigned int* ticket, cudaStream_t stream) {
   STSWIN_CHECK_ARG(xn && lab_nat && lab_sorted && glab && hist && qmap && qlab && kmap && klab && stats && loss &&
                        err_flag && partial && ticket, "pixloss_fwd: null pointer");
   STSWIN_CHECK_ARG(n_terms >= 1 && n_terms <= 3, "pixloss_fwd: n_terms=%d out of range [1,3]", n_terms);
@@ -1128,9 +1132,8 @@ int pixloss_fwd(const void* xn, int n_slots, int n_label_slots, const uint8_t* l
   f.stats = stats; f.lab_nat = lab_nat; f.hist = hist; f.err = err_flag;
   f.loss = loss; f.loss_q = loss_per_query; f.coef = coef; f.partial = partial; f.ticket = ticket;
   const long rows = (long)N * HW;
-  f.zero = reinterpret_cast<float4*>(dq32_to_clear);
-  f.n_zero4 = (long)Q * N * HW * C / 4;
-  STSWIN_CUDA(launch_pdl(pixloss_finalize_kernel, dim3((unsigned)((rows + 255) / 256), Q), dim3(256), 0, stream, tab, f));
+  STSWIN_CUDA(launch_pdl(pixloss_finalize_kernel, dim3((unsigned)((rows + FIN_THREADS - 1) / FIN_THREADS), Q), dim3(FIN_THREADS), 0,
+                         stream, tab, f));
   return kOk;
 }
 
