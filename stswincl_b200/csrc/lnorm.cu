@@ -347,6 +347,8 @@ __global__ void transpose_kernel(const TI* __restrict__ in, TO* __restrict__ out
 // dst[b][i] = src[b][i], 16 bytes per access, four loads in flight per thread
 __global__ void __launch_bounds__(256)
 copy_strided_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src, long dst_stride16, long src_stride16, long n16) {
+  pdl_wait();
+  pdl_launch_dependents();
   const uint4* s = src + (long)blockIdx.y * src_stride16;
   uint4* d = dst + (long)blockIdx.y * dst_stride16;
   const long step = (long)gridDim.x * blockDim.x;
@@ -364,6 +366,8 @@ copy_strided_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src, long
 // neighbouring lanes) and reads two 8-element segments of the transposed tile back.
 __global__ void __launch_bounds__(256)
 transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int R, int Cc) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ __align__(16) __nv_bfloat16 tile[64][72];     // tile[c][r]
   const long b = blockIdx.z;
   const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
@@ -487,6 +491,8 @@ int layernorm_bwd(const void* dy, const void* x, const float* mean, const float*
 // group; fp32 partial sums leave through one atomic per column and CTA
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, long R,
                                                            int C, int rows_per_cta) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int groups = C >> 3;                              // 16-byte groups per row
   const int lanes_r = 256 / groups > 0 ? 256 / groups : 1; // rows walked in parallel by the CTA
   __shared__ float s_acc[256][9];
@@ -525,8 +531,8 @@ int copy_strided(void* dst, long dst_stride, const void* src, long src_stride, l
   if (per > cap) per = cap;
   if (per < 1) per = 1;
   dim3 grid((unsigned)per, (unsigned)batches);
-  copy_strided_kernel<<<grid, 256, 0, stream>>>(static_cast<uint4*>(dst), static_cast<const uint4*>(src), dst_stride / 16,
-                                                src_stride / 16, n16);
+  STSWIN_CUDA(launch_pdl(copy_strided_kernel, dim3(grid), dim3(256), 0, stream, static_cast<uint4*>(dst), static_cast<const uint4*>(src), dst_stride / 16,
+                                                src_stride / 16, n16));
   STSWIN_CUDA(cudaGetLastError());
   return kOk;
 }
@@ -538,7 +544,7 @@ int transpose_cvt(const void* in, int in_f32, void* out, int out_f32, long batch
   if (!in_f32 && !out_f32 && R % 8 == 0 && Cc % 8 == 0 &&
       ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
     dim3 g64((Cc + 63) / 64, (R + 63) / 64, (unsigned)batch);
-    transpose_bf16_kernel<<<g64, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(in), static_cast<__nv_bfloat16*>(out), R, Cc);
+    STSWIN_CUDA(launch_pdl(transpose_bf16_kernel, g64, dim3(256), 0, stream, static_cast<const __nv_bfloat16*>(in), static_cast<__nv_bfloat16*>(out), R, Cc));
     STSWIN_CUDA(cudaGetLastError());
     return kOk;
   }
@@ -563,7 +569,7 @@ int colsum_bf16(const void* x, float* out, long R, int C, cudaStream_t stream) {
   long rows_per_cta = (R + ctas - 1) / ctas;
   if (rows_per_cta < 32) rows_per_cta = 32;
   ctas = (int)((R + rows_per_cta - 1) / rows_per_cta);
-  colsum_bf16_kernel<<<ctas, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), out, R, C, (int)rows_per_cta);
+  STSWIN_CUDA(launch_pdl(colsum_bf16_kernel, dim3(ctas), dim3(256), 0, stream, static_cast<const __nv_bfloat16*>(x), out, R, C, (int)rows_per_cta));
   STSWIN_CUDA(cudaGetLastError());
   return kOk;
 }

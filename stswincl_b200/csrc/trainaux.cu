@@ -548,6 +548,8 @@ struct AdamArgs {
 __global__ void adam_tick_kernel(float* step) { *step += 1.0f; }
 
 __global__ void __launch_bounds__(kThreads) adam_kernel(const __grid_constant__ AdamArgs t) {
+  pdl_wait();
+  pdl_launch_dependents();
   int lo = 0, hi = t.n - 1;
   while (lo < hi) {
     const int mid = (lo + hi + 1) >> 1;
@@ -777,7 +779,7 @@ int adam_step(void* const* params, const void* const* grads, void* const* exp_av
     a.grad_bf16 = grads_are_bf16; a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.wd = weight_decay;
     a.grad_scale = grad_scale; a.step = step;
     if (blocks == 0) continue;
-    adam_kernel<<<blocks, kThreads, 0, stream>>>(a);
+    STSWIN_CUDA(launch_pdl(adam_kernel, dim3(blocks), dim3(kThreads), 0, stream, a));
   }
   STSWIN_CUDA(cudaGetLastError());
   return kOk;
