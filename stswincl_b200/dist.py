@@ -251,8 +251,11 @@ class SegmentedStep:
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            for _ in range(2):
-                self._eager(self._static_x)
+            for _ in range(2):                      # warm-up without side effects: no all-reduce, no optimizer step
+                self.opt.zero_grad(set_to_none=True)
+                self._forward(self._static_x)
+                for k in reversed(range(len(self._stage_fns))):
+                    self._backward_segment(k)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.opt.zero_grad(set_to_none=True)
