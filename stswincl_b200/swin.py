@@ -188,9 +188,11 @@ class _BlockFn(torch.autograd.Function):
         d_qkv = ops.winattn_bwd(qkv.view(*shp, 3 * C), table, lse2, d_attn.view(*shp, C), H, W, nH, ws, shift,
                                 d_table, d_bqkv, qk_scale=qk_scale)
         dq2 = d_qkv.view(-1, 3 * C)
-        d_x = ops.gemm(dq2, wq, b_mn_major=True, mode=ops.EPI_BIAS_RES, aux=dy)      # + residual path
+        d_x = None
+        if ctx.needs_input_grad[0]:          # the first block of a head fed with features that carry no gradient skips this GEMM
+            d_x = ops.gemm(dq2, wq, b_mn_major=True, mode=ops.EPI_BIAS_RES, aux=dy).view(*shp, C)      # + residual path
         d_wqkv = _linear_wgrad(dq2, x2, wq.shape, d_wqkv_)
-        return (d_x.view(*shp, C), d_table, d_wqkv, d_bqkv, d_wproj, d_bproj, d_g1, d_be1, d_g2, d_be2,
+        return (d_x, d_table, d_wqkv, d_bqkv, d_wproj, d_bproj, d_g1, d_be1, d_g2, d_be2,
                 d_wfc1, d_bfc1, d_wfc2, d_bfc2, None)
 
 

@@ -25,3 +25,11 @@ def rel_err(a, b):
     a = torch.as_tensor(a).detach().double()
     b = torch.as_tensor(b).detach().double()
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def rel_l2(a, b):
+    """||a - b||_2 / ||b||_2 -- complements rel_err (max-abs / max-abs), which cannot see many small outliers."""
+    import torch
+    a = torch.as_tensor(a).detach().double()
+    b = torch.as_tensor(b).detach().double()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
