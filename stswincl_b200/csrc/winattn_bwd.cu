@@ -57,7 +57,7 @@ STSWIN_TRACE_DECL(g_trace_bwd)
 // L, GEN as in the forward kernel.  WS > 0: fast path for the shipped geometries (compile-time column
 // maps; the bias-table gradient is summed in registers).  ORDER: 0 unshifted (row-major), 2 shifted
 // (quadrant order for the windows that wrap).  SHT: heads per 64-channel group (2 when head_dim is 32).
-template <int L, int WS, int ORDER, int SHT, bool GEN>
+template <int L, int WS, int ORDER, int SHT, bool GEN, int LWT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 winattn_bwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant__ WinMaps tm_do,
                    __nv_bfloat16* __restrict__ d_qkv, const float* __restrict__ bias_table, const float* __restrict__ lse2, float* __restrict__ d_table,
@@ -341,10 +341,10 @@ winattn_bwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant
       const uint32_t tmem_dPu = tmem_dP + (u & 1) * 128;
       if (sub == 0) {
         if (tr) WTRACE(g_trace_bwd, k, 7);
-        if constexpr (WS > 0) rg = row_geom_fast<L, WS, ORDER>(gm, tile, row);
+        if constexpr (WS > 0) rg = row_geom_fast<L, WS, ORDER, LWT>(gm, tile, row);
         else                  rg = row_geom(gm, tile, row);
         key_i = (rg.rr + gm.ws - 1) * (2 * gm.ws - 1) + rg.cc + gm.ws - 1;
-        col0 = GEN ? 0 : rg.g * L;
+        col0 = GEN ? (L == 128 ? 0 : (row / L) * L) : rg.g * L;   // GEN with L = 32: the warp's own 32-column band
         if constexpr (REG_BACC) {
           if (key_i != bacc_key) {           // the row's own position changed (token-order switch)
             flush_bacc();
@@ -359,7 +359,8 @@ winattn_bwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant
       const float* tab = s_tab + sub * (TAB_MAX + 1);
       float* bins = s_bacc + sub * (TAB_MAX + 1);
       // lse2 is indexed by the forward's tiling (natural window order): tile = window / G, row = (window % G)*L + ...
-      const float lse_i = (GEN && !rg.inrange) ? 0.f
+      // (fetching it one item ahead was measured: no gain -- the S / dP wait takes the stall over -- and 44-144 bytes of spills)
+      const float lse_i = !rg.inrange ? 0.f
                           : lse2[((size_t)(rg.gw / gm.G) * gm.nH + head) * 128 + (rg.gw % gm.G) * gm.L + (rg.canon - rg.g * gm.L)];
       float delta = 0.f;
 
@@ -367,7 +368,7 @@ winattn_bwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant
         // ---- fast path: compile-time column map, instantiated per token order of the row's window
         auto softmax_bwd_fast = [&](auto quad_tag) {
           constexpr bool QUAD = decltype(quad_tag)::value;
-          constexpr int LW = win_tokens<L, WS>();      // real columns of the window (98 of 128 for 7x7x2)
+          constexpr int LW = LWT;                      // real columns of the window (e.g. 98 of 128 for 7x7x2)
           constexpr int RA = (WS + 1) / 2;             // rows / columns of the first rectangle pair
           const float* tp = tab + key_i;
           // shift mask: one additive constant per quadrant of columns (see the forward kernel); folded with -lse
@@ -428,9 +429,9 @@ winattn_bwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant
                   const int jj = j8 * 8 + 2 * h + e, j = jb + jj;
                   pv[e] = 0.f;
                   if (j < LW) {                        // compile-time: padding columns stay zero
-                    const float bias = REG_BIAS ? breg[REG_BIAS ? col_pos<L, WS, QUAD>(j) : 0] : tp[-col_key<L, WS, QUAD>(j)];
+                    const float bias = REG_BIAS ? breg[REG_BIAS ? col_pos<LW, WS, QUAD>(j) : 0] : tp[-col_key<LW, WS, QUAD>(j)];
                     const float x = fmaf(__uint_as_float(v[jj]), gm.scale_log2e, bias);
-                    pv[e] = fast_exp2(x + nq[col_rect<L, WS, QUAD>(j)]);
+                    pv[e] = fast_exp2(x + nq[col_rect<LW, WS, QUAD>(j)]);
                     if (LW < L && !rg.inrange) pv[e] = 0.f;    // padding row of the slot
                     delta = fmaf(pv[e], __uint_as_float(w[jj]), delta);
                   }
@@ -474,11 +475,11 @@ winattn_bwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant
                 const float d1 = rg.valid ? pf.y * (__uint_as_float(w[jj + 1]) - delta) : 0.f;
                 dk[h] = pack_bf16(d0, d1);
                 if constexpr (REG_BACC) {
-                  if (j < LW) bacc[col_pos<L, WS, QUAD>(j < LW ? j : 0)] += d0;
-                  if (j + 1 < LW) bacc[col_pos<L, WS, QUAD>(j + 1 < LW ? j + 1 : 0)] += d1;
+                  if (j < LW) bacc[col_pos<LW, WS, QUAD>(j < LW ? j : 0)] += d0;
+                  if (j + 1 < LW) bacc[col_pos<LW, WS, QUAD>(j + 1 < LW ? j + 1 : 0)] += d1;
                 } else {
-                  if (j < LW && d0 != 0.f) atomicAdd(&bins[key_i - col_key<L, WS, QUAD>(j < LW ? j : 0)], d0);
-                  if (j + 1 < LW && d1 != 0.f) atomicAdd(&bins[key_i - col_key<L, WS, QUAD>(j + 1 < LW ? j + 1 : 0)], d1);
+                  if (j < LW && d0 != 0.f) atomicAdd(&bins[key_i - col_key<LW, WS, QUAD>(j < LW ? j : 0)], d0);
+                  if (j + 1 < LW && d1 != 0.f) atomicAdd(&bins[key_i - col_key<LW, WS, QUAD>(j + 1 < LW ? j + 1 : 0)], d1);
                 }
               }
               *reinterpret_cast<uint4*>(s_ds + off) = make_uint4(dk[0], dk[1], dk[2], dk[3]);
@@ -598,7 +599,7 @@ winattn_bwd_kernel(const __grid_constant__ WinMaps tm_qkv, const __grid_constant
       const int item = int(blockIdx.x) + k * int(gridDim.x);
       const int tile = item / gm.ngrp;
       RowGeom rg;
-      if constexpr (WS > 0) rg = row_geom_fast<L, WS, ORDER>(gm, tile, row);
+      if constexpr (WS > 0) rg = row_geom_fast<L, WS, ORDER, LWT>(gm, tile, row);
       else                  rg = row_geom(gm, tile, row);
       __nv_bfloat16* row_out = d_qkv + rg.tok * (3 * gm.C) + hg * gm.gch;
 #pragma unroll 1
@@ -694,25 +695,34 @@ int winattn_bwd(const void* qkv, const float* bias_table, const float* lse2, con
   int grid = items < num_sms() ? items : num_sms();
   grid -= grid % gm.ngrp;                 // one head group per CTA (items is a multiple of ngrp, so grid >= ngrp)
   if (grid < gm.ngrp) return set_error(kErrUnsupported, "winattn_bwd: %d head groups exceed the SM count", gm.ngrp);
-#define STSWIN_LAUNCH_BWD(LL, WW, OO, SS, GG)                                                                  \
+#define STSWIN_LAUNCH_BWD(LL, WW, OO, SS, GG, PP)                                                              \
   {                                                                                                            \
-    if ((rc = set_smem_bwd(winattn_bwd_kernel<LL, WW, OO, SS, GG>, SMEM_BYTES)) != kOk) return rc;             \
-    STSWIN_CUDA(launch_pdl(winattn_bwd_kernel<LL, WW, OO, SS, GG>, dim3(grid), dim3(NUM_THREADS), (size_t)SMEM_BYTES, stream, \
+    if ((rc = set_smem_bwd(winattn_bwd_kernel<LL, WW, OO, SS, GG, PP>, SMEM_BYTES)) != kOk) return rc;         \
+    STSWIN_CUDA(launch_pdl(winattn_bwd_kernel<LL, WW, OO, SS, GG, PP>, dim3(grid), dim3(NUM_THREADS), (size_t)SMEM_BYTES, stream, \
                            tq, td, static_cast<__nv_bfloat16*>(d_qkv), bias_table, lse2, d_table, d_qkv_colsum, gm)); \
   }
-#define STSWIN_LAUNCH_BWD_S(LL, WW, OO, GG)                 \
-  {                                                         \
-    if (gm.SH == 1) STSWIN_LAUNCH_BWD(LL, WW, OO, 1, GG)    \
-    else STSWIN_LAUNCH_BWD(LL, WW, OO, 2, GG)               \
+#define STSWIN_LAUNCH_BWD_P(LL, WW, OO, GG, PP)                 \
+  {                                                             \
+    if (gm.SH == 1) STSWIN_LAUNCH_BWD(LL, WW, OO, 1, GG, PP)    \
+    else STSWIN_LAUNCH_BWD(LL, WW, OO, 2, GG, PP)               \
   }
+#define STSWIN_LAUNCH_BWD_S(LL, WW, OO, GG) STSWIN_LAUNCH_BWD_P(LL, WW, OO, GG, LL)
   // fast path: the shipped geometries (ws 8 or 4, 1 or 2 frames per window, shift 0 or ws/2, no dense mask)
   const bool fast = !gm.general && mask == nullptr && (shift == 0 || 2 * shift == ws) &&
                     ((ws == 8 && (gm.L == 128 || gm.L == 64)) || (ws == 4 && gm.L == 32));
   const bool shifted = shift > 0;
-  // 7x7 windows with two frames (98 of the 128 tile rows) and shift 0 or 3: compile-time maps as well
-  const bool fast7 = mask == nullptr && ws == 7 && gm.L == 98 && (shift == 0 || shift == 3);
-  if (fast7 && !shifted) STSWIN_LAUNCH_BWD_S(128, 7, 0, false)
-  else if (fast7) STSWIN_LAUNCH_BWD_S(128, 7, 2, false)
+  // odd windows in padded slots (7x7 and 5x5 with one or two frames), shift 0 or ws/2: compile-time maps as well
+  const bool fastp = mask == nullptr && (shift == 0 || shift == ws / 2) &&
+                     ((ws == 7 && (gm.L == 49 || gm.L == 98)) || (ws == 5 && (gm.L == 25 || gm.L == 50)));
+  if (fastp && ws == 7 && gm.L == 98 && !shifted) STSWIN_LAUNCH_BWD_P(128, 7, 0, false, 98)
+  else if (fastp && ws == 7 && gm.L == 98) STSWIN_LAUNCH_BWD_P(128, 7, 2, false, 98)
+  else if (fastp && ws == 7 && !shifted) STSWIN_LAUNCH_BWD_P(64, 7, 0, false, 49)
+  else if (fastp && ws == 7) STSWIN_LAUNCH_BWD_P(64, 7, 2, false, 49)
+  else if (fastp && gm.L == 50 && !shifted) STSWIN_LAUNCH_BWD_P(64, 5, 0, false, 50)
+  else if (fastp && gm.L == 50) STSWIN_LAUNCH_BWD_P(64, 5, 2, false, 50)
+  else if (fastp && !shifted) STSWIN_LAUNCH_BWD_P(32, 5, 0, false, 25)
+  else if (fastp) STSWIN_LAUNCH_BWD_P(32, 5, 2, false, 25)
+  else if (gm.general && gm.slot <= 8 && 32 % gm.slot == 0) STSWIN_LAUNCH_BWD_S(32, 0, 0, true)   // windows of 4 / 8 tokens
   else if (gm.general) STSWIN_LAUNCH_BWD_S(128, 0, 0, true)
   else if (fast && gm.L == 128 && !shifted) STSWIN_LAUNCH_BWD_S(128, 8, 0, false)
   else if (fast && gm.L == 128) STSWIN_LAUNCH_BWD_S(128, 8, 2, false)
@@ -724,6 +734,7 @@ int winattn_bwd(const void* qkv, const float* bias_table, const float* lse2, con
   else if (gm.L == 32) STSWIN_LAUNCH_BWD_S(32, 0, 0, false)
   else if (gm.L == 64) STSWIN_LAUNCH_BWD_S(64, 0, 0, false)
   else STSWIN_LAUNCH_BWD_S(128, 0, 0, false)
+#undef STSWIN_LAUNCH_BWD_P
 #undef STSWIN_LAUNCH_BWD_S
 #undef STSWIN_LAUNCH_BWD
   STSWIN_CUDA(cudaGetLastError());

@@ -1,7 +1,10 @@
 // Geometry shared by the window-attention forward and backward kernels.
 //
-// A "tile" is 128 token rows = G consecutive windows of L = T*ws*ws tokens each (G = 128/L, rounded
-// down; when L does not divide 128 the last rows of the tile are padding and stay zero).
+// A "tile" is 128 token rows = G consecutive windows of L = T*ws*ws tokens each.  Window g of the tile
+// starts at row g * slot: slot = L for L <= 16, else L rounded up to a power of two (49 -> 64, 25 -> 32,
+// 98 -> 128), G = 128 / slot; rows slot*g + [L, slot) and rows >= G*slot are padding and stay zero.  A warp of
+// the row-per-thread groups (32 rows) then never straddles two windows with more than 16 tokens, which is what
+// the compile-time column maps below need.
 // Work item = (tile, head).  Each operand chunk is [128 rows x 64 channels] bf16 in the
 // 128B-swizzled K-major layout, filled by TMA boxes taken straight from the un-rolled,
 // un-partitioned [B, T, H, W, channels] tensor: the cyclic shift and the window partition
@@ -32,6 +35,8 @@ namespace stswin {
 struct WinGeom {
   int B, T, H, W, C, nH, ws, shift;
   int hd, N, L, G, nWh, nWw, nW, total_windows, num_tiles, nc;   // nc = 64-channel chunks per head group
+  int slot;           // tile rows from one window of the tile to the next (>= L, see above)
+  int lag;            // forward: the S product of unit u+1 is issued before the P V product of unit u
   int SH, ngrp, gch;   // head_dim >= 64: SH = 1, a "head group" is one head (gch = hd channels).
                        // head_dim 32  : SH = 2 heads share one 64-channel chunk (gch = 64); S / dP use
                        // the head's 32-channel K sub-range of the chunk, the output products run over
@@ -40,7 +45,7 @@ struct WinGeom {
   float scale;                                                    // hd^-0.5
   int ra, rb;         // a shifted window that wraps is moved as 2x2 rectangles of (ws-shift | shift) rows x columns
   int roff[5];        // first tile row of rectangle k inside its window's L rows (roff[4] = L)
-  int general;        // 1: L is not 16/32/64/128 -> kernels run their "whole row + window tag" path
+  int general;        // 1: L is not 16/32/64/128 -> the look-up-table kernels run their "whole row + window tag" path
   const float* mask;  // optional dense additive mask [mask_nw, N, N] (WindowAttention.forward's `mask`
   int mask_nw;        //   argument, swin_512.py:127-131), applied ON TOP of the closed-form shift mask; or null
   unsigned long long mg_nW, mg_nWw;   // ceil(2^32 / nW), ceil(2^32 / nWw): exact division of window indices by multiply-shift
@@ -58,7 +63,7 @@ struct RowGeom {
   long tok;    // index of the source token in the natural [B*T, H, W] order (roll + partition undone)
   bool wraps;  // window crosses the image border (the only windows with a non-zero mask)
   bool valid;  // false for rows of a padding window in the last tile, and for padding rows
-  bool inrange; // false for the padding rows r >= G*L of a tile (general mode only)
+  bool inrange; // false for the padding rows of a tile (behind a window's L tokens in its slot, or behind the last slot)
 };
 
 struct WinMaps {     // tensor maps over one [B*T, H, W, channels] tensor
@@ -116,10 +121,10 @@ __device__ __forceinline__ void rect_dims(const WinGeom& gm, int k, int& h_off, 
 // geometry of tile row r of tile `tile`
 __device__ __forceinline__ RowGeom row_geom(const WinGeom& gm, int tile, int r) {
   RowGeom o;
-  o.g = r / gm.L;
-  o.inrange = o.g < gm.G;
-  if (!o.inrange) o.g = gm.G - 1;
-  const int rem = o.inrange ? r - o.g * gm.L : 0;
+  o.g = r / gm.slot;
+  o.inrange = o.g < gm.G && r - o.g * gm.slot < gm.L;
+  if (o.g > gm.G - 1) o.g = gm.G - 1;
+  const int rem = o.inrange ? r - o.g * gm.slot : 0;
   int gw = tile * gm.G + o.g;
   o.valid = o.inrange && gw < gm.total_windows;
   if (gw > gm.total_windows - 1) gw = gm.total_windows - 1;
@@ -155,46 +160,44 @@ __device__ __forceinline__ RowGeom row_geom(const WinGeom& gm, int tile, int r) 
 }
 
 // Compile-time column maps of the fast-path geometries.  WS is the window size; L the tile rows one
-// window slot spans (a power of two, <= 128); the window really holds LW = win_tokens<L, WS>() tokens:
-// LW = L for ws 8 / 4, and 98 of the 128 rows for 7x7 windows with two frames (rows / columns >= LW
-// are padding).  Shift is 0 or WS/2, so a window that wraps splits into 2x2 rectangles of
+// window slot spans (a power of two, <= 128); the window really holds LW = T*WS*WS tokens:
+// LW = L for ws 8 / 4; 49 of 64 / 98 of 128 rows for 7x7 windows with one / two frames, 25 of 32 / 50 of 64
+// for 5x5 (rows / columns >= LW of a slot are padding).  Shift is 0 or WS/2, so a window that wraps splits into 2x2 rectangles of
 // RA = ceil(WS/2) and RB = WS - RA rows / columns (quadrants when WS is even).
 // Column j (< LW) of a window, in row-major order (QUAD = false: t, row, column) or rectangle order
 // (QUAD = true: rectangle, t, row, column inside the rectangle):
 //   col_rect : rectangle index 0..3 (0 in row-major order)
 //   col_pos  : spatial position rr*WS + cc of the token
 //   col_key  : rr*(2*WS-1) + cc, so that key_i - col_key(j) indexes the relative-position bias table
-template <int L, int WS>
-__host__ __device__ constexpr int win_tokens() { return WS == 7 ? 98 : L; }
-template <int L, int WS>
+template <int LW, int WS>
 __host__ __device__ constexpr int rect_off(int k) {    // first column of rectangle k (k = 4: LW)
-  constexpr int W1 = WS > 0 ? WS : 1, T = win_tokens<L, WS>() / (W1 * W1) > 0 ? win_tokens<L, WS>() / (W1 * W1) : 1;
+  constexpr int W1 = WS > 0 ? WS : 1, T = LW / (W1 * W1) > 0 ? LW / (W1 * W1) : 1;
   constexpr int RA = (W1 + 1) / 2, RB = W1 - RA;
   int off = 0;
   for (int q = 0; q < k; ++q) off += ((q >> 1) ? RB : RA) * ((q & 1) ? RB : RA) * T;
   return off;
 }
-template <int L, int WS, bool QUAD>
+template <int LW, int WS, bool QUAD>
 __host__ __device__ constexpr int col_rect(int j) {
   // loop-free (the optimiser must fold this to a constant for every unrolled column)
-  constexpr int o1 = rect_off<L, WS>(1), o2 = rect_off<L, WS>(2), o3 = rect_off<L, WS>(3);
+  constexpr int o1 = rect_off<LW, WS>(1), o2 = rect_off<LW, WS>(2), o3 = rect_off<LW, WS>(3);
   return QUAD ? (j >= o1 ? 1 : 0) + (j >= o2 ? 1 : 0) + (j >= o3 ? 1 : 0) : 0;
 }
-template <int L, int WS, bool QUAD>
+template <int LW, int WS, bool QUAD>
 __host__ __device__ constexpr int col_pos(int j) {
   constexpr int W1 = WS > 0 ? WS : 1, N = W1 * W1, RA = (W1 + 1) / 2, RB = W1 - RA;
-  constexpr int o1 = rect_off<L, WS>(1), o2 = rect_off<L, WS>(2), o3 = rect_off<L, WS>(3);
+  constexpr int o1 = rect_off<LW, WS>(1), o2 = rect_off<LW, WS>(2), o3 = rect_off<LW, WS>(3);
   if (!QUAD) return j % N;
-  const int k = col_rect<L, WS, true>(j);
+  const int k = col_rect<LW, WS, true>(j);
   const int hext = (k >> 1) ? RB : RA, wext = (k & 1) ? RB : RA;
   const int off = k == 0 ? 0 : (k == 1 ? o1 : (k == 2 ? o2 : o3));
   const int p = (j - off) % (hext * wext);
   return (((k >> 1) ? RA : 0) + p / wext) * W1 + ((k & 1) ? RA : 0) + p % wext;
 }
-template <int L, int WS, bool QUAD>
+template <int LW, int WS, bool QUAD>
 __host__ __device__ constexpr int col_key(int j) {
   constexpr int W1 = WS > 0 ? WS : 1;
-  const int pos = col_pos<L, WS, QUAD>(j);
+  const int pos = col_pos<LW, WS, QUAD>(j);
   return (pos / W1) * (2 * W1 - 1) + pos % W1;
 }
 
@@ -203,11 +206,11 @@ __device__ __forceinline__ int fast_div(int n, unsigned long long mg) {
   return int((static_cast<unsigned long long>(static_cast<unsigned>(n)) * mg) >> 32);
 }
 
-// row_geom for the fast-path geometries: L, ws compile-time (shifts / constant divisions), shift 0 or ws/2.
-// ORDER 0: row-major.  1: every window in quadrant order.  2: quadrant order for the windows that wrap.
-template <int L, int WS, int ORDER>
+// row_geom for the fast-path geometries: slot L, tokens per window LW, ws compile-time (shifts / constant divisions),
+// shift 0 or ws/2.  ORDER 0: row-major.  1: every window in quadrant order.  2: quadrant order for the windows that wrap.
+template <int L, int WS, int ORDER, int LW>
 __device__ __forceinline__ RowGeom row_geom_fast(const WinGeom& gm, int tile, int r) {
-  constexpr int N = WS * WS, G = 128 / L, LW = win_tokens<L, WS>(), RA = (WS + 1) / 2, RB = WS - RA;
+  constexpr int N = WS * WS, G = 128 / L, RA = (WS + 1) / 2, RB = WS - RA;
   RowGeom o;
   o.g = r / L;
   const int rin = r % L;
@@ -236,9 +239,9 @@ __device__ __forceinline__ RowGeom row_geom_fast(const WinGeom& gm, int tile, in
   } else {
     int k = 0;
 #pragma unroll
-    for (int q = 1; q < 4; ++q) k += (rem >= rect_off<L, WS>(q)) ? 1 : 0;
+    for (int q = 1; q < 4; ++q) k += (rem >= rect_off<LW, WS>(q)) ? 1 : 0;
     const int hext = (k >> 1) ? RB : RA, wext = (k & 1) ? RB : RA, area = hext * wext;
-    const int r2 = rem - ((k == 0) ? 0 : (k == 1) ? rect_off<L, WS>(1) : (k == 2) ? rect_off<L, WS>(2) : rect_off<L, WS>(3));
+    const int r2 = rem - ((k == 0) ? 0 : (k == 1) ? rect_off<LW, WS>(1) : (k == 2) ? rect_off<LW, WS>(2) : rect_off<LW, WS>(3));
     t = r2 / area;
     const int p = r2 - t * area;
     o.rr = ((k >> 1) ? RA : 0) + p / wext;
@@ -272,7 +275,7 @@ __device__ __forceinline__ void tile_boxes(const WinGeom& gm, int tile, int ch0,
     int b, wh, ww;
     bool wraps;
     window_coords(gm, gw, b, wh, ww, wraps);
-    uint8_t* dst = buf + (g * gm.L) * 128;
+    uint8_t* dst = buf + (g * gm.slot) * 128;
     if (!quad_order(gm, wraps)) {
       if (q != 0) continue;
       const int w0 = ww * gm.ws + gm.shift, h0 = wh * gm.ws + gm.shift;
@@ -290,7 +293,7 @@ __device__ __forceinline__ void tile_boxes(const WinGeom& gm, int tile, int ch0,
   }
 }
 
-// bytes one chunk load brings in (only the G*L real rows of the 128-row buffer)
+// bytes one chunk load brings in (only the G*L real rows of the 128-row buffer; padding rows are never written)
 __device__ __forceinline__ uint32_t chunk_tx_bytes(const WinGeom& gm) { return uint32_t(gm.G * gm.L) * 128u; }
 
 __device__ __forceinline__ float fast_exp2(float x) {

@@ -17,6 +17,7 @@
 // both; a softmax and an epilogue warp share each SM sub-partition, so the MUFU-heavy softmax of
 // item k overlaps the TMEM / store-heavy drain of item k-1).  Operand chunks stream through a ring
 // of 16 KB slots.  The tensor core runs one item ahead: S(k+1) is issued before P V(k).
+#include <cstdlib>
 #include <type_traits>
 
 #include "winattn_common.cuh"
@@ -38,16 +39,17 @@ constexpr int SMEM_BYTES = 1024 + NSLOT * SLOT_BYTES + P_BYTES + STG_BYTES + 128
 constexpr float kMaskLog2e = -100.0f * 1.4426950408889634f;
 STSWIN_TRACE_DECL(g_trace_fwd)
 
-// L   : window columns a thread walks (16/32/64/128).  GEN (only with L = 128): the tile holds G windows of
-//       gm.L tokens with gm.L not a power of two (e.g. 7x7x2 = 98); every thread then walks the whole
-//       128-column row and keeps only the columns tagged with its own window.
+// L   : window columns a thread walks (16/32/64/128).  GEN: the tile holds G windows of gm.L tokens with gm.L not
+//       16/32/64/128 (e.g. 3x3x2 = 18); every thread then walks the whole 128-column row (L = 128) -- or, when the
+//       windows have 4 / 8 tokens and never straddle a warp, the 32-column band of its warp (L = 32) -- and keeps only
+//       the columns tagged with its own window.
 //
-// WS > 0 selects the fast softmax for the shipped geometries (L = T*WS*WS, whole launch in one token
-// order, or one order per window: see ORDER below).  The
+// WS > 0 selects the fast softmax (compile-time geometry: slot L, LWT = T*WS*WS <= L tokens per window, whole launch
+// in one token order, or one order per window: see ORDER below).  The
 // column -> (relative-position key, quadrant) map is then a compile-time function of the column,
 // so the bias is one LDS at an immediate offset and the shift mask is one additive constant per
 // quadrant.  WS == 0 is the generic path (look-up table per column: dense mask, L = 16, GEN).
-template <int L, int WS, int ORDER, bool GEN>
+template <int L, int WS, int ORDER, bool GEN, int LWT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 winattn_fwd_kernel(const __grid_constant__ WinMaps tm_qkv, __nv_bfloat16* __restrict__ out,
                    const float* __restrict__ bias_table, float* __restrict__ lse2, const WinGeom gm) {
@@ -80,9 +82,8 @@ winattn_fwd_kernel(const __grid_constant__ WinMaps tm_qkv, __nv_bfloat16* __rest
   const int hg = blockIdx.x % gm.ngrp;              // constant per CTA: gridDim.x % ngrp == 0
   const int n_local = (num_items - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);   // items of this CTA
   const int n_units = n_local * SH;                 // unit = (item, head of the group)
-  // One head per group: S of item k+1 is issued before P V of item k (the softmax of k+1 then never
-  // waits for a tensor-core round trip).
-  const bool lag = (SH == 1);
+  // S of unit u+1 is issued before P V of unit u (the softmax of u+1 then never waits for a tensor-core round trip).
+  const bool lag = gm.lag != 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_qkv.full);
@@ -257,10 +258,10 @@ winattn_fwd_kernel(const __grid_constant__ WinMaps tm_qkv, __nv_bfloat16* __rest
       const int head = hg * SH + sub;
       if (sub == 0) {
         if (tr) WTRACE(g_trace_fwd, k, 5);
-        if constexpr (WS > 0) rg = row_geom_fast<L, WS, ORDER>(gm, tile, row);
+        if constexpr (WS > 0) rg = row_geom_fast<L, WS, ORDER, LWT>(gm, tile, row);
         else                  rg = row_geom(gm, tile, row);
         key_i = (rg.rr + gm.ws - 1) * (2 * gm.ws - 1) + rg.cc + gm.ws - 1;
-        col0 = GEN ? 0 : rg.g * L;
+        col0 = GEN ? (L == 128 ? 0 : (row / L) * L) : rg.g * L;   // GEN with L = 32: the warp's own 32-column band
         if (tr) WTRACE(g_trace_fwd, k, 6);
       }
       const float* tab = s_tab + sub * (TAB_MAX + 1);
@@ -273,7 +274,7 @@ winattn_fwd_kernel(const __grid_constant__ WinMaps tm_qkv, __nv_bfloat16* __rest
         auto softmax_fast = [&](auto quad_tag) {
           constexpr bool QUAD = decltype(quad_tag)::value;
           constexpr int NQ = QUAD ? 4 : 1;
-          constexpr int LW = win_tokens<L, WS>();      // real columns of the window (98 of 128 for 7x7x2)
+          constexpr int LW = LWT;                      // real columns of the window (e.g. 98 of 128 for 7x7x2)
           constexpr int RA = (WS + 1) / 2;             // rows / columns of the first rectangle pair
           const float* tp = tab + key_i;
           float mq[NQ];
@@ -290,9 +291,9 @@ winattn_fwd_kernel(const __grid_constant__ WinMaps tm_qkv, __nv_bfloat16* __rest
             for (int jj = 0; jj < CH; ++jj) {
               const int j = cb * CH + jj;
               if (j < LW) {                            // compile-time: padding columns are never touched
-                const float x = fmaf(__uint_as_float(v[jj]), gm.scale_log2e, tp[-col_key<L, WS, QUAD>(j)]);
+                const float x = fmaf(__uint_as_float(v[jj]), gm.scale_log2e, tp[-col_key<LW, WS, QUAD>(j)]);
                 s[j] = x;
-                mq[col_rect<L, WS, QUAD>(j)] = fmaxf(mq[col_rect<L, WS, QUAD>(j)], x);
+                mq[col_rect<LW, WS, QUAD>(j)] = fmaxf(mq[col_rect<LW, WS, QUAD>(j)], x);
               }
             }
           }
@@ -328,8 +329,8 @@ winattn_fwd_kernel(const __grid_constant__ WinMaps tm_qkv, __nv_bfloat16* __rest
             for (int h = 0; h < 4; ++h) {
               const int j = j8 * 8 + 2 * h;
               float p0 = 0.f, p1 = 0.f;
-              if (j < LW) p0 = fast_exp2(s[j] + nq[col_rect<L, WS, QUAD>(j)]);
-              if (j + 1 < LW) p1 = fast_exp2(s[j + 1] + nq[col_rect<L, WS, QUAD>(j + 1)]);
+              if (j < LW) p0 = fast_exp2(s[j] + nq[col_rect<LW, WS, QUAD>(j)]);
+              if (j + 1 < LW) p1 = fast_exp2(s[j + 1] + nq[col_rect<LW, WS, QUAD>(j + 1)]);
               sum += p0 + p1;
               w[h] = pack_bf16(p0, p1);
             }
@@ -411,7 +412,7 @@ winattn_fwd_kernel(const __grid_constant__ WinMaps tm_qkv, __nv_bfloat16* __rest
       const int item = int(blockIdx.x) + k * int(gridDim.x);
       const int tile = item / gm.ngrp;
       RowGeom rg;
-      if constexpr (WS > 0) rg = row_geom_fast<L, WS, ORDER>(gm, tile, row);
+      if constexpr (WS > 0) rg = row_geom_fast<L, WS, ORDER, LWT>(gm, tile, row);
       else                  rg = row_geom(gm, tile, row);
       const long tok = rg.valid ? rg.tok : -1;
       uint8_t* rowp[8];
@@ -486,7 +487,10 @@ int fill_geom(WinGeom* gm, int B, int T, int H, int W, int C, int nH, int ws, in
     return set_error(kErrInvalidArg, "winattn: shift %d must be in [0, window_size = %d)", shift, ws);
   if (ws > 8) return set_error(kErrUnsupported, "winattn: window size %d > 8 unsupported", ws);
   gm->general = !(gm->L == 16 || gm->L == 32 || gm->L == 64 || gm->L == 128);
-  gm->G = 128 / gm->L;
+  // rows per window slot of a tile: windows of more than 16 tokens start at a power-of-two row (49 -> 64, 25 -> 32, 98 -> 128)
+  gm->slot = gm->L;
+  if (gm->L > 16) { gm->slot = 32; while (gm->slot < gm->L) gm->slot *= 2; }
+  gm->G = 128 / gm->slot;
   gm->nWh = H / ws; gm->nWw = W / ws; gm->nW = gm->nWh * gm->nWw;
   gm->total_windows = B * gm->nW;
   gm->num_tiles = (gm->total_windows + gm->G - 1) / gm->G;
@@ -507,6 +511,7 @@ int fill_geom(WinGeom* gm, int B, int T, int H, int W, int C, int nH, int ws, in
   }
   gm->uniform_quad = 0;
   gm->perm = 0;
+  gm->lag = 1;
   gm->mask = nullptr; gm->mask_nw = 0;
   // exact multiply-shift division of window indices (row_geom_fast)
   if ((unsigned long long)gm->total_windows * (unsigned long long)gm->nW >= (1ull << 32))
@@ -561,28 +566,39 @@ int winattn_fwd(const void* qkv, const float* bias_table, void* out, float* lse2
   if (qk_scale > 0.f) { gm.scale = qk_scale; gm.scale_log2e = qk_scale * 1.4426950408889634f; }
   STSWIN_CHECK_ARG(mask == nullptr || mask_windows > 0, "winattn: mask given with mask_windows <= 0");
   gm.mask = mask; gm.mask_nw = mask_windows;
+  if (const char* e = getenv("STSWIN_FWD_LAG")) gm.lag = atoi(e);      // A/B switch (tools/sweep_attn.py)
   STSWIN_CHECK_ARG((reinterpret_cast<uintptr_t>(out) & 15) == 0, "winattn_fwd: out must be 16-byte aligned");
   WinMaps tq;
   if ((rc = make_window_tmaps(&tq, qkv, gm, 3 * C)) != kOk) return rc;
   const int items = gm.num_tiles * gm.ngrp;
   int grid = items < num_sms() ? items : num_sms();
   grid -= grid % gm.ngrp;                 // every CTA keeps one head group (its bias tables live in smem)
-#define STSWIN_LAUNCH_FWD(LL, WW, QQ, GG)                                                                      \
+#define STSWIN_LAUNCH_FWD_P(LL, WW, QQ, GG, PP)                                                                \
   {                                                                                                            \
-    if ((rc = set_smem(winattn_fwd_kernel<LL, WW, QQ, GG>, SMEM_BYTES)) != kOk) return rc;                     \
-    STSWIN_CUDA(launch_pdl(winattn_fwd_kernel<LL, WW, QQ, GG>, dim3(grid), dim3(NUM_THREADS), (size_t)SMEM_BYTES, stream, tq,  \
+    if ((rc = set_smem(winattn_fwd_kernel<LL, WW, QQ, GG, PP>, SMEM_BYTES)) != kOk) return rc;                 \
+    STSWIN_CUDA(launch_pdl(winattn_fwd_kernel<LL, WW, QQ, GG, PP>, dim3(grid), dim3(NUM_THREADS), (size_t)SMEM_BYTES, stream, tq,  \
                            static_cast<__nv_bfloat16*>(out), bias_table, lse2, gm));                             \
   }
+#define STSWIN_LAUNCH_FWD(LL, WW, QQ, GG) STSWIN_LAUNCH_FWD_P(LL, WW, QQ, GG, LL)
   // fast softmax: the shipped geometries (ws 8 or 4, 1 or 2 frames per window, shift 0 or ws/2, no dense mask)
   const bool fast = !gm.general && mask == nullptr && (shift == 0 || 2 * shift == ws) &&
                     ((ws == 8 && (gm.L == 128 || gm.L == 64)) || (ws == 4 && gm.L == 32));
   // token order of a shifted block: quadrant order only for the windows that wrap (one box per
   // interior window measured faster than four quadrant boxes for every window, at every L)
   const int order = shift == 0 ? 0 : (gm.uniform_quad ? 1 : 2);
-  // 7x7 windows with two frames (98 of the 128 tile rows) and shift 0 or 3: compile-time maps as well
-  const bool fast7 = gm.general && mask == nullptr && ws == 7 && gm.L == 98 && (shift == 0 || shift == 3);
-  if (fast7 && order == 0) STSWIN_LAUNCH_FWD(128, 7, 0, false)
-  else if (fast7) STSWIN_LAUNCH_FWD(128, 7, 2, false)
+  // odd windows in padded slots (7x7 and 5x5 with one or two frames: 49 of 64 / 98 of 128 / 25 of 32 / 50 of 64 rows),
+  // shift 0 or ws/2: compile-time maps as well
+  const bool fastp = gm.general && mask == nullptr && (shift == 0 || shift == ws / 2) && order != 1 &&
+                     ((ws == 7 && (gm.L == 49 || gm.L == 98)) || (ws == 5 && (gm.L == 25 || gm.L == 50)));
+  if (fastp && ws == 7 && gm.L == 98 && order == 0) STSWIN_LAUNCH_FWD_P(128, 7, 0, false, 98)
+  else if (fastp && ws == 7 && gm.L == 98) STSWIN_LAUNCH_FWD_P(128, 7, 2, false, 98)
+  else if (fastp && ws == 7 && order == 0) STSWIN_LAUNCH_FWD_P(64, 7, 0, false, 49)
+  else if (fastp && ws == 7) STSWIN_LAUNCH_FWD_P(64, 7, 2, false, 49)
+  else if (fastp && gm.L == 50 && order == 0) STSWIN_LAUNCH_FWD_P(64, 5, 0, false, 50)
+  else if (fastp && gm.L == 50) STSWIN_LAUNCH_FWD_P(64, 5, 2, false, 50)
+  else if (fastp && order == 0) STSWIN_LAUNCH_FWD_P(32, 5, 0, false, 25)
+  else if (fastp) STSWIN_LAUNCH_FWD_P(32, 5, 2, false, 25)
+  else if (gm.general && gm.slot <= 8 && 32 % gm.slot == 0) STSWIN_LAUNCH_FWD(32, 0, 0, true)   // windows of 4 / 8 tokens
   else if (gm.general) STSWIN_LAUNCH_FWD(128, 0, 0, true)
   else if (fast && gm.L == 128 && order == 0) STSWIN_LAUNCH_FWD(128, 8, 0, false)
   else if (fast && gm.L == 128 && order == 1) STSWIN_LAUNCH_FWD(128, 8, 1, false)
@@ -595,6 +611,7 @@ int winattn_fwd(const void* qkv, const float* bias_table, void* out, float* lse2
   else if (gm.L == 32) STSWIN_LAUNCH_FWD(32, 0, 0, false)
   else if (gm.L == 64) STSWIN_LAUNCH_FWD(64, 0, 0, false)
   else STSWIN_LAUNCH_FWD(128, 0, 0, false)
+#undef STSWIN_LAUNCH_FWD_P
 #undef STSWIN_LAUNCH_FWD
   STSWIN_CUDA(cudaGetLastError());
   return kOk;

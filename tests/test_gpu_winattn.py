@@ -46,6 +46,20 @@ CASES = [
     (2, 2, 8, 12, 128, 2, 4, 1),
     (2, 2, 9, 12, 64, 1, 3, 1),       # 18-token windows, 7 per tile
     (1, 2, 10, 15, 128, 2, 5, 2),     # 50-token windows
+    # odd windows in padded slots (49 of 64, 25 of 32, 50 of 64 rows): compile-time paths, and the look-up-table
+    # path on the same slots for shifts other than ws // 2
+    (3, 1, 14, 21, 128, 2, 7, 0),
+    (1, 1, 56, 84, 512, 16, 7, 3),    # the shape north_star names: 49 tokens, head_dim 32
+    (1, 1, 56, 84, 512, 8, 7, 0),
+    (3, 1, 10, 15, 128, 2, 5, 2),     # 25-token windows, 4 per tile, 18 windows (partial last tile)
+    (3, 1, 10, 15, 128, 2, 5, 0),
+    (3, 2, 10, 15, 128, 4, 5, 0),     # 50-token windows, head_dim 32
+    (1, 1, 60, 120, 512, 16, 5, 2),
+    (2, 1, 14, 21, 128, 2, 7, 2),     # look-up-table path, padded slots
+    (2, 2, 10, 15, 128, 2, 5, 1),
+    (2, 1, 9, 12, 64, 1, 3, 1),       # 9-token windows, 14 per tile (packed slots)
+    (2, 2, 8, 12, 128, 2, 2, 1),      # 2x2 windows: 8 tokens, 16 per tile
+    (2, 1, 8, 12, 128, 4, 2, 0),      # 4 tokens, 32 per tile, head_dim 32
 ]
 
 

@@ -14,10 +14,13 @@ if stage == 1:
     H, W, C, nH, ws, shift = 64, 80, 512, 4, 8, 4
 else:
     H, W, C, nH, ws, shift = 32, 40, 1024, 4, 4, 2
+T = 2
+if os.environ.get("TRACE_GEOM"):       # "H,W,C,nH,ws,shift,T,B": any other geometry (e.g. 64,120,512,16,8,0,1,8)
+    H, W, C, nH, ws, shift, T, Bp = (int(v) for v in os.environ["TRACE_GEOM"].split(","))
 g = torch.Generator(device="cuda").manual_seed(0)
-qkv = torch.randn(Bp, 2, H * W, 3 * C, generator=g, device="cuda").to(torch.bfloat16)
+qkv = torch.randn(Bp, T, H * W, 3 * C, generator=g, device="cuda").to(torch.bfloat16)
 table = torch.randn((2 * ws - 1) ** 2, nH, generator=g, device="cuda") * 0.5
-do = torch.randn(Bp, 2, H * W, C, generator=g, device="cuda").to(torch.bfloat16)
+do = torch.randn(Bp, T, H * W, C, generator=g, device="cuda").to(torch.bfloat16)
 lib = _lib.load()
 NPT = 16
 buf = torch.zeros(64 * NPT, dtype=torch.int64, device="cuda")
