@@ -338,27 +338,6 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
   return cdf + x * pdf;
 }
-// erf-GELU and its derivative in one go (nn.GELU default, swin_512.py:13):
-//   gelu(u) = u * Phi(u)        gelu'(u) = Phi(u) + u * phi(u)
-// Phi through the hardware tanh: Phi(u) = 0.5 + 0.5 tanh(u (a + b u^2 + c u^4)), coefficients fitted to
-// the exact normal CDF (max |error| 4.9e-5 on Phi, 5.6e-5 on gelu -- two orders below the bf16
-// rounding of the stored result); phi through ex2.  11 instructions, 2 of them MUFU, per element:
-// the GELU epilogue is instruction-issue bound (profiles/r1b_gemm_gelu_ncu_summary.txt).
-__device__ __forceinline__ void gelu_and_grad(float u, float& h, float& g) {
-  // Phi(u) ~ 0.5 + 0.5 tanh(a(u)),  a(u) = u (c0 + c1 u^2 + c2 u^4)   (|error| < 5e-5 against erf);
-  // the gradient uses the derivative of the same approximation, 0.5 (1 - t^2) a'(u)  (|error| < 2e-4
-  // against Phi + u phi), so one MUFU per element instead of two.  u^2 is clamped where tanh has
-  // saturated (|u| > 8): the quartic would change sign beyond |u| ~ 11.
-  constexpr float c0 = 7.97735401e-01f, c1 = 3.69307910e-02f, c2 = -3.55393957e-04f;
-  const float s = fminf(u * u, 64.0f);
-  float t;
-  const float arg = u * fmaf(s, fmaf(s, c2, c1), c0);
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(arg));
-  const float cdf = fmaf(0.5f, t, 0.5f);
-  h = u * cdf;
-  const float da = fmaf(s, fmaf(s, 5.0f * c2, 3.0f * c1), c0);
-  g = fmaf(0.5f * u * fmaf(-t, t, 1.0f), da, cdf);
-}
 // 256-bit global store (STG.256 on sm_100): a full 32-byte sector per lane and instruction
 __device__ __forceinline__ void st_global_v8(void* p, const uint32_t (&v)[8]) {
   asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]),
@@ -406,26 +385,28 @@ __device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
   return r;
 }
-// gelu_and_grad for two values at once (same approximation, packed arithmetic): u = acc + bias,
-// returns the packed bf16 pairs of GELU(u) and GELU'(u)
+// erf-GELU (nn.GELU default, swin_512.py:13) and its derivative for two values at once, packed fp32x2 arithmetic: u = acc + bias, returns the packed bf16
+// pairs of GELU(u) and GELU'(u).  The GELU epilogue is bound by FP32 issue slots (ncu, profiles/r2u_gemm_gelu_roles.txt:
+// the eight epilogue warps issue in 53 % of all cycles and the tensor pipe idles at 52 %), so this version spends
+// 12 packed operations + 2 MUFU per pair instead of 17 + 2:
+//   Phi(u) ~ 0.5 + 0.5 tanh(u (c0 + c1 u^2))   -- cubic argument fitted to the exact normal CDF: |error| 2.7e-4 on GELU,
+//            8.7e-4 on GELU' (the quartic fit of round 1: 5.6e-5 / 1.8e-4, at 17 operations and a clamp; tanh.approx itself is good to ~2.4e-4 on Phi, and the
+//            stored bf16 results round at 2e-3 relative) -- positive for every u, so no clamp of u^2 is needed;
+//   GELU'(u) = Phi + u (1 - Phi) * 2 Phi a'(u) = Phi + Phi * (u - h) * 2 a'(u)   with h = u Phi   (1 - t^2 = 4 Phi (1 - Phi))
+constexpr float kGeluC0 = 0.80015708f, kGeluC1 = 0.03470089f;
 __device__ __forceinline__ void gelu_and_grad_x2(float acc0, float acc1, float b0, float b1, uint32_t& h_bf16x2,
                                                  uint32_t& g_bf16x2) {
-  constexpr float c0 = 7.97735401e-01f, c1 = 3.69307910e-02f, c2 = -3.55393957e-04f;
   const uint64_t u = f2_add(f2_pack(acc0, acc1), f2_pack(b0, b1));
-  float s0, s1;
-  f2_unpack(f2_mul(u, u), s0, s1);
-  const uint64_t s = f2_pack(fminf(s0, 64.0f), fminf(s1, 64.0f));
-  const uint64_t p = f2_fma(s, f2_fma(s, f2_pack(c2, c2), f2_pack(c1, c1)), f2_pack(c0, c0));
+  const uint64_t s = f2_mul(u, u);
   float a0, a1, t0, t1;
-  f2_unpack(f2_mul(u, p), a0, a1);
+  f2_unpack(f2_mul(u, f2_fma(s, f2_pack(kGeluC1, kGeluC1), f2_pack(kGeluC0, kGeluC0))), a0, a1);
   asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(a0));
   asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(a1));
-  const uint64_t t = f2_pack(t0, t1);
-  const uint64_t cdf = f2_fma(t, f2_pack(0.5f, 0.5f), f2_pack(0.5f, 0.5f));
+  const uint64_t cdf = f2_fma(f2_pack(t0, t1), f2_pack(0.5f, 0.5f), f2_pack(0.5f, 0.5f));
   const uint64_t h = f2_mul(u, cdf);
-  const uint64_t da = f2_fma(s, f2_fma(s, f2_pack(5.0f * c2, 5.0f * c2), f2_pack(3.0f * c1, 3.0f * c1)), f2_pack(c0, c0));
-  const uint64_t w = f2_fma(t, t, f2_pack(-1.0f, -1.0f));                    // t^2 - 1
-  const uint64_t g = f2_fma(f2_mul(f2_mul(u, w), da), f2_pack(-0.5f, -0.5f), cdf);
+  const uint64_t da2 = f2_fma(s, f2_pack(6.0f * kGeluC1, 6.0f * kGeluC1), f2_pack(2.0f * kGeluC0, 2.0f * kGeluC0));   // 2 a'(u)
+  const uint64_t d = f2_fma(h, f2_pack(-1.0f, -1.0f), u);                       // u - h = u (1 - Phi)
+  const uint64_t g = f2_fma(f2_mul(cdf, d), da2, cdf);
   float h0, h1, g0, g1;
   f2_unpack(h, h0, h1);
   f2_unpack(g, g0, g1);
@@ -434,14 +415,9 @@ __device__ __forceinline__ void gelu_and_grad_x2(float acc0, float acc1, float b
 }
 // forward-only GELU of two values (inference: no derivative output)
 __device__ __forceinline__ uint32_t gelu_x2(float acc0, float acc1, float b0, float b1) {
-  constexpr float c0 = 7.97735401e-01f, c1 = 3.69307910e-02f, c2 = -3.55393957e-04f;
   const uint64_t u = f2_add(f2_pack(acc0, acc1), f2_pack(b0, b1));
-  float s0, s1;
-  f2_unpack(f2_mul(u, u), s0, s1);
-  const uint64_t s = f2_pack(fminf(s0, 64.0f), fminf(s1, 64.0f));
-  const uint64_t p = f2_fma(s, f2_fma(s, f2_pack(c2, c2), f2_pack(c1, c1)), f2_pack(c0, c0));
   float a0, a1, t0, t1;
-  f2_unpack(f2_mul(u, p), a0, a1);
+  f2_unpack(f2_mul(u, f2_fma(f2_mul(u, u), f2_pack(kGeluC1, kGeluC1), f2_pack(kGeluC0, kGeluC0))), a0, a1);
   asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(a0));
   asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(a1));
   const uint64_t h = f2_mul(u, f2_fma(f2_pack(t0, t1), f2_pack(0.5f, 0.5f), f2_pack(0.5f, 0.5f)));

@@ -10,11 +10,14 @@
 // weight gradient dW = dy^T x, which reduces over tokens, is (1,1) without any transposed
 // copy of an activation.
 //
-// CTA = 10 warps: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM allocation), warps 2-9 epilogue.
-// Tile 128 x 256 x 64, 4-stage TMA->smem ring (128B swizzle), two 256-column TMEM accumulators so
+// CTA = 3 warpgroups: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM allocation), warps 2-3 idle, warps 4-11 epilogue;
+// setmaxnreg gives the producer group 40 registers and the epilogue groups 232 (the epilogue keeps two 32-column
+// accumulator pieces, the bias and the next tile's auxiliary data in registers).
+// Tile 128 x 256 x 64, 5-stage TMA->smem ring (128B swizzle), two 256-column TMEM accumulators so
 // the epilogue of tile i overlaps the main loop of tile i+1.  The epilogue goes TMEM -> registers
-// -> swizzled smem (transpose) -> coalesced 128-bit global stores, with an optional auxiliary tile
-// (residual or multiplier, prefetched one chunk ahead with coalesced loads), bias, erf-GELU together
+// -> swizzled smem (transpose) -> TMA stores, software-pipelined: the TMEM load of the next 32-column piece is in
+// flight while the current piece is processed (tcgen05.wait::ld waits for every outstanding load, so a piece is
+// requested right after the wait for its predecessor).  Fused: bias, residual / multiplier tile, erf-GELU together
 // with its derivative (stored for the backward, which then only multiplies), column sums (bias
 // gradients), and an fp32 TMA add-reduction for split-K weight gradients.
 // (A first version stored through TMA from a single staging buffer and serialised on the store's
@@ -37,7 +40,8 @@ constexpr int B_STAGE_BYTES = (BN / 2) * BK * 2;   // 16 KB: this CTA's half of 
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int EPI_WARPS = 8;
 constexpr int EPI_BUF_BYTES = 2 * 32 * 128;  // two 32-row x 128-byte staging tiles per epilogue warp (ping-pong)
-constexpr int NUM_THREADS = 32 * (2 + EPI_WARPS);
+constexpr int EPI_WARP0 = 4;                  // warpgroup 0: TMA producer, MMA issuer, two idle warps; warpgroups 1-2: epilogue
+constexpr int NUM_THREADS = 32 * (EPI_WARP0 + EPI_WARPS);
 constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + EPI_WARPS * EPI_BUF_BYTES + 256;
 
 enum Mode : int {
@@ -122,7 +126,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   pdl_wait();
   pdl_launch_dependents();
 
-  if (warp == 0) {
+  if (warp < EPI_WARP0) {
+   asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0;
@@ -156,7 +162,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       }
     }
-  } else if (warp == 1) {
+   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     // The whole warp runs the loop, one elected lane issues: with warp-uniform control flow the
     // descriptors live in uniform registers.  (Issued from inside `if (lane == 0)` every tcgen05.mma was
@@ -200,11 +206,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
+   }
   } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
     // ------------------------------------------------------------------ epilogue (8 warps)
     // warp w may touch TMEM lanes 32*(w%4)..+31; the two warps of a lane quarter split the 256
     // accumulator columns in halves (two 64-column chunks each).
-    const int ew = warp - 2;                         // 0..7
+    const int ew = warp - EPI_WARP0;                 // 0..7
     const int wq = warp & 3;                         // TMEM lane quarter
     const int chalf = ew >> 2;                       // column half of the tile
     uint8_t* const my_bufs = s_out + ew * EPI_BUF_BYTES;   // two 32-row x 128-byte staging tiles
@@ -216,6 +224,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // coalesced access pattern of a 32-row x 64-col bf16 chunk: instruction i of lane l touches
     // row 4*i + l/8, 16-byte column group l%8  (8 lanes = one 128-byte line)
     const int crow = lane >> 3, cchunk = lane & 7;
+    uint4 auxr[has_aux ? 2 : 1][8];                  // aux of this warp's two chunks
+    auto load_aux = [&](uint4 (&dst)[8], int r0, int cb) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = r0 + 4 * i + crow, n = cb + cchunk * 8;
+        dst[i] = (r < p.M && n < p.N) ? __ldg(reinterpret_cast<const uint4*>(p.aux + (size_t)r * p.ld_aux + n))
+                                      : make_uint4(0, 0, 0, 0);
+      }
+    };
     for (int item = cluster_id; item < num_items; item += num_clusters) {
       const int n_blk = item % num_n;
       const int m_blk = 2 * ((item / num_n) % num_mp) + int(crank);
@@ -247,19 +264,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         }
       } else {
-        // aux (residual / multiplier) for BOTH 64-column chunks of this warp is requested up front:
-        // 8 KB per warp, 64 KB per SM in flight -- one chunk ahead left the loads latency-bound
-        uint4 auxr[has_aux ? 2 : 1][8];
+        // aux (residual / multiplier) for BOTH 64-column chunks of this warp is requested up front, ahead of the wait
+        // for the accumulator: 8 KB per warp, 64 KB per SM in flight -- one chunk ahead left the loads latency-bound.
+        // (Requesting the NEXT item's aux as soon as a chunk's registers were staged was measured: x-aux mode
+        // 964 -> 921 TFLOP/s at K = 512; these modes sit on the SM's shared-memory bandwidth, not on this latency.)
         if constexpr (has_aux) {
-#pragma unroll
-          for (int cc = 0; cc < 2; ++cc)
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int r = row0 + 4 * i + crow, n = col0 + cc * 64 + cchunk * 8;
-              auxr[cc][i] = (r < p.M && n < p.N)
-                                ? __ldg(reinterpret_cast<const uint4*>(p.aux + (size_t)r * p.ld_aux + n))
-                                : make_uint4(0, 0, 0, 0);
+          load_aux(auxr[0], row0, col0);
+          load_aux(auxr[1], row0, col0 + 64);
+          // ... and the next item's aux lines are pulled into L2 now (one 128-byte line per lane and chunk; no register,
+          // no scoreboard): its loads then pay the L2 latency instead of the HBM latency
+          const int nitem = item + num_clusters;
+          if (nitem < num_items) {
+            const int nr = (2 * ((nitem / num_n) % num_mp) + int(crank)) * BM + wq * 32 + lane;
+            const int nc = (nitem % num_n) * BN + chalf * (BN / 2);
+            if (nr < p.M && nc < p.N) {
+              const __nv_bfloat16* pa = p.aux + (size_t)nr * p.ld_aux + nc;
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(pa));
+              if (nc + 64 < p.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(pa + 64));
             }
+          }
         }
         // staged 32 x 64 chunk -> global: one TMA box per warp and chunk (clipped at the matrix edge by the
         // tensor map); the warp goes on while the TMA engine reads the tile
@@ -273,8 +296,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         };
         mbar_wait(&acc_full[acc], acc_phase);
         tc_fence_after();
-        auto do_chunk = [&](const int c, auto aux_sel) {
-          constexpr int kAuxSel = decltype(aux_sel)::value;   // which prefetched aux register set to consume
+        // The accumulator is read in four 32-column pieces (two per 64-column chunk) through two register sets: the
+        // load of piece i+1 is issued right after the wait for piece i, so it is in flight while piece i is processed.
+        // (Straight-line code on purpose: the destination registers of a load in flight must not be touched, which a
+        // loop back-edge does not guarantee.)
+        uint32_t va[32], vb[32];
+        tmem_ld32(t_row, va);
+        auto do_chunk = [&](auto c_tag) {
+          constexpr int c = decltype(c_tag)::value;     // chunk of this warp's column half; also the aux register set
+          constexpr bool last_chunk = (c == BN / 128 - 1);
           const int cbase = col0 + c * 64;
           // this chunk's staging tile; its previous TMA store (two chunks ago; the GELU mode's second
           // output: one chunk ago) must have been read out
@@ -285,13 +315,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if constexpr (has_aux) {
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-              *reinterpret_cast<uint4*>(my_buf + sw128_offset(4 * i + crow, cchunk)) = auxr[kAuxSel][i];
+              *reinterpret_cast<uint4*>(my_buf + sw128_offset(4 * i + crow, cchunk)) = auxr[c][i];
           }
           __syncwarp();     // aux staged (each lane then only touches its own row: reads aux, writes output)
           uint32_t out2w[MODE == kBiasGelu ? 32 : 1];     // second output of the GELU mode (gelu'(u))
-          // the 64 columns are processed as two halves of 32 (rolled, except in the two-output mode
-          // whose second output has to stay in registers) to keep the code I-cache resident
-          // bias of the chunk's 64 columns, requested before the TMEM loads so that its latency overlaps theirs
+          // bias of the chunk's 64 columns, requested before the TMEM waits so that its latency overlaps theirs
           // (the first bias add was the top long-scoreboard stall of the epilogue); N is a multiple of 8, so a
           // group of four columns is inside the matrix or entirely outside
           float bias_r[2][32];
@@ -307,24 +335,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
             for (int j = 0; j < 32; ++j) { bias_r[0][j] = 0.f; bias_r[1][j] = 0.f; }
           }
-          auto do_half = [&](int half, uint32_t (&v)[32], bool load_here) {
-            if (load_here) tmem_ld32(t_row + c * 64 + half * 32, v);
+          auto do_piece = [&](auto half_tag, uint32_t (&v)[32]) {
+            constexpr int half = decltype(half_tag)::value;
             const float (&bv)[32] = bias_r[half];        // bias of the 32 columns (same for every row)
-            uint32_t auxw[has_aux ? 16 : 1];             // this row's aux for the 32 columns of this half
+            uint32_t auxw[has_aux ? 16 : 1];             // this row's aux for the 32 columns of this piece
             if constexpr (has_aux) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const uint4 q = *reinterpret_cast<const uint4*>(my_buf + sw128_offset(lane, half * 4 + j));
                 auxw[4 * j] = q.x; auxw[4 * j + 1] = q.y; auxw[4 * j + 2] = q.z; auxw[4 * j + 3] = q.w;
               }
-            }
-            tmem_ld_wait();
-            // the tile's last TMEM read of this warp has landed in registers: hand the accumulator back now (the MMA
-            // warp waits for it), not after the arithmetic, staging and stores of this chunk
-            if (c == BN / 128 - 1 && half == (MODE == kBiasGelu ? 1 : 0)) {
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive_cluster(mapa_u32(&acc_empty[acc], 0));   // the leader's MMA warp owns both accumulators
             }
             uint32_t outw[16];
 #pragma unroll
@@ -360,32 +380,56 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               *reinterpret_cast<uint4*>(my_buf + sw128_offset(lane, half * 4 + j)) =
                   make_uint4(outw[4 * j], outw[4 * j + 1], outw[4 * j + 2], outw[4 * j + 3]);
           };
-          if constexpr (MODE == kBiasGelu) {
-            uint32_t va[32];
-            do_half(0, va, true);
-            do_half(1, va, true);
+          // piece 0 of the chunk has landed in va; piece 1 goes into vb while piece 0 is processed
+          tmem_ld_wait();
+          tmem_ld32(t_row + c * 64 + 32, vb);
+          do_piece(std::integral_constant<int, 0>{}, va);
+          tmem_ld_wait();
+          if constexpr (last_chunk) {
+            // the tile's last TMEM read of this warp has landed in registers: hand the accumulator back now (the MMA
+            // warp waits for it), not after the arithmetic, staging and stores of this piece
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_u32(&acc_empty[acc], 0));   // the leader's MMA warp owns both accumulators
           } else {
-            // both TMEM loads of the chunk are issued before the first wait: the MMA warp was measured waiting for
-            // this accumulator (acc_empty) while the epilogue warps sat in tcgen05.wait::ld four times per tile
-            uint32_t va[32], vb[32];
-            tmem_ld32(t_row + c * 64, va);
-            tmem_ld32(t_row + c * 64 + 32, vb);
-            do_half(0, va, false);
-            do_half(1, vb, false);
+            tmem_ld32(t_row + (c + 1) * 64, va);        // the next chunk's piece 0
           }
+          do_piece(std::integral_constant<int, 1>{}, vb);
           store_staged(&tmD, my_buf, cbase);
           if (p.colsum != nullptr) {
-            // lane owns columns (2*lane, 2*lane+1) of this 64-wide chunk: sum the 32 staged rows
-            float s0 = 0.f, s1 = 0.f;
-#pragma unroll 8
-            for (int r = 0; r < 32; ++r) {
-              const uint32_t w = *reinterpret_cast<const uint32_t*>(my_buf + sw128_offset(r, lane >> 2) + (lane & 3) * 4);
-              const float2 f = unpack_bf16(w);
-              s0 += f.x; s1 += f.y;
+            // column sums of the staged 32 x 64 chunk: lane (rp = lane / 8, g = lane % 8) sums the 8 columns of 16-byte
+            // group g over rows rp, rp + 4, ...; two shuffle steps fold the four row phases; lanes 0-7 then add 8 columns
+            // each with two 16-byte vector reductions (16 L2 atomic transactions per warp and chunk instead of 64 scalar
+            // ones: every CTA hits the same N addresses, and their serialisation cost 38 us of a 386 us launch)
+            float cs[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) cs[e] = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const uint4 q = *reinterpret_cast<const uint4*>(my_buf + sw128_offset(4 * i + crow, cchunk));
+              const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = unpack_bf16(w[e]);
+                cs[2 * e] += f.x; cs[2 * e + 1] += f.y;
+              }
             }
-            const int n = cbase + 2 * lane;
-            if (n < p.N) atomicAdd(p.colsum + n, s0);
-            if (n + 1 < p.N) atomicAdd(p.colsum + n + 1, s1);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], 8);
+              cs[e] += __shfl_xor_sync(0xffffffffu, cs[e], 16);
+            }
+            const int n = cbase + 8 * cchunk;             // N is a multiple of 8: the group is inside the matrix or outside
+            if (lane < 8 && n < p.N) {
+              float* dst = p.colsum + n;
+              if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(cs[0]), "f"(cs[1]), "f"(cs[2]), "f"(cs[3]) : "memory");
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(cs[4]), "f"(cs[5]), "f"(cs[6]), "f"(cs[7]) : "memory");
+              } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) atomicAdd(dst + e, cs[e]);
+              }
+            }
           }
           if constexpr (MODE == kBiasGelu) {
             uint8_t* buf2 = my_bufs + 32 * 128;           // the second output has its own tile
@@ -398,13 +442,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             store_staged(&tmD2, buf2, cbase);
           }
         };
-        if constexpr (has_aux) {       // unrolled: each chunk consumes its own prefetched registers
-          do_chunk(0, std::integral_constant<int, 0>{});
-          do_chunk(1, std::integral_constant<int, has_aux ? 1 : 0>{});
-        } else {
-#pragma unroll 1
-          for (int c = 0; c < BN / 128; ++c) do_chunk(c, std::integral_constant<int, 0>{});
-        }
+        static_assert(BN / 128 == 2, "two 64-column chunks per epilogue warp");
+        do_chunk(std::integral_constant<int, 0>{});
+        do_chunk(std::integral_constant<int, 1>{});
       }
       if constexpr (MODE == kF32Reduce) {
         // all TMEM reads of this accumulator are done -> hand it back to the MMA warp (the bf16 modes did so right
