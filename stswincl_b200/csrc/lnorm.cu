@@ -360,35 +360,36 @@ copy_strided_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src, long
   for (; i < n16; i += step) d[i] = __ldg(s + i);
 }
 
-// bf16 [batch, R, Cc] -> [batch, Cc, R]: 64 x 64 tiles, 16-byte global accesses on both sides.
-// Each thread loads two 8-element row segments, scatters them transposed into shared memory
-// (row stride 72 elements: the eight 2-byte stores of a segment land in different banks for
-// neighbouring lanes) and reads two 8-element segments of the transposed tile back.
+// bf16 [batch, R, Cc] -> [batch, Cc, R] without shared memory: a thread loads an 8 x 8 block (eight 16-byte row
+// segments, all in flight together), transposes it in registers -- one PRMT per output word pairs the elements of two
+// source rows; the rest is register renaming -- and stores eight 16-byte segments of the transposed block.  A warp covers
+// 64 rows x 32 columns (lane = 4 * row block + column group): loads are 64-byte row pieces, stores are whole 128-byte lines
+// of the output (writes are the scarcer direction of this GPU's HBM).  CTA tile 128 x 128, no barrier.
+// (The 64 x 64 shared-memory version with 2-byte scattered stores reached 39-44 % of the HBM roofline inside the step.)
 __global__ void __launch_bounds__(256)
 transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int R, int Cc) {
   pdl_wait();
   pdl_launch_dependents();
-  __shared__ __align__(16) __nv_bfloat16 tile[64][72];     // tile[c][r]
   const long b = blockIdx.z;
-  const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
-  const __nv_bfloat16* ib = in + b * (long)R * Cc;
-  __nv_bfloat16* ob = out + b * (long)R * Cc;
-  const int t = threadIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.y * 128 + (warp >> 2) * 64 + (lane >> 2) * 8;      // first of this thread's 8 rows
+  const int c = blockIdx.x * 128 + (warp & 3) * 32 + (lane & 3) * 8;        // first of its 8 columns
+  if (r >= R || c >= Cc) return;                                            // R, Cc are multiples of 8: whole blocks
+  const __nv_bfloat16* ib = in + b * (long)R * Cc + (long)r * Cc + c;
+  __nv_bfloat16* ob = out + b * (long)R * Cc + (long)c * R + r;
+  uint4 q[8];
 #pragma unroll
-  for (int p = 0; p < 2; ++p) {
-    const int r = p * 32 + (t >> 3), cg = (t & 7) * 8;      // row of the tile, first of 8 columns
-    uint4 q = make_uint4(0, 0, 0, 0);
-    if (r0 + r < R && c0 + cg < Cc) q = __ldg(reinterpret_cast<const uint4*>(ib + (long)(r0 + r) * Cc + c0 + cg));
-    const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(&q);
+  for (int i = 0; i < 8; ++i) q[i] = __ldg(reinterpret_cast<const uint4*>(ib + (long)i * Cc));
 #pragma unroll
-    for (int k = 0; k < 8; ++k) tile[cg + k][r] = e[k];
-  }
-  __syncthreads();
+  for (int k = 0; k < 8; ++k) {                   // output row c + k = source column c + k of rows r .. r + 7
+    uint32_t w[4];
 #pragma unroll
-  for (int p = 0; p < 2; ++p) {
-    const int c = p * 32 + (t >> 3), rg = (t & 7) * 8;
-    if (c0 + c < Cc && r0 + rg < R)
-      *reinterpret_cast<uint4*>(ob + (long)(c0 + c) * R + r0 + rg) = *reinterpret_cast<const uint4*>(&tile[c][rg]);
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t lo = reinterpret_cast<const uint32_t*>(&q[2 * j])[k >> 1];        // row 2j,   columns k & ~1, +1
+      const uint32_t hi = reinterpret_cast<const uint32_t*>(&q[2 * j + 1])[k >> 1];    // row 2j+1
+      w[j] = __byte_perm(lo, hi, (k & 1) ? 0x7632 : 0x5410);
+    }
+    *reinterpret_cast<uint4*>(ob + (long)k * R) = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
 
@@ -543,7 +544,7 @@ int transpose_cvt(const void* in, int in_f32, void* out, int out_f32, long batch
   STSWIN_CHECK_ARG(batch <= 65535, "transpose: batch %ld exceeds gridDim.z", batch);
   if (!in_f32 && !out_f32 && R % 8 == 0 && Cc % 8 == 0 &&
       ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
-    dim3 g64((Cc + 63) / 64, (R + 63) / 64, (unsigned)batch);
+    dim3 g64((Cc + 127) / 128, (R + 127) / 128, (unsigned)batch);
     STSWIN_CUDA(launch_pdl(transpose_bf16_kernel, g64, dim3(256), 0, stream, static_cast<const __nv_bfloat16*>(in), static_cast<__nv_bfloat16*>(out), R, Cc));
     STSWIN_CUDA(cudaGetLastError());
     return kOk;
