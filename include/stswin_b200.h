@@ -59,6 +59,12 @@ int stswin_set_device(int device);
 #define STSWIN_EPI_MUL_AUX 3       /* D = acc * aux     (dgrad through GELU: aux = D2)  */
 #define STSWIN_EPI_F32_REDUCE 4    /* D(fp32) += acc, split-K                          */
 #define STSWIN_EPI_BIAS_GELU_FWD 5 /* D = gelu_erf(acc + bias)      (inference: no D2) */
+/* The derivative is only ever a multiplier of the backward and lies in [-0.13, 1.13]: the two modes below keep it as ONE
+ * byte per element (D2 / aux are uint8 [M,N] with the leading dimension of D / ld_aux in bytes; N and the leading dimensions
+ * multiples of 16): q = round((gelu'(u) + 0.14) * 255 / 1.28), i.e. a step of 0.005 (|error| <= 0.0025, the bf16 rounding of
+ * a value near 1 is 0.002-0.004).  fc1 + GELU writes 1.28 GB per stage-1 launch in the bf16 form and is HBM-write bound. */
+#define STSWIN_EPI_BIAS_GELU_Q8 6  /* D = gelu_erf(acc + bias) ; D2(uint8) = quantised gelu_erf'(acc + bias) */
+#define STSWIN_EPI_MUL_AUX_Q8 7    /* D = acc * dequant(aux)        (aux = the uint8 D2 of mode 6) */
 
 int stswin_gemm_bf16(const void* A, int a_major, int64_t lda,
                      const void* B, int b_major, int64_t ldb,

@@ -5,7 +5,7 @@
 
 extern "C" {
 
-int stswin_abi_version(void) { return 3; }
+int stswin_abi_version(void) { return 4; }
 const char* stswin_last_error(void) { return stswin::last_error(); }
 int stswin_set_device(int device) {
   STSWIN_CUDA(cudaSetDevice(device));

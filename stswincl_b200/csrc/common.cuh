@@ -413,6 +413,38 @@ __device__ __forceinline__ void gelu_and_grad_x2(float acc0, float acc1, float b
   h_bf16x2 = pack_bf16(h0, h1);
   g_bf16x2 = pack_bf16(g0, g1);
 }
+// The same with GELU' quantised to one byte (STSWIN_EPI_BIAS_GELU_Q8): q = round((g + 0.14) * 255 / 1.28) through the
+// 2^23 trick -- the low byte of the returned words is q (g is bounded by [-0.13, 1.13], so no clamp).
+constexpr float kGeluQ8Scale = 255.0f / 1.28f, kGeluQ8Off = 0.14f;
+__device__ __forceinline__ void gelu_and_grad_q8_x2(float acc0, float acc1, float b0, float b1, uint32_t& h_bf16x2,
+                                                    uint32_t& q0, uint32_t& q1) {
+  const uint64_t u = f2_add(f2_pack(acc0, acc1), f2_pack(b0, b1));
+  const uint64_t s = f2_mul(u, u);
+  float a0, a1, t0, t1;
+  f2_unpack(f2_mul(u, f2_fma(s, f2_pack(kGeluC1, kGeluC1), f2_pack(kGeluC0, kGeluC0))), a0, a1);
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(a0));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(a1));
+  const uint64_t cdf = f2_fma(f2_pack(t0, t1), f2_pack(0.5f, 0.5f), f2_pack(0.5f, 0.5f));
+  const uint64_t h = f2_mul(u, cdf);
+  const uint64_t da2 = f2_fma(s, f2_pack(6.0f * kGeluC1, 6.0f * kGeluC1), f2_pack(2.0f * kGeluC0, 2.0f * kGeluC0));
+  const uint64_t d = f2_fma(h, f2_pack(-1.0f, -1.0f), u);
+  const uint64_t g = f2_fma(f2_mul(cdf, d), da2, cdf);
+  constexpr float kMagic = 8388608.0f + kGeluQ8Off * kGeluQ8Scale;
+  const uint64_t t = f2_fma(g, f2_pack(kGeluQ8Scale, kGeluQ8Scale), f2_pack(kMagic, kMagic));
+  float h0, h1, f0, f1;
+  f2_unpack(h, h0, h1);
+  f2_unpack(t, f0, f1);
+  h_bf16x2 = pack_bf16(h0, h1);
+  q0 = __float_as_uint(f0);
+  q1 = __float_as_uint(f1);
+}
+// two quantised GELU' values (bytes k0, k1 of w) back to fp32, packed
+__device__ __forceinline__ uint64_t gelu_q8_dequant_x2(uint32_t w, int k0, int k1) {
+  const float f0 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650u + k0));     // 2^23 + byte, exactly
+  const float f1 = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650u + k1));
+  const uint64_t x = f2_add(f2_pack(f0, f1), f2_pack(-8388608.0f, -8388608.0f));
+  return f2_fma(x, f2_pack(1.0f / kGeluQ8Scale, 1.0f / kGeluQ8Scale), f2_pack(-kGeluQ8Off, -kGeluQ8Off));
+}
 // forward-only GELU of two values (inference: no derivative output)
 __device__ __forceinline__ uint32_t gelu_x2(float acc0, float acc1, float b0, float b1) {
   const uint64_t u = f2_add(f2_pack(acc0, acc1), f2_pack(b0, b1));

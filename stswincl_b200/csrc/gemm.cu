@@ -51,6 +51,8 @@ enum Mode : int {
   kMulAux = 3,      // D = acc * aux
   kF32Reduce = 4,   // D(fp32) += acc          (split-K, TMA add-reduction)
   kBiasGeluFwd = 5, // D = gelu(acc + bias)    (inference: no derivative output)
+  kBiasGeluQ8 = 6,  // as kBiasGelu with D2 = gelu'(u) quantised to one byte (include/stswin_b200.h)
+  kMulAuxQ8 = 7,    // D = acc * dequant(aux), aux = the uint8 D2 of kBiasGeluQ8
 };
 
 struct GemmArgs {
@@ -61,7 +63,7 @@ struct GemmArgs {
   float* colsum;       // [N] fp32, += column sums of the (bf16-rounded) D, or null
   __nv_bfloat16* D;    // bf16 outputs / aux are accessed with plain coalesced loads and stores
   __nv_bfloat16* D2;
-  const __nv_bfloat16* aux;
+  const __nv_bfloat16* aux;   // (uint8 in the kMulAuxQ8 mode; ld_aux in elements = bytes there)
   long ldd, ld_aux;
 };
 
@@ -218,21 +220,36 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint8_t* const my_bufs = s_out + ew * EPI_BUF_BYTES;   // two 32-row x 128-byte staging tiles
     uint8_t* my_buf = my_bufs;
     int chunk_no = 0;                                // chunks staged so far (selects the tile)
-    constexpr bool has_aux = (MODE == kBiasRes || MODE == kMulAux);
+    constexpr bool has_aux = (MODE == kBiasRes || MODE == kMulAux || MODE == kMulAuxQ8);
+    constexpr bool kQ8Aux = (MODE == kMulAuxQ8);           // one-byte aux: a 32 x 64-byte tile per chunk
+    constexpr bool kGelu2 = (MODE == kBiasGelu || MODE == kBiasGeluQ8);   // two outputs
+    constexpr bool kQ8Out = (MODE == kBiasGeluQ8);
     int acc = 0;
     uint32_t acc_phase = 0;
     // coalesced access pattern of a 32-row x 64-col bf16 chunk: instruction i of lane l touches
     // row 4*i + l/8, 16-byte column group l%8  (8 lanes = one 128-byte line)
     const int crow = lane >> 3, cchunk = lane & 7;
-    uint4 auxr[has_aux ? 2 : 1][8];                  // aux of this warp's two chunks
-    auto load_aux = [&](uint4 (&dst)[8], int r0, int cb) {
+    constexpr int AUXV = kQ8Aux ? 4 : 8;             // 16-byte loads per lane and chunk
+    uint4 auxr[has_aux ? 2 : 1][AUXV];               // aux of this warp's two chunks
+    auto load_aux = [&](uint4 (&dst)[AUXV], int r0, int cb) {
+      if constexpr (kQ8Aux) {                        // rows of 64 bytes: four lanes per row, eight rows per instruction
+        const uint8_t* a8 = reinterpret_cast<const uint8_t*>(p.aux);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = r0 + 4 * i + crow, n = cb + cchunk * 8;
-        dst[i] = (r < p.M && n < p.N) ? __ldg(reinterpret_cast<const uint4*>(p.aux + (size_t)r * p.ld_aux + n))
-                                      : make_uint4(0, 0, 0, 0);
+        for (int i = 0; i < 4; ++i) {
+          const int r = r0 + 8 * i + (lane >> 2), n = cb + (lane & 3) * 16;
+          dst[i] = (r < p.M && n < p.N) ? __ldg(reinterpret_cast<const uint4*>(a8 + (size_t)r * p.ld_aux + n)) : make_uint4(0, 0, 0, 0);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = r0 + 4 * i + crow, n = cb + cchunk * 8;
+          dst[i] = (r < p.M && n < p.N) ? __ldg(reinterpret_cast<const uint4*>(p.aux + (size_t)r * p.ld_aux + n))
+                                        : make_uint4(0, 0, 0, 0);
+        }
       }
     };
+    // 16-byte group `chunk` (0..3) of row `row` inside a 64B-swizzled tile of 64-byte rows (the one-byte tiles)
+    auto sw64_offset = [](uint32_t row, uint32_t chunk) { return row * 64u + ((chunk ^ ((row >> 1) & 3u)) << 4); };
     for (int item = cluster_id; item < num_items; item += num_clusters) {
       const int n_blk = item % num_n;
       const int m_blk = 2 * ((item / num_n) % num_mp) + int(crank);
@@ -278,9 +295,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const int nr = (2 * ((nitem / num_n) % num_mp) + int(crank)) * BM + wq * 32 + lane;
             const int nc = (nitem % num_n) * BN + chalf * (BN / 2);
             if (nr < p.M && nc < p.N) {
-              const __nv_bfloat16* pa = p.aux + (size_t)nr * p.ld_aux + nc;
+              constexpr int esz = kQ8Aux ? 1 : 2;
+              const uint8_t* pa = reinterpret_cast<const uint8_t*>(p.aux) + ((size_t)nr * p.ld_aux + nc) * esz;
               asm volatile("prefetch.global.L2 [%0];" ::"l"(pa));
-              if (nc + 64 < p.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(pa + 64));
+              if (!kQ8Aux && nc + 64 < p.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(pa + 128));
             }
           }
         }
@@ -308,17 +326,30 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const int cbase = col0 + c * 64;
           // this chunk's staging tile; its previous TMA store (two chunks ago; the GELU mode's second
           // output: one chunk ago) must have been read out
-          my_buf = my_bufs + (MODE == kBiasGelu ? 0 : (chunk_no & 1)) * (32 * 128);
+          my_buf = my_bufs + (kGelu2 ? 0 : (chunk_no & 1)) * (32 * 128);
           ++chunk_no;
           if (lane == 0) tma_wait_group_read<1>();
           __syncwarp();
-          if constexpr (has_aux) {
+          uint32_t auxq[kQ8Aux ? 16 : 1];                 // one-byte aux: this row's 64 bytes
+          if constexpr (kQ8Aux) {
+            // the byte tile (32 x 64 bytes, 64B swizzle) has another row pitch than the output tile that is written over
+            // it: every lane takes its whole row out before any output is staged
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              *reinterpret_cast<uint4*>(my_buf + sw64_offset(8 * i + (lane >> 2), lane & 3)) = auxr[c][i];
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 q = *reinterpret_cast<const uint4*>(my_buf + sw64_offset(lane, j));
+              auxq[4 * j] = q.x; auxq[4 * j + 1] = q.y; auxq[4 * j + 2] = q.z; auxq[4 * j + 3] = q.w;
+            }
+          } else if constexpr (has_aux) {
 #pragma unroll
             for (int i = 0; i < 8; ++i)
               *reinterpret_cast<uint4*>(my_buf + sw128_offset(4 * i + crow, cchunk)) = auxr[c][i];
           }
           __syncwarp();     // aux staged (each lane then only touches its own row: reads aux, writes output)
-          uint32_t out2w[MODE == kBiasGelu ? 32 : 1];     // second output of the GELU mode (gelu'(u))
+          uint32_t out2w[kGelu2 ? (kQ8Out ? 16 : 32) : 1];     // second output of the GELU modes (gelu'(u); bytes when quantised)
           // bias of the chunk's 64 columns, requested before the TMEM waits so that its latency overlaps theirs
           // (the first bias add was the top long-scoreboard stall of the epilogue); N is a multiple of 8, so a
           // group of four columns is inside the matrix or entirely outside
@@ -338,8 +369,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           auto do_piece = [&](auto half_tag, uint32_t (&v)[32]) {
             constexpr int half = decltype(half_tag)::value;
             const float (&bv)[32] = bias_r[half];        // bias of the 32 columns (same for every row)
-            uint32_t auxw[has_aux ? 16 : 1];             // this row's aux for the 32 columns of this piece
-            if constexpr (has_aux) {
+            uint32_t auxw[(has_aux && !kQ8Aux) ? 16 : 1];             // this row's aux for the 32 columns of this piece
+            if constexpr (has_aux && !kQ8Aux) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const uint4 q = *reinterpret_cast<const uint4*>(my_buf + sw128_offset(lane, half * 4 + j));
@@ -354,6 +385,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               } else if constexpr (MODE == kBiasGelu) {
                 gelu_and_grad_x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]), bv[2 * j], bv[2 * j + 1], outw[j],
                                  out2w[half * 16 + j]);
+              } else if constexpr (kQ8Out) {
+                if ((j & 1) == 0) {                        // four columns -> one word of bytes
+                  uint32_t q0, q1, q2, q3;
+                  gelu_and_grad_q8_x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]), bv[2 * j], bv[2 * j + 1], outw[j], q0, q1);
+                  gelu_and_grad_q8_x2(__uint_as_float(v[2 * j + 2]), __uint_as_float(v[2 * j + 3]), bv[2 * j + 2], bv[2 * j + 3],
+                                      outw[j + 1], q2, q3);
+                  out2w[half * 8 + (j >> 1)] = __byte_perm(__byte_perm(q0, q1, 0x0040), __byte_perm(q2, q3, 0x0040), 0x5410);
+                }
+              } else if constexpr (kQ8Aux) {
+                const uint64_t g2 = gelu_q8_dequant_x2(auxq[half * 8 + (j >> 1)], (2 * j) & 3, (2 * j + 1) & 3);
+                float a0, a1;
+                f2_unpack(f2_mul(f2_pack(__uint_as_float(v[2 * j]) + bv[2 * j], __uint_as_float(v[2 * j + 1]) + bv[2 * j + 1]), g2), a0, a1);
+                outw[j] = pack_bf16(a0, a1);
               } else {
                 float a0 = __uint_as_float(v[2 * j]) + bv[2 * j];
                 float a1 = __uint_as_float(v[2 * j + 1]) + bv[2 * j + 1];
@@ -373,6 +417,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               if constexpr (MODE == kBiasGelu) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) out2w[half * 16 + j] = 0u;
+              }
+              if constexpr (kQ8Out) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) out2w[half * 8 + j] = 0u;
               }
             }
 #pragma unroll
@@ -431,14 +479,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               }
             }
           }
-          if constexpr (MODE == kBiasGelu) {
+          if constexpr (kGelu2) {
             uint8_t* buf2 = my_bufs + 32 * 128;           // the second output has its own tile
             if (lane == 0) tma_wait_group_read<1>();      // its store of the previous chunk (the D store above may be in flight)
             __syncwarp();
+            if constexpr (kQ8Out) {                       // 32 rows x 64 bytes, 64B swizzle
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              *reinterpret_cast<uint4*>(buf2 + sw128_offset(lane, j)) =
-                  make_uint4(out2w[4 * j], out2w[4 * j + 1], out2w[4 * j + 2], out2w[4 * j + 3]);
+              for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<uint4*>(buf2 + sw64_offset(lane, j)) =
+                    make_uint4(out2w[4 * j], out2w[4 * j + 1], out2w[4 * j + 2], out2w[4 * j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<uint4*>(buf2 + sw128_offset(lane, j)) =
+                    make_uint4(out2w[4 * j], out2w[4 * j + 1], out2w[4 * j + 2], out2w[4 * j + 3]);
+            }
             store_staged(&tmD2, buf2, cbase);
           }
         };
@@ -489,6 +544,8 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tm
     case kBiasGelu: return launch_mode<A_MN, B_MN, kBiasGelu>(tmA, tmB, tmD, tmD2, args, stream);
     case kBiasGeluFwd: return launch_mode<A_MN, B_MN, kBiasGeluFwd>(tmA, tmB, tmD, tmD2, args, stream);
     case kMulAux: return launch_mode<A_MN, B_MN, kMulAux>(tmA, tmB, tmD, tmD2, args, stream);
+    case kBiasGeluQ8: return launch_mode<A_MN, B_MN, kBiasGeluQ8>(tmA, tmB, tmD, tmD2, args, stream);
+    case kMulAuxQ8: return launch_mode<A_MN, B_MN, kMulAuxQ8>(tmA, tmB, tmD, tmD2, args, stream);
     default: return launch_mode<A_MN, B_MN, kF32Reduce>(tmA, tmB, tmD, tmD2, args, stream);
   }
 }
@@ -500,7 +557,7 @@ int gemm_bf16(const void* A, int a_major, long lda, const void* B, int b_major, 
               const void* aux, long ld_aux, const float* bias, float* colsum, int M, int N, int K, int mode,
               int k_splits, cudaStream_t stream) {
   STSWIN_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
-  STSWIN_CHECK_ARG(mode >= kBias && mode <= kBiasGeluFwd, "gemm: unknown epilogue mode %d", mode);
+  STSWIN_CHECK_ARG(mode >= kBias && mode <= kMulAuxQ8, "gemm: unknown epilogue mode %d", mode);
   STSWIN_CHECK_ARG(a_major == 0 || a_major == 1, "gemm: a_major must be 0 or 1");
   STSWIN_CHECK_ARG(b_major == 0 || b_major == 1, "gemm: b_major must be 0 or 1");
   STSWIN_CHECK_ARG(!(a_major == 1 && b_major == 0), "gemm: (A MN-major, B K-major) is not instantiated");
@@ -508,8 +565,10 @@ int gemm_bf16(const void* A, int a_major, long lda, const void* B, int b_major, 
   STSWIN_CHECK_ARG(A && B && D, "gemm: null operand");
   if (k_splits < 1) k_splits = 1;
   STSWIN_CHECK_ARG(k_splits == 1 || mode == kF32Reduce, "gemm: split-K requires the fp32 reduce epilogue");
-  STSWIN_CHECK_ARG(mode != kBiasGelu || D2 != nullptr, "gemm: gelu epilogue needs the pre-activation output D2");
-  STSWIN_CHECK_ARG((mode != kBiasRes && mode != kMulAux) || aux != nullptr, "gemm: epilogue mode %d needs aux", mode);
+  STSWIN_CHECK_ARG((mode != kBiasGelu && mode != kBiasGeluQ8) || D2 != nullptr, "gemm: gelu epilogue needs the derivative output D2");
+  STSWIN_CHECK_ARG((mode != kBiasRes && mode != kMulAux && mode != kMulAuxQ8) || aux != nullptr, "gemm: epilogue mode %d needs aux", mode);
+  STSWIN_CHECK_ARG((mode != kBiasGeluQ8 && mode != kMulAuxQ8) || (N % 16 == 0 && (mode == kBiasGeluQ8 ? ldd : ld_aux) % 16 == 0),
+                   "gemm: the one-byte GELU' modes need N and the leading dimension of the byte matrix to be multiples of 16");
   const int kb_total = (K + BK - 1) / BK;
   if (k_splits > kb_total) k_splits = kb_total;
   // every split must own at least one k-block (an empty split would publish an unwritten accumulator)
@@ -539,6 +598,8 @@ int gemm_bf16(const void* A, int a_major, long lda, const void* B, int b_major, 
       STSWIN_CHECK_ARG(ldd % 8 == 0 && N % 8 == 0, "gemm: N and ldd must be multiples of 8 elements");
       STSWIN_CHECK_ARG((reinterpret_cast<uintptr_t>(D) & 15) == 0, "gemm: D must be 16-byte aligned");
       STSWIN_CHECK_ARG(D2 == nullptr || (reinterpret_cast<uintptr_t>(D2) & 15) == 0, "gemm: D2 must be 16-byte aligned");
+      if (mode == kMulAuxQ8)
+        STSWIN_CHECK_ARG((reinterpret_cast<uintptr_t>(aux) & 15) == 0, "gemm: aux must be 16-byte aligned");
       if (mode == kBiasRes || mode == kMulAux)
         STSWIN_CHECK_ARG(ld_aux % 8 == 0 && (reinterpret_cast<uintptr_t>(aux) & 15) == 0,
                          "gemm: aux must be 16-byte aligned with ld_aux a multiple of 8");
@@ -546,7 +607,11 @@ int gemm_bf16(const void* A, int a_major, long lda, const void* B, int b_major, 
       dims[0] = N; dims[1] = M;
       str[0] = (uint64_t)ldd * 2; box[0] = 64; box[1] = 32;
       if ((rc = make_tmap(&tmD, TmapDtype::BF16, 2, D, dims, str, box, true)) != kOk) return rc;
-      if (D2 != nullptr && (rc = make_tmap(&tmD2, TmapDtype::BF16, 2, D2, dims, str, box, true)) != kOk) return rc;
+      if (D2 != nullptr && mode != kBiasGeluQ8 && (rc = make_tmap(&tmD2, TmapDtype::BF16, 2, D2, dims, str, box, true)) != kOk) return rc;
+      if (mode == kBiasGeluQ8) {      // one byte per element: [32 rows x 64 bytes] boxes, 64B swizzle
+        str[0] = (uint64_t)ldd;
+        if ((rc = make_tmap(&tmD2, TmapDtype::U8, 2, D2, dims, str, box, false, true)) != kOk) return rc;
+      }
     }
   }
   GemmArgs args{M, N, K, mode, k_splits, bias, colsum, static_cast<__nv_bfloat16*>(D), static_cast<__nv_bfloat16*>(D2),

@@ -56,7 +56,7 @@ static EncodeTiledFn encode_fn() {
 }
 
 int make_tmap(CUtensorMap* out, TmapDtype dt, int rank, const void* base, const uint64_t* dims,
-              const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128) {
+              const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128, bool swizzle64) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return set_error(kErrDriver, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
   if (rank < 1 || rank > 5) return set_error(kErrInvalidArg, "tensor map rank %d out of range", rank);
@@ -80,7 +80,8 @@ int make_tmap(CUtensorMap* out, TmapDtype dt, int rank, const void* base, const 
                             : dt == TmapDtype::F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
                                                    : CU_TENSOR_MAP_DATA_TYPE_UINT8;
   CUresult r = fn(out, cdt, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : (swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE),
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return set_error(kErrDriver,

@@ -39,10 +39,10 @@ int num_sms();   // of the current device
 enum class TmapDtype { BF16, F32, U8 };
 
 // Tiled tensor map over `rank` dims (innermost first). strides_bytes has rank-1 entries
-// (stride of dim 1.., the innermost is dense). swizzle128: 128-byte swizzle, else none.
+// (stride of dim 1.., the innermost is dense). swizzle128: 128-byte swizzle, else none (swizzle64: 64-byte swizzle instead).
 // Returns kOk or a negative error (message in last_error()).
 int make_tmap(CUtensorMap* out, TmapDtype dt, int rank, const void* base, const uint64_t* dims,
-              const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128);
+              const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128, bool swizzle64 = false);
 
 // Launch with programmatic dependent launch allowed (the kernel MUST call pdl_wait() before it touches anything a
 // preceding kernel of the stream wrote).  STSWIN_PDL=0 in the environment falls back to plain serialised launches.

@@ -13,6 +13,7 @@ from . import _lib
 from ._lib import StswinError
 
 EPI_BIAS, EPI_BIAS_RES, EPI_BIAS_GELU, EPI_MUL_AUX, EPI_F32_REDUCE, EPI_BIAS_GELU_FWD = 0, 1, 2, 3, 4, 5
+EPI_BIAS_GELU_Q8, EPI_MUL_AUX_Q8 = 6, 7      # GELU' kept as one byte per element (include/stswin_b200.h)
 
 # ---------------------------------------------------------------------------------------------
 # launch accounting (bench.py): every C-ABI kernel launch is counted; with an EventProfiler
@@ -160,12 +161,13 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn_major: bool = False, b_mn_maj
     elif out is None:
         out = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
     assert out.shape == (M, N) and out.stride(1) == 1
-    if mode == EPI_BIAS_GELU and out2 is None:
-        out2 = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+    if mode in (EPI_BIAS_GELU, EPI_BIAS_GELU_Q8) and out2 is None:
+        out2 = torch.empty((M, N), dtype=torch.uint8 if mode == EPI_BIAS_GELU_Q8 else torch.bfloat16, device=a.device)
     if out2 is not None:
+        _req(out2, torch.uint8 if mode == EPI_BIAS_GELU_Q8 else torch.bfloat16, "out2")
         assert out2.shape == (M, N) and out2.stride() == out.stride()
     if aux is not None:
-        _req(aux, torch.bfloat16, "aux"); assert aux.shape == (M, N) and aux.stride(1) == 1
+        _req(aux, torch.uint8 if mode == EPI_MUL_AUX_Q8 else torch.bfloat16, "aux"); assert aux.shape == (M, N) and aux.stride(1) == 1
     if bias is not None:
         bias = _al16(bias)
         _req(bias, torch.float32, "bias"); assert bias.numel() == N

@@ -31,6 +31,10 @@ from ._lib import StswinError
 from .optim import bf16_weight as _w16
 
 _BF16 = torch.bfloat16
+# bf16 mode: keep GELU'(fc1 output) for the backward as one byte per element (step 0.005 over [-0.14, 1.14]; the bf16 rounding
+# of a value near 1 is 0.002-0.004) instead of bf16 -- the fc1 + GELU layer is HBM-write bound.  False
+# restores the bf16 form.
+GELU_GRAD_Q8 = True
 
 
 def to_2tuple(x):
@@ -149,8 +153,10 @@ class _BlockFn(torch.autograd.Function):
             z = ops.gemm(h, w2, bias=b_fc2, aux=y, mode=ops.EPI_BIAS_RES)
             out, _, _ = ops.layernorm_fwd(z, g1, be1, eps)
             return out.view(Bp, T, L, C)
-        dgelu = torch.empty((x2.shape[0], w1.shape[0]), dtype=_BF16, device=x.device)   # gelu'(fc1 out), for the backward
-        h = ops.gemm(yn, w1, bias=b_fc1, mode=ops.EPI_BIAS_GELU, out2=dgelu)
+        # gelu'(fc1 out) for the backward, one byte per element (a bounded multiplier; fc1 + GELU is HBM-write bound)
+        q8 = GELU_GRAD_Q8 and w1.shape[0] % 16 == 0
+        dgelu = torch.empty((x2.shape[0], w1.shape[0]), dtype=torch.uint8 if q8 else _BF16, device=x.device)
+        h = ops.gemm(yn, w1, bias=b_fc1, mode=ops.EPI_BIAS_GELU_Q8 if q8 else ops.EPI_BIAS_GELU, out2=dgelu)
         z = ops.gemm(h, w2, bias=b_fc2, aux=y, mode=ops.EPI_BIAS_RES)
         out, mean1, rstd1 = ops.layernorm_fwd(z, g1, be1, eps)
         ctx.save_for_backward(x2, qkv, attn, lse2, y, yn, mean2, rstd2, dgelu, h, z, mean1, rstd1,
@@ -176,7 +182,8 @@ class _BlockFn(torch.autograd.Function):
         # out = norm1(z)
         dz = ops.layernorm_bwd(d2, z, mean1, rstd1, g1, d_g1, d_be1, dx_colsum=d_bfc2)
         # z = y + h W2^T + b2 ; h = gelu(u), and the forward stored gelu'(u)
-        du = ops.gemm(dz, w2, b_mn_major=True, mode=ops.EPI_MUL_AUX, aux=dgelu, colsum=d_bfc1)
+        du = ops.gemm(dz, w2, b_mn_major=True, mode=ops.EPI_MUL_AUX_Q8 if dgelu.dtype == torch.uint8 else ops.EPI_MUL_AUX,
+                      aux=dgelu, colsum=d_bfc1)
         d_wfc2 = _linear_wgrad(dz, h, w2.shape, d_wfc2_)
         # u = yn W1^T + b1 ; yn = norm2(y)
         dyn = ops.gemm(du, w1, b_mn_major=True)
@@ -297,8 +304,9 @@ class _MlpFn(torch.autograd.Function):
     def forward(ctx, x, w1, b1, w2, b2):
         x2 = x.reshape(-1, x.shape[-1])
         w1b, w2b = _w16(w1), _w16(w2)
-        dgelu = torch.empty((x2.shape[0], w1b.shape[0]), dtype=_BF16, device=x.device)
-        h = ops.gemm(x2, w1b, bias=b1, mode=ops.EPI_BIAS_GELU, out2=dgelu)
+        q8 = GELU_GRAD_Q8 and w1b.shape[0] % 16 == 0
+        dgelu = torch.empty((x2.shape[0], w1b.shape[0]), dtype=torch.uint8 if q8 else _BF16, device=x.device)
+        h = ops.gemm(x2, w1b, bias=b1, mode=ops.EPI_BIAS_GELU_Q8 if q8 else ops.EPI_BIAS_GELU, out2=dgelu)
         y = ops.gemm(h, w2b, bias=b2)
         ctx.save_for_backward(x2, h, dgelu, w1b, w2b)
         return y.view(*x.shape[:-1], w2b.shape[0])
@@ -309,7 +317,8 @@ class _MlpFn(torch.autograd.Function):
         d2 = dy.contiguous().view(-1, w2b.shape[0])
         d_b2, d_b1, d_w2_, d_w1_ = _zeros_like_many([(w2b.shape[0],), (w1b.shape[0],), tuple(w2b.shape), tuple(w1b.shape)], d2.device)
         ops.colsum(d2, d_b2)
-        du = ops.gemm(d2, w2b, b_mn_major=True, mode=ops.EPI_MUL_AUX, aux=dgelu, colsum=d_b1)
+        du = ops.gemm(d2, w2b, b_mn_major=True, mode=ops.EPI_MUL_AUX_Q8 if dgelu.dtype == torch.uint8 else ops.EPI_MUL_AUX,
+                      aux=dgelu, colsum=d_b1)
         d_w2 = _linear_wgrad(d2, h, w2b.shape, d_w2_)
         dx = ops.gemm(du, w1b, b_mn_major=True)
         d_w1 = _linear_wgrad(du, x2, w1b.shape, d_w1_)

@@ -62,6 +62,32 @@ def test_gemm_epilogues(M, N, K):
     assert _rel(d.float(), acc * R.float()) < 1e-2
 
 
+def test_gemm_gelu_derivative_as_bytes():
+    """STSWIN_EPI_BIAS_GELU_Q8 / STSWIN_EPI_MUL_AUX_Q8: GELU' stored as one byte per element (step 1.28 / 255) and consumed by
+    the x-aux epilogue of the backward; ragged M / N edges included."""
+    from stswincl_b200 import ops
+    for (M, N, K) in ((300, 272, 192), (512, 2048, 512)):
+        A, B = _mk((M, K), 11), _mk((N, K), 12)
+        bias = torch.randn(N, generator=torch.Generator().manual_seed(13)).cuda()
+        q = torch.full((M, N), 77, dtype=torch.uint8, device="cuda")
+        cs = torch.zeros(N, device="cuda")
+        h = ops.gemm(A, B, mode=ops.EPI_BIAS_GELU_Q8, bias=bias, out2=q, colsum=cs)
+        u = (A.float() @ B.float().t() + bias).double().requires_grad_(True)
+        href = torch.nn.functional.gelu(u)
+        href.sum().backward()
+        assert _rel(h.float(), href.detach().float()) < 1e-2
+        deq = q.float() * (1.28 / 255.0) - 0.14
+        assert (deq - u.grad.float()).abs().max() < 0.5 * 1.28 / 255 + 1.5e-3      # half a step + the tanh-form error
+        # backward side: D = acc * dequant(aux) (+ column sums), against the same product with the exact derivative
+        A2, B2 = _mk((M, 64), 14), _mk((64, N), 15)
+        cs2 = torch.zeros(N, device="cuda")
+        d = ops.gemm(A2, B2, b_mn_major=True, mode=ops.EPI_MUL_AUX_Q8, aux=q, colsum=cs2)
+        acc2 = A2.float() @ B2.float()
+        assert _rel(d.float(), acc2 * deq) < 1e-2
+        assert _rel(d.float(), acc2 * u.grad.float()) < 1e-2
+        assert _rel(cs2, d.float().sum(0)) < 1e-3
+
+
 def test_gemm_gelu_outliers():
     """Pre-activations far outside the usual range (|u| up to ~60): GELU(u) -> u or 0 and GELU'(u) -> 1 or 0.
     (The polynomial inside the tanh form changes sign beyond |u| ~ 11 unless u^2 is clamped.)"""

@@ -6,7 +6,7 @@ from stswincl_b200 import ops
 M, N, K = (int(a) for a in sys.argv[1:4])
 mode = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 b_mn = bool(int(sys.argv[5])) if len(sys.argv) > 5 else False
-use_cs = bool(int(sys.argv[6])) if len(sys.argv) > 6 else (mode == 3)
+use_cs = bool(int(sys.argv[6])) if len(sys.argv) > 6 else (mode in (3, 7))
 g = torch.Generator().manual_seed(0)
 A = (torch.randn(M, K, generator=g) * K ** -0.5).to(torch.bfloat16).cuda()
 B = torch.randn(N, K, generator=g).to(torch.bfloat16).cuda()
@@ -14,10 +14,14 @@ if b_mn:
     B = B.t().contiguous()
 bias = torch.randn(N, generator=g).cuda()
 aux = torch.randn(M, N, generator=g).to(torch.bfloat16).cuda() if mode in (1, 3) else None
+if mode == 7:
+    aux = torch.randint(0, 256, (M, N), generator=g, dtype=torch.uint8).cuda()
 out = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
 out2 = torch.empty(M, N, dtype=torch.bfloat16, device="cuda") if mode == 2 else None
+if mode == 6:
+    out2 = torch.empty(M, N, dtype=torch.uint8, device="cuda")
 cs = torch.zeros(N, device="cuda") if use_cs else None
-kw = dict(b_mn_major=b_mn, mode=mode, bias=None if mode == 3 else bias, aux=aux, out=out, out2=out2, colsum=cs)
+kw = dict(b_mn_major=b_mn, mode=mode, bias=None if mode in (3, 7) else bias, aux=aux, out=out, out2=out2, colsum=cs)
 for _ in range(4):
     ops.gemm(A, B, **kw)
 torch.cuda.synchronize()
