@@ -6,6 +6,10 @@ sys.path.insert(0, "."); sys.path.insert(0, "tests")
 from conftest import rel_err
 from oracle import swin_oracle as so
 from stswincl_b200 import swin
+import os
+if os.environ.get("GELU_GRAD_Q8") is not None:      # A/B of the one-byte GELU' storage
+    swin.GELU_GRAD_Q8 = os.environ["GELU_GRAD_Q8"] != "0"
+print("GELU_GRAD_Q8 =", swin.GELU_GRAD_Q8)
 CASES = [("S1_unshifted", 512, (64, 80), 4, 8, 0), ("S1_shifted", 512, (64, 80), 4, 8, 4),
          ("S2_unshifted", 1024, (32, 40), 4, 4, 0), ("S2_shifted", 1024, (32, 40), 4, 4, 2)]
 for tag, dim, res, heads, ws, shift in CASES:
