@@ -21,7 +21,7 @@ per call.  There is no CPU path and no PyTorch fallback: CPU tensors raise.
 from __future__ import annotations
 
 import math
-from typing import Optional, Tuple
+from typing import Optional
 
 import torch
 import torch.nn as nn
