@@ -72,9 +72,10 @@ def test_transpose(dt_in, dt_out):
     assert torch.equal(out.float().cpu(), ref.contiguous())
 
 
-@pytest.mark.parametrize("shape", [(3, 5120, 512), (2, 1280, 1024), (2, 200, 72), (1, 64, 64)])
+@pytest.mark.parametrize("shape", [(3, 5120, 512), (2, 1280, 1024), (2, 200, 72), (1, 64, 64), (2, 136, 264), (1, 8, 8)])
 def test_transpose_bf16_vectorised(shape):
-    """bf16 -> bf16 with both extents multiples of 8 takes the 64x64-tile kernel (16-byte accesses); ragged tiles too."""
+    """bf16 -> bf16 with both extents multiples of 8 takes the register-transpose kernel (8x8 blocks per thread, 128x128 per
+    CTA, 16-byte accesses); ragged tiles too."""
     from stswincl_b200 import ops
     x = torch.randn(*shape, generator=torch.Generator().manual_seed(1)).to(torch.bfloat16)
     out = ops.transpose(x.cuda(), torch.bfloat16)
