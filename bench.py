@@ -78,6 +78,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pixloss", action="store_true", help="skip the pixel contrastive loss object")
     ap.add_argument("--no-graph", action="store_true", help="do not capture the step in a CUDA graph")
+    ap.add_argument("--gelu-grad", default="q8", choices=["q8", "bf16"],
+                    help="storage of the MLP's saved GELU derivative: one byte per element (default) or bf16")
     ap.add_argument("--dp", default="flat", choices=["flat", "ddp"],
                     help="N > 1: 'flat' = forward + backward replayed from CUDA graph segments whose gradient buckets are "
                          "all-reduced (NCCL, average) on a side stream while the next segment runs, then the optimizer "
@@ -329,6 +331,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     from stswincl_b200 import contrast, ops, optim as soptim, swin
+    swin.GELU_GRAD_Q8 = args.gelu_grad == "q8"
 
     RES, _, opt_kind, _ = CONFIGS[args.config]
     pretrain = args.config == "pretrain"
@@ -667,7 +670,10 @@ def run_ours(args):
         line = {"metric": METRIC, "value": frames / (ms_step * 1e-3), "unit": "frames/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": dict(workload_config(args.config, B, graph is not None), parallelism=par),
+                "config": dict(workload_config(args.config, B, graph is not None), parallelism=par,
+                               saved_activations="bf16" + ("; the MLP's GELU derivative (a multiplier in [-0.13, 1.13] that only the backward's "
+                                                           "epilogue reads) as a one-byte code with step 0.005, parity tests at the unchanged "
+                                                           "2e-2 bar (--gelu-grad bf16 keeps it in bf16)" if args.gelu_grad == "q8" else "")),
                 "clocks": clocks,
                 "e2e": {"value": frames / (ms_e2e * 1e-3), "unit": "frames/s", "ms_per_step": ms_e2e,
                         "h2d_bytes_per_step": x_host.numel() * x_host.element_size(), "d2h_bytes_per_step": d2h_bytes},
